@@ -1,0 +1,177 @@
+/*
+ * chordb200.h — C-ABI of libchordb200.so: B200 (sm_100a) kernels for the per-frame
+ * DSP of sevagh/chord-detection's four multipitch methods.
+ *
+ * The reference is pure Python and has NO FFI / operator ABI; its only
+ * extension point is the Python class protocol `Multipitch*.compute_pitches()`.  Each
+ * entry point below replaces the per-frame loop of one such method and is what a
+ * maintainer's ctypes binding would call (INTEGRATION.md shows the stub):
+ *
+ *   cdb_he_chroma      <- chord_detection/harmonic_energy.py:31-73   (method 2, the metric)
+ *   cdb_esacf_chroma   <- chord_detection/esacf.py:41-134 + dsp/wfir.py:25-43, dsp/lowpass.py:6-8
+ *   cdb_iterf0_chroma  <- chord_detection/iterative_f0.py:54-96,171-193 + periodicity.py:48-163
+ *   cdb_prime_chroma   <- chord_detection/prime_multif0.py:41-91
+ *   framing rule       <- chord_detection/dsp/frame.py:5-14 (ceil(n/frame) frames, zero-padded tail)
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every `d_*` pointer is DEVICE memory owned by the
+ *     caller (e.g. torch tensor .data_ptr()); `h_*`/struct pointers are host memory read
+ *     during the call.  The library owns only per-handle constant tables / workspace,
+ *     freed by cdb_destroy.  No host<->device copies of signal data happen inside a call.
+ *   - A batch is `n_clips` clips of `clip_len` float32 samples; clip c starts at
+ *     d_x + c*clip_stride.  Frames never span clips.
+ *   - Outputs (any may be NULL): d_chroma_total[12] double = sum over all frames of all
+ *     clips; d_chroma_clips[n_clips*12] double; d_chroma_frames float (per method layout).
+ *     Outputs are zeroed by the call unless CDB_FLAG_ACCUMULATE is set.
+ *   - `stream` is a cudaStream_t (NULL = default stream).  Calls are asynchronous and
+ *     stream-ordered; the first call with a new parameter set builds and uploads the
+ *     constant tables for it (synchronous, cached in the handle).
+ *   - Return value: 0 = OK; <0 = argument error (CDB_E_*); >0 = cudaError_t.
+ *     cdb_last_error(h) returns a message for the last non-zero return on this handle.
+ *   - One handle per (host thread, device).  No global mutable state.
+ */
+#ifndef CHORDB200_H
+#define CHORDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDB_VERSION 100 /* 0.1.0 */
+
+#define CDB_E_INVALID (-1)     /* bad argument value */
+#define CDB_E_UNSUPPORTED (-2) /* valid in the reference but not implemented on device */
+#define CDB_E_NULL (-3)        /* NULL handle / pointer */
+#define CDB_E_NOGPU (-4)       /* no CUDA device / wrong architecture */
+
+#define CDB_FLAG_ACCUMULATE 1 /* do not zero the outputs first */
+
+#define CDB_WINDOW_HAMMING 0 /* scipy.signal.hamming(N) symmetric (harmonic_energy.py:42) */
+#define CDB_WINDOW_HANN 1    /* symmetric Hann (north_star wording; not the reference) */
+#define CDB_WINDOW_RECT 2
+
+typedef struct cdb_handle cdb_handle;
+
+int cdb_version(void);
+int cdb_create(cdb_handle** out, int device);
+int cdb_destroy(cdb_handle* h);
+const char* cdb_last_error(cdb_handle* h);
+/* number of kernels launched through this handle since creation (bench `gpu_launches`) */
+int64_t cdb_launch_count(cdb_handle* h);
+
+/* frame.py:9-14 generalised with a hop: frames start at g*hop for every
+ * g*hop < clip_len; hop == frame_size reproduces the reference exactly. */
+int64_t cdb_num_frames(int64_t clip_len, int frame_size, int hop);
+
+/* ---------------- method 2: harmonic energy (harmonic_energy.py:31-73) ---------------- */
+typedef struct {
+  double fs;        /* sample rate of d_x (multipitch.py:25 gives 22050) */
+  int frame_size;   /* :15 default 8192; power of two in [64, 16384] */
+  int hop;          /* 0 or frame_size = the reference's non-overlapping frames */
+  int window_kind;  /* CDB_WINDOW_* ; reference = HAMMING */
+  int num_harmonic; /* :15 default 2 */
+  int num_octave;   /* :15 default 2 */
+  int num_bins;     /* :15 default 2 */
+  int64_t frames_per_clip; /* <=0: cdb_num_frames(clip_len, frame_size, hop); >0: exactly this
+                              many frames per clip (samples past clip_len read as zero) — used
+                              when a long signal is sharded by frame ranges with a halo */
+} cdb_he_params;
+
+/* host-only: the probe windows the reference's triple loop visits (harmonic_energy.py:44-66),
+ * in loop order.  Arrays must hold 12*num_octave*num_harmonic entries.  Returns that count,
+ * or <0.  Needs no GPU (used by CPU tests of the host logic). */
+int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k1, double* weight);
+
+/* d_chroma_frames: [n_clips*frames_per_clip, 12] float32 or NULL */
+int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float* d_x, int64_t n_clips,
+                  int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
+                  double* d_chroma_clips, float* d_chroma_frames, int flags, void* stream);
+
+/* ---------------- method 1: ESACF (esacf.py:41-134) ---------------- */
+#define CDB_STRETCH_TRUNCATE 0 /* librosa>=0.8 time_stretch on a <1024-sample SACF */
+#define CDB_STRETCH_NONE 1     /* librosa<=0.7 (README-era): clipping only */
+
+typedef struct {
+  double fs;
+  int ham_samples;      /* esacf.py:27 int(fs*ham_ms/1000); 3..4096 */
+  double k;             /* esacf.py:93-96: |FFT|^k, reference always uses 0.67 */
+  int n_peaks_elim;     /* :22 default 6 */
+  double peak_thresh;   /* :23 default 0.1 */
+  int peak_min_dist;    /* :24 default 10 */
+  int stretch_mode;     /* CDB_STRETCH_* */
+  /* filter designs, done once on the host in float64 with the same SciPy calls the
+   * reference makes per frame (setup, not per-frame DSP): */
+  double wfir_lambda;   /* dsp/wfir.py:6-10 */
+  double wfir_taps[13]; /* dsp/wfir.py:13-21 remez(13, ...) */
+  double lp_b[3], lp_a[3]; /* dsp/lowpass.py:7 butter(2, 1000/(fs/2), 'low')  */
+  double hp_b[3], hp_a[3]; /* esacf.py:133   butter(2, 1000/(fs/2), 'high') */
+} cdb_esacf_params;
+
+/* d_chroma_frames: [n_clips*frames_per_clip, 12] float64 or NULL (frames = ceil(clip_len/ham_samples)).
+ * d_debug: NULL, or a caller buffer receiving per-frame intermediates (layout in DESIGN.md). */
+int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x, int64_t n_clips,
+                     int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
+                     double* d_chroma_clips, double* d_chroma_frames, double* d_debug, int flags,
+                     void* stream);
+
+/* ---------------- method 3: iterative F0 (iterative_f0.py, periodicity.py) ---------------- */
+#define CDB_ITERF0_MAX_CHANNELS 128
+typedef struct {
+  double fs;
+  int frame_size;  /* iterative_f0.py:25 default 8192 (power of two, <= 8192) */
+  double power;    /* :26 default 1.0 */
+  int channels;    /* :27 default 70 */
+  /* periodicity.py:15-28 */
+  int max_voices;  /* 4 */
+  double tau_min, tau_max, tau_prec; /* 1/2100, 1/40, 1e-7 */
+  int Q, M;        /* 20, 20 */
+  double epsilon1, epsilon2, gamma; /* 20, 320, 0.66 */
+  /* per-channel second-order sections designed on the host in float64 (iterative_f0.py:171-193
+   * with its swapped arguments, dsp/lowpass.py:7 at the channel frequency), then the shared
+   * whitening filter (dsp/wfir.py) */
+  double res1_b[CDB_ITERF0_MAX_CHANNELS][3], res1_a[CDB_ITERF0_MAX_CHANNELS][3];
+  double res2_b[CDB_ITERF0_MAX_CHANNELS][3], res2_a[CDB_ITERF0_MAX_CHANNELS][3];
+  double lp_b[CDB_ITERF0_MAX_CHANNELS][3], lp_a[CDB_ITERF0_MAX_CHANNELS][3];
+  double wfir_lambda;
+  double wfir_taps[13];
+} cdb_iterf0_params;
+
+/* d_workspace: caller-owned scratch of cdb_iterf0_workspace_bytes(...) bytes.
+ * d_chroma_frames: [n_clips*frames_per_clip, 12] float64 or NULL.
+ * d_voices: NULL or [n_frames, 2*max_voices] float64 (saliences then periods). */
+int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params* p, int64_t n_clips, int64_t clip_len);
+int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_x, int64_t n_clips,
+                      int64_t clip_len, int64_t clip_stride, void* d_workspace,
+                      int64_t workspace_bytes, double* d_chroma_total, double* d_chroma_clips,
+                      double* d_chroma_frames, double* d_voices, int flags, void* stream);
+
+/* ---------------- method 4: prime multi-F0 (prime_multif0.py:41-91) ---------------- */
+typedef struct {
+  double fs;
+  int num_harmonic;            /* :22 default 1 */
+  int num_octave;              /* :23 default 2 */
+  int harmonic_multiples_elim; /* :24 default 5 -> multiples 1..4 */
+  int harmonic_elim_runs;      /* :25 default 2 */
+} cdb_prime_params;
+
+/* host-only: window sizes int(8/f*fs) of the candidates in loop order (prime_multif0.py:49-53).
+ * Returns the count (12*num_octave*num_harmonic) or <0. */
+int cdb_prime_window_sizes(const cdb_prime_params* p, int* sizes);
+
+/* d_chroma_cands: NULL or [n_clips, n_candidates, 12] float64 */
+int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x, int64_t n_clips,
+                     int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
+                     double* d_chroma_clips, double* d_chroma_cands, int flags, void* stream);
+
+/* ---------------- batched result post-processing (chromagram.py:50-126), SURVEY 8f-1 ---------------- */
+/* d_chroma [n,12] double -> d_digits [n,12] uint8 (the 12-digit string, chromagram.py:50-74) and
+ * d_key [n] int32: 0..11 = <note>maj, 12..23 = <note>min, 24+12*a+b... see DESIGN.md.  Either output may be NULL. */
+int cdb_pack_and_key(cdb_handle* h, const double* d_chroma, int64_t n, uint8_t* d_digits,
+                     int32_t* d_key, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHORDB200_H */
