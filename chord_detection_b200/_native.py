@@ -1,0 +1,166 @@
+"""ctypes binding of libchordb200.so (include/chordb200.h).
+
+The product has NO CPU fallback: if the shared library is missing or no sm_100
+device is present, calls raise (RuntimeError) instead of silently computing elsewhere.
+"""
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libchordb200.so")
+
+CDB_FLAG_ACCUMULATE = 1
+WINDOW_KINDS = {"hamming": 0, "hann": 1, "rect": 2}
+STRETCH_MODES = {"truncate": 0, "none": 1}
+ITERF0_MAX_CHANNELS = 128
+
+
+class HeParams(C.Structure):
+    _fields_ = [("fs", C.c_double), ("frame_size", C.c_int), ("hop", C.c_int),
+                ("window_kind", C.c_int), ("num_harmonic", C.c_int), ("num_octave", C.c_int),
+                ("num_bins", C.c_int), ("frames_per_clip", C.c_int64)]
+
+
+class EsacfParams(C.Structure):
+    _fields_ = [("fs", C.c_double), ("ham_samples", C.c_int), ("k", C.c_double),
+                ("n_peaks_elim", C.c_int), ("peak_thresh", C.c_double),
+                ("peak_min_dist", C.c_int), ("stretch_mode", C.c_int),
+                ("wfir_lambda", C.c_double), ("wfir_taps", C.c_double * 13),
+                ("lp_b", C.c_double * 3), ("lp_a", C.c_double * 3),
+                ("hp_b", C.c_double * 3), ("hp_a", C.c_double * 3)]
+
+
+_SOS = (C.c_double * 3) * ITERF0_MAX_CHANNELS
+
+
+class IterF0Params(C.Structure):
+    _fields_ = [("fs", C.c_double), ("frame_size", C.c_int), ("power", C.c_double),
+                ("channels", C.c_int), ("max_voices", C.c_int), ("tau_min", C.c_double),
+                ("tau_max", C.c_double), ("tau_prec", C.c_double), ("Q", C.c_int), ("M", C.c_int),
+                ("epsilon1", C.c_double), ("epsilon2", C.c_double), ("gamma", C.c_double),
+                ("res1_b", _SOS), ("res1_a", _SOS), ("res2_b", _SOS), ("res2_a", _SOS),
+                ("lp_b", _SOS), ("lp_a", _SOS),
+                ("wfir_lambda", C.c_double), ("wfir_taps", C.c_double * 13)]
+
+
+class PrimeParams(C.Structure):
+    _fields_ = [("fs", C.c_double), ("num_harmonic", C.c_int), ("num_octave", C.c_int),
+                ("harmonic_multiples_elim", C.c_int), ("harmonic_elim_runs", C.c_int)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+EXPORTS = [
+    "cdb_version", "cdb_create", "cdb_destroy", "cdb_last_error", "cdb_launch_count",
+    "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
+    "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
+    "cdb_prime_chroma", "cdb_pack_and_key",
+]
+
+
+def lib():
+    """Load libchordb200.so (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libchordb200.so not found at %s: build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+        L.cdb_version.restype = C.c_int
+        L.cdb_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.cdb_destroy.argtypes = [vp]
+        L.cdb_last_error.argtypes = [vp]
+        L.cdb_last_error.restype = C.c_char_p
+        L.cdb_launch_count.argtypes = [vp]
+        L.cdb_launch_count.restype = i64
+        L.cdb_num_frames.argtypes = [i64, C.c_int, C.c_int]
+        L.cdb_num_frames.restype = i64
+        L.cdb_he_windows.argtypes = [C.POINTER(HeParams), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(dbl)]
+        L.cdb_he_chroma.argtypes = [vp, C.POINTER(HeParams), vp, i64, i64, i64, vp, vp, vp,
+                                    C.c_int, vp]
+        L.cdb_esacf_chroma.argtypes = [vp, C.POINTER(EsacfParams), vp, i64, i64, i64, vp, vp, vp,
+                                       vp, C.c_int, vp]
+        L.cdb_iterf0_workspace_bytes.argtypes = [C.POINTER(IterF0Params), i64, i64]
+        L.cdb_iterf0_workspace_bytes.restype = i64
+        L.cdb_iterf0_chroma.argtypes = [vp, C.POINTER(IterF0Params), vp, i64, i64, i64, vp, i64,
+                                        vp, vp, vp, vp, C.c_int, vp]
+        L.cdb_prime_window_sizes.argtypes = [C.POINTER(PrimeParams), C.POINTER(C.c_int)]
+        L.cdb_prime_chroma.argtypes = [vp, C.POINTER(PrimeParams), vp, i64, i64, i64, vp, vp, vp,
+                                       C.c_int, vp]
+        L.cdb_pack_and_key.argtypes = [vp, vp, i64, vp, vp, vp]
+        _lib = L
+        return _lib
+
+
+class Handle:
+    """One cdb_handle per (thread, device)."""
+
+    _tls = threading.local()
+
+    def __init__(self, device):
+        self.L = lib()
+        self.device = int(device)
+        p = C.c_void_p()
+        rc = self.L.cdb_create(C.byref(p), self.device)
+        if rc != 0:
+            raise RuntimeError(
+                "cdb_create(device=%d) failed with %d: a B200 (sm_100) CUDA device is required; "
+                "there is no CPU fallback" % (self.device, rc))
+        self.ptr = p
+
+    @classmethod
+    def get(cls, device):
+        cache = getattr(cls._tls, "cache", None)
+        if cache is None:
+            cache = cls._tls.cache = {}
+        h = cache.get(int(device))
+        if h is None:
+            h = cache[int(device)] = cls(device)
+        return h
+
+    def check(self, rc, what):
+        if rc == 0:
+            return
+        msg = self.L.cdb_last_error(self.ptr)
+        msg = msg.decode() if msg else ""
+        if rc < 0:
+            raise ValueError("%s: %s (code %d)" % (what, msg, rc))
+        raise RuntimeError("%s: CUDA error %d: %s" % (what, rc, msg))
+
+    @property
+    def launches(self):
+        return int(self.L.cdb_launch_count(self.ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                self.L.cdb_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def he_windows(fs, frame_size, num_harmonic=2, num_octave=2, num_bins=2):
+    """Host-only (no GPU): the probe windows of harmonic_energy.py:44-66 as the library sees them."""
+    L = lib()
+    p = HeParams(float(fs), int(frame_size), 0, 0, int(num_harmonic), int(num_octave),
+                 int(num_bins), 0)
+    n = 12 * num_octave * num_harmonic
+    note, k0, k1 = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+    w = (C.c_double * n)()
+    rc = L.cdb_he_windows(C.byref(p), note, k0, k1, w)
+    if rc < 0:
+        raise ValueError("cdb_he_windows failed: %d" % rc)
+    return [(note[i], k0[i], k1[i], w[i]) for i in range(rc)]
+
+
+def num_frames(clip_len, frame_size, hop=0):
+    return int(lib().cdb_num_frames(int(clip_len), int(frame_size), int(hop)))

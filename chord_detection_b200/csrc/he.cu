@@ -1,0 +1,579 @@
+// Harmonic-energy chromagram (method 2) — replaces the per-frame loop of
+// /root/reference/chord_detection/harmonic_energy.py:31-73 and dsp/frame.py:5-14.
+//
+// Per frame: window (:42) -> real FFT -> sqrt|X| (:43) -> for every (note, octave, harmonic)
+// the max of sqrt|X| over a half-open bin window, weighted 1/harmonic (:44-66) -> 12 pitch
+// classes (:67) -> summed over frames (:69).  Everything is fused into one kernel: the only
+// HBM traffic is the fp32 samples (4*hop bytes per frame) and 12 doubles out.
+//
+// Two kernels:
+//   he2048_kernel  — frame_size 2048 (the BASELINE metric shape).  One warp per frame; a CTA
+//                    stages a tile of W consecutive frames ((W-1)*hop+2048 samples, overlap
+//                    shared) into shared memory with one 1-D bulk async copy (TMA engine,
+//                    mbarrier completion); 2048-pt real FFT = 1024-pt complex FFT done as
+//                    radix-32 x radix-32 entirely in registers with ONE shared-memory
+//                    transpose; split post-processing only for the probed bins; window maxima
+//                    and the 12 sums via shared memory + fp64 accumulators.
+//   he_generic_kernel — any power-of-two frame_size in [64, 16384]; one CTA per frame,
+//                    shared-memory radix-2 FFT.  Correctness path for the other shapes
+//                    (reference default 8192).
+// No tensor cores: there is no dense contraction here (BASELINE.json north_star).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+struct HeWin {
+  int k0, k1, note, pad;
+  double weight;
+};
+
+struct HePlan {
+  cdb_he_params p;
+  int N, M, hop, log2M;
+  int n_windows, wins_per_note;
+  int kmin, kmax;  // probed bins, inclusive
+  bool force_generic;
+  float* d_win = nullptr;      // [N]
+  float2* d_tw32 = nullptr;    // [32*32]: W_1024^(t*k1) at [k1*32+t]   (N == 2048)
+  float2* d_wsplit = nullptr;  // [M+1]: (cos, sin)(2*pi*k/N)
+  float2* d_twgen = nullptr;   // [M/2]: W_M^q = (cos, -sin)(2*pi*q/M)
+  HeWin* d_wins = nullptr;
+};
+
+void cdb_free_he_plans(cdb_handle* h) {
+  for (auto& kv : h->he_plans) delete kv.second;  // device tables are in h->owned
+  h->he_plans.clear();
+}
+
+// ------------------------------------------------------------------ host tables
+static const double kPi = 3.14159265358979323846;
+
+// librosa.note_to_hz('C3') and cqt_frequencies(12, fmin) (harmonic_energy.py:33)
+static void he_notes(double notes[12]) {
+  const double fmin = 440.0 * std::pow(2.0, (48 - 69.0) / 12.0);
+  for (int k = 0; k < 12; ++k) notes[k] = 1.0 * fmin * std::pow(2.0, (double)k / 12.0);
+}
+
+static int he_build_windows(const cdb_he_params* p, std::vector<HeWin>& out) {
+  if (!p) return CDB_E_NULL;
+  if (p->num_harmonic < 1 || p->num_octave < 1 || p->num_bins < 1 || p->frame_size < 2 ||
+      !(p->fs > 0))
+    return CDB_E_INVALID;
+  double notes[12];
+  he_notes(notes);
+  const double divisor_ratio = (p->fs / 4.0) / (double)p->frame_size;  // :35
+  out.clear();
+  for (int n = 0; n < 12; ++n)
+    for (int octave = 1; octave <= p->num_octave; ++octave)
+      for (int harmonic = 1; harmonic <= p->num_harmonic; ++harmonic) {
+        // numpy.round == rint (half to even) (:51)
+        const double k_prime = std::nearbyint((notes[n] * octave * harmonic) / divisor_ratio);
+        HeWin w;
+        w.k0 = (int)(k_prime - (double)(p->num_bins * harmonic));  // :54
+        w.k1 = (int)(k_prime + (double)(p->num_bins * harmonic));  // :55
+        w.note = n;
+        w.pad = 0;
+        w.weight = 1.0 / (double)harmonic;  // :64
+        out.push_back(w);
+      }
+  return (int)out.size();
+}
+
+extern "C" int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k1,
+                              double* weight) {
+  std::vector<HeWin> w;
+  int n = he_build_windows(p, w);
+  if (n < 0) return n;
+  for (int i = 0; i < n; ++i) {
+    if (note) note[i] = w[i].note;
+    if (k0) k0[i] = w[i].k0;
+    if (k1) k1[i] = w[i].k1;
+    if (weight) weight[i] = w[i].weight;
+  }
+  return n;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+#define HE_MAX_WINDOWS 192
+
+static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
+  cdb_he_params key = *p;
+  if (key.hop <= 0) key.hop = key.frame_size;
+  key.frames_per_clip = 0;  // not part of the tables
+  const char* fg = std::getenv("CDB_HE_FORCE_GENERIC");
+  const bool force_generic = fg && fg[0] == '1';
+  std::string ks = pod_key(key) + (force_generic ? "g" : "f");
+  auto it = h->he_plans.find(ks);
+  if (it != h->he_plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (!is_pow2(key.frame_size) || key.frame_size < 64 || key.frame_size > 16384)
+    return cdb_fail(h, CDB_E_UNSUPPORTED,
+                    "frame_size %d: device path needs a power of two in [64, 16384]",
+                    key.frame_size);
+  if (key.hop > key.frame_size)
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "hop %d > frame_size %d", key.hop, key.frame_size);
+  if (key.window_kind < 0 || key.window_kind > 2)
+    return cdb_fail(h, CDB_E_INVALID, "window_kind %d", key.window_kind);
+  std::vector<HeWin> wins;
+  int nw = he_build_windows(&key, wins);
+  if (nw < 0) return cdb_fail(h, nw, "invalid harmonic-energy parameters");
+  if (nw > HE_MAX_WINDOWS)
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "num_octave*num_harmonic*12 = %d > %d", nw,
+                    HE_MAX_WINDOWS);
+  const int N = key.frame_size, M = N / 2;
+  int kmin = 1 << 30, kmax = -1;
+  for (auto& w : wins) {
+    // the reference would wrap negative indices / raise IndexError here
+    if (w.k0 < 0 || w.k1 > M + 1 || w.k1 <= w.k0)
+      return cdb_fail(h, CDB_E_UNSUPPORTED,
+                      "probe window [%d,%d) outside the %d rfft bins (reference would wrap/raise)",
+                      w.k0, w.k1, M + 1);
+    kmin = std::min(kmin, w.k0);
+    kmax = std::max(kmax, w.k1 - 1);
+  }
+  HePlan* pl = new HePlan();
+  pl->p = key;
+  pl->N = N;
+  pl->M = M;
+  pl->hop = key.hop;
+  pl->log2M = 0;
+  while ((1 << pl->log2M) < M) ++pl->log2M;
+  pl->n_windows = nw;
+  pl->wins_per_note = nw / 12;
+  pl->kmin = kmin;
+  pl->kmax = kmax;
+  pl->force_generic = force_generic;
+
+  std::vector<float> win(N);
+  for (int n = 0; n < N; ++n) {
+    double w = 1.0;
+    if (key.window_kind == CDB_WINDOW_HAMMING)  // scipy.signal.hamming(N), symmetric (:42)
+      w = 0.54 - 0.46 * std::cos(2.0 * kPi * n / (double)(N - 1));
+    else if (key.window_kind == CDB_WINDOW_HANN)
+      w = 0.5 - 0.5 * std::cos(2.0 * kPi * n / (double)(N - 1));
+    win[n] = (float)w;
+  }
+  std::vector<float2> wsplit(M + 1), twgen(M / 2), tw32;
+  for (int k = 0; k <= M; ++k) {
+    double a = 2.0 * kPi * k / (double)N;
+    wsplit[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  for (int q = 0; q < M / 2; ++q) {
+    double a = 2.0 * kPi * q / (double)M;
+    twgen[q] = make_float2((float)std::cos(a), (float)-std::sin(a));
+  }
+  if (N == 2048) {
+    tw32.resize(1024);
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int t = 0; t < 32; ++t) {
+        double a = 2.0 * kPi * (double)(t * k1) / 1024.0;
+        tw32[k1 * 32 + t] = make_float2((float)std::cos(a), (float)-std::sin(a));
+      }
+  }
+  int rc;
+  if ((rc = cdb_upload(h, win, &pl->d_win))) return rc;
+  if ((rc = cdb_upload(h, wsplit, &pl->d_wsplit))) return rc;
+  if ((rc = cdb_upload(h, twgen, &pl->d_twgen))) return rc;
+  if ((rc = cdb_upload(h, tw32, &pl->d_tw32))) return rc;
+  if ((rc = cdb_upload(h, wins, &pl->d_wins))) return rc;
+  h->he_plans[ks] = pl;
+  *out = pl;
+  return 0;
+}
+
+// ------------------------------------------------------------------ device code
+struct HeArgs {
+  const float* x;
+  int64_t n_clips, clip_len, clip_stride, frames_per_clip;
+  int64_t tiles_per_clip, total_tiles;  // fast path
+  int hop, N, M, log2M;
+  int n_windows, wins_per_note, kmin, kmax;
+  int tile_cap;  // floats reserved for the staged tile (fast path)
+  const float* win;
+  const float2* tw32;
+  const float2* wsplit;
+  const float2* twgen;
+  const HeWin* wins;
+  double* total;
+  double* clips;
+  float* frames;
+};
+
+__host__ __device__ constexpr int br5(int k) {
+  return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+// 32-point complex DIF FFT in registers; X[k] ends up in v[br5(k)].
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+  constexpr float C[16] = {1.0f,           0.980785280f,  0.923879533f,  0.831469612f,
+                           0.707106781f,   0.555570233f,  0.382683432f,  0.195090322f,
+                           0.0f,           -0.195090322f, -0.382683432f, -0.555570233f,
+                           -0.707106781f,  -0.831469612f, -0.923879533f, -0.980785280f};
+  constexpr float S[16] = {0.0f,          0.195090322f, 0.382683432f, 0.555570233f,
+                           0.707106781f,  0.831469612f, 0.923879533f, 0.980785280f,
+                           1.0f,          0.980785280f, 0.923879533f, 0.831469612f,
+                           0.707106781f,  0.555570233f, 0.382683432f, 0.195090322f};
+  constexpr float R = 0.707106781f;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int g = 0; g < 32; g += 2 * s) {
+#pragma unroll
+      for (int j = 0; j < s; ++j) {
+        const int m = j * (16 / s);  // W_{2s}^j = W_32^m = C[m] - i S[m]
+        const float2 a = v[g + j], b = v[g + j + s];
+        v[g + j] = make_float2(a.x + b.x, a.y + b.y);
+        const float dr = a.x - b.x, di = a.y - b.y;
+        if (m == 0)
+          v[g + j + s] = make_float2(dr, di);
+        else if (m == 8)
+          v[g + j + s] = make_float2(di, -dr);
+        else if (m == 4)
+          v[g + j + s] = make_float2((dr + di) * R, (di - dr) * R);
+        else if (m == 12)
+          v[g + j + s] = make_float2((di - dr) * R, -(dr + di) * R);
+        else
+          v[g + j + s] = make_float2(dr * C[m] + di * S[m], di * C[m] - dr * S[m]);
+      }
+    }
+  }
+}
+
+constexpr int kScr = 32 * 33;  // per-warp transpose scratch (float2), row stride 33
+
+template <int W>
+__global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  double* cta_acc = reinterpret_cast<double*>(smem + 16);  // [12]
+  float* inbuf = reinterpret_cast<float*>(smem + 128);
+  float* swin = inbuf + a.tile_cap;
+  float2* stw = reinterpret_cast<float2*>(swin + 2048);
+  float2* scr_all = stw + 1024;
+  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * kScr);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2048; i += W * 32) swin[i] = a.win[i];
+  for (int i = tid; i < 1024; i += W * 32) stw[i] = a.tw32[i];
+  for (int i = tid; i < a.n_windows; i += W * 32) swins[i] = a.wins[i];
+  if (tid < 12) cta_acc[tid] = 0.0;
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int64_t t_begin = (a.total_tiles * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t t_end = (a.total_tiles * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+
+  // stage one tile; returns true when it went through the bulk-async (TMA) path
+  auto issue_load = [&](int64_t tile) -> bool {
+    const int64_t clip = tile / a.tiles_per_clip;
+    const int64_t f0 = (tile - clip * a.tiles_per_clip) * W;
+    const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
+    const int64_t s0 = f0 * a.hop;
+    const int need = (int)((nf - 1) * a.hop + 2048);
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const bool full = (s0 + need <= a.clip_len);
+    const bool tma_ok =
+        full && ((need & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (tma_ok) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (uint32_t)need * 4u);
+        tma_load_1d(inbuf, src, (uint32_t)need * 4u, mbar);
+      }
+    } else {
+      const int64_t avail = a.clip_len - s0;  // may be <= 0
+      for (int i = tid; i < need; i += W * 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
+    }
+    return tma_ok;
+  };
+
+  float2* scr = scr_all + warp * kScr;
+  float* pw = reinterpret_cast<float*>(scr);               // [M+1] power spectrum
+  double* wv = reinterpret_cast<double*>(scr) + 520;        // [n_windows] (byte offset 4160)
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+
+  bool cur_tma = false;
+  uint32_t phase = 0;
+  if (t_begin < t_end) cur_tma = issue_load(t_begin);
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const int64_t clip = tile / a.tiles_per_clip;
+    const int64_t f0 = (tile - clip * a.tiles_per_clip) * W;
+    const int nf = (int)min((int64_t)W, a.frames_per_clip - f0);
+    if (cur_tma) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    } else {
+      __syncthreads();
+    }
+    float2 v[32];
+    const bool active = warp < nf;
+    if (active) {
+      // ---- pass 1: window, radix-32 over n1 (n = 32*n1 + lane), twiddle, transpose
+      const float* fr = inbuf + warp * a.hop;
+      if ((a.hop & 1) == 0) {
+        const float2* fr2 = reinterpret_cast<const float2*>(fr);
+        const float2* w2 = reinterpret_cast<const float2*>(swin);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float2 xv = fr2[32 * n1 + lane], wv2 = w2[32 * n1 + lane];
+          v[n1] = make_float2(xv.x * wv2.x, xv.y * wv2.y);
+        }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int i = 2 * (32 * n1 + lane);
+          v[n1] = make_float2(fr[i] * swin[i], fr[i + 1] * swin[i + 1]);
+        }
+      }
+      fft32(v);
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) {
+        const float2 z = v[br5(k1)], w = stw[k1 * 32 + lane];
+        scr[k1 * 33 + lane] = make_float2(z.x * w.x - z.y * w.y, z.x * w.y + z.y * w.x);
+      }
+    }
+    __syncthreads();  // every warp is done reading the staged tile
+    bool next_tma = false;
+    if (tile + 1 < t_end) next_tma = issue_load(tile + 1);  // overlaps pass 2 below
+
+    if (active) {
+      // ---- pass 2: radix-32 over n2 for k1 = lane  ->  Z[lane + 32*k2] in v[br5(k2)]
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) v[n2] = scr[lane * 33 + n2];
+      fft32(v);
+      __syncwarp();  // scratch is re-used for the power spectrum below
+      // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2
+      const int src_lane = (32 - lane) & 31;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        if (k2 * 32 + 31 >= a.kmin && k2 * 32 <= a.kmax) {  // warp-uniform
+          const int k = lane + 32 * k2;
+          const float2 z = v[br5(k2)];
+          float pr = __shfl_sync(0xffffffffu, v[br5(31 - k2)].x, src_lane);
+          float pi = __shfl_sync(0xffffffffu, v[br5(31 - k2)].y, src_lane);
+          if (lane == 0) {  // partner of Z[32*k2] is Z[1024-32*k2], held by lane 0 itself
+            pr = v[br5((32 - k2) & 31)].x;
+            pi = v[br5((32 - k2) & 31)].y;
+          }
+          const float2 cs = __ldg(&a.wsplit[k]);
+          const float er = z.x + pr, ei = z.y - pi, dr = z.x - pr, di = z.y + pi;
+          const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+          const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+          pw[k] = xr * xr + xi * xi;
+        }
+      }
+      if (a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
+        const float xn = v[br5(0)].x - v[br5(0)].y;
+        pw[1024] = xn * xn;
+      }
+      __syncwarp();
+      // ---- window maxima (harmonic_energy.py:58-64); max|X|^2 then one 4th root
+      for (int wi = lane; wi < a.n_windows; wi += 32) {
+        const HeWin hw = swins[wi];
+        float m = pw[hw.k0];
+        for (int k = hw.k0 + 1; k < hw.k1; ++k) m = fmaxf(m, pw[k]);
+        wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
+      }
+      __syncwarp();
+      if (lane < 12) {
+        double s = 0.0;
+        for (int j = 0; j < a.wins_per_note; ++j) s += wv[lane * a.wins_per_note + j];
+        if (a.clips) {
+          if (clip != my_clip) {
+            if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+            my_clip = clip;
+            acc_clip = 0.0;
+          }
+          acc_clip += s;
+        }
+        acc_total += s;
+        if (a.frames) a.frames[(clip * a.frames_per_clip + f0 + warp) * 12 + lane] = (float)s;
+      }
+      __syncwarp();
+    }
+    cur_tma = next_tma;
+  }
+  if (lane < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+    if (a.total) atomicAdd(&cta_acc[lane], acc_total);
+  }
+  __syncthreads();
+  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
+}
+
+// Generic power-of-two path: one CTA per frame at a time, in-place radix-2 DIT in shared memory.
+constexpr int kGenThreads = 256;
+
+__global__ void __launch_bounds__(kGenThreads) he_generic_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float2* s = reinterpret_cast<float2*>(smem);               // [M]
+  float* pw = reinterpret_cast<float*>(s + a.M);             // [M+1]
+  double* wv = reinterpret_cast<double*>(pw + a.M + 2);      // [n_windows]  (8-byte aligned: M even)
+  const int tid = threadIdx.x;
+  const int M = a.M;
+  const int64_t total_frames = a.n_clips * a.frames_per_clip;
+  const int64_t f_begin = (total_frames * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t f_end = (total_frames * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+
+  for (int64_t gf = f_begin; gf < f_end; ++gf) {
+    const int64_t clip = gf / a.frames_per_clip;
+    const int64_t f = gf - clip * a.frames_per_clip;
+    const int64_t s0 = f * a.hop;
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    for (int m = tid; m < M; m += kGenThreads) {
+      const float x0 = (2 * m < avail) ? src[2 * m] : 0.0f;
+      const float x1 = (2 * m + 1 < avail) ? src[2 * m + 1] : 0.0f;
+      const int r = (int)(__brev((unsigned)m) >> (32 - a.log2M));
+      s[r] = make_float2(x0 * a.win[2 * m], x1 * a.win[2 * m + 1]);
+    }
+    __syncthreads();
+    for (int st = 0; st < a.log2M; ++st) {
+      const int span = 1 << st;
+      for (int b = tid; b < M / 2; b += kGenThreads) {
+        const int j = b & (span - 1);
+        const int i0 = ((b >> st) << (st + 1)) + j, i1 = i0 + span;
+        const float2 w = __ldg(&a.twgen[j * (M / (2 * span))]);
+        const float2 u = s[i0], q = s[i1];
+        const float2 t = make_float2(q.x * w.x - q.y * w.y, q.x * w.y + q.y * w.x);
+        s[i0] = make_float2(u.x + t.x, u.y + t.y);
+        s[i1] = make_float2(u.x - t.x, u.y - t.y);
+      }
+      __syncthreads();
+    }
+    for (int k = a.kmin + tid; k <= a.kmax; k += kGenThreads) {
+      float p;
+      if (k == M) {
+        const float xn = s[0].x - s[0].y;
+        p = xn * xn;
+      } else {
+        const float2 z = s[k], pz = s[(M - k) & (M - 1)];
+        const float2 cs = __ldg(&a.wsplit[k]);
+        const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+        const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+        const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+        p = xr * xr + xi * xi;
+      }
+      pw[k] = p;
+    }
+    __syncthreads();
+    for (int wi = tid; wi < a.n_windows; wi += kGenThreads) {
+      const HeWin hw = a.wins[wi];
+      float m = pw[hw.k0];
+      for (int k = hw.k0 + 1; k < hw.k1; ++k) m = fmaxf(m, pw[k]);
+      wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double sum = 0.0;
+      for (int j = 0; j < a.wins_per_note; ++j) sum += wv[tid * a.wins_per_note + j];
+      if (a.clips) {
+        if (clip != my_clip) {
+          if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+          my_clip = clip;
+          acc_clip = 0.0;
+        }
+        acc_clip += sum;
+      }
+      acc_total += sum;
+      if (a.frames) a.frames[gf * 12 + tid] = (float)sum;
+    }
+    __syncthreads();
+  }
+  if (tid < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+    if (a.total) atomicAdd(&a.total[tid], acc_total);
+  }
+}
+
+// ------------------------------------------------------------------ C-ABI entry
+constexpr int kHeW = 8;  // warps (= frames) per tile in the fast path
+
+extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float* d_x,
+                             int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                             double* d_chroma_total, double* d_chroma_clips,
+                             float* d_chroma_frames, int flags, void* stream) {
+  if (!h) return CDB_E_NULL;
+  if (!p || !d_x) return cdb_fail(h, CDB_E_NULL, "null params / input");
+  if (n_clips < 0 || clip_len < 0 || (n_clips > 1 && clip_stride < clip_len))
+    return cdb_fail(h, CDB_E_INVALID, "bad batch shape");
+  CDB_CUDA(h, cudaSetDevice(h->device));
+  HePlan* pl = nullptr;
+  int rc = he_get_plan(h, p, &pl);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t fpc =
+      p->frames_per_clip > 0 ? p->frames_per_clip : cdb_num_frames(clip_len, pl->N, pl->hop);
+  if (!(flags & CDB_FLAG_ACCUMULATE)) {
+    if (d_chroma_total) CDB_CUDA(h, cudaMemsetAsync(d_chroma_total, 0, 12 * sizeof(double), st));
+    if (d_chroma_clips && n_clips > 0)
+      CDB_CUDA(h, cudaMemsetAsync(d_chroma_clips, 0, n_clips * 12 * sizeof(double), st));
+  }
+  if (n_clips == 0 || fpc == 0) return 0;
+
+  HeArgs a;
+  a.x = d_x;
+  a.n_clips = n_clips;
+  a.clip_len = clip_len;
+  a.clip_stride = clip_stride;
+  a.frames_per_clip = fpc;
+  a.hop = pl->hop;
+  a.N = pl->N;
+  a.M = pl->M;
+  a.log2M = pl->log2M;
+  a.n_windows = pl->n_windows;
+  a.wins_per_note = pl->wins_per_note;
+  a.kmin = pl->kmin;
+  a.kmax = pl->kmax;
+  a.win = pl->d_win;
+  a.tw32 = pl->d_tw32;
+  a.wsplit = pl->d_wsplit;
+  a.twgen = pl->d_twgen;
+  a.wins = pl->d_wins;
+  a.total = d_chroma_total;
+  a.clips = d_chroma_clips;
+  a.frames = d_chroma_frames;
+  a.tiles_per_clip = a.total_tiles = 0;
+  a.tile_cap = 0;
+
+  if (pl->N == 2048 && !pl->force_generic) {
+    a.tiles_per_clip = (fpc + kHeW - 1) / kHeW;
+    a.total_tiles = a.tiles_per_clip * n_clips;
+    a.tile_cap = (((kHeW - 1) * pl->hop + 2048) + 3) & ~3;
+    const size_t smem = 128 + (size_t)a.tile_cap * 4 + 2048 * 4 + 1024 * 8 +
+                        (size_t)kHeW * kScr * 8 + HE_MAX_WINDOWS * sizeof(HeWin);
+    CDB_CUDA(h, cudaFuncSetAttribute(he2048_kernel<kHeW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he2048_kernel<kHeW>,
+                                                              kHeW * 32, smem));
+    if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "tile does not fit in shared memory");
+    int64_t grid = std::min<int64_t>(a.total_tiles, (int64_t)h->num_sms * per_sm);
+    he2048_kernel<kHeW><<<(unsigned)grid, kHeW * 32, smem, st>>>(a);
+  } else {
+    const size_t smem = (size_t)pl->M * 8 + (size_t)(pl->M + 2) * 4 + HE_MAX_WINDOWS * 8;
+    CDB_CUDA(h, cudaFuncSetAttribute(he_generic_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he_generic_kernel,
+                                                              kGenThreads, smem));
+    if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
+    int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
+    he_generic_kernel<<<(unsigned)grid, kGenThreads, smem, st>>>(a);
+  }
+  h->launches += 1;
+  CDB_CUDA(h, cudaGetLastError());
+  return 0;
+}

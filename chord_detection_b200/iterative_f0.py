@@ -1,0 +1,54 @@
+"""Method 3 — Iterative F0 (Klapuri, Anssi).
+
+Same constructor / compute_pitches() contract as
+/root/reference/chord_detection/iterative_f0.py:21-96 (+ periodicity.py); the filterbank,
+summary spectrum and periodicity search run on the GPU (csrc/iterf0.cu) through cdb_iterf0_chroma.
+"""
+import math
+
+from . import ops
+from .chromagram import Chromagram
+from .multipitch import Multipitch
+
+
+class MultipitchIterativeF0(Multipitch):
+    def __init__(
+        self,
+        audio_path,
+        frame_size=8192,
+        power=1.0,
+        channels=70,
+        zeta0=2.3,
+        zeta1=0.39,
+        peak_thresh=0.5,
+        peak_min_dist=10,
+        harmonic_multiples_elim=5,
+        fs=None,
+        device=None,
+    ):
+        super().__init__(audio_path, fs=fs, device=device)
+        self.frame_size = frame_size
+        n = self.x.shape[0] if self.x is not None else self._x_dev.shape[0]
+        self.num_frames = math.ceil(n / self.frame_size)
+        self.power = power
+        self.channels = [
+            229 * (10 ** ((zeta1 * c + zeta0) / 21.4) - 1) for c in range(channels)
+        ]
+        # accepted and unused, exactly like the reference (iterative_f0.py:30-32,41-43)
+        self.peak_thresh = peak_thresh
+        self.peak_min_dist = peak_min_dist
+        self.harmonic_multiples_elim = harmonic_multiples_elim
+
+    @staticmethod
+    def display_name():
+        return "Iterative F0 (Klapuri, Anssi)"
+
+    @staticmethod
+    def method_number():
+        return 3
+
+    def compute_pitches(self, display_plot_frame=-1):
+        x = self._device_samples()
+        res = ops.iterative_f0(x, self.fs, frame_size=self.frame_size, power=self.power,
+                               channel_freqs=self.channels)
+        return Chromagram(res.total.cpu().numpy())
