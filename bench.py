@@ -223,11 +223,16 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     barrier()
+    prof = os.environ.get("CDB_PROFILE_RANGE") == "1"  # ncu --profile-from-start off
+    if prof:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    if prof:
+        torch.cuda.cudart().cudaProfilerStop()
     sampler.stop_flag = True
     ms_total = e0.elapsed_time(e1)
     launches = ops.launch_count(local_rank) - launches0
