@@ -56,7 +56,8 @@ EXPORTS = [
     "cdb_version", "cdb_create", "cdb_destroy", "cdb_last_error", "cdb_launch_count",
     "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
-    "cdb_prime_chroma", "cdb_pack_and_key",
+    "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
+    "cdb_host_find_peaks",
 ]
 
 
@@ -96,6 +97,12 @@ def lib():
         L.cdb_prime_chroma.argtypes = [vp, C.POINTER(PrimeParams), vp, i64, i64, i64, vp, vp, vp,
                                        C.c_int, vp]
         L.cdb_pack_and_key.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.cdb_esacf_debug_stride.argtypes = [C.c_int]
+        L.cdb_esacf_debug_stride.restype = i64
+        L.cdb_host_gauss_fit.argtypes = [C.c_int, dbl, C.POINTER(dbl), C.POINTER(dbl),
+                                         C.POINTER(C.c_int)]
+        L.cdb_host_find_peaks.argtypes = [C.POINTER(dbl), C.c_int, dbl, C.c_int,
+                                          C.POINTER(C.c_int)]
         _lib = L
         return _lib
 
@@ -164,3 +171,29 @@ def he_windows(fs, frame_size, num_harmonic=2, num_octave=2, num_bins=2):
 
 def num_frames(clip_len, frame_size, hop=0):
     return int(lib().cdb_num_frames(int(clip_len), int(frame_size), int(hop)))
+
+
+def host_gauss_fit(x0, y):
+    """Host build of the device Levenberg-Marquardt Gaussian fit (test hook, no GPU).
+    -> (info, [ampl, centre, dev], nfev)"""
+    import numpy as np
+
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    p = (C.c_double * 3)()
+    nfev = C.c_int(0)
+    info = lib().cdb_host_gauss_fit(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
+                                    C.byref(nfev))
+    return info, [p[0], p[1], p[2]], nfev.value
+
+
+def host_find_peaks(y, thres, min_dist):
+    """Host build of the device peak picker (test hook, no GPU) -> list of indices."""
+    import numpy as np
+
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = (C.c_int * (len(y) + 4))()
+    n = lib().cdb_host_find_peaks(y.ctypes.data_as(C.POINTER(C.c_double)), len(y), float(thres),
+                                  int(min_dist), out)
+    if n < 0:
+        raise ValueError("cdb_host_find_peaks failed")
+    return [out[i] for i in range(n)]

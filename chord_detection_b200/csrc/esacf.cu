@@ -1,6 +1,462 @@
+// ESACF (method 1, Tolonen-Karjalainen) — replaces the per-frame chain of
+// /root/reference/chord_detection/esacf.py:44-72 (+ dsp/wfir.py:25-43, dsp/lowpass.py:6-8,
+// esacf.py:93-134) for batches of frames.  All arithmetic is FP64 (B200 runs FP64 at 1/2 the
+// FP32 rate) because the output is decided by discrete peak picking.
+//
+// Three kernels per batch of B frames (workspace is per handle, grow-only):
+//   esacf_filter_kernel : one thread per frame; warped-FIR whitening (12 cascaded first-order
+//                         all-passes + 13 taps, wfir.py:28-43) and the three Butterworth biquads
+//                         (esacf.py:47-51) as direct-form-II-transposed recurrences in the same
+//                         operation order as scipy.signal.lfilter (un-fused mul/add), zero state
+//                         per frame.  Output x_lo / x_hi, frame-minor so stores coalesce.
+//   esacf_acf_kernel    : one CTA per frame; |DFT_N(x_lo)|^k + |DFT_N(x_hi)|^k for the N-point
+//                         (N = 1023 / 2046, not a power of two, no padding: circular ACF,
+//                         esacf.py:98-105) via Goertzel recurrences, several bins per thread;
+//                         inverse real-even DFT for the first (N-1)/2 lags via Chebyshev
+//                         recurrences; clip + prefix-zero "enhancement" (esacf.py:108-129, see
+//                         SURVEY.md A.2).
+//   esacf_peaks_kernel  : one warp per frame; peakutils.indexes (peaks.cuh) by lane 0, one
+//                         Levenberg-Marquardt Gaussian fit per lane (lm_gauss.cuh), fs/tau ->
+//                         pitch class (librosa.hz_to_note), chroma += ESACF[peak] (esacf.py:65-71).
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
-struct EsacfPlan {};
-void cdb_free_esacf_plans(cdb_handle* h) { for (auto& kv : h->esacf_plans) delete kv.second; h->esacf_plans.clear(); }
-extern "C" int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params*, const float*, int64_t, int64_t, int64_t, double*, double*, double*, double*, int, void*) {
-  return cdb_fail(h, CDB_E_UNSUPPORTED, "esacf: not built yet");
+#include "lm_gauss.cuh"
+#include "peaks.cuh"
+
+struct EsacfPlan {
+  cdb_esacf_params p;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+void cdb_free_esacf_plans(cdb_handle* h) {
+  for (auto& kv : h->esacf_plans) {
+    if (kv.second->ws) cudaFree(kv.second->ws);
+    delete kv.second;
+  }
+  h->esacf_plans.clear();
 }
+
+constexpr int kMaxN = 4096;      // ham_samples limit (shared-memory staging of one frame)
+constexpr int kAcfThreads = 256;
+constexpr int kMaxPeaksDbg = 64;
+
+struct EsacfArgs {
+  const float* x;
+  int64_t clip_len, clip_stride, frames_per_clip;
+  int64_t frame0;  // first global frame of this batch
+  int B;           // frames in this batch
+  int N, L, K;     // frame length, lags kept, forward bins (N/2+1)
+  int prefix;      // lags [0, prefix) forced to zero by the enhancement
+  int clip_pos;    // 1: clip to >= 0 (n_peaks_elim >= 2)
+  double kexp;     // |X|^k
+  double lam, taps[13];
+  double lp_b[3], lp_a[3], hp_b[3], hp_a[3];
+  double fs, peak_thresh;
+  int peak_min_dist;
+  double* ws_lo;  // [N][B]
+  double* ws_hi;  // [N][B]
+  double* ws_y;   // [B][L] enhanced SACF
+  double* ws_s;   // [B][L] raw SACF (debug only, may be null)
+  double* total;
+  double* clips;
+  double* frames;  // [n_frames, 12]
+  double* debug;
+  int64_t debug_stride;
+};
+
+// scipy.signal.lfilter second-order section, direct form II transposed, un-fused (sigtools
+// DOUBLE_filt): y = z0 + b0*x; z0 = z1 + b1*x - a1*y; z1 = b2*x - a2*y
+struct Biquad {
+  double b0, b1, b2, a1, a2, z0, z1;
+  __device__ __forceinline__ void init(const double* b, const double* a) {
+    b0 = b[0] / a[0];
+    b1 = b[1] / a[0];
+    b2 = b[2] / a[0];
+    a1 = a[1] / a[0];
+    a2 = a[2] / a[0];
+    z0 = z1 = 0.0;
+  }
+  __device__ __forceinline__ double step(double x) {
+    const double y = __dadd_rn(z0, __dmul_rn(b0, x));
+    z0 = __dsub_rn(__dadd_rn(z1, __dmul_rn(x, b1)), __dmul_rn(y, a1));
+    z1 = __dsub_rn(__dmul_rn(x, b2), __dmul_rn(y, a2));
+    return y;
+  }
+};
+
+__global__ void __launch_bounds__(64) esacf_filter_kernel(const EsacfArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.B) return;
+  const int64_t gf = a.frame0 + t;
+  const int64_t clip = gf / a.frames_per_clip;
+  const int64_t s0 = (gf - clip * a.frames_per_clip) * a.N;
+  const float* src = a.x + clip * a.clip_stride + s0;
+  const int64_t avail = a.clip_len - s0;
+  double z[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) z[i] = 0.0;
+  Biquad hp, lp_hi, lp_lo;
+  hp.init(a.hp_b, a.hp_a);
+  lp_hi.init(a.lp_b, a.lp_a);
+  lp_lo.init(a.lp_b, a.lp_a);
+  const double lam = a.lam, mlam = -a.lam;
+  for (int n = 0; n < a.N; ++n) {
+    const double x = (n < avail) ? (double)__ldg(src + n) : 0.0;
+    // wfir.py:28-43 — all-pass B=[-lam,1], A=[1,-lam]: y = z + (-lam)*u ; z = u - (-lam)*y
+    double u = x;
+    double xhat = __dmul_rn(a.taps[0], x);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const double y = __dadd_rn(z[i], __dmul_rn(mlam, u));
+      z[i] = __dsub_rn(__dmul_rn(u, 1.0), __dmul_rn(y, mlam));
+      xhat = __dadd_rn(xhat, __dmul_rn(a.taps[i + 1], y));
+      u = y;
+    }
+    const double r = __dsub_rn(x, xhat);
+    double hi = hp.step(r);           // esacf.py:47
+    hi = hi > 0.0 ? hi : 0.0;         // :48 (numpy.clip(x, 0, None))
+    hi = lp_hi.step(hi);              // :49
+    const double lo = lp_lo.step(r);  // :51
+    a.ws_lo[(int64_t)n * a.B + t] = lo;
+    a.ws_hi[(int64_t)n * a.B + t] = hi;
+    (void)lam;
+  }
+}
+
+template <int BINS>
+__global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double2* xs = reinterpret_cast<double2*>(smem);          // [N] (lo, hi)
+  double* S = reinterpret_cast<double*>(xs + a.N);         // [K]
+  const int tid = threadIdx.x;
+  const int fb = blockIdx.x;
+  const int N = a.N, K = a.K, L = a.L;
+  for (int n = tid; n < N; n += kAcfThreads)
+    xs[n] = make_double2(a.ws_lo[(int64_t)n * a.B + fb], a.ws_hi[(int64_t)n * a.B + fb]);
+  __syncthreads();
+  // forward: Goertzel, s[n] = x[n] + c*s[n-1] - s[n-2];  |X_k|^2 = s1^2 + s2^2 - c*s1*s2
+  const double invN = 1.0 / (double)N;
+  constexpr int kBinsPerPass = BINS;
+  for (int k0 = 0; k0 < K; k0 += kAcfThreads * kBinsPerPass) {
+    double c[kBinsPerPass], l1[kBinsPerPass], l2[kBinsPerPass], h1[kBinsPerPass], h2[kBinsPerPass];
+#pragma unroll
+    for (int j = 0; j < kBinsPerPass; ++j) {
+      const int k = k0 + tid + j * kAcfThreads;
+      c[j] = 2.0 * cospi(2.0 * (double)k * invN);
+      l1[j] = l2[j] = h1[j] = h2[j] = 0.0;
+    }
+    for (int n = 0; n < N; ++n) {
+      const double2 v = xs[n];
+#pragma unroll
+      for (int j = 0; j < kBinsPerPass; ++j) {
+        const double tl = fma(c[j], l1[j], v.x) - l2[j];
+        l2[j] = l1[j];
+        l1[j] = tl;
+        const double th = fma(c[j], h1[j], v.y) - h2[j];
+        h2[j] = h1[j];
+        h1[j] = th;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBinsPerPass; ++j) {
+      const int k = k0 + tid + j * kAcfThreads;
+      if (k < K) {
+        double pl = l1[j] * l1[j] + l2[j] * l2[j] - c[j] * l1[j] * l2[j];
+        double ph = h1[j] * h1[j] + h2[j] * h2[j] - c[j] * h1[j] * h2[j];
+        pl = pl > 0.0 ? pl : 0.0;
+        ph = ph > 0.0 ? ph : 0.0;
+        S[k] = pow(pl, 0.5 * a.kexp) + pow(ph, 0.5 * a.kexp);  // |X|^k = (|X|^2)^(k/2)
+      }
+    }
+  }
+  __syncthreads();
+  // inverse (real, even): acf[t] = (S0 + 2*sum_{k=1}^{(N-1)/2} S_k cos(2 pi k t/N) [+ S_{N/2}(-1)^t]) / N
+  const int Kh = (N - 1) / 2;
+  for (int t = tid; t < L; t += kAcfThreads) {
+    const double ct = cospi(2.0 * (double)t * invN);
+    const double c2 = 2.0 * ct;
+    double cm1 = 1.0, c0 = ct;  // cos(0), cos(phi)
+    double acc = 0.0;
+    for (int k = 1; k <= Kh; ++k) {
+      acc = fma(S[k], c0, acc);
+      const double cn = fma(c2, c0, -cm1);
+      cm1 = c0;
+      c0 = cn;
+    }
+    double v = S[0] + 2.0 * acc;
+    if ((N & 1) == 0) v += S[N / 2] * ((t & 1) ? -1.0 : 1.0);
+    v *= invN;
+    if (a.ws_s) a.ws_s[(int64_t)fb * L + t] = v;
+    if (a.clip_pos) {
+      v = v > 0.0 ? v : 0.0;
+      if (t < a.prefix) v = 0.0;
+    }
+    a.ws_y[(int64_t)fb * L + t] = v;
+  }
+}
+
+constexpr int kPeakWarps = 8;
+
+__global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const EsacfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L;
+  const int half = L / 2 + 2;
+  // per-warp: y[L] doubles | sgn[L] int8 (padded to 8) | cand[half] int16 | order[half] int16 | chroma[12]
+  const size_t per_warp = (size_t)L * 8 + (((size_t)L + 7) & ~(size_t)7) + 2 * (((size_t)half * 2 + 7) & ~(size_t)7) + 12 * 8;
+  unsigned char* base = smem + per_warp * warp;
+  double* y = reinterpret_cast<double*>(base);
+  int8_t* sgn = reinterpret_cast<int8_t*>(y + L);
+  int16_t* cand = reinterpret_cast<int16_t*>(sgn + (((size_t)L + 7) & ~(size_t)7));
+  int16_t* order = cand + (((size_t)half * 2 + 7) & ~(size_t)7) / 2;
+  double* chroma = reinterpret_cast<double*>(order + (((size_t)half * 2 + 7) & ~(size_t)7) / 2);
+  __shared__ double cta_total[12];
+  if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const int warps_total = gridDim.x * kPeakWarps;
+  for (int fb = blockIdx.x * kPeakWarps + warp; fb < a.B; fb += warps_total) {
+    const int64_t gf = a.frame0 + fb;
+    const int64_t clip = gf / a.frames_per_clip;
+    for (int i = lane; i < L; i += 32) y[i] = a.ws_y[(int64_t)fb * L + i];
+    if (lane < 12) chroma[lane] = 0.0;
+    __syncwarp();
+    int np = 0;
+    if (lane == 0) np = pk::find_peaks(y, L, a.peak_thresh, a.peak_min_dist, sgn, cand, order);
+    np = __shfl_sync(0xffffffffu, np, 0);
+    __syncwarp();
+    double* dbg = a.debug ? a.debug + gf * a.debug_stride : nullptr;
+    if (dbg && lane == 0) dbg[2 * a.N + 2 * L] = (double)np;
+    // one Gaussian fit per lane; failed fits are dropped and the survivors re-paired with the
+    // peak list BY POSITION, reproducing the latent misalignment of esacf.py:65-69
+    int done = 0;  // successful fits so far (warp-uniform)
+    for (int p0 = 0; p0 < np; p0 += 32) {
+      const int pi = p0 + lane;
+      bool ok = false;
+      double center = 0.0;
+      if (pi < np) {
+        const int idx = cand[pi];
+        const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
+        if (lo >= 0 && hi - lo >= 3) {
+          lmg::Problem pr;
+          pr.m = hi - lo;
+          pr.x0 = (double)lo;
+          double ymax = y[lo];
+          for (int i = 0; i < pr.m; ++i) {
+            pr.y[i] = y[lo + i];
+            ymax = fmax(ymax, pr.y[i]);
+          }
+          double p[3] = {ymax, (double)lo, 5.0};
+          int nfev = 0;
+          const int info = lmg::lmdif(pr, p, &nfev);
+          ok = (info >= 1 && info <= 4) && isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+          center = p[1];
+        }
+      }
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int slot = done + __popc(okmask & ((1u << lane) - 1u));  // position in interp[]
+        const int paired = cand[slot];                                   // peak_indices[slot]
+        if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = center;
+        const double pitch = a.fs / center;
+        // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
+        if (pitch > 0.0 && isfinite(pitch)) {
+          const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
+          long long nn = (long long)nearbyint(midi);
+          int note = (int)(nn % 12);
+          if (note < 0) note += 12;
+          atomicAdd(&chroma[note], y[paired]);
+        }
+      }
+      done += __popc(okmask);
+    }
+    if (dbg) {
+      for (int i = lane; i < np && i < kMaxPeaksDbg; i += 32) dbg[2 * a.N + 2 * L + 1 + i] = (double)cand[i];
+      if (lane == 0) dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)done;
+    }
+    __syncwarp();
+    if (lane < 12) {
+      const double v = chroma[lane];
+      if (a.frames) a.frames[gf * 12 + lane] = v;
+      if (a.clips && v != 0.0) atomicAdd(&a.clips[clip * 12 + lane], v);
+      if (a.total && v != 0.0) atomicAdd(&cta_total[lane], v);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (a.total && threadIdx.x < 12 && cta_total[threadIdx.x] != 0.0)
+    atomicAdd(&a.total[threadIdx.x], cta_total[threadIdx.x]);
+}
+
+// copies x_lo / x_hi / sacf / esacf of every frame of the batch into the debug buffer
+__global__ void esacf_debug_copy_kernel(const EsacfArgs a) {
+  const int fb = blockIdx.x;
+  double* dbg = a.debug + (a.frame0 + fb) * a.debug_stride;
+  for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+    dbg[n] = a.ws_lo[(int64_t)n * a.B + fb];
+    dbg[a.N + n] = a.ws_hi[(int64_t)n * a.B + fb];
+  }
+  for (int t = threadIdx.x; t < a.L; t += blockDim.x) {
+    dbg[2 * a.N + t] = a.ws_s[(int64_t)fb * a.L + t];
+    dbg[2 * a.N + a.L + t] = a.ws_y[(int64_t)fb * a.L + t];
+  }
+}
+
+extern "C" {
+
+// host-only test hooks (no GPU): the same code the kernels run, callable from CPU tests
+int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev) {
+  if (m > lmg::MMAX || m < 0 || !y || !p_out) return -1;
+  lmg::Problem pr;
+  pr.m = m;
+  pr.x0 = x0;
+  double ymax = m ? y[0] : 0.0;
+  for (int i = 0; i < m; ++i) {
+    pr.y[i] = y[i];
+    ymax = std::fmax(ymax, y[i]);
+  }
+  double p[3] = {ymax, x0, 5.0};
+  int nf = 0;
+  const int info = lmg::lmdif(pr, p, &nf);
+  p_out[0] = p[0];
+  p_out[1] = p[1];
+  p_out[2] = p[2];
+  if (nfev) *nfev = nf;
+  return info;
+}
+
+int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out) {
+  if (!y || L < 0 || L > 32767) return -1;
+  std::vector<int8_t> sgn(L + 8);
+  std::vector<int16_t> cand(L / 2 + 4), order(L / 2 + 4);
+  const int n = pk::find_peaks(y, L, thres, min_dist, sgn.data(), cand.data(), order.data());
+  for (int i = 0; i < n; ++i) peaks_out[i] = cand[i];
+  return n;
+}
+
+int64_t cdb_esacf_debug_stride(int ham_samples) {
+  const int L = (ham_samples - 1) / 2;
+  return 2 * (int64_t)ham_samples + 2 * L + 2 + 2 * kMaxPeaksDbg;
+}
+
+int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x, int64_t n_clips,
+                     int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
+                     double* d_chroma_clips, double* d_chroma_frames, double* d_debug, int flags,
+                     void* stream) {
+  if (!h) return CDB_E_NULL;
+  if (!p || !d_x) return cdb_fail(h, CDB_E_NULL, "null params / input");
+  if (n_clips < 0 || clip_len < 0 || (n_clips > 1 && clip_stride < clip_len))
+    return cdb_fail(h, CDB_E_INVALID, "bad batch shape");
+  const int N = p->ham_samples;
+  if (N < 3 || N > kMaxN)
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "ham_samples %d outside [3, %d]", N, kMaxN);
+  if (!(p->fs > 0) || p->peak_min_dist < 0 || p->stretch_mode < 0 || p->stretch_mode > 1)
+    return cdb_fail(h, CDB_E_INVALID, "invalid ESACF parameters");
+  const int L = (int)((N - 1) / 2);  // esacf.py:105 int((shape-1)/2)
+  if (L >= 1024 && p->stretch_mode == CDB_STRETCH_TRUNCATE && p->n_peaks_elim >= 2)
+    return cdb_fail(h, CDB_E_UNSUPPORTED,
+                    "SACF of %d lags: librosa's phase vocoder is no longer a prefix copy "
+                    "(SURVEY.md A.2); only stretch_mode none is available", L);
+  CDB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  EsacfPlan* pl;
+  {
+    std::string key = pod_key(*p);
+    auto it = h->esacf_plans.find(key);
+    if (it == h->esacf_plans.end()) {
+      pl = new EsacfPlan();
+      pl->p = *p;
+      h->esacf_plans[key] = pl;
+    } else {
+      pl = it->second;
+    }
+  }
+  const int64_t fpc = cdb_num_frames(clip_len, N, N);  // dsp/frame.py: non-overlapping
+  const int64_t n_frames = fpc * n_clips;
+  if (!(flags & CDB_FLAG_ACCUMULATE)) {
+    if (d_chroma_total) CDB_CUDA(h, cudaMemsetAsync(d_chroma_total, 0, 12 * sizeof(double), st));
+    if (d_chroma_clips && n_clips > 0)
+      CDB_CUDA(h, cudaMemsetAsync(d_chroma_clips, 0, n_clips * 12 * sizeof(double), st));
+  }
+  if (n_frames == 0) return 0;
+
+  const int64_t Bmax = std::min<int64_t>(n_frames, 16384);
+  const size_t need = (size_t)Bmax * (2 * (size_t)N + 2 * (size_t)L) * sizeof(double);
+  if (pl->ws_bytes < need) {
+    CDB_CUDA(h, cudaStreamSynchronize(st));
+    if (pl->ws) cudaFree(pl->ws);
+    pl->ws = nullptr;
+    pl->ws_bytes = 0;
+    CDB_CUDA(h, cudaMalloc(&pl->ws, need));
+    pl->ws_bytes = need;
+  }
+
+  EsacfArgs a;
+  a.x = d_x;
+  a.clip_len = clip_len;
+  a.clip_stride = clip_stride;
+  a.frames_per_clip = fpc;
+  a.N = N;
+  a.L = L;
+  a.K = N / 2 + 1;
+  a.kexp = p->k ? p->k : 0.67;  // esacf.py:95-96 `if not k`
+  a.clip_pos = p->n_peaks_elim >= 2;
+  a.prefix = 0;
+  if (a.clip_pos && p->stretch_mode == CDB_STRETCH_TRUNCATE)
+    a.prefix = (int)std::nearbyint((double)L / 2.0);  // python round(L/2): half to even
+  a.lam = p->wfir_lambda;
+  std::memcpy(a.taps, p->wfir_taps, sizeof(a.taps));
+  std::memcpy(a.lp_b, p->lp_b, sizeof(a.lp_b));
+  std::memcpy(a.lp_a, p->lp_a, sizeof(a.lp_a));
+  std::memcpy(a.hp_b, p->hp_b, sizeof(a.hp_b));
+  std::memcpy(a.hp_a, p->hp_a, sizeof(a.hp_a));
+  a.fs = p->fs;
+  a.peak_thresh = p->peak_thresh;
+  a.peak_min_dist = p->peak_min_dist;
+  a.total = d_chroma_total;
+  a.clips = d_chroma_clips;
+  a.frames = d_chroma_frames;
+  a.debug = d_debug;
+  a.debug_stride = cdb_esacf_debug_stride(N);
+
+  const size_t acf_smem = (size_t)N * 16 + (size_t)a.K * 8;
+  int bins = (a.K + kAcfThreads - 1) / kAcfThreads;
+  bins = bins > 4 ? 4 : bins;
+  void (*acf_kernel)(const EsacfArgs) =
+      bins == 1 ? esacf_acf_kernel<1> : bins == 2 ? esacf_acf_kernel<2>
+      : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
+  CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)acf_smem));
+  const size_t half = (size_t)L / 2 + 2;
+  const size_t per_warp = (size_t)L * 8 + (((size_t)L + 7) & ~(size_t)7) +
+                          2 * ((half * 2 + 7) & ~(size_t)7) + 12 * 8;
+  const size_t pk_smem = per_warp * kPeakWarps;
+  CDB_CUDA(h, cudaFuncSetAttribute(esacf_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)pk_smem));
+  for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {
+    const int B = (int)std::min<int64_t>(Bmax, n_frames - f0);
+    a.frame0 = f0;
+    a.B = B;
+    double* w = reinterpret_cast<double*>(pl->ws);
+    a.ws_lo = w;
+    a.ws_hi = w + (size_t)N * B;
+    a.ws_y = w + 2 * (size_t)N * B;
+    a.ws_s = d_debug ? (w + 2 * (size_t)N * B + (size_t)L * B) : nullptr;
+    esacf_filter_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
+    acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
+    if (d_debug) {
+      esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);
+      h->launches += 1;
+    }
+    const int pgrid = std::min<int>((B + kPeakWarps - 1) / kPeakWarps, h->num_sms * 4);
+    esacf_peaks_kernel<<<pgrid, kPeakWarps * 32, pk_smem, st>>>(a);
+    h->launches += 3;
+    CDB_CUDA(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

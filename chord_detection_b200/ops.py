@@ -131,3 +131,77 @@ class HostPipeline:
             self.host_out.copy_(self.total, non_blocking=True)
         self.compute_stream.synchronize()
         return self.host_out.numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# filter designs: done once on the host in float64 with the same SciPy calls the reference makes
+# on every frame (dsp/lowpass.py:7, dsp/wfir.py:6-21, esacf.py:133) -- setup, not per-frame DSP
+# ---------------------------------------------------------------------------------------------
+_design_cache = {}
+
+
+def bark_warp_coef(fs):
+    return float(1.0674 * np.sqrt((2.0 / np.pi) * np.arctan(0.06583 * fs / 1000.0)) - 0.1916)
+
+
+def wfir_design(fs, order=12):
+    key = ("wfir", float(fs), order)
+    if key not in _design_cache:
+        import scipy.signal
+
+        lo, r, t = 20, min(20000, fs / 2 - 1), 1
+        taps = scipy.signal.remez(order + 1, [0, lo - t, lo, r, r + t, 0.5 * fs], [0, 1, 0], fs=fs)
+        _design_cache[key] = (bark_warp_coef(fs), [float(v) for v in taps])
+    return _design_cache[key]
+
+
+def butter2(fs, band, btype):
+    key = ("butter", float(fs), float(band), btype)
+    if key not in _design_cache:
+        import scipy.signal
+
+        b, a = scipy.signal.butter(2, [band / (fs / 2)], btype=btype)
+        _design_cache[key] = ([float(v) for v in b], [float(v) for v in a])
+    return _design_cache[key]
+
+
+def esacf_params(fs, ham_samples, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
+                 stretch_mode="truncate"):
+    p = nat.EsacfParams()
+    p.fs, p.ham_samples, p.k = float(fs), int(ham_samples), float(k)
+    p.n_peaks_elim, p.peak_thresh, p.peak_min_dist = int(n_peaks_elim), float(peak_thresh), int(peak_min_dist)
+    p.stretch_mode = nat.STRETCH_MODES[stretch_mode]
+    lam, taps = wfir_design(fs, 12)
+    p.wfir_lambda = lam
+    for i, v in enumerate(taps):
+        p.wfir_taps[i] = v
+    (lb, la), (hb, ha) = butter2(fs, 1000, "low"), butter2(fs, 1000, "high")
+    for i in range(3):
+        p.lp_b[i], p.lp_a[i], p.hp_b[i], p.hp_a[i] = lb[i], la[i], hb[i], ha[i]
+    return p
+
+
+def esacf(x, fs, ham_samples=None, ham_ms=46.4, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
+          stretch_mode="truncate", per_clip=False, per_frame=False, debug=False):
+    """ESACF chromagram (reference esacf.py:41-90) -> ChromaResult (float64 outputs).
+
+    debug=True additionally returns, in ``extra``, a [n_frames, stride] float64 tensor of
+    per-frame intermediates (x_lo | x_hi | sacf | esacf | n_peaks | peaks | centres | n_fitted)."""
+    x, n_clips, clip_len, stride = _batch_view(x)
+    if ham_samples is None:
+        ham_samples = int(fs * ham_ms / 1000.0)
+    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    p = esacf_params(fs, ham_samples, 0.67, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode)
+    fpc = nat.num_frames(clip_len, ham_samples, ham_samples)
+    total = torch.empty(12, dtype=torch.float64, device=x.device)
+    clips = torch.empty((n_clips, 12), dtype=torch.float64, device=x.device) if per_clip else None
+    frames = torch.empty((n_clips * fpc, 12), dtype=torch.float64, device=x.device) if per_frame else None
+    dbg = None
+    if debug:
+        ds = int(h.L.cdb_esacf_debug_stride(int(ham_samples)))
+        dbg = torch.zeros((n_clips * fpc, ds), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = h.L.cdb_esacf_chroma(h.ptr, C.byref(p), _ptr(x), n_clips, clip_len, stride, _ptr(total),
+                                  _ptr(clips), _ptr(frames), _ptr(dbg), 0, _stream_ptr(x))
+    h.check(rc, "cdb_esacf_chroma")
+    return ChromaResult(total, clips, frames, dbg)

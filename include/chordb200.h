@@ -116,6 +116,18 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
                      double* d_chroma_clips, double* d_chroma_frames, double* d_debug, int flags,
                      void* stream);
 
+/* size (in doubles) of one frame's record in d_debug:
+ * [x_lo N | x_hi N | sacf L | esacf L | n_peaks | peak idx x64 | fitted centres x64 | n_fitted] */
+int64_t cdb_esacf_debug_stride(int ham_samples);
+
+/* host-only test hooks (no GPU): the exact peak-picking / Gaussian-fit code the kernels run,
+ * compiled for the host so CPU tests can check it against scipy (peakutils.indexes semantics,
+ * esacf.py:56-58; peakutils.interpolate -> scipy curve_fit / MINPACK lmdif, esacf.py:60-62).
+ * cdb_host_gauss_fit: abscissae x0..x0+m-1, m <= 21; p_out[3] = (ampl, centre, dev); returns the
+ * MINPACK info code (1..4 = converged). */
+int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev);
+int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out);
+
 /* ---------------- method 3: iterative F0 (iterative_f0.py, periodicity.py) ---------------- */
 #define CDB_ITERF0_MAX_CHANNELS 128
 typedef struct {
