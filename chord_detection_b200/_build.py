@@ -8,6 +8,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libchordb200.so")
 SOURCES = ["api.cu", "he.cu", "esacf.cu", "iterf0.cu", "prime.cu"]
+# esacf.cu: the Levenberg-Marquardt fit and the lfilter recurrences mirror host (scipy) arithmetic,
+# which has no fused multiply-add; the DFT loops there call fma() explicitly.
+NO_FMAD = {"esacf.cu"}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "--fmad=true",
@@ -37,7 +40,10 @@ def build(force=False, verbose=False):
     objs = []
     for s in SOURCES:
         o = os.path.join(LIBDIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        flags = list(NVCC_FLAGS)
+        if s in NO_FMAD:
+            flags[flags.index("--fmad=true")] = "--fmad=false"
+        cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:

@@ -272,7 +272,9 @@ def esacf_frame(x_frame, fs, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
     x_sacf = sacf([x_lo, x_hi])  # :53 (self.k is never passed)
     x_esacf = esacf_enhance(x_sacf, n_peaks_elim, stretch_mode)  # :54
     peaks = tp.peak_indexes(x_esacf, thres=peak_thresh, min_dist=peak_min_dist)  # :56-58
-    interp = tp.peak_interpolate(np.arange(x_esacf.shape[0]), x_esacf, ind=peaks)  # :60-62
+    nfev = [] if detail else None
+    fit = (lambda xx, yy: tp.gaussian_fit(xx, yy, _log=nfev)) if detail else tp.gaussian_fit
+    interp = tp.peak_interpolate(np.arange(x_esacf.shape[0]), x_esacf, ind=peaks, func=fit)  # :60-62
     chroma = np.zeros(12)
     for i, tau in enumerate(interp):  # :65-71 (pairs interp[i] with peaks[i]: latent misalignment kept)
         with np.errstate(divide="ignore"):
@@ -284,20 +286,57 @@ def esacf_frame(x_frame, fs, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
         chroma[note] += x_esacf[int(peaks[i])]
     if detail:
         return chroma, dict(x=x, x_lo=x_lo, x_hi=x_hi, sacf=x_sacf, esacf=x_esacf,
-                            peaks=np.asarray(peaks, dtype=np.int64), interp=np.asarray(interp))
+                            peaks=np.asarray(peaks, dtype=np.int64), interp=np.asarray(interp),
+                            nfev=np.asarray(nfev, dtype=np.int64))
     return chroma
 
 
+RUNAWAY_NFEV = 150       # well-posed 3-parameter fits here take 30-100 function evaluations
+RUNAWAY_SHIFT = 10.0     # ... and stay inside the +-10-sample window they were given
+BOUNDARY_SEMITONES = 1e-3
+
+
+def esacf_peak_is_sensitive(fs, peak_index, tau, nfev):
+    """True when the pitch class of this peak is decided by rounding noise: the Levenberg-Marquardt
+    fit ran away from its data window / needed an abnormal number of evaluations (its end point is
+    then chaotic in the last bits of exp()), or fs/tau lies within BOUNDARY_SEMITONES of the
+    boundary between two semitones (the converged centre itself is only defined to ~1e-6 by
+    xtol = 1.49e-8).  Any implementation other than the very same scipy/libm build may put such a
+    peak in a different bin; the GPU parity tests bound the chroma difference by their mass."""
+    if nfev > RUNAWAY_NFEV or abs(tau - peak_index) > RUNAWAY_SHIFT or not np.isfinite(tau) or tau <= 0:
+        return True
+    midi = 12 * (np.log2(fs / tau) - np.log2(440.0)) + 69
+    return abs(midi - np.round(midi)) > 0.5 - BOUNDARY_SEMITONES
+
+
 def esacf(x, fs, ham_ms=46.4, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
-          stretch_mode="truncate", per_frame=False):
+          stretch_mode="truncate", per_frame=False, sensitivity=False):
+    """sensitivity=True (oracle-only extra) also returns, per frame, the summed height of the
+    rounding-sensitive peaks (esacf_peak_is_sensitive) plus the whole frame's mass when a fit
+    failed (a dropped fit shifts the peak/centre pairing of esacf.py:65-69 for the rest of
+    the frame)."""
     ham_samples = int(fs * ham_ms / 1000.0)  # :27
     total = np.zeros(12)
-    outs = []
+    outs, loose = [], []
     for xf in cut_frames(x, ham_samples):
-        c = esacf_frame(xf, fs, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode)
+        if sensitivity:
+            c, d = esacf_frame(xf, fs, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode,
+                               detail=True)
+            lm = 0.0
+            if len(d["interp"]) != len(d["peaks"]):
+                lm = float(np.sum(np.abs(d["esacf"][d["peaks"]])))
+            else:
+                for j, nf in enumerate(d["nfev"]):
+                    if esacf_peak_is_sensitive(fs, int(d["peaks"][j]), d["interp"][j], nf):
+                        lm += abs(d["esacf"][int(d["peaks"][j])])
+            loose.append(lm)
+        else:
+            c = esacf_frame(xf, fs, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode)
         total += c
-        if per_frame:
+        if per_frame or sensitivity:
             outs.append(c)
+    if sensitivity:
+        return total, np.asarray(outs).reshape(-1, 12), np.asarray(loose)
     if per_frame:
         return total, np.asarray(outs).reshape(-1, 12)
     return total
