@@ -205,3 +205,66 @@ def esacf(x, fs, ham_samples=None, ham_ms=46.4, n_peaks_elim=6, peak_thresh=0.1,
                                   _ptr(clips), _ptr(frames), _ptr(dbg), 0, _stream_ptr(x))
     h.check(rc, "cdb_esacf_chroma")
     return ChromaResult(total, clips, frames, dbg)
+
+
+def prime_multif0(x, fs, num_harmonic=1, num_octave=2, harmonic_multiples_elim=5,
+                  harmonic_elim_runs=2, per_clip=False, per_candidate=False):
+    """Prime-multiF0 chromagram (reference prime_multif0.py:41-91) -> ChromaResult (float64).
+    per_candidate=True returns [n_clips, n_candidates, 12] in ``extra``."""
+    x, n_clips, clip_len, stride = _batch_view(x)
+    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    p = nat.PrimeParams(float(fs), int(num_harmonic), int(num_octave), int(harmonic_multiples_elim),
+                        int(harmonic_elim_runs))
+    n_cand = 12 * int(num_octave) * int(num_harmonic)
+    total = torch.empty(12, dtype=torch.float64, device=x.device)
+    clips = torch.empty((n_clips, 12), dtype=torch.float64, device=x.device) if per_clip else None
+    cands = (torch.empty((n_clips, n_cand, 12), dtype=torch.float64, device=x.device)
+             if per_candidate else None)
+    with torch.cuda.device(x.device):
+        rc = h.L.cdb_prime_chroma(h.ptr, C.byref(p), _ptr(x), n_clips, clip_len, stride, _ptr(total),
+                                  _ptr(clips), _ptr(cands), 0, _stream_ptr(x))
+    h.check(rc, "cdb_prime_chroma")
+    return ChromaResult(total, clips, None, cands)
+
+
+def prime_window_sizes(fs, num_harmonic=1, num_octave=2):
+    """Host-only: the candidate window sizes int(8/f*fs) (prime_multif0.py:49-53)."""
+    p = nat.PrimeParams(float(fs), int(num_harmonic), int(num_octave), 5, 2)
+    n = 12 * num_octave * num_harmonic
+    out = (C.c_int * n)()
+    rc = nat.lib().cdb_prime_window_sizes(C.byref(p), out)
+    if rc < 0:
+        raise ValueError("cdb_prime_window_sizes failed: %d" % rc)
+    return [out[i] for i in range(rc)]
+
+
+_NOTE = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
+
+
+def key_code_to_str(code):
+    """Inverse of cdb_pack_and_key's key code (chromagram.py:114-126 result strings)."""
+    code = int(code)
+    if code < 12:
+        return "%smaj" % _NOTE[code]
+    if code < 24:
+        return "%smin" % _NOTE[code - 12]
+    if code < 36:
+        return "%smajmin" % _NOTE[code - 24]
+    code -= 36
+    return "%smaj OR %smin" % (_NOTE[code // 12], _NOTE[code % 12])
+
+
+def pack_and_key(chroma):
+    """Batched Chromagram._pack + detect_key on the device.
+    chroma: CUDA float64 [n, 12] -> (digits uint8 [n, 12], key codes int32 [n])."""
+    if not chroma.is_cuda or chroma.dtype != torch.float64 or chroma.dim() != 2 or chroma.shape[1] != 12:
+        raise ValueError("expected a CUDA float64 tensor of shape [n, 12]")
+    chroma = chroma.contiguous()
+    n = chroma.shape[0]
+    h = nat.Handle.get(chroma.device.index)
+    digits = torch.empty((n, 12), dtype=torch.uint8, device=chroma.device)
+    keys = torch.empty(n, dtype=torch.int32, device=chroma.device)
+    with torch.cuda.device(chroma.device):
+        rc = h.L.cdb_pack_and_key(h.ptr, _ptr(chroma), n, _ptr(digits), _ptr(keys), _stream_ptr(chroma))
+    h.check(rc, "cdb_pack_and_key")
+    return digits, keys

@@ -1,0 +1,118 @@
+"""GPU parity tests for prime-multiF0 (cdb_prime_chroma) and the batched pack/key kernel."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import cases, ref_numpy as rn  # noqa: E402
+
+RTOL = 1e-4
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _close(got, want, tol=RTOL):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(np.max(np.abs(want)), 1e-300)
+    assert np.max(np.abs(got - want)) / scale <= tol, (got, want)
+
+
+def _ids():
+    import json
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_golden.json")) as f:
+        g = json.load(f)
+    return sorted(k for k, v in g["cases"].items() if v["method"] == 4)
+
+
+@pytest.mark.parametrize("cid", _ids())
+def test_prime_matches_reference_golden(golden, cid):
+    from chord_detection_b200 import ops
+
+    g = golden["cases"][cid]
+    x, fs = cases.make_input(g["input"])
+    xd = torch.from_numpy(x).to(_dev())
+    got = ops.prime_multif0(xd, fs, **g["kwargs"]).total.cpu().numpy()
+    _close(got, g["chroma"])
+    assert rn.pack_chroma(got) == g["digits"]
+
+
+def test_prime_per_candidate_and_params():
+    from chord_detection_b200 import ops
+
+    x, fs = cases.make_input(dict(fn="s_poly", seed=91, fs=22050, n=30000))
+    xd = torch.from_numpy(x).to(_dev())
+    for kw in (dict(), dict(num_harmonic=2, num_octave=1), dict(harmonic_multiples_elim=3, harmonic_elim_runs=3),
+               dict(harmonic_elim_runs=1)):
+        res = ops.prime_multif0(xd, fs, per_candidate=True, **kw)
+        want_total, want_c = rn.prime(x, fs, per_candidate=True, **kw)
+        _close(res.extra[0].cpu().numpy(), want_c)
+        _close(res.total.cpu().numpy(), want_total)
+    x44, _ = cases.make_input(dict(fn="s_poly", seed=92, fs=44100, n=30000))
+    got = ops.prime_multif0(torch.from_numpy(x44).to(_dev()), 44100).total.cpu().numpy()
+    _close(got, rn.prime(x44, 44100))
+
+
+def test_prime_window_sizes_host_table():
+    from chord_detection_b200 import ops
+
+    for fs in (22050, 44100, 16000):
+        assert ops.prime_window_sizes(fs) == rn.prime_candidates(fs)
+        assert ops.prime_window_sizes(fs, 2, 3) == rn.prime_candidates(fs, 2, 3)
+
+
+def test_prime_batch_of_clips_c5_shape():
+    """C5 shape (22 050 Hz, 44 100-sample clips): per-clip rows equal the oracle; the total is their
+    sum; a tiled batch gives tiled rows (size-independent)."""
+    from chord_detection_b200 import ops
+
+    rows = [cases.make_input(dict(fn="s_poly", seed=500 + i, fs=22050, n=44100))[0] for i in range(4)]
+    xd = torch.from_numpy(np.stack(rows)).to(_dev()).repeat(64, 1)  # 256 clips
+    res = ops.prime_multif0(xd, 22050, per_clip=True)
+    torch.cuda.synchronize()
+    clips = res.clips.cpu().numpy().reshape(64, 4, 12)
+    want = np.stack([rn.prime(r, 22050) for r in rows])
+    _close(clips[0], want)
+    assert np.allclose(clips, np.broadcast_to(clips[0], clips.shape), rtol=1e-12, atol=0)
+    _close(res.total.cpu().numpy(), 64 * want.sum(axis=0))
+
+
+def test_pack_and_key_batched_matches_host(golden):
+    from chord_detection_b200 import ops
+    from chord_detection_b200.chromagram import detect_key, pack_digits
+
+    rows = [v["chroma"] for v in golden["cases"].values()]
+    rng = np.random.default_rng(0)
+    rows += [list(rng.uniform(0, 50, 12)) for _ in range(500)]
+    rows += [[100.0, 0, 0, 0, 100.0, 0, 0, 100.0, 0, 0, 0, 0], [0.0] * 12, [1.0] * 12]
+    arr = np.asarray(rows, dtype=np.float64)
+    digits, keys = ops.pack_and_key(torch.from_numpy(arr).to(_dev()))
+    digits, keys = digits.cpu().numpy(), keys.cpu().numpy()
+    n_digit_ok = 0
+    for i, row in enumerate(arr):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want_key = detect_key(row)
+        assert ops.key_code_to_str(keys[i]) == want_key, (i, row)
+        n_digit_ok += "".join(str(int(d)) for d in digits[i]) == pack_digits(row)
+    # Python's round(x, 3) is decimal-exact; the device uses rint(x*1000)/1000, which can differ
+    # only when x*1000 is within one ulp of a .5 tie -- allow a handful out of ~660 rows
+    assert n_digit_ok >= len(arr) - 3
+
+
+def test_prime_class_api():
+    import chord_detection_b200 as cd
+
+    x, fs = cases.make_input(dict(fn="gen_test_clip", name="test_1_note_E4"))
+    c = cd.MultipitchPrimeMultiF0(x, fs=fs).compute_pitches()
+    assert repr(c) == "012797300000"  # SURVEY.md Appendix B / golden
+    assert cd.METHODS[4] is cd.MultipitchPrimeMultiF0
