@@ -1,7 +1,511 @@
+// Iterative F0 (method 3, Klapuri) — replaces /root/reference/chord_detection/iterative_f0.py:54-96
+// (+ :171-193 filterbank, dsp/wfir.py:25-43, dsp/lowpass.py:6-8) and the whole of periodicity.py.
+//
+// Three kernels per batch of clips (workspace supplied by the caller):
+//   iterf0_filter_kernel      one thread per (clip, channel): the auditory channel is an IIR chain
+//                             over the WHOLE clip (state spans frames, iterative_f0.py:57-65):
+//                             2+2 resonator biquads (:182-191), 12 all-passes + 13 taps (wfir),
+//                             |.| (:60), (y + lowpass_fc(y))/2 (:61-63).  FP64 recurrences; the
+//                             result is stored as fp32 [clip][channel][n], zero past the clip end.
+//   iterf0_spectrum_kernel    one CTA per (clip, frame): for each channel, Hamming window (:75),
+//                             zero-pad x2 (:76), 2*frame_size-point real FFT (as a frame_size-point
+//                             complex FFT in shared memory, fp32) and U[k] += |X_c[k]|^power in
+//                             fp64 (:80-85).  Only k <= frame_size is kept (|X[N-k]| = |X[k]|).
+//   iterf0_periodicity_kernel one CTA per frame (one warp per harmonic): the interval-splitting
+//                             tau search (periodicity.py:114-163), polyphony test (:72-75),
+//                             harmonic cancellation with the 9-tap spread (:78-99), up to
+//                             max_voices voices, fs/tau -> pitch class (:105-110).
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
-struct IterF0Plan {};
-void cdb_free_iterf0_plans(cdb_handle* h) { for (auto& kv : h->iterf0_plans) delete kv.second; h->iterf0_plans.clear(); }
-extern "C" int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params*, int64_t, int64_t) { return 0; }
-extern "C" int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params*, const float*, int64_t, int64_t, int64_t, void*, int64_t, double*, double*, double*, double*, int, void*) {
-  return cdb_fail(h, CDB_E_UNSUPPORTED, "iterf0: not built yet");
+
+struct IterF0Plan {
+  cdb_iterf0_params p;
+  int M, log2M;  // complex FFT size = frame_size
+  float* d_win = nullptr;      // [frame_size] hamming
+  float2* d_tw = nullptr;      // [M/2] W_M^q
+  float2* d_wsplit = nullptr;  // [M+1] (cos, sin)(2*pi*k/(2M))
+  double* d_coef = nullptr;    // [channels][30]: res1 b,a | res2 b,a | lp b,a (each 3) ... see below
+};
+
+void cdb_free_iterf0_plans(cdb_handle* h) {
+  for (auto& kv : h->iterf0_plans) delete kv.second;
+  h->iterf0_plans.clear();
 }
+
+constexpr int kCoefStride = 18;  // res1 b[3] a[3] | res2 b[3] a[3] | lp b[3] a[3]
+constexpr int kSpecThreads = 256;
+
+struct IterArgs {
+  const float* x;
+  int64_t clip_len, clip_stride;
+  int64_t clip0;       // first clip of this batch
+  int n_batch_clips;   // clips in this batch
+  int64_t n_pad;       // frames_per_clip * frame_size
+  int64_t fpc;         // frames per clip
+  int C, F, M, log2M;  // channels, frame_size, complex FFT size (= F), log2
+  double power;
+  const double* coef;
+  double lam, taps[13];
+  const float* win;
+  const float2* tw;
+  const float2* wsplit;
+  float* yc;    // [n_batch_clips][C][n_pad]
+  double* Ut;   // [n_batch_clips*fpc][M+1]
+  double* Ud;   // [grid][2M] cancellation scratch
+  // periodicity
+  double fs, K, tau_min, tau_max, tau_prec, e1, e2, gamma;
+  int max_voices, Q, Mh;
+  double* total;
+  double* clips;
+  double* frames;
+  double* voices;
+};
+
+struct Sos {
+  double b0, b1, b2, a1, a2, z0, z1;
+  __device__ __forceinline__ void init(const double* c) {  // c = b[3], a[3]
+    const double a0 = c[3];
+    b0 = c[0] / a0;
+    b1 = c[1] / a0;
+    b2 = c[2] / a0;
+    a1 = c[4] / a0;
+    a2 = c[5] / a0;
+    z0 = z1 = 0.0;
+  }
+  __device__ __forceinline__ double step(double x) {  // scipy lfilter, direct form II transposed
+    const double y = z0 + b0 * x;
+    z0 = (z1 + x * b1) - y * a1;
+    z1 = x * b2 - y * a2;
+    return y;
+  }
+};
+
+__global__ void __launch_bounds__(64) iterf0_filter_kernel(const IterArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_batch_clips * a.C) return;
+  const int lc = t / a.C, ch = t - lc * a.C;
+  const float* src = a.x + (a.clip0 + lc) * a.clip_stride;
+  float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
+  const double* cf = a.coef + ch * kCoefStride;
+  Sos r1a, r1b, r2a, r2b, lp;
+  r1a.init(cf);
+  r1b.init(cf);
+  r2a.init(cf + 6);
+  r2b.init(cf + 6);
+  lp.init(cf + 12);
+  double z[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) z[i] = 0.0;
+  const double mlam = -a.lam;
+  for (int64_t n = 0; n < a.clip_len; ++n) {
+    double v = (double)__ldg(src + n);
+    v = r1a.step(v);  // iterative_f0.py:188-191
+    v = r1b.step(v);
+    v = r2a.step(v);
+    v = r2b.step(v);
+    double u = v, xhat = a.taps[0] * v;  // wfir.py:28-43
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const double y = z[i] + mlam * u;
+      z[i] = u - y * mlam;
+      xhat += a.taps[i + 1] * y;
+      u = y;
+    }
+    double y = fabs(v - xhat);       // iterative_f0.py:60
+    y = (y + lp.step(y)) / 2.0;      // :61-63
+    dst[n] = (float)y;
+  }
+  for (int64_t n = a.clip_len; n < a.n_pad; ++n) dst[n] = 0.0f;  // frame_cutter pads the FILTERED signal
+}
+
+__global__ void __launch_bounds__(kSpecThreads) iterf0_spectrum_kernel(const IterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float2* s = reinterpret_cast<float2*>(smem);        // [M]
+  double* U = reinterpret_cast<double*>(s + a.M);     // [M+1]
+  const int tid = threadIdx.x;
+  const int M = a.M, F = a.F;
+  const int64_t gf = blockIdx.x;  // frame within this batch
+  const int64_t lc = gf / a.fpc, f = gf - lc * a.fpc;
+  for (int k = tid; k <= M; k += kSpecThreads) U[k] = 0.0;
+  for (int ch = 0; ch < a.C; ++ch) {
+    const float* src = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad + f * F;
+    // z[m] = x[2m] + i x[2m+1] of the zero-padded 2F-point frame: m >= F/2 is zero
+    for (int m = tid; m < M; m += kSpecThreads) {
+      float2 v = make_float2(0.f, 0.f);
+      if (2 * m < F) v = make_float2(src[2 * m] * a.win[2 * m], src[2 * m + 1] * a.win[2 * m + 1]);
+      s[(int)(__brev((unsigned)m) >> (32 - a.log2M))] = v;
+    }
+    __syncthreads();
+    for (int st = 0; st < a.log2M; ++st) {
+      const int span = 1 << st;
+      for (int b = tid; b < M / 2; b += kSpecThreads) {
+        const int j = b & (span - 1);
+        const int i0 = ((b >> st) << (st + 1)) + j, i1 = i0 + span;
+        const float2 w = __ldg(&a.tw[j * (M / (2 * span))]);
+        const float2 u = s[i0], q = s[i1];
+        const float2 t = make_float2(q.x * w.x - q.y * w.y, q.x * w.y + q.y * w.x);
+        s[i0] = make_float2(u.x + t.x, u.y + t.y);
+        s[i1] = make_float2(u.x - t.x, u.y - t.y);
+      }
+      __syncthreads();
+    }
+    for (int k = tid; k <= M; k += kSpecThreads) {
+      float mag2;
+      if (k == M) {
+        const float xn = s[0].x - s[0].y;
+        mag2 = xn * xn;
+      } else {
+        const float2 z = s[k], pz = s[(M - k) & (M - 1)];
+        const float2 cs = __ldg(&a.wsplit[k]);
+        const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+        const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+        const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+        mag2 = xr * xr + xi * xi;
+      }
+      const double mag = sqrt((double)mag2);
+      U[k] += (a.power == 1.0) ? mag : pow(mag, a.power);
+    }
+    __syncthreads();
+  }
+  double* out = a.Ut + gf * (int64_t)(M + 1);
+  for (int k = tid; k <= M; k += kSpecThreads) out[k] = U[k];
+}
+
+__constant__ double kHW9[9] = {0.0011244659258033, 0.11559343551383, 0.42817348241183,
+                               0.81822361914331,   1.0,              0.81822361914331,
+                               0.42817348241183,   0.11559343551383, 0.0011244659258033};
+
+__global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* Ur = reinterpret_cast<double*>(smem);  // [nb]
+  __shared__ double lo[32], up[32], smax[32], part[2][32];
+  __shared__ double sal[8], per[8], chroma[12];
+  __shared__ int s_q, s_qb;
+  __shared__ double s_tau, s_best;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int M = a.M, nb = 2 * a.M;
+  double* Ud = a.Ud + (int64_t)blockIdx.x * nb;
+
+  for (int64_t gf = blockIdx.x; gf < (int64_t)a.n_batch_clips * a.fpc; gf += gridDim.x) {
+    const double* Uk = a.Ut + gf * (int64_t)(M + 1);
+    for (int i = tid; i < nb; i += nthr) {
+      Ur[i] = Uk[i <= M ? i : nb - i];
+      Ud[i] = 0.0;
+    }
+    if (tid < 8) sal[tid] = per[tid] = 0.0;
+    if (tid < 12) chroma[tid] = 0.0;
+    __syncthreads();
+    int nv = 0;
+    double prev = 0.0, mix = 0.0;
+    for (;;) {
+      // ---- min_search (periodicity.py:114-142)
+      if (tid == 0) {
+        lo[0] = a.tau_min;
+        up[0] = a.tau_max;
+        s_q = 0;
+        s_qb = 0;
+      }
+      __syncthreads();
+      for (;;) {
+        const int qb = s_qb;
+        int q = s_q;
+        if (!((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1)) break;
+        __syncthreads();
+        if (tid == 0) {
+          q = q + 1;
+          lo[q] = (lo[qb] + up[qb]) * 0.5;
+          up[q] = up[qb];
+          up[qb] = lo[q];
+          s_q = q;
+        }
+        __syncthreads();
+        q = s_q;
+        if (warp >= 1 && warp < a.Mh) {  // smax_fn (:144-163), one warp per harmonic m
+          const int m = warp;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            const int qq = which == 0 ? q : qb;
+            const double tau = 0.5 * (lo[qq] + up[qq]);
+            const double dt = up[qq] - lo[qq];
+            int lowk = (int)((double)m * a.K / (tau + 0.5 * dt) + 0.5);
+            int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
+            if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
+            double mx = -INFINITY;
+            for (int i = lowk + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) part[which][m] = ((double)m * a.fs / up[qq] + a.e2) * mx;
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          for (int which = 0; which < 2; ++which) {
+            const int qq = which == 0 ? q : qb;
+            double sacc = 0.0;
+            for (int m = 1; m < a.Mh; ++m) sacc += part[which][m];
+            smax[qq] = sacc * (a.fs / lo[qq] + a.e1);
+          }
+          int best = 0;
+          double bv = smax[0];
+          for (int j = 1; j <= q; ++j)
+            if (smax[j] > bv) {
+              bv = smax[j];
+              best = j;
+            }
+          s_qb = best;
+        }
+        __syncthreads();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const int qb = s_qb;
+        s_tau = (lo[qb] + up[qb]) * 0.5;
+        s_best = smax[qb];
+        sal[nv] = s_best;
+        per[nv] = s_tau;
+      }
+      __syncthreads();
+      const double tau = s_tau, best = s_best;
+      nv += 1;
+      mix += best;
+      const double test = mix / pow((double)nv, a.gamma);
+      if (nv >= a.max_voices || test <= prev) break;
+      prev = test;
+      // ---- harmonic cancellation (:78-99)
+      const int topm = (int)(tau * (a.fs / (double)a.F) * (double)nb);
+      const double srt = a.fs / tau;
+      const double weight = srt + a.e1;
+      for (int m = 1 + tid; m < topm; m += nthr) {
+        const double pk = (double)m * a.K / tau + 0.5;
+        if (pk <= (double)nb) {
+          const int ip = (int)pk;
+          if (ip < nb) {
+            const double uw = Ur[ip] * (weight / ((double)m * srt + a.e2));
+            int lowk = (int)(pk - 4.0);
+            if (lowk < 0) lowk = 0;
+            int highk = (int)(pk + 4.0);
+            if (highk > nb) highk = nb;
+            for (int j = lowk; j <= highk && j < nb; ++j) {
+              int hi = (int)((double)j - pk + 4.0);
+              hi = hi < 0 ? 0 : (hi > 8 ? 8 : hi);
+              atomicAdd(&Ud[j], kHW9[hi] * uw);
+            }
+          }
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+      for (int i = tid; i < nb; i += nthr) {
+        const double d = Uk[i <= M ? i : nb - i] - __ldcg(&Ud[i]);
+        Ur[i] = d > 0.0 ? d : 0.0;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 0; i < a.max_voices; ++i) {
+        if (per[i] == 0.0) continue;  // fs/0 -> inf -> OverflowError -> continue (:109-110)
+        const double f = a.fs / per[i];
+        if (!(f > 0.0) || !isfinite(f)) continue;
+        const double midi = 12.0 * (log2(f) - log2(440.0)) + 69.0;
+        long long nn = (long long)nearbyint(midi);
+        int note = (int)(nn % 12);
+        if (note < 0) note += 12;
+        chroma[note] += sal[i];
+      }
+      if (a.voices)
+        for (int i = 0; i < a.max_voices; ++i) {
+          a.voices[gf * 2 * a.max_voices + i] = sal[i];
+          a.voices[gf * 2 * a.max_voices + a.max_voices + i] = per[i];
+        }
+    }
+    __syncthreads();
+    if (tid < 12) {
+      const double v = chroma[tid];
+      const int64_t gframe = a.clip0 * a.fpc + gf;
+      if (a.frames) a.frames[gframe * 12 + tid] = v;
+      if (v != 0.0) {
+        if (a.clips) atomicAdd(&a.clips[(a.clip0 + gf / a.fpc) * 12 + tid], v);
+        if (a.total) atomicAdd(&a.total[tid], v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int iterf0_get_plan(cdb_handle* h, const cdb_iterf0_params* p, IterF0Plan** out) {
+  std::string key = pod_key(*p);
+  auto it = h->iterf0_plans.find(key);
+  if (it != h->iterf0_plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  const int F = p->frame_size;
+  if (F < 64 || F > 8192 || (F & (F - 1)))
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "frame_size %d: need a power of two in [64, 8192]", F);
+  if (p->channels < 1 || p->channels > CDB_ITERF0_MAX_CHANNELS)
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "channels %d outside [1, %d]", p->channels,
+                    CDB_ITERF0_MAX_CHANNELS);
+  if (p->Q < 2 || p->Q > 32 || p->M < 2 || p->M > 32 || p->max_voices < 1 || p->max_voices > 8)
+    return cdb_fail(h, CDB_E_UNSUPPORTED, "Q, M must be in [2, 32], max_voices in [1, 8]");
+  if (!(p->fs > 0) || !(p->tau_min > 0) || !(p->tau_max > p->tau_min))
+    return cdb_fail(h, CDB_E_INVALID, "invalid iterative-F0 parameters");
+  IterF0Plan* pl = new IterF0Plan();
+  pl->p = *p;
+  pl->M = F;
+  pl->log2M = 0;
+  while ((1 << pl->log2M) < F) ++pl->log2M;
+  const double pi = 3.14159265358979323846;
+  std::vector<float> win(F);
+  for (int n = 0; n < F; ++n)  // scipy.signal.hamming(F), symmetric (iterative_f0.py:75)
+    win[n] = (float)(0.54 - 0.46 * std::cos(2.0 * pi * n / (double)(F - 1)));
+  std::vector<float2> tw(F / 2), ws(F + 1);
+  for (int q = 0; q < F / 2; ++q) {
+    const double ang = 2.0 * pi * q / (double)F;
+    tw[q] = make_float2((float)std::cos(ang), (float)-std::sin(ang));
+  }
+  for (int k = 0; k <= F; ++k) {
+    const double ang = 2.0 * pi * k / (double)(2 * F);
+    ws[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+  }
+  std::vector<double> coef((size_t)p->channels * kCoefStride);
+  for (int c = 0; c < p->channels; ++c) {
+    double* o = &coef[(size_t)c * kCoefStride];
+    for (int i = 0; i < 3; ++i) {
+      o[i] = p->res1_b[c][i];
+      o[3 + i] = p->res1_a[c][i];
+      o[6 + i] = p->res2_b[c][i];
+      o[9 + i] = p->res2_a[c][i];
+      o[12 + i] = p->lp_b[c][i];
+      o[15 + i] = p->lp_a[c][i];
+    }
+  }
+  int rc;
+  if ((rc = cdb_upload(h, win, &pl->d_win)) || (rc = cdb_upload(h, tw, &pl->d_tw)) ||
+      (rc = cdb_upload(h, ws, &pl->d_wsplit)) || (rc = cdb_upload(h, coef, &pl->d_coef))) {
+    delete pl;
+    return rc;
+  }
+  h->iterf0_plans[key] = pl;
+  *out = pl;
+  return 0;
+}
+
+static int64_t per_clip_bytes(const cdb_iterf0_params* p, int64_t clip_len) {
+  const int64_t fpc = cdb_num_frames(clip_len, p->frame_size, p->frame_size);
+  const int64_t n_pad = fpc * p->frame_size;
+  return (int64_t)p->channels * n_pad * 4 + fpc * (int64_t)(p->frame_size + 1) * 8;
+}
+
+static int64_t ud_bytes(const cdb_iterf0_params* p, int num_sms) {
+  return (int64_t)num_sms * 2 * p->frame_size * 8;
+}
+
+extern "C" {
+
+int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params* p, int64_t n_clips, int64_t clip_len) {
+  if (!p || n_clips < 0 || clip_len < 0) return -1;
+  // enough for min(n_clips, 1024) clips per batch, capped at 8 GiB of per-clip scratch
+  int64_t per = per_clip_bytes(p, clip_len);
+  int64_t b = std::min<int64_t>(n_clips, 1024);
+  const int64_t cap = (int64_t)8 << 30;
+  if (per > 0 && b * per > cap) b = std::max<int64_t>(1, cap / per);
+  return b * per + ud_bytes(p, 1024) + 1024;
+}
+
+int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_x, int64_t n_clips,
+                      int64_t clip_len, int64_t clip_stride, void* d_workspace,
+                      int64_t workspace_bytes, double* d_chroma_total, double* d_chroma_clips,
+                      double* d_chroma_frames, double* d_voices, int flags, void* stream) {
+  if (!h) return CDB_E_NULL;
+  if (!p || !d_x) return cdb_fail(h, CDB_E_NULL, "null params / input");
+  if (n_clips < 0 || clip_len < 0 || (n_clips > 1 && clip_stride < clip_len))
+    return cdb_fail(h, CDB_E_INVALID, "bad batch shape");
+  CDB_CUDA(h, cudaSetDevice(h->device));
+  IterF0Plan* pl = nullptr;
+  int rc = iterf0_get_plan(h, p, &pl);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & CDB_FLAG_ACCUMULATE)) {
+    if (d_chroma_total) CDB_CUDA(h, cudaMemsetAsync(d_chroma_total, 0, 12 * sizeof(double), st));
+    if (d_chroma_clips && n_clips > 0)
+      CDB_CUDA(h, cudaMemsetAsync(d_chroma_clips, 0, n_clips * 12 * sizeof(double), st));
+  }
+  if (n_clips == 0 || clip_len == 0) return 0;
+  const int F = p->frame_size;
+  const int64_t fpc = cdb_num_frames(clip_len, F, F);
+  const int64_t n_pad = fpc * F;
+  const int pgrid_max = h->num_sms;
+  const int64_t fixed = ud_bytes(p, pgrid_max) + 2048;  // + alignment slack
+  const int64_t per = per_clip_bytes(p, clip_len);
+  if (!d_workspace || workspace_bytes < fixed + per)
+    return cdb_fail(h, CDB_E_INVALID, "workspace too small: need at least %lld bytes",
+                    (long long)(fixed + per));
+  const int64_t bmax = std::min<int64_t>(n_clips, (workspace_bytes - fixed) / per);
+
+  IterArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.x = d_x;
+  a.clip_len = clip_len;
+  a.clip_stride = clip_stride;
+  a.n_pad = n_pad;
+  a.fpc = fpc;
+  a.C = p->channels;
+  a.F = F;
+  a.M = pl->M;
+  a.log2M = pl->log2M;
+  a.power = p->power;
+  a.coef = pl->d_coef;
+  a.lam = p->wfir_lambda;
+  std::memcpy(a.taps, p->wfir_taps, sizeof(a.taps));
+  a.win = pl->d_win;
+  a.tw = pl->d_tw;
+  a.wsplit = pl->d_wsplit;
+  a.fs = p->fs;
+  a.K = (double)F / p->fs;  // periodicity.py:31
+  a.tau_min = p->tau_min;
+  a.tau_max = p->tau_max;
+  a.tau_prec = p->tau_prec;
+  a.e1 = p->epsilon1;
+  a.e2 = p->epsilon2;
+  a.gamma = p->gamma;
+  a.max_voices = p->max_voices;
+  a.Q = p->Q;
+  a.Mh = p->M;
+  a.total = d_chroma_total;
+  a.clips = d_chroma_clips;
+  a.frames = d_chroma_frames;
+  a.voices = d_voices;
+  unsigned char* w = reinterpret_cast<unsigned char*>(d_workspace);
+  w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 255) & ~(uintptr_t)255);
+  a.Ud = reinterpret_cast<double*>(w);
+  unsigned char* wrest = w + ud_bytes(p, pgrid_max);
+
+  const size_t spec_smem = (size_t)pl->M * 8 + (size_t)(pl->M + 1) * 8;
+  CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
+  const size_t per_smem = (size_t)2 * pl->M * 8;
+  CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_smem));
+  for (int64_t c0 = 0; c0 < n_clips; c0 += bmax) {
+    const int nb = (int)std::min<int64_t>(bmax, n_clips - c0);
+    a.clip0 = c0;
+    a.n_batch_clips = nb;
+    a.yc = reinterpret_cast<float*>(wrest);
+    a.Ut = reinterpret_cast<double*>(wrest + (((size_t)nb * a.C * n_pad * 4 + 255) & ~(size_t)255));
+    if (d_voices) a.voices = d_voices + c0 * fpc * 2 * p->max_voices;
+    const int threads = nb * a.C;
+    iterf0_filter_kernel<<<(threads + 63) / 64, 64, 0, st>>>(a);
+    const int64_t nframes = (int64_t)nb * fpc;
+    iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
+    const int pgrid = (int)std::min<int64_t>(nframes, pgrid_max);
+    iterf0_periodicity_kernel<<<pgrid, 32 * p->M, per_smem, st>>>(a);
+    h->launches += 3;
+    CDB_CUDA(h, cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -268,3 +268,79 @@ def pack_and_key(chroma):
         rc = h.L.cdb_pack_and_key(h.ptr, _ptr(chroma), n, _ptr(digits), _ptr(keys), _stream_ptr(chroma))
     h.check(rc, "cdb_pack_and_key")
     return digits, keys
+
+
+def iterf0_channel_freqs(channels=70, zeta0=2.3, zeta1=0.39):
+    return [229 * (10 ** ((zeta1 * c + zeta0) / 21.4) - 1) for c in range(channels)]  # iterative_f0.py:38-40
+
+
+def iterf0_params(fs, frame_size=8192, power=1.0, channel_freqs=None, max_voices=4,
+                  tau_min=1.0 / 2100.0, tau_max=1.0 / 40.0, tau_prec=0.0000001, Q=20, M=20,
+                  epsilon1=20, epsilon2=320, gamma=0.66):
+    """Host-side float64 designs for cdb_iterf0_chroma.  The resonator coefficients reproduce
+    iterative_f0.py:171-193 INCLUDING its swapped arguments: the call site passes (x, fs, fc) into
+    def _auditory_filterbank(x, fc, fs) (:58 vs :171), so inside the function "fc" is the sample
+    rate and "fs" is the channel frequency."""
+    if channel_freqs is None:
+        channel_freqs = iterf0_channel_freqs()
+    if len(channel_freqs) > nat.ITERF0_MAX_CHANNELS:
+        raise ValueError("at most %d channels" % nat.ITERF0_MAX_CHANNELS)
+    p = nat.IterF0Params()
+    p.fs, p.frame_size, p.power, p.channels = float(fs), int(frame_size), float(power), len(channel_freqs)
+    p.max_voices, p.tau_min, p.tau_max, p.tau_prec = int(max_voices), float(tau_min), float(tau_max), float(tau_prec)
+    p.Q, p.M, p.epsilon1, p.epsilon2, p.gamma = int(Q), int(M), float(epsilon1), float(epsilon2), float(gamma)
+    for c, ch_hz in enumerate(channel_freqs):
+        fc_in, fs_in = fs, ch_hz  # swapped on purpose
+        J = 4
+        A = np.exp(-(3 / J) * np.pi / (fs_in * np.sqrt(2 ** (1 / J) - 1)))
+        cos_theta1 = (1 + A * A) / (2 * A) * np.cos(2 * np.pi * fc_in / fs_in)
+        cos_theta2 = (2 * A) / (1 + A * A) * np.cos(2 * np.pi * fc_in / fs_in)
+        rho1 = (1 / 2) * (1 - A * A)
+        rho2 = (1 - A * A) * np.sqrt(1 - cos_theta2 ** 2)
+        r1b, r1a = [rho1, 0.0, -rho1], [1.0, -A * cos_theta1, A * A]
+        r2b, r2a = [rho2, 0.0, 0.0], [1.0, -A * cos_theta2, A * A]
+        lb, la = butter2(fs, ch_hz, "low")  # iterative_f0.py:62 lowpass at the channel frequency
+        for i in range(3):
+            p.res1_b[c][i], p.res1_a[c][i] = float(r1b[i]), float(r1a[i])
+            p.res2_b[c][i], p.res2_a[c][i] = float(r2b[i]), float(r2a[i])
+            p.lp_b[c][i], p.lp_a[c][i] = float(lb[i]), float(la[i])
+    lam, taps = wfir_design(fs, 12)
+    p.wfir_lambda = lam
+    for i, v in enumerate(taps):
+        p.wfir_taps[i] = v
+    return p
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    w = _workspaces.get(key)
+    if w is None or w.numel() < nbytes:
+        _workspaces[key] = None
+        w = _workspaces[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    return w
+
+
+def iterative_f0(x, fs, frame_size=8192, power=1.0, channel_freqs=None, per_clip=False,
+                 per_frame=False, voices=False, **periodicity_kwargs):
+    """Iterative-F0 chromagram (reference iterative_f0.py:54-96 + periodicity.py) -> ChromaResult.
+    voices=True returns [n_frames, 2*max_voices] (saliences | periods) in ``extra``."""
+    x, n_clips, clip_len, stride = _batch_view(x)
+    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    p = iterf0_params(fs, frame_size, power, channel_freqs, **periodicity_kwargs)
+    fpc = nat.num_frames(clip_len, frame_size, frame_size)
+    need = int(h.L.cdb_iterf0_workspace_bytes(C.byref(p), n_clips, clip_len))
+    ws = _workspace(x.device, need)
+    total = torch.empty(12, dtype=torch.float64, device=x.device)
+    clips = torch.empty((n_clips, 12), dtype=torch.float64, device=x.device) if per_clip else None
+    frames = torch.empty((n_clips * fpc, 12), dtype=torch.float64, device=x.device) if per_frame else None
+    vo = (torch.zeros((n_clips * fpc, 2 * p.max_voices), dtype=torch.float64, device=x.device)
+          if voices else None)
+    with torch.cuda.device(x.device):
+        rc = h.L.cdb_iterf0_chroma(h.ptr, C.byref(p), _ptr(x), n_clips, clip_len, stride, _ptr(ws),
+                                   ws.numel(), _ptr(total), _ptr(clips), _ptr(frames), _ptr(vo), 0,
+                                   _stream_ptr(x))
+    h.check(rc, "cdb_iterf0_chroma")
+    return ChromaResult(total, clips, frames, vo)

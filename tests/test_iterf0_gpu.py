@@ -1,0 +1,95 @@
+"""GPU parity tests for iterative F0 (cdb_iterf0_chroma)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import cases, ref_numpy as rn  # noqa: E402
+
+RTOL = 1e-4
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _close(got, want, tol=RTOL):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(np.max(np.abs(want)), 1e-300)
+    assert np.max(np.abs(got - want)) / scale <= tol, (got, want)
+
+
+def _ids():
+    import json
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "reference_golden.json")) as f:
+        g = json.load(f)
+    return sorted(k for k, v in g["cases"].items() if v["method"] == 3)
+
+
+@pytest.mark.parametrize("cid", _ids())
+def test_iterf0_matches_reference_golden(golden, cid):
+    from chord_detection_b200 import ops
+
+    g = golden["cases"][cid]
+    x, fs = cases.make_input(g["input"])
+    xd = torch.from_numpy(x).to(_dev())
+    got = ops.iterative_f0(xd, fs, **g["kwargs"]).total.cpu().numpy()
+    _close(got, g["chroma"])
+    assert rn.pack_chroma(got) == g["digits"]
+
+
+def test_iterf0_voices_match_oracle():
+    """Per frame: the (salience, period) of every voice slot, i.e. the whole tau search."""
+    from chord_detection_b200 import ops
+
+    x, fs = cases.make_input(dict(fn="s_poly", seed=210, fs=22050, n=3 * 8192 + 1000))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        total, Ut, det = rn.iterf0(x, fs, detail=True)
+    res = ops.iterative_f0(torch.from_numpy(x).to(_dev()), fs, voices=True, per_frame=True)
+    vo = res.extra.cpu().numpy()
+    assert vo.shape == (len(det), 8)
+    for f, (sal, per) in enumerate(det):
+        assert np.allclose(vo[f, 4:], per, rtol=1e-9, atol=0), (f, vo[f, 4:], per)
+        assert np.allclose(vo[f, :4], sal, rtol=1e-5, atol=0), (f, vo[f, :4], sal)
+    _close(res.total.cpu().numpy(), total)
+    _close(res.frames.sum(dim=0).cpu().numpy(), res.total.cpu().numpy(), tol=1e-12)
+
+
+def test_iterf0_params_and_batch():
+    from chord_detection_b200 import ops
+
+    rows = [cases.make_input(dict(fn="s_poly", seed=220 + i, fs=22050, n=20000))[0] for i in range(3)]
+    xd = torch.from_numpy(np.stack(rows)).to(_dev())
+    res = ops.iterative_f0(xd, 22050, per_clip=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.stack([rn.iterf0(r, 22050) for r in rows])
+    _close(res.clips.cpu().numpy(), want)
+    _close(res.total.cpu().numpy(), want.sum(axis=0))
+    # non-default frame size / channel count / power
+    kw = dict(frame_size=4096, power=0.67, channels=20)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        w2 = rn.iterf0(rows[0], 22050, **kw)
+    g2 = ops.iterative_f0(xd[0], 22050, frame_size=4096, power=0.67,
+                          channel_freqs=ops.iterf0_channel_freqs(20)).total.cpu().numpy()
+    _close(g2, w2)
+
+
+def test_iterf0_class_api():
+    import chord_detection_b200 as cd
+
+    x, fs = cases.make_input(dict(fn="gen_test_clip", name="test_2_notes_G3_Asharp4"))
+    c = cd.MultipitchIterativeF0(x, fs=fs).compute_pitches()
+    assert repr(c) == "090000000000"  # SURVEY.md Appendix B / golden
+    assert c.key() == "C#maj"
+    assert cd.METHODS[3] is cd.MultipitchIterativeF0
