@@ -1,0 +1,99 @@
+"""Multi-GPU: one process per GPU (torchrun), data-parallel over frames or clips, ONE all-reduce.
+
+The reference has no parallelism of any kind.  Every method's frames (HE,
+ESACF, prime) or clips (iterative F0 carries IIR state across a clip) are independent, so rank r
+takes a contiguous shard, runs the same kernels, and the per-rank 12-bin sums are combined with a
+single `all_reduce(SUM)` of 12 doubles per method (NCCL over NVLink on GPUs; gloo in CPU tests).
+No data-path collective exists or is needed.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend=None):
+    """Initialise torch.distributed from the torchrun environment (RANK / WORLD_SIZE / LOCAL_RANK).
+    Returns (rank, world, device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cuda = torch.cuda.is_available()
+    device = torch.device("cuda", local) if cuda else torch.device("cpu")
+    if cuda:
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if cuda else "gloo"
+        if backend == "nccl":
+            dist.init_process_group(backend, device_id=device)
+        else:
+            dist.init_process_group(backend)
+    return rank, world, device
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [begin, end) of n_items for this rank (sizes differ by at most 1)."""
+    return (n_items * rank) // world, (n_items * (rank + 1)) // world
+
+
+def shard_frames(n_samples, frame_size, hop, rank, world):
+    """Shard the frames of ONE long signal.  Returns (f0, f1, s0, s1): this rank owns frames
+    [f0, f1) and must hold samples [s0, s1) -- its frames plus the frame_size-hop halo; frames that
+    run past n_samples are zero padded by the kernel (explicit frames_per_clip)."""
+    hop = frame_size if not hop else hop
+    n_frames = (n_samples + hop - 1) // hop if n_samples > 0 else 0
+    f0, f1 = shard_range(n_frames, rank, world)
+    if f1 <= f0:
+        return f0, f1, 0, 0
+    s0 = f0 * hop
+    s1 = min(n_samples, (f1 - 1) * hop + frame_size)
+    return f0, f1, s0, s1
+
+
+def all_reduce_chroma(t):
+    """Sum the per-rank chroma tensor(s) ([12] or [k, 12]) over all ranks, in place."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def harmonic_energy_sharded(x_local, fs, frames_local, frame_size, hop=None, **kw):
+    """HE over this rank's shard of a long signal (x_local = samples [s0, s1) of shard_frames),
+    then the all-reduce.  Returns the GLOBAL 12-bin sum on every rank (CUDA float64 tensor)."""
+    from . import ops
+
+    total = torch.zeros(12, dtype=torch.float64, device=x_local.device)
+    if frames_local > 0:
+        ops.harmonic_energy(x_local, fs, frame_size=frame_size, hop=hop,
+                            frames_per_clip=frames_local, out_total=total, **kw)
+    return all_reduce_chroma(total)
+
+
+def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4)):
+    """Config C5: every rank runs the requested methods on its shard of clips ([n_local, clip_len]
+    CUDA float32) and ONE all-reduce combines the [n_methods, 12] sums.  Returns (global sums
+    [n_methods, 12], dict of per-clip results that stay sharded)."""
+    from . import ops
+
+    dev = clips_local.device
+    sums = torch.zeros((len(methods), 12), dtype=torch.float64, device=dev)
+    per_clip = {}
+    for i, m in enumerate(methods):
+        if clips_local.shape[0] == 0:
+            continue
+        if m == 1:
+            r = ops.esacf(clips_local, fs, per_clip=True)
+        elif m == 2:
+            r = ops.harmonic_energy(clips_local, fs, per_clip=True)
+        elif m == 3:
+            r = ops.iterative_f0(clips_local, fs, per_clip=True)
+        elif m == 4:
+            r = ops.prime_multif0(clips_local, fs, per_clip=True)
+        else:
+            raise ValueError("valid methods: 1, 2, 3, 4")
+        sums[i] = r.total
+        per_clip[m] = r.clips
+    return all_reduce_chroma(sums), per_clip

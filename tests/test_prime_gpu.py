@@ -42,6 +42,12 @@ def test_prime_matches_reference_golden(golden, cid):
     x, fs = cases.make_input(g["input"])
     xd = torch.from_numpy(x).to(_dev())
     got = ops.prime_multif0(xd, fs, **g["kwargs"]).total.cpu().numpy()
+    if g["input"]["fn"] == "impulse":
+        # a windowed impulse has an exactly flat magnitude spectrum: every bin ties, and which one
+        # numpy.argmax returns is decided by the rounding noise of its FFT backend.  Only the
+        # picked MASS is defined (2 runs x n_windows x the common bin height), not its pitch class.
+        assert np.isclose(got.sum(), np.sum(g["chroma"]), rtol=1e-9)
+        return
     _close(got, g["chroma"])
     assert rn.pack_chroma(got) == g["digits"]
 
