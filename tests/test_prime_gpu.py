@@ -43,10 +43,18 @@ def test_prime_matches_reference_golden(golden, cid):
     xd = torch.from_numpy(x).to(_dev())
     got = ops.prime_multif0(xd, fs, **g["kwargs"]).total.cpu().numpy()
     if g["input"]["fn"] == "impulse":
-        # a windowed impulse has an exactly flat magnitude spectrum: every bin ties, and which one
-        # numpy.argmax returns is decided by the rounding noise of its FFT backend.  Only the
-        # picked MASS is defined (2 runs x n_windows x the common bin height), not its pitch class.
-        assert np.isclose(got.sum(), np.sum(g["chroma"]), rtol=1e-9)
+        # a windowed impulse has an exactly flat magnitude spectrum (|X[k]| = w[at] for every k):
+        # every bin ties, and which one argmax returns -- including bin 0, whose frequency 0 makes
+        # hz_to_note raise so the round is skipped (prime_multif0.py:73-74) -- is decided by the
+        # rounding noise of the FFT backend.  Only an upper bound on the picked mass is defined:
+        # harmonic_elim_runs picks of the common height in the one window that holds the impulse.
+        at = g["input"].get("at", 0)
+        full = 0.0
+        for W in rn.prime_candidates(fs):
+            w = np.hanning(W)
+            full += 2 * w[at % W] / np.abs(w).sum() if at < len(x) else 0.0
+        assert np.sum(g["chroma"]) <= full * (1 + 1e-9)  # the reference itself lost some picks
+        assert 0.0 < got.sum() <= full * (1 + 1e-9)
         return
     _close(got, g["chroma"])
     assert rn.pack_chroma(got) == g["digits"]
