@@ -34,6 +34,7 @@ struct HePlan {
   int N, M, hop, log2M;
   int n_windows, wins_per_note;
   int kmin, kmax;  // probed bins, inclusive
+  int max_width;   // widest probe window
   bool force_generic;
   float* d_win = nullptr;      // [N]
   float2* d_tw32 = nullptr;    // [32*32]: W_1024^(t*k1) at [k1*32+t]   (N == 2048)
@@ -126,7 +127,7 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
     return cdb_fail(h, CDB_E_UNSUPPORTED, "num_octave*num_harmonic*12 = %d > %d", nw,
                     HE_MAX_WINDOWS);
   const int N = key.frame_size, M = N / 2;
-  int kmin = 1 << 30, kmax = -1;
+  int kmin = 1 << 30, kmax = -1, max_width = 0;
   for (auto& w : wins) {
     // the reference would wrap negative indices / raise IndexError here
     if (w.k0 < 0 || w.k1 > M + 1 || w.k1 <= w.k0)
@@ -134,6 +135,7 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
                       "probe window [%d,%d) outside the %d rfft bins (reference would wrap/raise)",
                       w.k0, w.k1, M + 1);
     kmin = std::min(kmin, w.k0);
+    max_width = std::max(max_width, w.k1 - w.k0);
     kmax = std::max(kmax, w.k1 - 1);
   }
   HePlan* pl = new HePlan();
@@ -147,6 +149,7 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
   pl->wins_per_note = nw / 12;
   pl->kmin = kmin;
   pl->kmax = kmax;
+  pl->max_width = max_width;
   pl->force_generic = force_generic;
 
   std::vector<float> win(N);
@@ -192,7 +195,7 @@ struct HeArgs {
   int64_t n_clips, clip_len, clip_stride, frames_per_clip;
   int64_t tiles_per_clip, total_tiles;  // fast path
   int hop, N, M, log2M;
-  int n_windows, wins_per_note, kmin, kmax;
+  int n_windows, wins_per_note, kmin, kmax, max_width;
   int tile_cap;  // floats reserved for the staged tile (fast path)
   const float* win;
   const float2* tw32;
@@ -208,8 +211,10 @@ __host__ __device__ constexpr int br5(int k) {
   return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
 }
 
-// 32-point complex DIF FFT in registers; X[k] ends up in v[br5(k)].
-__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+// One radix-2 DIT butterfly in registers: (a, b) -> (a + w b, a - w b), w = W_32^m = C[m] - i S[m].
+// FMA-fused: 6 instructions with a twiddle (second output as 2a - first), 4 without.
+template <int m>
+__device__ __forceinline__ void bfly(float2& a, float2& b) {
   constexpr float C[16] = {1.0f,           0.980785280f,  0.923879533f,  0.831469612f,
                            0.707106781f,   0.555570233f,  0.382683432f,  0.195090322f,
                            0.0f,           -0.195090322f, -0.382683432f, -0.555570233f,
@@ -219,32 +224,54 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
                            1.0f,          0.980785280f, 0.923879533f, 0.831469612f,
                            0.707106781f,  0.555570233f, 0.382683432f, 0.195090322f};
   constexpr float R = 0.707106781f;
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-#pragma unroll
-    for (int g = 0; g < 32; g += 2 * s) {
-#pragma unroll
-      for (int j = 0; j < s; ++j) {
-        const int m = j * (16 / s);  // W_{2s}^j = W_32^m = C[m] - i S[m]
-        const float2 a = v[g + j], b = v[g + j + s];
-        v[g + j] = make_float2(a.x + b.x, a.y + b.y);
-        const float dr = a.x - b.x, di = a.y - b.y;
-        if (m == 0)
-          v[g + j + s] = make_float2(dr, di);
-        else if (m == 8)
-          v[g + j + s] = make_float2(di, -dr);
-        else if (m == 4)
-          v[g + j + s] = make_float2((dr + di) * R, (di - dr) * R);
-        else if (m == 12)
-          v[g + j + s] = make_float2((di - dr) * R, -(dr + di) * R);
-        else
-          v[g + j + s] = make_float2(dr * C[m] + di * S[m], di * C[m] - dr * S[m]);
-      }
-    }
+  const float ar = a.x, ai = a.y, br = b.x, bi = b.y;
+  if (m == 0) {
+    a = make_float2(ar + br, ai + bi);
+    b = make_float2(ar - br, ai - bi);
+  } else if (m == 8) {  // w = -i: w b = (bi, -br)
+    a = make_float2(ar + bi, ai - br);
+    b = make_float2(ar - bi, ai + br);
+  } else if (m == 4) {  // w b = R(br + bi) + i R(bi - br)
+    const float t1 = br + bi, t2 = bi - br;
+    a = make_float2(fmaf(R, t1, ar), fmaf(R, t2, ai));
+    b = make_float2(fmaf(-R, t1, ar), fmaf(-R, t2, ai));
+  } else if (m == 12) {  // w b = R(bi - br) - i R(bi + br)
+    const float t1 = bi - br, t2 = bi + br;
+    a = make_float2(fmaf(R, t1, ar), fmaf(-R, t2, ai));
+    b = make_float2(fmaf(-R, t1, ar), fmaf(R, t2, ai));
+  } else {  // w b = (C br + S bi) + i (C bi - S br)
+    const float o0r = fmaf(S[m], bi, fmaf(C[m], br, ar));
+    const float o0i = fmaf(-S[m], br, fmaf(C[m], bi, ai));
+    a = make_float2(o0r, o0i);
+    b = make_float2(fmaf(2.0f, ar, -o0r), fmaf(2.0f, ai, -o0i));
   }
 }
 
-constexpr int kScr = 32 * 33;  // per-warp transpose scratch (float2), row stride 33
+template <int S_, int G, int J>
+struct StageJ {
+  static __device__ __forceinline__ void run(float2 (&v)[32]) {
+    bfly<J * (16 / S_)>(v[G + J], v[G + J + S_]);
+    if constexpr (J + 1 < S_) StageJ<S_, G, J + 1>::run(v);
+  }
+};
+template <int S_, int G>
+struct StageG {
+  static __device__ __forceinline__ void run(float2 (&v)[32]) {
+    StageJ<S_, G, 0>::run(v);
+    if constexpr (G + 2 * S_ < 32) StageG<S_, G + 2 * S_>::run(v);
+  }
+};
+// DIT stages with span 2, 4, 8, 16 (the span-1 stage is fused into the loads by the caller):
+// input v[i] = first-stage output at bit-reversed position i, output v[k] = X[k] in natural order.
+__device__ __forceinline__ void fft32_dit_tail(float2 (&v)[32]) {
+  StageG<2, 0>::run(v);
+  StageG<4, 0>::run(v);
+  StageG<8, 0>::run(v);
+  StageG<16, 0>::run(v);
+}
+
+constexpr int kRow = 34;          // transpose row stride in float2 (16-byte aligned rows, conflict-free)
+constexpr int kScr = 32 * kRow;   // per-warp transpose scratch (float2)
 
 template <int W>
 __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
@@ -296,8 +323,8 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
   };
 
   float2* scr = scr_all + warp * kScr;
-  float* pw = reinterpret_cast<float*>(scr);               // [M+1] power spectrum
-  double* wv = reinterpret_cast<double*>(scr) + 520;        // [n_windows] (byte offset 4160)
+  float* pw = reinterpret_cast<float*>(scr);          // [M+1] power spectrum (aliases the scratch)
+  double* wv = reinterpret_cast<double*>(scr) + 520;  // [n_windows] (byte offset 4160)
   double acc_total = 0.0, acc_clip = 0.0;
   int64_t my_clip = -1;
 
@@ -317,53 +344,76 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
     }
     float2 v[32];
     const bool active = warp < nf;
-    if (active) {
-      // ---- pass 1: window, radix-32 over n1 (n = 32*n1 + lane), twiddle, transpose
-      const float* fr = inbuf + warp * a.hop;
-      if ((a.hop & 1) == 0) {
-        const float2* fr2 = reinterpret_cast<const float2*>(fr);
-        const float2* w2 = reinterpret_cast<const float2*>(swin);
+    bool next_tma = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // one shared instance of the 32-point FFT code
+      if (active) {
+        if (pass == 0) {
+          // pass 1: n = 32*n1 + lane.  Hamming window fused into the span-1 butterflies
+          // (pairs n1, n1+16): v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
+          const float2* fr2 = reinterpret_cast<const float2*>(inbuf + warp * a.hop);  // hop is even
+          const float2* w2 = reinterpret_cast<const float2*>(swin);
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float2 xv = fr2[32 * n1 + lane], wv2 = w2[32 * n1 + lane];
-          v[n1] = make_float2(xv.x * wv2.x, xv.y * wv2.y);
+          for (int p = 0; p < 16; ++p) {
+            const int na = br5(2 * p), nb = na + 16;
+            const float2 xa = fr2[32 * na + lane], wa = w2[32 * na + lane];
+            const float2 xb = fr2[32 * nb + lane], wb = w2[32 * nb + lane];
+            const float mr = xb.x * wb.x, mi = xb.y * wb.y;
+            v[2 * p] = make_float2(fmaf(xa.x, wa.x, mr), fmaf(xa.y, wa.y, mi));
+            v[2 * p + 1] = make_float2(fmaf(xa.x, wa.x, -mr), fmaf(xa.y, wa.y, -mi));
+          }
+        } else {
+          // pass 2: k1 = lane, n2 = 0..31 from this lane's transpose row (128-bit loads)
+          const float4* row = reinterpret_cast<const float4*>(scr + lane * kRow);
+          float2 in[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 q = row[i];
+            in[2 * i] = make_float2(q.x, q.y);
+            in[2 * i + 1] = make_float2(q.z, q.w);
+          }
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int na = br5(2 * p), nb = na + 16;
+            v[2 * p] = make_float2(in[na].x + in[nb].x, in[na].y + in[nb].y);
+            v[2 * p + 1] = make_float2(in[na].x - in[nb].x, in[na].y - in[nb].y);
+          }
         }
-      } else {
+        fft32_dit_tail(v);
+        if (pass == 0) {
+          // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1
+          scr[lane] = v[0];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const int i = 2 * (32 * n1 + lane);
-          v[n1] = make_float2(fr[i] * swin[i], fr[i + 1] * swin[i + 1]);
+          for (int k1 = 1; k1 < 32; ++k1) {
+            const float2 z = v[k1], w = stw[k1 * 32 + lane];
+            scr[k1 * kRow + lane] =
+                make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
+          }
         }
       }
-      fft32(v);
-#pragma unroll
-      for (int k1 = 0; k1 < 32; ++k1) {
-        const float2 z = v[br5(k1)], w = stw[k1 * 32 + lane];
-        scr[k1 * 33 + lane] = make_float2(z.x * w.x - z.y * w.y, z.x * w.y + z.y * w.x);
+      if (pass == 0) {
+        __syncthreads();  // every warp is done reading the staged tile; transposes are visible
+        if (tile + 1 < t_end) next_tma = issue_load(tile + 1);  // overlaps pass 2 below
       }
     }
-    __syncthreads();  // every warp is done reading the staged tile
-    bool next_tma = false;
-    if (tile + 1 < t_end) next_tma = issue_load(tile + 1);  // overlaps pass 2 below
 
     if (active) {
-      // ---- pass 2: radix-32 over n2 for k1 = lane  ->  Z[lane + 32*k2] in v[br5(k2)]
-#pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) v[n2] = scr[lane * 33 + n2];
-      fft32(v);
+      // Z[lane + 32*k2] is in v[k2]
       __syncwarp();  // scratch is re-used for the power spectrum below
       // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2
       const int src_lane = (32 - lane) & 31;
+      const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;  // warp-uniform range of needed k2
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) {
-        if (k2 * 32 + 31 >= a.kmin && k2 * 32 <= a.kmax) {  // warp-uniform
+        if (k2 > k2b) break;
+        if (k2 >= k2a) {
           const int k = lane + 32 * k2;
-          const float2 z = v[br5(k2)];
-          float pr = __shfl_sync(0xffffffffu, v[br5(31 - k2)].x, src_lane);
-          float pi = __shfl_sync(0xffffffffu, v[br5(31 - k2)].y, src_lane);
+          const float2 z = v[k2];
+          float pr = __shfl_sync(0xffffffffu, v[31 - k2].x, src_lane);
+          float pi = __shfl_sync(0xffffffffu, v[31 - k2].y, src_lane);
           if (lane == 0) {  // partner of Z[32*k2] is Z[1024-32*k2], held by lane 0 itself
-            pr = v[br5((32 - k2) & 31)].x;
-            pi = v[br5((32 - k2) & 31)].y;
+            pr = v[(32 - k2) & 31].x;
+            pi = v[(32 - k2) & 31].y;
           }
           const float2 cs = __ldg(&a.wsplit[k]);
           const float er = z.x + pr, ei = z.y - pi, dr = z.x - pr, di = z.y + pi;
@@ -373,7 +423,7 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
         }
       }
       if (a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
-        const float xn = v[br5(0)].x - v[br5(0)].y;
+        const float xn = v[0].x - v[0].y;
         pw[1024] = xn * xn;
       }
       __syncwarp();
@@ -381,7 +431,8 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
       for (int wi = lane; wi < a.n_windows; wi += 32) {
         const HeWin hw = swins[wi];
         float m = pw[hw.k0];
-        for (int k = hw.k0 + 1; k < hw.k1; ++k) m = fmaxf(m, pw[k]);
+        for (int j = 1; j < a.max_width; ++j)  // uniform trip count, clamped index: no divergence
+          m = fmaxf(m, pw[min(hw.k0 + j, hw.k1 - 1)]);
         wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
       }
       __syncwarp();
@@ -537,6 +588,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.wins_per_note = pl->wins_per_note;
   a.kmin = pl->kmin;
   a.kmax = pl->kmax;
+  a.max_width = pl->max_width;
   a.win = pl->d_win;
   a.tw32 = pl->d_tw32;
   a.wsplit = pl->d_wsplit;
@@ -548,7 +600,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.tiles_per_clip = a.total_tiles = 0;
   a.tile_cap = 0;
 
-  if (pl->N == 2048 && !pl->force_generic) {
+  if (pl->N == 2048 && !pl->force_generic && (pl->hop % 2) == 0) {
     a.tiles_per_clip = (fpc + kHeW - 1) / kHeW;
     a.total_tiles = a.tiles_per_clip * n_clips;
     a.tile_cap = (((kHeW - 1) * pl->hop + 2048) + 3) & ~3;

@@ -72,9 +72,10 @@ def harmonic_energy_sharded(x_local, fs, frames_local, frame_size, hop=None, **k
     return all_reduce_chroma(total)
 
 
-def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4)):
+def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4), reduce=True):
     """Config C5: every rank runs the requested methods on its shard of clips ([n_local, clip_len]
-    CUDA float32) and ONE all-reduce combines the [n_methods, 12] sums.  Returns (global sums
+    CUDA float32) and ONE all-reduce combines the [n_methods, 12] sums (reduce=False leaves the
+    local sums for callers that loop over chunks and reduce once at the end).  Returns (global sums
     [n_methods, 12], dict of per-clip results that stay sharded)."""
     from . import ops
 
@@ -96,4 +97,4 @@ def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4)):
             raise ValueError("valid methods: 1, 2, 3, 4")
         sums[i] = r.total
         per_clip[m] = r.clips
-    return all_reduce_chroma(sums), per_clip
+    return (all_reduce_chroma(sums) if reduce else sums), per_clip
