@@ -298,10 +298,9 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
   const int64_t t_begin = (a.total_tiles * (int64_t)blockIdx.x) / gridDim.x;
   const int64_t t_end = (a.total_tiles * (int64_t)(blockIdx.x + 1)) / gridDim.x;
 
-  // stage one tile; returns true when it went through the bulk-async (TMA) path
-  auto issue_load = [&](int64_t tile) -> bool {
-    const int64_t clip = tile / a.tiles_per_clip;
-    const int64_t f0 = (tile - clip * a.tiles_per_clip) * W;
+  // stage one tile (clip `clip`, first frame `f0`); returns true when it went through the
+  // bulk-async (TMA) path
+  auto issue_load = [&](int64_t clip, int64_t f0) -> bool {
     const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
     const int64_t s0 = f0 * a.hop;
     const int need = (int)((nf - 1) * a.hop + 2048);
@@ -330,12 +329,18 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
 
   bool cur_tma = false;
   uint32_t phase = 0;
-  if (t_begin < t_end) cur_tma = issue_load(t_begin);
+  // running (clip, first frame) of the current tile: one division up front, none in the loop
+  int64_t clip = t_begin / a.tiles_per_clip;
+  int64_t f0 = (t_begin - clip * a.tiles_per_clip) * W;
+  if (t_begin < t_end) cur_tma = issue_load(clip, f0);
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    const int64_t clip = tile / a.tiles_per_clip;
-    const int64_t f0 = (tile - clip * a.tiles_per_clip) * W;
     const int nf = (int)min((int64_t)W, a.frames_per_clip - f0);
+    int64_t nclip = clip, nf0 = f0 + W;  // coordinates of the next tile
+    if (nf0 >= a.frames_per_clip) {
+      nclip = clip + 1;
+      nf0 = 0;
+    }
     if (cur_tma) {
       mbar_wait(mbar, phase);
       phase ^= 1;
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
       }
       if (pass == 0) {
         __syncthreads();  // every warp is done reading the staged tile; transposes are visible
-        if (tile + 1 < t_end) next_tma = issue_load(tile + 1);  // overlaps pass 2 below
+        if (tile + 1 < t_end) next_tma = issue_load(nclip, nf0);  // overlaps pass 2 below
       }
     }
 
@@ -453,6 +458,8 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
       __syncwarp();
     }
     cur_tma = next_tma;
+    clip = nclip;
+    f0 = nf0;
   }
   if (lane < 12) {
     if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
