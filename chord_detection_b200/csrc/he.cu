@@ -38,6 +38,8 @@ struct HePlan {
   bool force_generic;
   float* d_win = nullptr;      // [N]
   float2* d_tw32 = nullptr;    // [32*32]: W_1024^(t*k1) at [k1*32+t]   (N == 2048)
+  float2* d_tw8a = nullptr;    // [16*256]: W_4096^(t*k1) at [k1*256+t]  (N == 8192)
+  float2* d_tw8b = nullptr;    // [16*16]:  W_256^(n3*k2) at [k2*16+n3]
   float2* d_wsplit = nullptr;  // [M+1]: (cos, sin)(2*pi*k/N)
   float2* d_twgen = nullptr;   // [M/2]: W_M^q = (cos, -sin)(2*pi*q/M)
   HeWin* d_wins = nullptr;
@@ -178,7 +180,24 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
         tw32[k1 * 32 + t] = make_float2((float)std::cos(a), (float)-std::sin(a));
       }
   }
+  std::vector<float2> tw8a, tw8b;
+  if (N == 8192) {
+    tw8a.resize(16 * 256);
+    tw8b.resize(16 * 16);
+    for (int k1 = 0; k1 < 16; ++k1)
+      for (int t = 0; t < 256; ++t) {
+        double a = 2.0 * kPi * (double)(t * k1) / 4096.0;
+        tw8a[k1 * 256 + t] = make_float2((float)std::cos(a), (float)-std::sin(a));
+      }
+    for (int k2 = 0; k2 < 16; ++k2)
+      for (int n3 = 0; n3 < 16; ++n3) {
+        double a = 2.0 * kPi * (double)(n3 * k2) / 256.0;
+        tw8b[k2 * 16 + n3] = make_float2((float)std::cos(a), (float)-std::sin(a));
+      }
+  }
   int rc;
+  if ((rc = cdb_upload(h, tw8a, &pl->d_tw8a))) return rc;
+  if ((rc = cdb_upload(h, tw8b, &pl->d_tw8b))) return rc;
   if ((rc = cdb_upload(h, win, &pl->d_win))) return rc;
   if ((rc = cdb_upload(h, wsplit, &pl->d_wsplit))) return rc;
   if ((rc = cdb_upload(h, twgen, &pl->d_twgen))) return rc;
@@ -199,6 +218,8 @@ struct HeArgs {
   int tile_cap;  // floats reserved for the staged tile (fast path)
   const float* win;
   const float2* tw32;
+  const float2* tw8a;  // [16][256] W_4096^(t*k1)   (N == 8192)
+  const float2* tw8b;  // [16][16]  W_256^(n3*k2)
   const float2* wsplit;
   const float2* twgen;
   const HeWin* wins;
@@ -247,27 +268,36 @@ __device__ __forceinline__ void bfly(float2& a, float2& b) {
   }
 }
 
-template <int S_, int G, int J>
+template <int NP, int S_, int G, int J>
 struct StageJ {
-  static __device__ __forceinline__ void run(float2 (&v)[32]) {
+  static __device__ __forceinline__ void run(float2 (&v)[NP]) {
     bfly<J * (16 / S_)>(v[G + J], v[G + J + S_]);
-    if constexpr (J + 1 < S_) StageJ<S_, G, J + 1>::run(v);
+    if constexpr (J + 1 < S_) StageJ<NP, S_, G, J + 1>::run(v);
   }
 };
-template <int S_, int G>
+template <int NP, int S_, int G>
 struct StageG {
-  static __device__ __forceinline__ void run(float2 (&v)[32]) {
-    StageJ<S_, G, 0>::run(v);
-    if constexpr (G + 2 * S_ < 32) StageG<S_, G + 2 * S_>::run(v);
+  static __device__ __forceinline__ void run(float2 (&v)[NP]) {
+    StageJ<NP, S_, G, 0>::run(v);
+    if constexpr (G + 2 * S_ < NP) StageG<NP, S_, G + 2 * S_>::run(v);
   }
 };
 // DIT stages with span 2, 4, 8, 16 (the span-1 stage is fused into the loads by the caller):
 // input v[i] = first-stage output at bit-reversed position i, output v[k] = X[k] in natural order.
 __device__ __forceinline__ void fft32_dit_tail(float2 (&v)[32]) {
-  StageG<2, 0>::run(v);
-  StageG<4, 0>::run(v);
-  StageG<8, 0>::run(v);
-  StageG<16, 0>::run(v);
+  StageG<32, 2, 0>::run(v);
+  StageG<32, 4, 0>::run(v);
+  StageG<32, 8, 0>::run(v);
+  StageG<32, 16, 0>::run(v);
+}
+// 16-point version (W_16^j = W_32^(2j): the same twiddle indexing works unchanged)
+__device__ __forceinline__ void fft16_dit_tail(float2 (&v)[16]) {
+  StageG<16, 2, 0>::run(v);
+  StageG<16, 4, 0>::run(v);
+  StageG<16, 8, 0>::run(v);
+}
+__host__ __device__ constexpr int br4(int k) {
+  return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3);
 }
 
 constexpr int kRow = 34;          // transpose row stride in float2 (16-byte aligned rows, conflict-free)
@@ -469,6 +499,159 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
   if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
 }
 
+// ------------------------------------------------------------------------------------------
+// frame_size 8192 (the reference default, harmonic_energy.py:15): one CTA of 256 threads per
+// frame.  8192-pt real FFT = 4096-pt complex FFT = radix-16 x radix-16 x radix-16, every 16-pt
+// DFT in registers, two shared-memory exchanges.  n = 256 n1 + 16 n2 + n3, k = k1 + 16 k2 + 256 k3.
+// Samples come straight from global memory with coalesced 64-bit loads (frames usually do not
+// overlap at this size); window and twiddle tables are read through L1.
+// ------------------------------------------------------------------------------------------
+constexpr int k8Threads = 256;
+constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
+
+__global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float2* bufA = reinterpret_cast<float2*>(smem);        // [16][256]; later Z[4096]
+  float2* bufB = bufA + 4096;                             // [256 rows][18]; later the power spectrum
+  double* wv = reinterpret_cast<double*>(bufB + 256 * k8RowB);  // [n_windows]
+  float* pw = reinterpret_cast<float*>(bufB);             // [4097]
+  const int tid = threadIdx.x;
+  const int M = 4096;
+  const int64_t total_frames = a.n_clips * a.frames_per_clip;
+  const int64_t f_begin = (total_frames * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t f_end = (total_frames * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+  int64_t clip = f_begin / a.frames_per_clip;
+  int64_t f = f_begin - clip * a.frames_per_clip;
+  const float2* win2 = reinterpret_cast<const float2*>(a.win);
+
+  for (int64_t gf = f_begin; gf < f_end; ++gf) {
+    const int64_t s0 = f * a.hop;
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    float2 v[16];
+    // ---- pass A: thread t holds z[256 n1 + t]; window fused into the span-1 butterflies
+    {
+      const bool vec = (avail >= 8192) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+      auto ld = [&](int m) -> float2 {  // complex point m = (x[2m], x[2m+1])
+        if (vec) return __ldg(reinterpret_cast<const float2*>(src) + m);
+        const int64_t i = 2 * (int64_t)m;
+        return make_float2(i < avail ? __ldg(src + i) : 0.0f, i + 1 < avail ? __ldg(src + i + 1) : 0.0f);
+      };
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        const float2 xa = ld(256 * na + tid), wa = __ldg(win2 + 256 * na + tid);
+        const float2 xb = ld(256 * nb + tid), wb = __ldg(win2 + 256 * nb + tid);
+        const float mr = xb.x * wb.x, mi = xb.y * wb.y;
+        v[2 * p] = make_float2(fmaf(xa.x, wa.x, mr), fmaf(xa.y, wa.y, mi));
+        v[2 * p + 1] = make_float2(fmaf(xa.x, wa.x, -mr), fmaf(xa.y, wa.y, -mi));
+      }
+      fft16_dit_tail(v);
+      bufA[tid] = v[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) {  // twiddle W_4096^(t*k1), table laid out [k1][t]
+        const float2 z = v[k1], w = __ldg(&a.tw8a[k1 * 256 + tid]);
+        bufA[k1 * 256 + tid] = make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
+      }
+    }
+    __syncthreads();
+    // ---- pass B: thread (k1 = t>>4, n3 = t&15): DFT over n2, twiddle W_256^(n3*k2)
+    {
+      const int k1 = tid >> 4, n3 = tid & 15;
+      float2 in[16];
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) in[n2] = bufA[k1 * 256 + 16 * n2 + n3];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        v[2 * p] = make_float2(in[na].x + in[nb].x, in[na].y + in[nb].y);
+        v[2 * p + 1] = make_float2(in[na].x - in[nb].x, in[na].y - in[nb].y);
+      }
+      fft16_dit_tail(v);
+      bufB[(0 * 16 + k1) * k8RowB + n3] = v[0];
+#pragma unroll
+      for (int k2 = 1; k2 < 16; ++k2) {
+        const float2 z = v[k2], w = __ldg(&a.tw8b[k2 * 16 + n3]);
+        bufB[(k2 * 16 + k1) * k8RowB + n3] =
+            make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
+      }
+    }
+    __syncthreads();
+    // ---- pass C: thread (k2 = t>>4, k1 = t&15): DFT over n3 -> Z[k1 + 16 k2 + 256 k3]
+    {
+      const int k2 = tid >> 4, k1 = tid & 15;
+      const float4* row = reinterpret_cast<const float4*>(bufB + (k2 * 16 + k1) * k8RowB);
+      float2 in[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = row[i];
+        in[2 * i] = make_float2(q.x, q.y);
+        in[2 * i + 1] = make_float2(q.z, q.w);
+      }
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        v[2 * p] = make_float2(in[na].x + in[nb].x, in[na].y + in[nb].y);
+        v[2 * p + 1] = make_float2(in[na].x - in[nb].x, in[na].y - in[nb].y);
+      }
+      fft16_dit_tail(v);
+#pragma unroll
+      for (int k3 = 0; k3 < 16; ++k3) bufA[k1 + 16 * k2 + 256 * k3] = v[k3];
+    }
+    __syncthreads();
+    // ---- real-FFT split for the probed bins only, |X|^2 into pw (aliases bufB)
+    for (int k = a.kmin + tid; k <= a.kmax; k += k8Threads) {
+      float pwr;
+      if (k == M) {
+        const float xn = bufA[0].x - bufA[0].y;
+        pwr = xn * xn;
+      } else {
+        const float2 z = bufA[k], pz = bufA[(M - k) & (M - 1)];
+        const float2 cs = __ldg(&a.wsplit[k]);
+        const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+        const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+        const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+        pwr = xr * xr + xi * xi;
+      }
+      pw[k] = pwr;
+    }
+    __syncthreads();
+    for (int wi = tid; wi < a.n_windows; wi += k8Threads) {
+      const HeWin hw = a.wins[wi];
+      float m = pw[hw.k0];
+      for (int k = hw.k0 + 1; k < hw.k1; ++k) m = fmaxf(m, pw[k]);
+      wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double sum = 0.0;
+      for (int j = 0; j < a.wins_per_note; ++j) sum += wv[tid * a.wins_per_note + j];
+      if (a.clips) {
+        if (clip != my_clip) {
+          if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+          my_clip = clip;
+          acc_clip = 0.0;
+        }
+        acc_clip += sum;
+      }
+      acc_total += sum;
+      if (a.frames) a.frames[gf * 12 + tid] = (float)sum;
+    }
+    // (the next iteration's first shared-memory write is to bufA; all reads of bufA finished
+    //  before the barrier above, and pw/wv are not touched again until after two more barriers)
+    if (++f >= a.frames_per_clip) {
+      f = 0;
+      ++clip;
+    }
+  }
+  if (tid < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+    if (a.total) atomicAdd(&a.total[tid], acc_total);
+  }
+}
+
 // Generic power-of-two path: one CTA per frame at a time, in-place radix-2 DIT in shared memory.
 constexpr int kGenThreads = 256;
 
@@ -598,6 +781,8 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.max_width = pl->max_width;
   a.win = pl->d_win;
   a.tw32 = pl->d_tw32;
+  a.tw8a = pl->d_tw8a;
+  a.tw8b = pl->d_tw8b;
   a.wsplit = pl->d_wsplit;
   a.twgen = pl->d_twgen;
   a.wins = pl->d_wins;
@@ -621,6 +806,16 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "tile does not fit in shared memory");
     int64_t grid = std::min<int64_t>(a.total_tiles, (int64_t)h->num_sms * per_sm);
     he2048_kernel<kHeW><<<(unsigned)grid, kHeW * 32, smem, st>>>(a);
+  } else if (pl->N == 8192 && !pl->force_generic) {
+    const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
+    CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    int per_sm = 0;
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he8192_kernel, k8Threads,
+                                                              smem));
+    if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
+    int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
+    he8192_kernel<<<(unsigned)grid, k8Threads, smem, st>>>(a);
   } else {
     const size_t smem = (size_t)pl->M * 8 + (size_t)(pl->M + 2) * 4 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he_generic_kernel,

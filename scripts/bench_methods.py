@@ -66,6 +66,15 @@ def main():
     ms = timed(lambda: ops.harmonic_energy(x, 22050, per_clip=True))
     out["he_default_c5"] = {"clips": nc, "frames": nc * 6, "ms": ms, "frames_per_s": nc * 6 / ms * 1e3,
                             "note": "reference defaults (frame 8192, generic kernel)"}
+    xl = x.reshape(-1)[: (x.numel() // 8192) * 8192]
+    ms = timed(lambda: ops.harmonic_energy(xl, 22050))
+    nf = xl.numel() // 8192
+    out["he_8192_long"] = {"frames": nf, "ms": ms, "frames_per_s": nf / ms * 1e3,
+                           "alg_GBps": nf * 32768 / ms / 1e6, "note": "frame 8192, hop 8192 (reference default), one long signal"}
+    x2 = xl[: 25000 * 2048]
+    ms = timed(lambda: ops.harmonic_energy(x2, 44100, frame_size=2048))
+    out["he_2048_hop2048"] = {"frames": 25000, "ms": ms, "frames_per_s": 25000 / ms * 1e3,
+                              "alg_GBps": 25000 * 8192 / ms / 1e6, "note": "metric kernel at hop = frame (HBM-heavier)"}
     nc4 = max(1, int(256 * scale))
     xs = x[:nc4]
 

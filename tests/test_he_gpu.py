@@ -85,11 +85,14 @@ def test_he_per_frame_matches_oracle(frame_size, hop):
     _assert_close(got_frames, want_frames, tol=2e-4)
 
 
-def test_he_fast_and_generic_kernels_agree(monkeypatch):
-    x, fs = cases.make_input(dict(fn="s_poly_long", seed=2, fs=44100, n=200 * 512))
-    a = _he(x, fs, frame_size=2048, hop=512, per_frame=True)
+@pytest.mark.parametrize("frame_size,hop,fs", [(2048, 512, 44100), (8192, None, 22050),
+                                               (8192, 2048, 22050), (8192, 1001, 44100)])
+def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
+    """The register-FFT kernels (he2048_kernel, he8192_kernel) against the generic radix-2 kernel."""
+    x, fs = cases.make_input(dict(fn="s_poly_long", seed=2, fs=fs, n=200 * 512 + 77))
+    a = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
     monkeypatch.setenv("CDB_HE_FORCE_GENERIC", "1")
-    b = _he(x, fs, frame_size=2048, hop=512, per_frame=True)
+    b = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
     _assert_close(a.total.cpu().numpy(), b.total.cpu().numpy(), tol=1e-5)
     _assert_close(a.frames.cpu().numpy(), b.frames.cpu().numpy(), tol=1e-4)
 
