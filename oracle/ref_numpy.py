@@ -149,14 +149,16 @@ def harmonic_energy(x, fs, frame_size=8192, num_harmonic=2, num_octave=2, num_bi
 
 
 def harmonic_energy_fast(x, fs, frame_size=8192, num_harmonic=2, num_octave=2, num_bins=2,
-                         hop=None, per_frame=False, chunk=4096):
-    """Vectorised float64 equivalent of harmonic_energy() for larger parity runs."""
+                         hop=None, per_frame=False, chunk=4096, window="hamming"):
+    """Vectorised float64 equivalent of harmonic_energy() for larger parity runs.  `window`:
+    "hamming" (the reference), or the product's extra "hann" / "rect" options."""
     rows = he_windows(fs, frame_size, num_harmonic, num_octave, num_bins)
     hop_ = frame_size if hop is None else hop
     x = np.asarray(x)
     n = x.shape[0]
     n_frames = int(math.ceil(n / float(hop_))) if n else 0
-    win = scipy.signal.windows.hamming(frame_size)
+    win = {"hamming": scipy.signal.windows.hamming, "hann": scipy.signal.windows.hann,
+           "rect": np.ones}[window](frame_size)
     padded = np.zeros((n_frames - 1) * hop_ + frame_size if n_frames else 0)
     padded[:n] = x
     total = np.zeros(12)

@@ -1,0 +1,128 @@
+"""GPU edge cases through the public API: empty / short / ragged inputs, batches, error behaviour,
+window options, and the chord-detect CLI on a WAV file (the reference's entry point,
+chord_detect.py:11-63)."""
+import io
+import contextlib
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import cases, ref_numpy as rn  # noqa: E402
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _close(got, want, tol=1e-4):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(np.max(np.abs(want)), 1e-300)
+    assert np.max(np.abs(got - want)) / scale <= tol, (got, want)
+
+
+def test_empty_and_tiny_inputs_all_methods():
+    from chord_detection_b200 import ops
+
+    dev = _dev()
+    empty = torch.zeros(0, dtype=torch.float32, device=dev)
+    for fn in (ops.harmonic_energy, ops.esacf, ops.iterative_f0, ops.prime_multif0):
+        r = fn(empty, 22050)
+        assert torch.all(r.total == 0)
+    one = torch.ones(1, dtype=torch.float32, device=dev)
+    x1 = np.ones(1, dtype=np.float32)
+    _close(ops.harmonic_energy(one, 22050).total.cpu().numpy(), rn.harmonic_energy_fast(x1, 22050))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _close(ops.prime_multif0(one, 22050).total.cpu().numpy(), rn.prime(x1, 22050), tol=1e-9)
+        want3 = rn.iterf0(x1, 22050)
+    _close(ops.iterative_f0(one, 22050).total.cpu().numpy(), want3)
+    zero_batch = torch.zeros((0, 100), dtype=torch.float32, device=dev)
+    assert torch.all(ops.harmonic_energy(zero_batch, 22050, per_clip=True).total == 0)
+
+
+def test_he_window_options_and_non_default_sizes():
+    from chord_detection_b200 import ops
+
+    x, fs = cases.make_input(dict(fn="s_poly", seed=71, fs=22050, n=20000))
+    xd = torch.from_numpy(x).to(_dev())
+    for window in ("hamming", "hann", "rect"):
+        for N in (2048, 8192, 512):
+            got = ops.harmonic_energy(xd, fs, frame_size=N, window=window).total.cpu().numpy()
+            _close(got, rn.harmonic_energy_fast(x, fs, frame_size=N, window=window))
+
+
+def test_argument_errors_are_loud():
+    from chord_detection_b200 import ops
+
+    dev = _dev()
+    x = torch.zeros(5000, dtype=torch.float32, device=dev)
+    with pytest.raises(ValueError):
+        ops.harmonic_energy(x, 22050, num_bins=0)
+    with pytest.raises(ValueError):
+        ops.harmonic_energy(x, 22050, frame_size=2048, hop=4096)
+    with pytest.raises(ValueError):  # probe windows beyond the rfft bins: the reference raises IndexError
+        ops.harmonic_energy(x, 4000, frame_size=2048)
+    with pytest.raises(ValueError):
+        ops.harmonic_energy(x.double(), 22050)
+    with pytest.raises(ValueError):
+        ops.esacf(x, 22050, ham_samples=2)
+    with pytest.raises(ValueError):
+        ops.iterative_f0(x, 22050, frame_size=3000)
+    with pytest.raises(ValueError):
+        ops.prime_multif0(x, 22050, harmonic_multiples_elim=20)
+    with pytest.raises(ValueError):
+        ops.harmonic_energy(torch.zeros((2, 3, 4), dtype=torch.float32, device=dev), 22050)
+
+
+def test_strided_batch_rows_all_methods():
+    from chord_detection_b200 import ops
+
+    dev = _dev()
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=80 + i, fs=22050, n=9000))[0] for i in range(3)])
+    big = torch.zeros((3, 9216), dtype=torch.float32, device=dev)
+    big[:, :9000] = torch.from_numpy(rows).to(dev)
+    view = big[:, :9000]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = {2: np.stack([rn.harmonic_energy_fast(r, 22050) for r in rows]),
+                4: np.stack([rn.prime(r, 22050) for r in rows]),
+                3: np.stack([rn.iterf0(r, 22050) for r in rows])}
+    _close(ops.harmonic_energy(view, 22050, per_clip=True).clips.cpu().numpy(), want[2])
+    _close(ops.prime_multif0(view, 22050, per_clip=True).clips.cpu().numpy(), want[4])
+    _close(ops.iterative_f0(view, 22050, per_clip=True).clips.cpu().numpy(), want[3])
+    e = ops.esacf(view, 22050, per_clip=True)
+    e2 = ops.esacf(torch.from_numpy(rows).to(dev), 22050, per_clip=True)
+    _close(e.clips.cpu().numpy(), e2.clips.cpu().numpy(), tol=1e-12)
+
+
+def test_cli_on_wav_file(tmp_path):
+    """chord-detect --method -1 --key <wav>: same output lines as chord_detect.py:56-63."""
+    import scipy.io.wavfile as wavfile
+
+    from chord_detection_b200 import chord_detect
+
+    _dev()
+    x, fs = cases.make_input(dict(fn="gen_test_clip", name="test_2_notes_G3_Asharp4", pcm16=True))
+    path = os.path.join(tmp_path, "clip.wav")
+    wavfile.write(path, fs, np.round(x * 32768.0).astype(np.int16))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        chord_detect.main_cli(["--method", "-1", "--key", path])
+    lines = buf.getvalue().strip().splitlines()
+    assert lines[0] == "1 - ESACF (Tolonen, Karjalainen)"
+    assert lines[3] == "2 - Harmonic Energy (Stark, Plumbley)"
+    assert lines[6] == "3 - Iterative F0 (Klapuri, Anssi)"
+    assert lines[9] == "4 - Prime-multiF0 (Camacho, Kaver-Oreamuno)"
+    # golden strings of the PCM16-clipped clip (tests/golden, made by the unmodified reference)
+    assert lines[4] == "234416722312" and lines[7] == "000000000090" and lines[10] == "000001343193"
+    assert lines[5] == "F#min" and lines[8] == "A#maj" and lines[11] == "A#min"
+    assert all(len(lines[i]) == 12 and lines[i].isdigit() for i in (1, 4, 7, 10))
+    with pytest.raises(ValueError):
+        chord_detect.main_cli(["--method", "9", path])
