@@ -420,7 +420,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
                       int64_t workspace_bytes, double* d_chroma_total, double* d_chroma_clips,
                       double* d_chroma_frames, double* d_voices, int flags, void* stream) {
   if (!h) return CDB_E_NULL;
-  if (!p || !d_x) return cdb_fail(h, CDB_E_NULL, "null params / input");
+  if (!p || (!d_x && n_clips > 0 && clip_len > 0))
+    return cdb_fail(h, CDB_E_NULL, "null params / input");
   if (n_clips < 0 || clip_len < 0 || (n_clips > 1 && clip_stride < clip_len))
     return cdb_fail(h, CDB_E_INVALID, "bad batch shape");
   CDB_CUDA(h, cudaSetDevice(h->device));

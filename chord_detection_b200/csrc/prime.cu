@@ -356,7 +356,8 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
                      int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
                      double* d_chroma_clips, double* d_chroma_cands, int flags, void* stream) {
   if (!h) return CDB_E_NULL;
-  if (!p || !d_x) return cdb_fail(h, CDB_E_NULL, "null params / input");
+  if (!p || (!d_x && n_clips > 0 && clip_len > 0))
+    return cdb_fail(h, CDB_E_NULL, "null params / input");
   if (n_clips < 0 || clip_len < 0 || (n_clips > 1 && clip_stride < clip_len))
     return cdb_fail(h, CDB_E_INVALID, "bad batch shape");
   CDB_CUDA(h, cudaSetDevice(h->device));
