@@ -87,7 +87,7 @@ struct Biquad {
   }
 };
 
-__global__ void __launch_bounds__(64) esacf_filter_kernel(const EsacfArgs a) {
+__global__ void __launch_bounds__(32) esacf_filter_kernel(const EsacfArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.B) return;
   const int64_t gf = a.frame0 + t;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(64) esacf_filter_kernel(const EsacfArgs a) {
   hp.init(a.hp_b, a.hp_a);
   lp_hi.init(a.lp_b, a.lp_a);
   lp_lo.init(a.lp_b, a.lp_a);
-  const double lam = a.lam, mlam = -a.lam;
+  const double mlam = -a.lam;
   for (int n = 0; n < a.N; ++n) {
     const double x = (n < avail) ? (double)__ldg(src + n) : 0.0;
     // wfir.py:28-43 — all-pass B=[-lam,1], A=[1,-lam]: y = z + (-lam)*u ; z = u - (-lam)*y
@@ -122,7 +122,6 @@ __global__ void __launch_bounds__(64) esacf_filter_kernel(const EsacfArgs a) {
     const double lo = lp_lo.step(r);  // :51
     a.ws_lo[(int64_t)n * a.B + t] = lo;
     a.ws_hi[(int64_t)n * a.B + t] = hi;
-    (void)lam;
   }
 }
 
@@ -446,7 +445,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.ws_hi = w + (size_t)N * B;
     a.ws_y = w + 2 * (size_t)N * B;
     a.ws_s = d_debug ? (w + 2 * (size_t)N * B + (size_t)L * B) : nullptr;
-    esacf_filter_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
+    esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
     acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
     if (d_debug) {
       esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);

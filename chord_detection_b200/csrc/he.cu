@@ -510,7 +510,7 @@ constexpr int k8Threads = 256;
 constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
 
 __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   float2* bufA = reinterpret_cast<float2*>(smem);        // [16][256]; later Z[4096]
   float2* bufB = bufA + 4096;                             // [256 rows][18]; later the power spectrum
   double* wv = reinterpret_cast<double*>(bufB + 256 * k8RowB);  // [n_windows]

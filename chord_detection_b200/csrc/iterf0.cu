@@ -82,7 +82,7 @@ struct Sos {
   }
 };
 
-__global__ void __launch_bounds__(64) iterf0_filter_kernel(const IterArgs a) {
+__global__ void __launch_bounds__(32) iterf0_filter_kernel(const IterArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_batch_clips * a.C) return;
   const int lc = t / a.C, ch = t - lc * a.C;
@@ -120,21 +120,28 @@ __global__ void __launch_bounds__(64) iterf0_filter_kernel(const IterArgs a) {
   for (int64_t n = a.clip_len; n < a.n_pad; ++n) dst[n] = 0.0f;  // frame_cutter pads the FILTERED signal
 }
 
+constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
+
 __global__ void __launch_bounds__(kSpecThreads) iterf0_spectrum_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  float2* s = reinterpret_cast<float2*>(smem);        // [M]
-  double* U = reinterpret_cast<double*>(s + a.M);     // [M+1]
+  float2* s = reinterpret_cast<float2*>(smem);  // [M]
   const int tid = threadIdx.x;
   const int M = a.M, F = a.F;
   const int64_t gf = blockIdx.x;  // frame within this batch
   const int64_t lc = gf / a.fpc, f = gf - lc * a.fpc;
-  for (int k = tid; k <= M; k += kSpecThreads) U[k] = 0.0;
+  double U[kSpecMaxPerThread];  // U[j] accumulates bin k = tid + j*kSpecThreads (registers)
+#pragma unroll
+  for (int j = 0; j < kSpecMaxPerThread; ++j) U[j] = 0.0;
   for (int ch = 0; ch < a.C; ++ch) {
     const float* src = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad + f * F;
     // z[m] = x[2m] + i x[2m+1] of the zero-padded 2F-point frame: m >= F/2 is zero
     for (int m = tid; m < M; m += kSpecThreads) {
       float2 v = make_float2(0.f, 0.f);
-      if (2 * m < F) v = make_float2(src[2 * m] * a.win[2 * m], src[2 * m + 1] * a.win[2 * m + 1]);
+      if (2 * m < F) {
+        const float2 x2 = *reinterpret_cast<const float2*>(src + 2 * m);
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(a.win + 2 * m));
+        v = make_float2(x2.x * w2.x, x2.y * w2.y);
+      }
       s[(int)(__brev((unsigned)m) >> (32 - a.log2M))] = v;
     }
     __syncthreads();
@@ -151,26 +158,34 @@ __global__ void __launch_bounds__(kSpecThreads) iterf0_spectrum_kernel(const Ite
       }
       __syncthreads();
     }
-    for (int k = tid; k <= M; k += kSpecThreads) {
-      float mag2;
-      if (k == M) {
-        const float xn = s[0].x - s[0].y;
-        mag2 = xn * xn;
-      } else {
-        const float2 z = s[k], pz = s[(M - k) & (M - 1)];
-        const float2 cs = __ldg(&a.wsplit[k]);
-        const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
-        const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
-        const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
-        mag2 = xr * xr + xi * xi;
+#pragma unroll
+    for (int j = 0; j < kSpecMaxPerThread; ++j) {
+      const int k = tid + j * kSpecThreads;
+      if (k <= M) {
+        float mag2;
+        if (k == M) {
+          const float xn = s[0].x - s[0].y;
+          mag2 = xn * xn;
+        } else {
+          const float2 z = s[k], pz = s[(M - k) & (M - 1)];
+          const float2 cs = __ldg(&a.wsplit[k]);
+          const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+          const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+          const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+          mag2 = xr * xr + xi * xi;
+        }
+        const double mag = sqrt((double)mag2);
+        U[j] += (a.power == 1.0) ? mag : pow(mag, a.power);
       }
-      const double mag = sqrt((double)mag2);
-      U[k] += (a.power == 1.0) ? mag : pow(mag, a.power);
     }
     __syncthreads();
   }
   double* out = a.Ut + gf * (int64_t)(M + 1);
-  for (int k = tid; k <= M; k += kSpecThreads) out[k] = U[k];
+#pragma unroll
+  for (int j = 0; j < kSpecMaxPerThread; ++j) {
+    const int k = tid + j * kSpecThreads;
+    if (k <= M) out[k] = U[j];
+  }
 }
 
 __constant__ double kHW9[9] = {0.0011244659258033, 0.11559343551383, 0.42817348241183,
@@ -484,7 +499,7 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   a.Ud = reinterpret_cast<double*>(w);
   unsigned char* wrest = w + ud_bytes(p, pgrid_max);
 
-  const size_t spec_smem = (size_t)pl->M * 8 + (size_t)(pl->M + 1) * 8;
+  const size_t spec_smem = (size_t)pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
   const size_t per_smem = (size_t)2 * pl->M * 8;
@@ -498,7 +513,7 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     a.Ut = reinterpret_cast<double*>(wrest + (((size_t)nb * a.C * n_pad * 4 + 255) & ~(size_t)255));
     if (d_voices) a.voices = d_voices + c0 * fpc * 2 * p->max_voices;
     const int threads = nb * a.C;
-    iterf0_filter_kernel<<<(threads + 63) / 64, 64, 0, st>>>(a);
+    iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
     const int64_t nframes = (int64_t)nb * fpc;
     iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     const int pgrid = (int)std::min<int64_t>(nframes, pgrid_max);

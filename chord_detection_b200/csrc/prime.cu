@@ -175,7 +175,6 @@ __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a)
   __shared__ double red_v[kPrimeThreads / 32];
   __shared__ int red_i[kPrimeThreads / 32];
   __shared__ double cta_total[12];
-  __shared__ int s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 12) cta_total[tid] = 0.0;
   __syncthreads();
@@ -257,7 +256,6 @@ __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a)
             bv = red_v[w];
             bi = red_i[w];
           }
-        s_best = bi;
         const int nt = (bi < H) ? note[bi] : -1;
         if (nt >= 0) {  // hz_to_note raised otherwise: `continue` skips the elimination too (:73-74)
           const double v = s[bi];
