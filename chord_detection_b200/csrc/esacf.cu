@@ -198,54 +198,75 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
 }
 
 constexpr int kPeakWarps = 8;
+constexpr int kFpw = 4;  // frames per warp: their peaks share the warp's 32 fit lanes
+
+__host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame
+  const size_t half = (size_t)L / 2 + 2;
+  return (((size_t)L + 7) & ~(size_t)7) + 2 * ((half * 2 + 7) & ~(size_t)7) + 12 * 8;
+}
 
 __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const EsacfArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L;
-  const int half = L / 2 + 2;
-  // per-warp: y[L] doubles | sgn[L] int8 (padded to 8) | cand[half] int16 | order[half] int16 | chroma[12]
-  const size_t per_warp = (size_t)L * 8 + (((size_t)L + 7) & ~(size_t)7) + 2 * (((size_t)half * 2 + 7) & ~(size_t)7) + 12 * 8;
-  unsigned char* base = smem + per_warp * warp;
-  double* y = reinterpret_cast<double*>(base);
-  int8_t* sgn = reinterpret_cast<int8_t*>(y + L);
-  int16_t* cand = reinterpret_cast<int16_t*>(sgn + (((size_t)L + 7) & ~(size_t)7));
-  int16_t* order = cand + (((size_t)half * 2 + 7) & ~(size_t)7) / 2;
-  double* chroma = reinterpret_cast<double*>(order + (((size_t)half * 2 + 7) & ~(size_t)7) / 2);
+  const size_t half = (size_t)L / 2 + 2;
+  const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = (half * 2 + 7) & ~(size_t)7;
+  const size_t per_frame = pad_l + 2 * pad_h + 12 * 8;
+  // per (warp, frame slot): sgn[L] int8 | cand[half] int16 | order[half] int16 | chroma[12] double
+  unsigned char* wbase = smem + per_frame * kFpw * warp;
   __shared__ double cta_total[12];
   if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
   __syncthreads();
 
   const int warps_total = gridDim.x * kPeakWarps;
-  for (int fb = blockIdx.x * kPeakWarps + warp; fb < a.B; fb += warps_total) {
-    const int64_t gf = a.frame0 + fb;
-    const int64_t clip = gf / a.frames_per_clip;
-    for (int i = lane; i < L; i += 32) y[i] = a.ws_y[(int64_t)fb * L + i];
-    if (lane < 12) chroma[lane] = 0.0;
+  for (int base = (blockIdx.x * kPeakWarps + warp) * kFpw; base < a.B; base += warps_total * kFpw) {
+    const int nfr = min(kFpw, a.B - base);
+    // ---- peak picking: lane j < nfr works on frame base+j (ESACF rows are read through L1)
+    int np_mine = 0;
+    if (lane < nfr) {
+      unsigned char* fb = wbase + per_frame * lane;
+      int8_t* sgn = reinterpret_cast<int8_t*>(fb);
+      int16_t* cand = reinterpret_cast<int16_t*>(fb + pad_l);
+      int16_t* order = reinterpret_cast<int16_t*>(fb + pad_l + pad_h);
+      np_mine = pk::find_peaks(a.ws_y + (int64_t)(base + lane) * L, L, a.peak_thresh,
+                               a.peak_min_dist, sgn, cand, order);
+    }
+    if (lane < 12 * nfr) {  // zero the per-frame chroma accumulators
+      const int j = lane / 12;
+      reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h)[lane - 12 * j] = 0.0;
+    }
+    int off[kFpw + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int j = 0; j < kFpw; ++j) off[j + 1] = off[j] + __shfl_sync(0xffffffffu, np_mine, j);
     __syncwarp();
-    int np = 0;
-    if (lane == 0) np = pk::find_peaks(y, L, a.peak_thresh, a.peak_min_dist, sgn, cand, order);
-    np = __shfl_sync(0xffffffffu, np, 0);
-    __syncwarp();
-    double* dbg = a.debug ? a.debug + gf * a.debug_stride : nullptr;
-    if (dbg && lane == 0) dbg[2 * a.N + 2 * L] = (double)np;
-    // one Gaussian fit per lane; failed fits are dropped and the survivors re-paired with the
-    // peak list BY POSITION, reproducing the latent misalignment of esacf.py:65-69
-    int done = 0;  // successful fits so far (warp-uniform)
-    for (int p0 = 0; p0 < np; p0 += 32) {
-      const int pi = p0 + lane;
+    int done[kFpw];
+#pragma unroll
+    for (int j = 0; j < kFpw; ++j) done[j] = 0;
+    if (a.debug && lane < nfr) a.debug[(a.frame0 + base + lane) * a.debug_stride + 2 * a.N + 2 * L] = (double)np_mine;
+
+    // ---- one Gaussian fit per lane over the concatenated peak lists; failed fits are dropped and
+    // the survivors re-paired with their frame's peak list BY POSITION (esacf.py:65-69)
+    for (int t0 = 0; t0 < off[kFpw]; t0 += 32) {
+      const int task = t0 + lane;
+      int j = 0;
+#pragma unroll
+      for (int q = 1; q < kFpw; ++q) j += (task >= off[q]);
+      const bool valid = task < off[kFpw];
+      const int16_t* cand = reinterpret_cast<const int16_t*>(wbase + per_frame * j + pad_l);
+      const double* y = a.ws_y + (int64_t)(base + j) * L;
       bool ok = false;
       double center = 0.0;
-      if (pi < np) {
-        const int idx = cand[pi];
+      if (valid) {
+        const int idx = cand[task - off[j]];
         const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
         if (lo >= 0 && hi - lo >= 3) {
           lmg::Problem pr;
           pr.m = hi - lo;
           pr.x0 = (double)lo;
-          double ymax = y[lo];
+          double ymax = __ldg(y + lo);
           for (int i = 0; i < pr.m; ++i) {
-            pr.y[i] = y[lo + i];
+            pr.y[i] = __ldg(y + lo + i);
             ymax = fmax(ymax, pr.y[i]);
           }
           double p[3] = {ymax, (double)lo, 5.0};
@@ -255,33 +276,45 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
           center = p[1];
         }
       }
-      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-      if (ok) {
-        const int slot = done + __popc(okmask & ((1u << lane) - 1u));  // position in interp[]
-        const int paired = cand[slot];                                   // peak_indices[slot]
-        if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = center;
-        const double pitch = a.fs / center;
-        // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
-        if (pitch > 0.0 && isfinite(pitch)) {
-          const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
-          long long nn = (long long)nearbyint(midi);
-          int note = (int)(nn % 12);
-          if (note < 0) note += 12;
-          atomicAdd(&chroma[note], y[paired]);
+#pragma unroll
+      for (int q = 0; q < kFpw; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok && j == q);
+        if (ok && j == q) {
+          const int slot = done[q] + __popc(m & ((1u << lane) - 1u));  // position in interp[]
+          const int paired = cand[slot];                                 // peak_indices[slot]
+          double* dbg = a.debug ? a.debug + (a.frame0 + base + q) * a.debug_stride : nullptr;
+          if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = center;
+          const double pitch = a.fs / center;
+          // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
+          if (pitch > 0.0 && isfinite(pitch)) {
+            const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
+            long long nn = (long long)nearbyint(midi);
+            int note = (int)(nn % 12);
+            if (note < 0) note += 12;
+            atomicAdd(reinterpret_cast<double*>(wbase + per_frame * q + pad_l + 2 * pad_h) + note,
+                      __ldg(y + paired));
+          }
         }
+        done[q] += __popc(m);
       }
-      done += __popc(okmask);
-    }
-    if (dbg) {
-      for (int i = lane; i < np && i < kMaxPeaksDbg; i += 32) dbg[2 * a.N + 2 * L + 1 + i] = (double)cand[i];
-      if (lane == 0) dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)done;
     }
     __syncwarp();
-    if (lane < 12) {
-      const double v = chroma[lane];
-      if (a.frames) a.frames[gf * 12 + lane] = v;
-      if (a.clips && v != 0.0) atomicAdd(&a.clips[clip * 12 + lane], v);
-      if (a.total && v != 0.0) atomicAdd(&cta_total[lane], v);
+    if (a.debug) {
+      for (int q = 0; q < nfr; ++q) {
+        double* dbg = a.debug + (a.frame0 + base + q) * a.debug_stride;
+        const int16_t* cand = reinterpret_cast<const int16_t*>(wbase + per_frame * q + pad_l);
+        const int npq = off[q + 1] - off[q];
+        for (int i = lane; i < npq && i < kMaxPeaksDbg; i += 32) dbg[2 * a.N + 2 * L + 1 + i] = (double)cand[i];
+        if (lane == 0) dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)done[q];
+      }
+    }
+    if (lane < 12 * nfr) {
+      const int j = lane / 12, n = lane - 12 * j;
+      const double v = reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h)[n];
+      const int64_t gf = a.frame0 + base + j;
+      if (a.frames) a.frames[gf * 12 + n] = v;
+      if (a.clips && v != 0.0) atomicAdd(&a.clips[(gf / a.frames_per_clip) * 12 + n], v);
+      if (a.total && v != 0.0) atomicAdd(&cta_total[n], v);
     }
     __syncwarp();
   }
@@ -430,10 +463,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
-  const size_t half = (size_t)L / 2 + 2;
-  const size_t per_warp = (size_t)L * 8 + (((size_t)L + 7) & ~(size_t)7) +
-                          2 * ((half * 2 + 7) & ~(size_t)7) + 12 * 8;
-  const size_t pk_smem = per_warp * kPeakWarps;
+  const size_t pk_smem = peaks_scratch_bytes(L) * kFpw * kPeakWarps;
   CDB_CUDA(h, cudaFuncSetAttribute(esacf_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)pk_smem));
   for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {
@@ -451,7 +481,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);
       h->launches += 1;
     }
-    const int pgrid = std::min<int>((B + kPeakWarps - 1) / kPeakWarps, h->num_sms * 4);
+    const int pgrid = std::min<int>((B + kPeakWarps * kFpw - 1) / (kPeakWarps * kFpw), h->num_sms * 4);
     esacf_peaks_kernel<<<pgrid, kPeakWarps * 32, pk_smem, st>>>(a);
     h->launches += 3;
     CDB_CUDA(h, cudaGetLastError());

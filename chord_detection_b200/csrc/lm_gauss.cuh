@@ -38,10 +38,12 @@ struct Problem {
 };
 
 LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
-  const double denom = 2.0 * p[2] * p[2] + EPSMCH;
+  // one reciprocal per evaluation instead of m divisions (FP64 division is ~30 instructions on
+  // the GPU); differs from -(d*d)/denom by at most one ulp in the exponent argument
+  const double ninv = -1.0 / (2.0 * p[2] * p[2] + EPSMCH);
   for (int i = 0; i < pr.m; ++i) {
     const double d = (pr.x0 + (double)i) - p[1];
-    f[i] = p[0] * exp(-(d * d) / denom) - pr.y[i];
+    f[i] = p[0] * exp((d * d) * ninv) - pr.y[i];
   }
 }
 
