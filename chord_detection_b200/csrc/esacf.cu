@@ -231,9 +231,9 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
       np_mine = pk::find_peaks(a.ws_y + (int64_t)(base + lane) * L, L, a.peak_thresh,
                                a.peak_min_dist, sgn, cand, order);
     }
-    if (lane < 12 * nfr) {  // zero the per-frame chroma accumulators
-      const int j = lane / 12;
-      reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h)[lane - 12 * j] = 0.0;
+    for (int i = lane; i < 12 * nfr; i += 32) {  // zero the per-frame chroma accumulators
+      const int j = i / 12;
+      reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h)[i - 12 * j] = 0.0;
     }
     int off[kFpw + 1];
     off[0] = 0;
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
         if (lane == 0) dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)done[q];
       }
     }
-    if (lane < 12 * nfr) {
-      const int j = lane / 12, n = lane - 12 * j;
+    for (int i = lane; i < 12 * nfr; i += 32) {
+      const int j = i / 12, n = i - 12 * j;
       const double v = reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h)[n];
       const int64_t gf = a.frame0 + base + j;
       if (a.frames) a.frames[gf * 12 + n] = v;
