@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
   }
 }
 
-constexpr int kPeakWarps = 8;
+constexpr int kPeakWarps = 5;  // limited by the shared-memory LM work arrays (26.9 KB per warp)
 constexpr int kFpw = 4;  // frames per warp: their peaks share the warp's 32 fit lanes
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame
@@ -212,8 +212,11 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
   const size_t half = (size_t)L / 2 + 2;
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = (half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h + 12 * 8;
-  // per (warp, frame slot): sgn[L] int8 | cand[half] int16 | order[half] int16 | chroma[12] double
-  unsigned char* wbase = smem + per_frame * kFpw * warp;
+  // per warp: LM work arrays [WORK_DOUBLES][32 lanes] doubles, then per frame slot:
+  // sgn[L] int8 | cand[half] int16 | order[half] int16 | chroma[12] double
+  const size_t lm_bytes = (size_t)lmg::WORK_DOUBLES * 32 * sizeof(double);
+  double* lm_work = reinterpret_cast<double*>(smem + (lm_bytes + per_frame * kFpw) * warp) + lane;
+  unsigned char* wbase = smem + (lm_bytes + per_frame * kFpw) * warp + lm_bytes;
   __shared__ double cta_total[12];
   if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
   __syncthreads();
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
           }
           double p[3] = {ymax, (double)lo, 5.0};
           int nfev = 0;
-          const int info = lmg::lmdif(pr, p, &nfev);
+          const int info = lmg::lmdif_work<32>(pr, p, &nfev, lm_work);
           ok = (info >= 1 && info <= 4) && isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
           center = p[1];
         }
@@ -463,7 +466,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
-  const size_t pk_smem = peaks_scratch_bytes(L) * kFpw * kPeakWarps;
+  const size_t pk_smem = (peaks_scratch_bytes(L) * kFpw + (size_t)lmg::WORK_DOUBLES * 32 * 8) * kPeakWarps;
   CDB_CUDA(h, cudaFuncSetAttribute(esacf_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)pk_smem));
   for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {

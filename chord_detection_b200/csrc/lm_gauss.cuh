@@ -25,9 +25,14 @@ constexpr int NP = 3;
 constexpr double EPSMCH = 2.220446049250313e-16;
 constexpr double DWARF = 2.2250738585072014e-308;
 
+// The three big per-fit arrays (residuals, trial residuals, m x 3 Jacobian) are addressed with a
+// compile-time element stride ST: 1 on the host; 32 on the GPU, where they live in shared memory
+// interleaved by lane ([element][lane]) so that a warp's accesses are conflict-free and nothing
+// spills to local memory.  Small 3-vectors stay in registers (stride 1).
+template <int ST = 1>
 LMG_HD inline double enorm(const double* v, int n) {
   double s = 0.0;
-  for (int i = 0; i < n; ++i) s += v[i] * v[i];
+  for (int i = 0; i < n; ++i) s += v[i * ST] * v[i * ST];
   return sqrt(s);
 }
 
@@ -37,21 +42,24 @@ struct Problem {
   double y[MMAX];
 };
 
+template <int ST>
 LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
   // one reciprocal per evaluation instead of m divisions (FP64 division is ~30 instructions on
   // the GPU); differs from -(d*d)/denom by at most one ulp in the exponent argument
   const double ninv = -1.0 / (2.0 * p[2] * p[2] + EPSMCH);
   for (int i = 0; i < pr.m; ++i) {
     const double d = (pr.x0 + (double)i) - p[1];
-    f[i] = p[0] * exp((d * d) * ninv) - pr.y[i];
+    f[i * ST] = p[0] * exp((d * d) * ninv) - pr.y[i];
   }
 }
 
-// a is column-major: a[i + j*MMAX], i < m, j < NP
+// a is column-major: element (i, j) at a[(i + j*MMAX)*ST], i < m, j < NP
+#define LMG_A(i, j) a[((i) + (j)*MMAX) * ST]
+template <int ST>
 LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm,
                              double* wa) {
   for (int j = 0; j < NP; ++j) {
-    acnorm[j] = enorm(a + j * MMAX, m);
+    acnorm[j] = enorm<ST>(a + (j * MMAX) * ST, m);
     rdiag[j] = acnorm[j];
     wa[j] = rdiag[j];
     ipvt[j] = j;
@@ -63,9 +71,9 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
       if (rdiag[k] > rdiag[kmax]) kmax = k;
     if (kmax != j) {
       for (int i = 0; i < m; ++i) {
-        const double t = a[i + j * MMAX];
-        a[i + j * MMAX] = a[i + kmax * MMAX];
-        a[i + kmax * MMAX] = t;
+        const double t = LMG_A(i, j);
+        LMG_A(i, j) = LMG_A(i, kmax);
+        LMG_A(i, kmax) = t;
       }
       rdiag[kmax] = rdiag[j];
       wa[kmax] = wa[j];
@@ -73,24 +81,24 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
       ipvt[j] = ipvt[kmax];
       ipvt[kmax] = k;
     }
-    double ajnorm = enorm(a + j + j * MMAX, m - j);
+    double ajnorm = enorm<ST>(a + (j + j * MMAX) * ST, m - j);
     if (ajnorm != 0.0) {
-      if (a[j + j * MMAX] < 0.0) ajnorm = -ajnorm;
-      for (int i = j; i < m; ++i) a[i + j * MMAX] /= ajnorm;
-      a[j + j * MMAX] += 1.0;
+      if (LMG_A(j, j) < 0.0) ajnorm = -ajnorm;
+      for (int i = j; i < m; ++i) LMG_A(i, j) /= ajnorm;
+      LMG_A(j, j) += 1.0;
       for (int k = j + 1; k < NP; ++k) {
         double sum = 0.0;
-        for (int i = j; i < m; ++i) sum += a[i + j * MMAX] * a[i + k * MMAX];
-        const double temp = sum / a[j + j * MMAX];
-        for (int i = j; i < m; ++i) a[i + k * MMAX] -= temp * a[i + j * MMAX];
+        for (int i = j; i < m; ++i) sum += LMG_A(i, j) * LMG_A(i, k);
+        const double temp = sum / LMG_A(j, j);
+        for (int i = j; i < m; ++i) LMG_A(i, k) -= temp * LMG_A(i, j);
         if (rdiag[k] != 0.0) {
-          double t = a[j + k * MMAX] / rdiag[k];
+          double t = LMG_A(j, k) / rdiag[k];
           double d = 1.0 - t * t;
           if (d < 0.0) d = 0.0;
           rdiag[k] *= sqrt(d);
           const double q = rdiag[k] / wa[k];
           if (0.05 * (q * q) <= EPSMCH) {
-            rdiag[k] = enorm(a + (j + 1) + k * MMAX, m - j - 1);
+            rdiag[k] = enorm<ST>(a + ((j + 1) + k * MMAX) * ST, m - j - 1);
             wa[k] = rdiag[k];
           }
         }
@@ -100,11 +108,13 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
   }
 }
 
+#define LMG_R(i, j) r[((i) + (j)*MMAX) * ST]
+template <int ST>
 LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const double* qtb,
                               double* x, double* sdiag, double* wa) {
   for (int j = 0; j < NP; ++j) {
-    for (int i = j; i < NP; ++i) r[i + j * MMAX] = r[j + i * MMAX];
-    x[j] = r[j + j * MMAX];
+    for (int i = j; i < NP; ++i) LMG_R(i, j) = LMG_R(j, i);
+    x[j] = LMG_R(j, j);
     wa[j] = qtb[j];
   }
   for (int j = 0; j < NP; ++j) {
@@ -116,28 +126,28 @@ LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const 
       for (int k = j; k < NP; ++k) {
         if (sdiag[k] == 0.0) continue;
         double c, s;
-        if (fabs(r[k + k * MMAX]) < fabs(sdiag[k])) {
-          const double cotan = r[k + k * MMAX] / sdiag[k];
+        if (fabs(LMG_R(k, k)) < fabs(sdiag[k])) {
+          const double cotan = LMG_R(k, k) / sdiag[k];
           s = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
           c = s * cotan;
         } else {
-          const double tn = sdiag[k] / r[k + k * MMAX];
+          const double tn = sdiag[k] / LMG_R(k, k);
           c = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
           s = c * tn;
         }
-        r[k + k * MMAX] = c * r[k + k * MMAX] + s * sdiag[k];
+        LMG_R(k, k) = c * LMG_R(k, k) + s * sdiag[k];
         const double temp = c * wa[k] + s * qtbpj;
         qtbpj = -s * wa[k] + c * qtbpj;
         wa[k] = temp;
         for (int i = k + 1; i < NP; ++i) {
-          const double t = c * r[i + k * MMAX] + s * sdiag[i];
-          sdiag[i] = -s * r[i + k * MMAX] + c * sdiag[i];
-          r[i + k * MMAX] = t;
+          const double t = c * LMG_R(i, k) + s * sdiag[i];
+          sdiag[i] = -s * LMG_R(i, k) + c * sdiag[i];
+          LMG_R(i, k) = t;
         }
       }
     }
-    sdiag[j] = r[j + j * MMAX];
-    r[j + j * MMAX] = x[j];
+    sdiag[j] = LMG_R(j, j);
+    LMG_R(j, j) = x[j];
   }
   int nsing = NP;
   for (int j = 0; j < NP; ++j) {
@@ -147,31 +157,32 @@ LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const 
   for (int k = 0; k < nsing; ++k) {
     const int j = nsing - 1 - k;
     double sum = 0.0;
-    for (int i = j + 1; i < nsing; ++i) sum += r[i + j * MMAX] * wa[i];
+    for (int i = j + 1; i < nsing; ++i) sum += LMG_R(i, j) * wa[i];
     wa[j] = (wa[j] - sum) / sdiag[j];
   }
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa[j];
 }
 
+template <int ST>
 LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const double* qtb,
                              double delta, double* par, double* x, double* sdiag, double* wa1,
                              double* wa2) {
   int nsing = NP;
   for (int j = 0; j < NP; ++j) {
     wa1[j] = qtb[j];
-    if (r[j + j * MMAX] == 0.0 && nsing == NP) nsing = j;
+    if (LMG_R(j, j) == 0.0 && nsing == NP) nsing = j;
     if (nsing < NP) wa1[j] = 0.0;
   }
   for (int k = 0; k < nsing; ++k) {
     const int j = nsing - 1 - k;
-    wa1[j] /= r[j + j * MMAX];
+    wa1[j] /= LMG_R(j, j);
     const double temp = wa1[j];
-    for (int i = 0; i < j; ++i) wa1[i] -= r[i + j * MMAX] * temp;
+    for (int i = 0; i < j; ++i) wa1[i] -= LMG_R(i, j) * temp;
   }
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa1[j];
   int iter = 0;
   for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
-  double dxnorm = enorm(wa2, NP);
+  double dxnorm = enorm<1>(wa2, NP);
   double fp = dxnorm - delta;
   if (fp <= 0.1 * delta) {
     *par = 0.0;
@@ -185,18 +196,18 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
     }
     for (int j = 0; j < NP; ++j) {
       double sum = 0.0;
-      for (int i = 0; i < j; ++i) sum += r[i + j * MMAX] * wa1[i];
-      wa1[j] = (wa1[j] - sum) / r[j + j * MMAX];
+      for (int i = 0; i < j; ++i) sum += LMG_R(i, j) * wa1[i];
+      wa1[j] = (wa1[j] - sum) / LMG_R(j, j);
     }
-    const double temp = enorm(wa1, NP);
+    const double temp = enorm<1>(wa1, NP);
     parl = ((fp / delta) / temp) / temp;
   }
   for (int j = 0; j < NP; ++j) {
     double sum = 0.0;
-    for (int i = 0; i <= j; ++i) sum += r[i + j * MMAX] * qtb[i];
+    for (int i = 0; i <= j; ++i) sum += LMG_R(i, j) * qtb[i];
     wa1[j] = sum / diag[ipvt[j]];
   }
-  const double gnorm = enorm(wa1, NP);
+  const double gnorm = enorm<1>(wa1, NP);
   double paru = gnorm / delta;
   if (paru == 0.0) paru = DWARF / fmin(delta, 0.1);
   *par = fmax(*par, parl);
@@ -207,9 +218,9 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
     if (*par == 0.0) *par = fmax(DWARF, 0.001 * paru);
     double temp = sqrt(*par);
     for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
-    qrsolv(r, ipvt, wa1, qtb, x, sdiag, wa2);
+    qrsolv<ST>(r, ipvt, wa1, qtb, x, sdiag, wa2);
     for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
-    dxnorm = enorm(wa2, NP);
+    dxnorm = enorm<1>(wa2, NP);
     temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
@@ -220,9 +231,9 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
     for (int j = 0; j < NP; ++j) {
       wa1[j] /= sdiag[j];
       const double t = wa1[j];
-      for (int i = j + 1; i < NP; ++i) wa1[i] -= r[i + j * MMAX] * t;
+      for (int i = j + 1; i < NP; ++i) wa1[i] -= LMG_R(i, j) * t;
     }
-    temp = enorm(wa1, NP);
+    temp = enorm<1>(wa1, NP);
     const double parc = ((fp / delta) / temp) / temp;
     if (fp > 0.0) parl = fmax(parl, *par);
     if (fp < 0.0) paru = fmin(paru, *par);
@@ -231,21 +242,26 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
 }
 
 // p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).
-LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
+// work: (MMAX + MMAX + MMAX*NP) doubles with element stride ST (fvec | wa4 | fjac)
+constexpr int WORK_DOUBLES = MMAX * (2 + NP);
+template <int ST>
+LMG_HD inline int lmdif_work(const Problem& pr, double* p, int* nfev_out, double* work) {
   const int m = pr.m;
   const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
   const int maxfev = 200 * (NP + 1);
-  double fvec[MMAX], wa4[MMAX], fjac[MMAX * NP];
-  double diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP];
+  double* fvec = work;
+  double* wa4 = work + MMAX * ST;
+  double* a = work + 2 * MMAX * ST;  // the Jacobian (LMG_A) / its R factor
+  double diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
   int ipvt[NP];
   int info = 0, nfev = 0;
   if (m < NP) {
     *nfev_out = 0;
     return 0;
   }
-  residuals(pr, p, fvec);
+  residuals<ST>(pr, p, fvec);
   nfev = 1;
-  double fnorm = enorm(fvec, m);
+  double fnorm = enorm<ST>(fvec, m);
   double par = 0.0, delta = 0.0, xnorm = 0.0;
   int iter = 1;
   const double eps = sqrt(EPSMCH);  // sqrt(max(epsfcn, epsmch)), epsfcn = epsmch
@@ -256,32 +272,32 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
       double h = eps * fabs(temp);
       if (h == 0.0) h = eps;
       p[j] = temp + h;
-      residuals(pr, p, wa4);
+      residuals<ST>(pr, p, wa4);
       p[j] = temp;
-      for (int i = 0; i < m; ++i) fjac[i + j * MMAX] = (wa4[i] - fvec[i]) / h;
+      for (int i = 0; i < m; ++i) LMG_A(i, j) = (wa4[i * ST] - fvec[i * ST]) / h;
     }
     nfev += NP;
-    qrfac(m, fjac, ipvt, wa1, wa2, wa3);
+    qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
     if (iter == 1) {
       for (int j = 0; j < NP; ++j) {
         diag[j] = wa2[j];
         if (wa2[j] == 0.0) diag[j] = 1.0;
       }
       for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
-      xnorm = enorm(wa3, NP);
+      xnorm = enorm<1>(wa3, NP);
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
-    for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
+    for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
     for (int j = 0; j < NP; ++j) {
-      if (fjac[j + j * MMAX] != 0.0) {
+      if (LMG_A(j, j) != 0.0) {
         double sum = 0.0;
-        for (int i = j; i < m; ++i) sum += fjac[i + j * MMAX] * wa4[i];
-        const double temp = -sum / fjac[j + j * MMAX];
-        for (int i = j; i < m; ++i) wa4[i] += fjac[i + j * MMAX] * temp;
+        for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
+        const double temp = -sum / LMG_A(j, j);
+        for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
       }
-      fjac[j + j * MMAX] = wa1[j];
-      qtf[j] = wa4[j];
+      LMG_A(j, j) = wa1[j];
+      qtf[j] = wa4[j * ST];
     }
     double gnorm = 0.0;
     if (fnorm != 0.0) {
@@ -289,7 +305,7 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
         const int l = ipvt[j];
         if (wa2[l] != 0.0) {
           double sum = 0.0;
-          for (int i = 0; i <= j; ++i) sum += fjac[i + j * MMAX] * (qtf[i] / fnorm);
+          for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * (qtf[i] / fnorm);
           gnorm = fmax(gnorm, fabs(sum / wa2[l]));
         }
       }
@@ -301,17 +317,17 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
     for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
     double ratio = 0.0;
     do {
-      lmpar(fjac, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
+      lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
       for (int j = 0; j < NP; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = p[j] + wa1[j];
         wa3[j] = diag[j] * wa1[j];
       }
-      const double pnorm = enorm(wa3, NP);
+      const double pnorm = enorm<1>(wa3, NP);
       if (iter == 1) delta = fmin(delta, pnorm);
-      residuals(pr, wa2, wa4);
+      residuals<ST>(pr, wa2, wa4);
       ++nfev;
-      const double fnorm1 = enorm(wa4, m);
+      const double fnorm1 = enorm<ST>(wa4, m);
       double actred = -1.0;
       if (0.1 * fnorm1 < fnorm) {
         const double q = fnorm1 / fnorm;
@@ -320,9 +336,9 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
       for (int j = 0; j < NP; ++j) {
         wa3[j] = 0.0;
         const double temp = wa1[ipvt[j]];
-        for (int i = 0; i <= j; ++i) wa3[i] += fjac[i + j * MMAX] * temp;
+        for (int i = 0; i <= j; ++i) wa3[i] += LMG_A(i, j) * temp;
       }
-      const double temp1 = enorm(wa3, NP) / fnorm;
+      const double temp1 = enorm<1>(wa3, NP) / fnorm;
       const double temp2 = (sqrt(par) * pnorm) / fnorm;
       const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
@@ -344,8 +360,8 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
           p[j] = wa2[j];
           wa2[j] = diag[j] * p[j];
         }
-        for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
-        xnorm = enorm(wa2, NP);
+        for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
+        xnorm = enorm<1>(wa2, NP);
         fnorm = fnorm1;
         ++iter;
       }
@@ -363,6 +379,12 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
   }
   *nfev_out = nfev;
   return info;
+}
+
+// convenience wrapper with private (stride-1) work arrays: host tests, simple callers
+LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
+  double work[WORK_DOUBLES];
+  return lmdif_work<1>(pr, p, nfev_out, work);
 }
 
 }  // namespace lmg
