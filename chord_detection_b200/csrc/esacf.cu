@@ -19,12 +19,10 @@
 //                         Levenberg-Marquardt Gaussian fit per lane (lm_gauss.cuh), fs/tau ->
 //                         pitch class (librosa.hz_to_note), chroma += ESACF[peak] (esacf.py:65-71).
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "lm_gauss.cuh"
-#include "lm_gauss_warp.cuh"
 #include "peaks.cuh"
 
 struct EsacfPlan {
@@ -58,7 +56,6 @@ struct EsacfArgs {
   double lp_b[3], lp_a[3], hp_b[3], hp_a[3];
   double fs, peak_thresh;
   int peak_min_dist;
-  int skip_fit;  // debug (CDB_ESACF_SKIP_FIT=1): time the peak picking alone
   double* ws_lo;  // [N][B]
   double* ws_hi;  // [N][B]
   double* ws_y;   // [B][L] enhanced SACF
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
   }
 }
 
-constexpr int kPeakWarps = 8;
+constexpr int kPeakWarps = 5;  // limited by the shared-memory LM work arrays (26.9 KB per warp)
 constexpr int kFpw = 4;  // frames per warp: their peaks share the warp's 32 fit lanes
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame
@@ -215,8 +212,11 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
   const size_t half = (size_t)L / 2 + 2;
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = (half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h + 12 * 8;
-  // per (warp, frame slot): sgn[L] int8 | cand[half] int16 | order[half] int16 | chroma[12] double
-  unsigned char* wbase = smem + per_frame * kFpw * warp;
+  // per warp: LM work arrays [WORK_DOUBLES][32 lanes] doubles, then per frame slot:
+  // sgn[L] int8 | cand[half] int16 | order[half] int16 | chroma[12] double
+  const size_t lm_bytes = (size_t)lmg::WORK_DOUBLES * 32 * sizeof(double);
+  double* lm_work = reinterpret_cast<double*>(smem + (lm_bytes + per_frame * kFpw) * warp) + lane;
+  unsigned char* wbase = smem + (lm_bytes + per_frame * kFpw) * warp + lm_bytes;
   __shared__ double cta_total[12];
   if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
   __syncthreads();
@@ -248,43 +248,57 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
     for (int j = 0; j < kFpw; ++j) done[j] = 0;
     if (a.debug && lane < nfr) a.debug[(a.frame0 + base + lane) * a.debug_stride + 2 * a.N + 2 * L] = (double)np_mine;
 
-    // ---- Gaussian fits, one at a time, the whole warp cooperating on each (lm_gauss_warp.cuh:
-    // lane i owns data point i).  Failed fits are dropped and the survivors re-paired with their
-    // frame's peak list BY POSITION (the latent misalignment of esacf.py:65-69 is reproduced).
-    for (int j = 0; j < nfr; ++j) {
+    // ---- one Gaussian fit per lane over the concatenated peak lists; failed fits are dropped and
+    // the survivors re-paired with their frame's peak list BY POSITION (esacf.py:65-69)
+    for (int t0 = 0; t0 < off[kFpw]; t0 += 32) {
+      const int task = t0 + lane;
+      int j = 0;
+#pragma unroll
+      for (int q = 1; q < kFpw; ++q) j += (task >= off[q]);
+      const bool valid = task < off[kFpw];
       const int16_t* cand = reinterpret_cast<const int16_t*>(wbase + per_frame * j + pad_l);
       const double* y = a.ws_y + (int64_t)(base + j) * L;
-      double* chroma = reinterpret_cast<double*>(wbase + per_frame * j + pad_l + 2 * pad_h);
-      double* dbg = a.debug ? a.debug + (a.frame0 + base + j) * a.debug_stride : nullptr;
-      const int npj = off[j + 1] - off[j];
-      for (int pi = 0; pi < npj; ++pi) {
-        const int idx = cand[pi];
+      bool ok = false;
+      double center = 0.0;
+      if (valid) {
+        const int idx = cand[task - off[j]];
         const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
-        if (a.skip_fit || lo < 0 || hi - lo < 3) continue;  // empty slice -> RuntimeError -> dropped
-        const int m = hi - lo;
-        const double yi = lane < m ? __ldg(y + lo + lane) : 0.0;
-        double ymax = lane < m ? yi : -INFINITY;
+        if (lo >= 0 && hi - lo >= 3) {
+          lmg::Problem pr;
+          pr.m = hi - lo;
+          pr.x0 = (double)lo;
+          double ymax = __ldg(y + lo);
+          for (int i = 0; i < pr.m; ++i) {
+            pr.y[i] = __ldg(y + lo + i);
+            ymax = fmax(ymax, pr.y[i]);
+          }
+          double p[3] = {ymax, (double)lo, 5.0};
+          int nfev = 0;
+          const int info = lmg::lmdif_work<32>(pr, p, &nfev, lm_work);
+          ok = (info >= 1 && info <= 4) && isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+          center = p[1];
+        }
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-        double p[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
-        int nfev = 0;
-        const int info = lmg::lmdif_warp(m, (double)lo, yi, p, &nfev);
-        const bool ok = (info >= 1 && info <= 4) && isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
-        if (!ok) continue;
-        const int slot = done[j]++;          // position in interp[]
-        const int paired = cand[slot];       // peak_indices[slot]
-        if (lane == 0) {
-          if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = p[1];
-          const double pitch = a.fs / p[1];
+      for (int q = 0; q < kFpw; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok && j == q);
+        if (ok && j == q) {
+          const int slot = done[q] + __popc(m & ((1u << lane) - 1u));  // position in interp[]
+          const int paired = cand[slot];                                 // peak_indices[slot]
+          double* dbg = a.debug ? a.debug + (a.frame0 + base + q) * a.debug_stride : nullptr;
+          if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = center;
+          const double pitch = a.fs / center;
           // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
           if (pitch > 0.0 && isfinite(pitch)) {
             const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
             long long nn = (long long)nearbyint(midi);
             int note = (int)(nn % 12);
             if (note < 0) note += 12;
-            chroma[note] += __ldg(y + paired);
+            atomicAdd(reinterpret_cast<double*>(wbase + per_frame * q + pad_l + 2 * pad_h) + note,
+                      __ldg(y + paired));
           }
         }
+        done[q] += __popc(m);
       }
     }
     __syncwarp();
@@ -438,10 +452,6 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   a.fs = p->fs;
   a.peak_thresh = p->peak_thresh;
   a.peak_min_dist = p->peak_min_dist;
-  {
-    const char* sf = std::getenv("CDB_ESACF_SKIP_FIT");
-    a.skip_fit = (sf && sf[0] == '1') ? 1 : 0;
-  }
   a.total = d_chroma_total;
   a.clips = d_chroma_clips;
   a.frames = d_chroma_frames;
@@ -456,7 +466,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
-  const size_t pk_smem = peaks_scratch_bytes(L) * kFpw * kPeakWarps;
+  const size_t pk_smem = (peaks_scratch_bytes(L) * kFpw + (size_t)lmg::WORK_DOUBLES * 32 * 8) * kPeakWarps;
   CDB_CUDA(h, cudaFuncSetAttribute(esacf_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)pk_smem));
   for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {

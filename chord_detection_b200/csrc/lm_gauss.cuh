@@ -108,8 +108,8 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
   }
 }
 
-#define LMG_R(i, j) r[((i) + (j)*LD) * ST]
-template <int ST, int LD = MMAX>
+#define LMG_R(i, j) r[((i) + (j)*MMAX) * ST]
+template <int ST>
 LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const double* qtb,
                               double* x, double* sdiag, double* wa) {
   for (int j = 0; j < NP; ++j) {
@@ -163,7 +163,7 @@ LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const 
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa[j];
 }
 
-template <int ST, int LD = MMAX>
+template <int ST>
 LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const double* qtb,
                              double delta, double* par, double* x, double* sdiag, double* wa1,
                              double* wa2) {
@@ -218,7 +218,7 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
     if (*par == 0.0) *par = fmax(DWARF, 0.001 * paru);
     double temp = sqrt(*par);
     for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
-    qrsolv<ST, LD>(r, ipvt, wa1, qtb, x, sdiag, wa2);
+    qrsolv<ST>(r, ipvt, wa1, qtb, x, sdiag, wa2);
     for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = enorm<1>(wa2, NP);
     temp = fp;
