@@ -260,11 +260,14 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
       const double* y = a.ws_y + (int64_t)(base + j) * L;
       bool ok = false;
       double center = 0.0;
+      // 32 fits advance in lock-step: one residual evaluation (21 exp) per round for every lane
+      lmg::Problem pr;
+      lmg::LmSM<32> sm;
+      bool run = false;
       if (valid) {
         const int idx = cand[task - off[j]];
         const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
         if (lo >= 0 && hi - lo >= 3) {
-          lmg::Problem pr;
           pr.m = hi - lo;
           pr.x0 = (double)lo;
           double ymax = __ldg(y + lo);
@@ -272,12 +275,23 @@ __global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const Esac
             pr.y[i] = __ldg(y + lo + i);
             ymax = fmax(ymax, pr.y[i]);
           }
-          double p[3] = {ymax, (double)lo, 5.0};
-          int nfev = 0;
-          const int info = lmg::lmdif_work<32>(pr, p, &nfev, lm_work);
-          ok = (info >= 1 && info <= 4) && isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
-          center = p[1];
+          const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
+          sm.init(lm_work, p0);
+          run = true;
         }
+      }
+      while (__any_sync(0xffffffffu, run)) {
+        if (run) {
+          lmg::residuals<32>(pr, sm.eval_point(), sm.wa4);
+          sm.advance(pr.m);
+          if (sm.phase == lmg::LmSM<32>::DONE) {
+            run = false;
+            ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
+                 isfinite(sm.p[2]);
+            center = sm.p[1];
+          }
+        }
+        __syncwarp();
       }
 #pragma unroll
       for (int q = 0; q < kFpw; ++q) {

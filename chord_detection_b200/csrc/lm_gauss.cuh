@@ -241,91 +241,74 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
   }
 }
 
-// p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).
 // work: (MMAX + MMAX + MMAX*NP) doubles with element stride ST (fvec | wa4 | fjac)
 constexpr int WORK_DOUBLES = MMAX * (2 + NP);
+
+// lmdif as an explicit state machine: the caller alternates
+//     residuals<ST>(pr, sm.eval_point(), sm.wa4);   sm.advance(m);
+// until sm.phase == DONE.  One residual evaluation per step, so that on the GPU 32 independent fits
+// (one per lane) advance in LOCK-STEP: every lane evaluates its 21 exponentials together, and lanes
+// that need the same follow-up (store a Jacobian column / QR / trust-region step) execute it
+// together.  (A plain per-lane lmdif loop lets lanes drift into different loop phases; the warp then
+// serialises them -- measured 4.4 active lanes of 32.)  Arithmetic and control flow are those of
+// MINPACK's lmdif: phases 1..3 = fdjac2 columns, QR block = qrfac + (Q^T)fvec + gnorm test,
+// step block = lmpar + trial point, phase 4 = the ratio / acceptance / convergence logic.
 template <int ST>
-LMG_HD inline int lmdif_work(const Problem& pr, double* p, int* nfev_out, double* work) {
-  const int m = pr.m;
-  const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
-  const int maxfev = 200 * (NP + 1);
-  double* fvec = work;
-  double* wa4 = work + MMAX * ST;
-  double* a = work + 2 * MMAX * ST;  // the Jacobian (LMG_A) / its R factor
-  double diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
+struct LmSM {
+  enum { INIT = 0, JAC0 = 1, TRIAL = 4, DONE = 5 };
+  double p[NP], diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
   int ipvt[NP];
-  int info = 0, nfev = 0;
-  if (m < NP) {
-    *nfev_out = 0;
-    return 0;
+  double par, delta, xnorm, fnorm, gnorm, pnorm, h, ptemp;
+  int iter, nfev, info, phase;
+  double* fvec;
+  double* wa4;
+  double* a;  // Jacobian / R factor, element (i, j) at a[(i + j*MMAX)*ST]
+
+  LMG_HD void init(double* work, const double* p0) {
+    fvec = work;
+    wa4 = work + MMAX * ST;
+    a = work + 2 * MMAX * ST;
+    for (int j = 0; j < NP; ++j) p[j] = p0[j];
+    par = delta = xnorm = fnorm = gnorm = pnorm = h = ptemp = 0.0;
+    iter = 1;
+    nfev = 0;
+    info = 0;
+    phase = INIT;
   }
-  residuals<ST>(pr, p, fvec);
-  nfev = 1;
-  double fnorm = enorm<ST>(fvec, m);
-  double par = 0.0, delta = 0.0, xnorm = 0.0;
-  int iter = 1;
-  const double eps = sqrt(EPSMCH);  // sqrt(max(epsfcn, epsmch)), epsfcn = epsmch
-  for (;;) {
-    // forward-difference Jacobian (fdjac2)
-    for (int j = 0; j < NP; ++j) {
-      const double temp = p[j];
-      double h = eps * fabs(temp);
-      if (h == 0.0) h = eps;
-      p[j] = temp + h;
-      residuals<ST>(pr, p, wa4);
-      p[j] = temp;
+  LMG_HD const double* eval_point() const { return phase == TRIAL ? wa2 : p; }
+
+  LMG_HD void jac_setup(int j) {  // fdjac2: perturb p[j]
+    const double eps = sqrt(EPSMCH);  // sqrt(max(epsfcn, epsmch)), epsfcn = epsmch
+    ptemp = p[j];
+    h = eps * fabs(ptemp);
+    if (h == 0.0) h = eps;
+    p[j] = ptemp + h;
+  }
+
+  // to be called right after the residuals at eval_point() were written to wa4
+  LMG_HD void advance(int m) {
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
+    const int maxfev = 200 * (NP + 1);
+    bool need_qr = false, need_step = false, need_jac = false;
+    if (phase == INIT) {
+      for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
+      nfev = 1;
+      fnorm = enorm<ST>(fvec, m);
+      par = 0.0;
+      iter = 1;
+      need_jac = true;
+    } else if (phase < TRIAL) {
+      const int j = phase - JAC0;
+      p[j] = ptemp;
       for (int i = 0; i < m; ++i) LMG_A(i, j) = (wa4[i * ST] - fvec[i * ST]) / h;
-    }
-    nfev += NP;
-    qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
-    if (iter == 1) {
-      for (int j = 0; j < NP; ++j) {
-        diag[j] = wa2[j];
-        if (wa2[j] == 0.0) diag[j] = 1.0;
+      if (j + 1 < NP) {
+        jac_setup(j + 1);
+        phase = phase + 1;
+      } else {
+        nfev += NP;
+        need_qr = true;
       }
-      for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
-      xnorm = enorm<1>(wa3, NP);
-      delta = factor * xnorm;
-      if (delta == 0.0) delta = factor;
-    }
-    for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
-    for (int j = 0; j < NP; ++j) {
-      if (LMG_A(j, j) != 0.0) {
-        double sum = 0.0;
-        for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
-        const double temp = -sum / LMG_A(j, j);
-        for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
-      }
-      LMG_A(j, j) = wa1[j];
-      qtf[j] = wa4[j * ST];
-    }
-    double gnorm = 0.0;
-    if (fnorm != 0.0) {
-      for (int j = 0; j < NP; ++j) {
-        const int l = ipvt[j];
-        if (wa2[l] != 0.0) {
-          double sum = 0.0;
-          for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * (qtf[i] / fnorm);
-          gnorm = fmax(gnorm, fabs(sum / wa2[l]));
-        }
-      }
-    }
-    if (gnorm <= gtol) {
-      info = 4;
-      break;
-    }
-    for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
-    double ratio = 0.0;
-    do {
-      lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
-      for (int j = 0; j < NP; ++j) {
-        wa1[j] = -wa1[j];
-        wa2[j] = p[j] + wa1[j];
-        wa3[j] = diag[j] * wa1[j];
-      }
-      const double pnorm = enorm<1>(wa3, NP);
-      if (iter == 1) delta = fmin(delta, pnorm);
-      residuals<ST>(pr, wa2, wa4);
+    } else {  // TRIAL: residuals at wa2 are in wa4
       ++nfev;
       const double fnorm1 = enorm<ST>(wa4, m);
       double actred = -1.0;
@@ -342,7 +325,7 @@ LMG_HD inline int lmdif_work(const Problem& pr, double* p, int* nfev_out, double
       const double temp2 = (sqrt(par) * pnorm) / fnorm;
       const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
-      ratio = 0.0;
+      double ratio = 0.0;
       if (prered != 0.0) ratio = actred / prered;
       if (ratio <= 0.25) {
         double temp;
@@ -368,23 +351,93 @@ LMG_HD inline int lmdif_work(const Problem& pr, double* p, int* nfev_out, double
       if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
       if (delta <= xtol * xnorm) info = 2;
       if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
-      if (info != 0) break;
-      if (nfev >= maxfev) info = 5;
-      if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) info = 6;
-      if (delta <= EPSMCH * xnorm) info = 7;
-      if (gnorm <= EPSMCH) info = 8;
-      if (info != 0) break;
-    } while (ratio < 1e-4);
-    if (info != 0) break;
+      if (info == 0) {
+        if (nfev >= maxfev) info = 5;
+        if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) info = 6;
+        if (delta <= EPSMCH * xnorm) info = 7;
+        if (gnorm <= EPSMCH) info = 8;
+      }
+      if (info != 0) phase = DONE;
+      else if (ratio < 1e-4) need_step = true;  // inner loop: new lmpar with the shrunk region
+      else need_jac = true;                     // outer loop: new Jacobian
+    }
+    if (need_qr) {
+      qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
+      if (iter == 1) {
+        for (int j = 0; j < NP; ++j) {
+          diag[j] = wa2[j];
+          if (wa2[j] == 0.0) diag[j] = 1.0;
+        }
+        for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
+        xnorm = enorm<1>(wa3, NP);
+        delta = factor * xnorm;
+        if (delta == 0.0) delta = factor;
+      }
+      for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
+      for (int j = 0; j < NP; ++j) {
+        if (LMG_A(j, j) != 0.0) {
+          double sum = 0.0;
+          for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
+          const double temp = -sum / LMG_A(j, j);
+          for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
+        }
+        LMG_A(j, j) = wa1[j];
+        qtf[j] = wa4[j * ST];
+      }
+      gnorm = 0.0;
+      if (fnorm != 0.0) {
+        for (int j = 0; j < NP; ++j) {
+          const int l = ipvt[j];
+          if (wa2[l] != 0.0) {
+            double sum = 0.0;
+            for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * (qtf[i] / fnorm);
+            gnorm = fmax(gnorm, fabs(sum / wa2[l]));
+          }
+        }
+      }
+      if (gnorm <= gtol) {
+        info = 4;
+        phase = DONE;
+      } else {
+        for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
+        need_step = true;
+      }
+    }
+    if (need_step) {
+      lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+      for (int j = 0; j < NP; ++j) {
+        wa1[j] = -wa1[j];
+        wa2[j] = p[j] + wa1[j];
+        wa3[j] = diag[j] * wa1[j];
+      }
+      pnorm = enorm<1>(wa3, NP);
+      if (iter == 1) delta = fmin(delta, pnorm);
+      phase = TRIAL;
+    }
+    if (need_jac) {
+      jac_setup(0);
+      phase = JAC0;
+    }
   }
-  *nfev_out = nfev;
-  return info;
-}
+};
 
-// convenience wrapper with private (stride-1) work arrays: host tests, simple callers
+// p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).  Single-fit driver
+// (host tests, simple callers); the GPU kernel steps 32 LmSM<32> instances in lock-step instead.
 LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
+  if (pr.m < NP) {
+    *nfev_out = 0;
+    return 0;
+  }
   double work[WORK_DOUBLES];
-  return lmdif_work<1>(pr, p, nfev_out, work);
+  LmSM<1> sm;
+  sm.init(work, p);
+  while (sm.phase != LmSM<1>::DONE) {
+    residuals<1>(pr, sm.eval_point(), sm.wa4);
+    sm.advance(pr.m);
+  }
+  for (int j = 0; j < NP; ++j) p[j] = sm.p[j];
+  *nfev_out = sm.nfev;
+  return sm.info;
 }
 
 }  // namespace lmg
