@@ -61,9 +61,11 @@ struct EsacfArgs {
   double* ws_hi;  // [N][B]
   double* ws_y;   // [B][L] enhanced SACF
   double* ws_s;   // [B][L] raw SACF (debug only, may be null)
-  int16_t* ws_cand;  // [B][L/2+2] peak indices
+  unsigned char* ws_scratch;  // [B][peaks_scratch_bytes]: sgn | peak list | order, per frame
   double* ws_res;    // [B][L/2+2] fitted centre per peak (NaN = fit failed / dropped)
-  int peak_group;    // frames per CTA pass of the peaks kernel
+  int* ws_np;        // [B] peaks per frame
+  int* ws_tasks;     // [B*(L/2+2)] (frame << 11) | peak
+  int* ws_counters;  // [0] tasks appended, [1] tasks handed out
   int skip_fit;      // debug (CDB_ESACF_SKIP_FIT=1): time the peak picking alone
   double* total;
   double* clips;
@@ -202,170 +204,162 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
   }
 }
 
-constexpr int kPeakWarps = 4;   // fit lanes per CTA = 128
-constexpr int kPeakGroup = 32;  // frames per CTA pass (one peak-picking thread per frame)
+constexpr int kFitWarps = 4;  // fit lanes per CTA = 128 (one LM work area of 26.9 KB per warp)
+constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * 32 * sizeof(double);
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;
   return (((size_t)L + 7) & ~(size_t)7) + 2 * ((half * 2 + 7) & ~(size_t)7);
 }
-constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * 32 * sizeof(double);
 
-// One CTA handles groups of G frames:
-//   1. peak picking, one thread per frame (pk::find_peaks, scratch in shared memory);
-//   2. every (frame, peak) pair becomes a task in a CTA-wide queue; the 128 lanes run one
-//      Levenberg-Marquardt state machine each in lock-step rounds (one residual evaluation per round)
-//      and pull the next task as soon as their fit finishes -- fits take 30..800 evaluations, a
-//      static assignment left ~5 of 32 lanes busy;
-//   3. one thread per frame pairs the surviving centres with the peak list BY POSITION (failed fits
-//      are dropped: the latent misalignment of esacf.py:65-69 is reproduced), maps fs/tau to a pitch
-//      class (librosa.hz_to_note) and accumulates chroma += ESACF[peak].
-__global__ void __launch_bounds__(kPeakWarps * 32) esacf_peaks_kernel(const EsacfArgs a) {
+// The peak stage is three kernels over a batch of B frames:
+//   esacf_pick_kernel  one thread per frame: pk::find_peaks (scratch in global memory, L1/L2
+//                      resident) -> peak list, and every (frame, peak) pair is appended to a
+//                      batch-global task list (one atomicAdd per frame reserves its range).
+//   esacf_fit_kernel   persistent warps; every lane runs one Levenberg-Marquardt state machine and
+//                      pulls its next task from a global counter the moment its fit finishes.  Fits
+//                      take 30..800 evaluations (heavy tail): any static assignment, or a queue per
+//                      CTA, left ~5-8 of 32 lanes busy.  All lanes of a warp advance in lock-step
+//                      rounds (one residual evaluation = 21 exp per round).
+//   esacf_bin_kernel   one thread per frame: pairs the surviving centres with the peak list BY
+//                      POSITION (failed fits are dropped: the latent misalignment of
+//                      esacf.py:65-69 is reproduced), fs/tau -> pitch class (librosa.hz_to_note),
+//                      chroma += ESACF[peak].
+__global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
+  const int fb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fb >= a.B) return;
+  const int L = a.L;
+  const int half = L / 2 + 2;
+  const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
+  unsigned char* sc = a.ws_scratch + (pad_l + 2 * pad_h) * (size_t)fb;
+  int8_t* sgn = reinterpret_cast<int8_t*>(sc);
+  int16_t* cand = reinterpret_cast<int16_t*>(sc + pad_l);  // the final peak list stays here
+  int16_t* order = reinterpret_cast<int16_t*>(sc + pad_l + pad_h);
+  const int np = pk::find_peaks(a.ws_y + (int64_t)fb * L, L, a.peak_thresh, a.peak_min_dist, sgn,
+                                cand, order);
+  a.ws_np[fb] = np;
+  if (np > 0) {
+    const int start = atomicAdd(&a.ws_counters[0], np);
+    for (int i = 0; i < np; ++i) a.ws_tasks[start + i] = (fb << 11) | i;
+  }
+}
+
+__global__ void __launch_bounds__(kFitWarps * 32) esacf_fit_kernel(const EsacfArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = a.L, G = a.peak_group;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = a.L;
   const int half = L / 2 + 2;
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h;
-  __shared__ int s_np[kPeakGroup], s_off[kPeakGroup + 1], s_next, s_total;
-  __shared__ double cta_total[12];
-  if (tid < 12) cta_total[tid] = 0.0;
-  __syncthreads();
-
-  for (int base = blockIdx.x * G; base < a.B; base += gridDim.x * G) {
-    const int nfr = min(G, a.B - base);
-    // ---- 1. peak picking (ESACF rows are read through L1)
-    if (tid < nfr) {
-      unsigned char* fb = smem + per_frame * tid;
-      int8_t* sgn = reinterpret_cast<int8_t*>(fb);
-      int16_t* cand = reinterpret_cast<int16_t*>(fb + pad_l);
-      int16_t* order = reinterpret_cast<int16_t*>(fb + pad_l + pad_h);
-      const int np = pk::find_peaks(a.ws_y + (int64_t)(base + tid) * L, L, a.peak_thresh,
-                                    a.peak_min_dist, sgn, cand, order);
-      s_np[tid] = np;
-      int16_t* out = a.ws_cand + (int64_t)(base + tid) * half;
-      for (int i = 0; i < np; ++i) out[i] = cand[i];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int acc = 0;
-      for (int j = 0; j < nfr; ++j) {
-        s_off[j] = acc;
-        acc += s_np[j];
-      }
-      s_off[nfr] = acc;
-      s_total = acc;
-      s_next = kPeakWarps * 32;  // tasks 0..127 are pre-assigned to the lanes
-    }
-    __syncthreads();
-    // ---- 2. fits: work queue + lock-step state machines (shared memory now holds the LM work arrays)
-    {
-      const int total = s_total;
-      double* lm_work = reinterpret_cast<double*>(smem + kLmWarpBytes * warp) + lane;
-      lmg::Problem pr;
-      lmg::LmSM<32> sm;
-      int task = tid;
-      int frame = 0, pi = 0;
-      bool need_init = true;
-      while (__any_sync(0xffffffffu, task < total)) {
-        if (task < total) {
-          bool fitting = true;
-          if (need_init) {
-            need_init = false;
-            int lo_f = 0, hi_f = nfr;  // largest frame with s_off[frame] <= task
-            while (hi_f - lo_f > 1) {
-              const int mid = (lo_f + hi_f) >> 1;
-              if (s_off[mid] <= task) lo_f = mid;
-              else hi_f = mid;
-            }
-            frame = lo_f;
-            pi = task - s_off[frame];
-            const int idx = a.ws_cand[(int64_t)(base + frame) * half + pi];
-            const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
-            if (a.skip_fit || lo < 0 || hi - lo < 3) {
-              fitting = false;  // empty slice -> RuntimeError in peakutils -> peak dropped
-              a.ws_res[(int64_t)(base + frame) * half + pi] = NAN;
-            } else {
-              const double* y = a.ws_y + (int64_t)(base + frame) * L;
-              pr.m = hi - lo;
-              pr.x0 = (double)lo;
-              double ymax = __ldg(y + lo);
-              for (int i = 0; i < pr.m; ++i) {
-                pr.y[i] = __ldg(y + lo + i);
-                ymax = fmax(ymax, pr.y[i]);
-              }
-              const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
-              sm.init(lm_work, p0);
-            }
+  const int total = a.ws_counters[0];
+  double* lm_work = reinterpret_cast<double*>(smem + kLmWarpBytes * warp) + lane;
+  lmg::Problem pr;
+  lmg::LmSM<32> sm;
+  int task = atomicAdd(&a.ws_counters[1], 1);
+  int fb = 0, pi = 0;
+  bool need_init = true;
+  while (__any_sync(0xffffffffu, task < total)) {
+    if (task < total) {
+      bool fitting = true;
+      if (need_init) {
+        need_init = false;
+        const int t = a.ws_tasks[task];
+        fb = t >> 11;
+        pi = t & 2047;
+        const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + per_frame * (size_t)fb + pad_l);
+        const int idx = cand[pi];
+        const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
+        if (a.skip_fit || lo < 0 || hi - lo < 3) {
+          fitting = false;  // empty slice -> RuntimeError in peakutils -> peak dropped
+          a.ws_res[(int64_t)fb * half + pi] = NAN;
+        } else {
+          const double* y = a.ws_y + (int64_t)fb * L;
+          pr.m = hi - lo;
+          pr.x0 = (double)lo;
+          double ymax = __ldg(y + lo);
+          for (int i = 0; i < pr.m; ++i) {
+            pr.y[i] = __ldg(y + lo + i);
+            ymax = fmax(ymax, pr.y[i]);
           }
-          if (fitting) {
-            lmg::residuals<32>(pr, sm.eval_point(), sm.wa4);
-            sm.advance(pr.m);
-            if (sm.phase == lmg::LmSM<32>::DONE) {
-              const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) &&
-                              isfinite(sm.p[1]) && isfinite(sm.p[2]);
-              a.ws_res[(int64_t)(base + frame) * half + pi] = ok ? sm.p[1] : NAN;
-              fitting = false;
-            }
-          }
-          if (!fitting) {  // fetch the next task
-            task = atomicAdd(&s_next, 1);
-            need_init = true;
-          }
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // ---- 3. pairing + chroma, one thread per frame
-    if (tid < nfr) {
-      const int64_t gf = a.frame0 + base + tid;
-      const double* y = a.ws_y + (int64_t)(base + tid) * L;
-      const int16_t* cand = a.ws_cand + (int64_t)(base + tid) * half;
-      const double* res = a.ws_res + (int64_t)(base + tid) * half;
-      double* dbg = a.debug ? a.debug + gf * a.debug_stride : nullptr;
-      double chroma[12];
-#pragma unroll
-      for (int n = 0; n < 12; ++n) chroma[n] = 0.0;
-      const int np = s_np[tid];
-      int slot = 0;
-      for (int i = 0; i < np; ++i) {
-        const double c = res[i];
-        if (isnan(c)) continue;
-        const int paired = cand[slot];  // peak_indices[slot]
-        if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = c;
-        ++slot;
-        const double pitch = a.fs / c;
-        // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
-        if (pitch > 0.0 && isfinite(pitch)) {
-          const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
-          long long nn = (long long)nearbyint(midi);
-          int note = (int)(nn % 12);
-          if (note < 0) note += 12;
-          const double v = __ldg(y + paired);
-#pragma unroll
-          for (int n = 0; n < 12; ++n)
-            if (n == note) chroma[n] += v;
+          const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
+          sm.init(lm_work, p0);
         }
       }
-      if (dbg) {
-        dbg[2 * a.N + 2 * L] = (double)np;
-        for (int i = 0; i < np && i < kMaxPeaksDbg; ++i) dbg[2 * a.N + 2 * L + 1 + i] = (double)cand[i];
-        dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)slot;
-      }
-#pragma unroll
-      for (int n = 0; n < 12; ++n) {
-        const double v = chroma[n];
-        if (a.frames) a.frames[gf * 12 + n] = v;
-        if (v != 0.0) {
-          if (a.clips) atomicAdd(&a.clips[(gf / a.frames_per_clip) * 12 + n], v);
-          if (a.total) atomicAdd(&cta_total[n], v);
+      if (fitting) {
+        lmg::residuals<32>(pr, sm.eval_point(), sm.wa4);
+        sm.advance(pr.m);
+        if (sm.phase == lmg::LmSM<32>::DONE) {
+          const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
+                          isfinite(sm.p[2]);
+          a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
+          fitting = false;
         }
       }
+      if (!fitting) {  // fetch the next task
+        task = atomicAdd(&a.ws_counters[1], 1);
+        need_init = true;
+      }
     }
-    __syncthreads();
+    __syncwarp();
   }
-  if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
+}
+
+__global__ void __launch_bounds__(64) esacf_bin_kernel(const EsacfArgs a) {
+  __shared__ double cta_total[12];
+  if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int fb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fb < a.B) {
+    const int L = a.L;
+    const int half = L / 2 + 2;
+    const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
+    const int64_t gf = a.frame0 + fb;
+    const double* y = a.ws_y + (int64_t)fb * L;
+    const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + (pad_l + 2 * pad_h) * (size_t)fb + pad_l);
+    const double* res = a.ws_res + (int64_t)fb * half;
+    double* dbg = a.debug ? a.debug + gf * a.debug_stride : nullptr;
+    double chroma[12];
+#pragma unroll
+    for (int n = 0; n < 12; ++n) chroma[n] = 0.0;
+    const int np = a.ws_np[fb];
+    int slot = 0;
+    for (int i = 0; i < np; ++i) {
+      const double c = res[i];
+      if (isnan(c)) continue;
+      const int paired = cand[slot];  // peak_indices[slot]
+      if (dbg && slot < kMaxPeaksDbg) dbg[2 * a.N + 2 * L + 1 + kMaxPeaksDbg + slot] = c;
+      ++slot;
+      const double pitch = a.fs / c;
+      // librosa.hz_to_note: int(round(12*(log2(f) - log2(440)) + 69)) % 12; f <= 0 / NaN -> ValueError -> skip
+      if (pitch > 0.0 && isfinite(pitch)) {
+        const double midi = 12.0 * (log2(pitch) - log2(440.0)) + 69.0;
+        long long nn = (long long)nearbyint(midi);
+        int note = (int)(nn % 12);
+        if (note < 0) note += 12;
+        const double v = __ldg(y + paired);
+#pragma unroll
+        for (int n = 0; n < 12; ++n)
+          if (n == note) chroma[n] += v;
+      }
+    }
+    if (dbg) {
+      dbg[2 * a.N + 2 * L] = (double)np;
+      for (int i = 0; i < np && i < kMaxPeaksDbg; ++i) dbg[2 * a.N + 2 * L + 1 + i] = (double)cand[i];
+      dbg[2 * a.N + 2 * L + 1 + 2 * kMaxPeaksDbg] = (double)slot;
+    }
+#pragma unroll
+    for (int n = 0; n < 12; ++n) {
+      const double v = chroma[n];
+      if (a.frames) a.frames[gf * 12 + n] = v;
+      if (v != 0.0) {
+        if (a.clips) atomicAdd(&a.clips[(gf / a.frames_per_clip) * 12 + n], v);
+        if (a.total) atomicAdd(&cta_total[n], v);
+      }
+    }
+  }
+  __syncthreads();
+  if (a.total && threadIdx.x < 12 && cta_total[threadIdx.x] != 0.0)
+    atomicAdd(&a.total[threadIdx.x], cta_total[threadIdx.x]);
 }
 
 // copies x_lo / x_hi / sacf / esacf of every frame of the batch into the debug buffer
@@ -463,8 +457,9 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
 
   const int64_t Bmax = std::min<int64_t>(n_frames, 16384);
   const size_t half = (size_t)L / 2 + 2;
+  const size_t scratch_pf = (peaks_scratch_bytes(L) + 15) & ~(size_t)15;
   const size_t need = (size_t)Bmax * ((2 * (size_t)N + 2 * (size_t)L + half) * sizeof(double) +
-                                      ((half * 2 + 15) & ~(size_t)15));
+                                      scratch_pf + half * sizeof(int) + sizeof(int)) + 64;
   if (pl->ws_bytes < need) {
     CDB_CUDA(h, cudaStreamSynchronize(st));
     if (pl->ws) cudaFree(pl->ws);
@@ -510,14 +505,14 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
-  // shared memory of the peaks kernel: the larger of (G frames of peak-picking scratch) and
-  // (one LM work area per warp); G as large as fits, at most kPeakGroup
-  const size_t lm_smem = kLmWarpBytes * kPeakWarps;
-  int group = (int)std::min<size_t>(kPeakGroup, std::max<size_t>(1, (200 * 1024) / peaks_scratch_bytes(L)));
-  const size_t pk_smem = std::max(lm_smem, peaks_scratch_bytes(L) * (size_t)group);
-  CDB_CUDA(h, cudaFuncSetAttribute(esacf_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)pk_smem));
-  a.peak_group = group;
+  if (half > 2048) return cdb_fail(h, CDB_E_UNSUPPORTED, "SACF too long for the task encoding");
+  const size_t fit_smem = kLmWarpBytes * kFitWarps;
+  CDB_CUDA(h, cudaFuncSetAttribute(esacf_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)fit_smem));
+  int fit_per_sm = 0;
+  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, esacf_fit_kernel,
+                                                            kFitWarps * 32, fit_smem));
+  if (fit_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "fit kernel does not fit");
   {
     const char* sf = std::getenv("CDB_ESACF_SKIP_FIT");
     a.skip_fit = (sf && sf[0] == '1') ? 1 : 0;
@@ -532,15 +527,21 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.ws_y = w + 2 * (size_t)N * B;
     a.ws_s = d_debug ? (w + 2 * (size_t)N * B + (size_t)L * B) : nullptr;  // raw SACF (debug only)
     a.ws_res = w + 2 * (size_t)N * B + 2 * (size_t)L * B;
-    a.ws_cand = reinterpret_cast<int16_t*>(a.ws_res + half * (size_t)B);
+    a.ws_scratch = reinterpret_cast<unsigned char*>(a.ws_res + half * (size_t)B);
+    a.ws_tasks = reinterpret_cast<int*>(a.ws_scratch + scratch_pf * (size_t)B);
+    a.ws_np = a.ws_tasks + half * (size_t)B;
+    a.ws_counters = a.ws_np + B;
+    CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 2 * sizeof(int), st));
     esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
     acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
     if (d_debug) {
       esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);
       h->launches += 1;
     }
-    const int pgrid = std::min<int>((B + group - 1) / group, h->num_sms * 4);
-    esacf_peaks_kernel<<<pgrid, kPeakWarps * 32, pk_smem, st>>>(a);
+    esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
+    esacf_fit_kernel<<<h->num_sms * fit_per_sm, kFitWarps * 32, fit_smem, st>>>(a);
+    esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
+    h->launches += 2;
     h->launches += 3;
     CDB_CUDA(h, cudaGetLastError());
   }
