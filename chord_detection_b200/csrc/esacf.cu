@@ -455,7 +455,9 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   }
   if (n_frames == 0) return 0;
 
-  const int64_t Bmax = std::min<int64_t>(n_frames, 16384);
+  // large batches: the fit kernel ends with a latency-bound tail (one 800-evaluation fit takes
+  // ~40 ms on its own), which is amortised over the batch
+  const int64_t Bmax = std::min<int64_t>(n_frames, 65536);
   const size_t half = (size_t)L / 2 + 2;
   const size_t scratch_pf = (peaks_scratch_bytes(L) + 15) & ~(size_t)15;
   const size_t need = (size_t)Bmax * ((2 * (size_t)N + 2 * (size_t)L + half) * sizeof(double) +

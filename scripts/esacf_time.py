@@ -4,7 +4,11 @@ import numpy as np, torch
 from chord_detection_b200 import ops, synth
 dev=torch.device('cuda:0')
 base = torch.from_numpy(np.stack([synth.s_poly(1 + i, 44100, 1_000_000) for i in range(8)])).to(dev)
-x = base.repeat(4,1)[:32].contiguous()
+import os
+NC=int(os.environ.get('NC','32'))
+x = base.repeat((NC+7)//8,1)[:NC].contiguous()
+g=torch.Generator(device=dev).manual_seed(0)
+x = x*(0.8+0.4*torch.rand(x.shape,device=dev,generator=g))
 def t(fn, reps=3):
     fn(); torch.cuda.synchronize(); ts=[]
     for _ in range(reps):
@@ -15,4 +19,4 @@ ms=t(lambda: ops.esacf(x,44100))
 r=ops.esacf(x[:2],44100,debug=True)
 d=r.extra.cpu().numpy(); N=2046; L=1022; o=2*N+2*L
 npk=d[:,o]; nfit=d[:,o+1+128]
-print(json.dumps({"skip":os.environ.get("CDB_ESACF_SKIP_FIT"),"frames":32*489,"ms":ms,"peaks_per_frame_mean":float(npk.mean()),"peaks_max":float(npk.max()),"fit_mean":float(nfit.mean())}))
+print(json.dumps({"skip":os.environ.get("CDB_ESACF_SKIP_FIT"),"frames":NC*489,"ms":ms,"peaks_per_frame_mean":float(npk.mean()),"peaks_max":float(npk.max()),"fit_mean":float(nfit.mean())}))
