@@ -204,8 +204,12 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
   }
 }
 
-constexpr int kFitWarps = 4;  // fit lanes per CTA = 128 (one LM work area of 26.9 KB per warp)
-constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * 32 * sizeof(double);
+// The LM state machine is a long dependent FP64 chain (warp IPC ~0.07): throughput comes from the
+// number of resident WARPS, not lanes.  Only kFitLanes lanes of each warp run fits, which shrinks the
+// per-warp shared-memory work area from 26.9 KB to 6.7 KB and lets 32 warps/SM stay resident.
+constexpr int kFitLanes = 8;
+constexpr int kFitWarps = 8;
+constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * kFitLanes * sizeof(double);
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kFitWarps * 32) esacf_fit_kernel(const EsacfArgs a) {
+__global__ void __launch_bounds__(kFitWarps * 32, 4) esacf_fit_kernel(const EsacfArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = a.L;
@@ -252,13 +256,15 @@ __global__ void __launch_bounds__(kFitWarps * 32) esacf_fit_kernel(const EsacfAr
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h;
   const int total = a.ws_counters[0];
+  if (lane >= kFitLanes) return;  // (no block-wide barrier below)
+  constexpr unsigned kMask = (1u << kFitLanes) - 1u;
   double* lm_work = reinterpret_cast<double*>(smem + kLmWarpBytes * warp) + lane;
   lmg::Problem pr;
-  lmg::LmSM<32> sm;
+  lmg::LmSM<kFitLanes> sm;
   int task = atomicAdd(&a.ws_counters[1], 1);
   int fb = 0, pi = 0;
   bool need_init = true;
-  while (__any_sync(0xffffffffu, task < total)) {
+  while (__any_sync(kMask, task < total)) {
     if (task < total) {
       bool fitting = true;
       if (need_init) {
@@ -286,9 +292,9 @@ __global__ void __launch_bounds__(kFitWarps * 32) esacf_fit_kernel(const EsacfAr
         }
       }
       if (fitting) {
-        lmg::residuals<32>(pr, sm.eval_point(), sm.wa4);
+        lmg::residuals<kFitLanes>(pr, sm.eval_point(), sm.wa4);
         sm.advance(pr.m);
-        if (sm.phase == lmg::LmSM<32>::DONE) {
+        if (sm.phase == lmg::LmSM<kFitLanes>::DONE) {
           const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
                           isfinite(sm.p[2]);
           a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(kFitWarps * 32) esacf_fit_kernel(const EsacfAr
         need_init = true;
       }
     }
-    __syncwarp();
+    __syncwarp(kMask);
   }
 }
 
