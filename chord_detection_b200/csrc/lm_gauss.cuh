@@ -18,7 +18,24 @@
 #define LMG_HD
 #endif
 
+#ifdef __CUDA_ARCH__
+#define LMG_UNROLL1 _Pragma("unroll 1")
+#else
+#define LMG_UNROLL1
+#endif
+
 namespace lmg {
+
+// FP64 division and square root are ~25-30 inlined instructions each on the GPU; the LM code has
+// ~110 of them after unrolling, which made the fit kernel 145 KB of SASS and instruction-cache
+// bound (66 % of stalls).  Routed through non-inlined helpers (same IEEE results).
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+#else
+inline double ddiv(double a, double b) { return a / b; }
+inline double dsqrt(double a) { return sqrt(a); }
+#endif
 
 constexpr int MMAX = 21;  // 2*width+1 with peakutils' width = 10
 constexpr int NP = 3;
@@ -33,7 +50,7 @@ template <int ST = 1>
 LMG_HD inline double enorm(const double* v, int n) {
   double s = 0.0;
   for (int i = 0; i < n; ++i) s += v[i * ST] * v[i * ST];
-  return sqrt(s);
+  return dsqrt(s);
 }
 
 struct Problem {
@@ -46,7 +63,7 @@ template <int ST>
 LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
   // one reciprocal per evaluation instead of m divisions (FP64 division is ~30 instructions on
   // the GPU); differs from -(d*d)/denom by at most one ulp in the exponent argument
-  const double ninv = -1.0 / (2.0 * p[2] * p[2] + EPSMCH);
+  const double ninv = ddiv(-1.0, 2.0 * p[2] * p[2] + EPSMCH);
   for (int i = 0; i < pr.m; ++i) {
     const double d = (pr.x0 + (double)i) - p[1];
     f[i * ST] = p[0] * exp((d * d) * ninv) - pr.y[i];
@@ -58,6 +75,7 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
 template <int ST>
 LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm,
                              double* wa) {
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
     acnorm[j] = enorm<ST>(a + (j * MMAX) * ST, m);
     rdiag[j] = acnorm[j];
@@ -65,11 +83,14 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
     ipvt[j] = j;
   }
   const int minmn = m < NP ? m : NP;
+  LMG_UNROLL1
   for (int j = 0; j < minmn; ++j) {
     int kmax = j;
+    LMG_UNROLL1
     for (int k = j; k < NP; ++k)
       if (rdiag[k] > rdiag[kmax]) kmax = k;
     if (kmax != j) {
+      LMG_UNROLL1
       for (int i = 0; i < m; ++i) {
         const double t = LMG_A(i, j);
         LMG_A(i, j) = LMG_A(i, kmax);
@@ -84,19 +105,23 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
     double ajnorm = enorm<ST>(a + (j + j * MMAX) * ST, m - j);
     if (ajnorm != 0.0) {
       if (LMG_A(j, j) < 0.0) ajnorm = -ajnorm;
-      for (int i = j; i < m; ++i) LMG_A(i, j) /= ajnorm;
+      LMG_UNROLL1
+      for (int i = j; i < m; ++i) LMG_A(i, j) = ddiv(LMG_A(i, j), ajnorm);
       LMG_A(j, j) += 1.0;
+      LMG_UNROLL1
       for (int k = j + 1; k < NP; ++k) {
         double sum = 0.0;
+        LMG_UNROLL1
         for (int i = j; i < m; ++i) sum += LMG_A(i, j) * LMG_A(i, k);
-        const double temp = sum / LMG_A(j, j);
+        const double temp = ddiv(sum, LMG_A(j, j));
+        LMG_UNROLL1
         for (int i = j; i < m; ++i) LMG_A(i, k) -= temp * LMG_A(i, j);
         if (rdiag[k] != 0.0) {
-          double t = LMG_A(j, k) / rdiag[k];
+          double t = ddiv(LMG_A(j, k), rdiag[k]);
           double d = 1.0 - t * t;
           if (d < 0.0) d = 0.0;
-          rdiag[k] *= sqrt(d);
-          const double q = rdiag[k] / wa[k];
+          rdiag[k] *= dsqrt(d);
+          const double q = ddiv(rdiag[k], wa[k]);
           if (0.05 * (q * q) <= EPSMCH) {
             rdiag[k] = enorm<ST>(a + ((j + 1) + k * MMAX) * ST, m - j - 1);
             wa[k] = rdiag[k];
@@ -112,33 +137,39 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
 template <int ST>
 LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const double* qtb,
                               double* x, double* sdiag, double* wa) {
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
+    LMG_UNROLL1
     for (int i = j; i < NP; ++i) LMG_R(i, j) = LMG_R(j, i);
     x[j] = LMG_R(j, j);
     wa[j] = qtb[j];
   }
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
     const int l = ipvt[j];
     if (diag[l] != 0.0) {
+      LMG_UNROLL1
       for (int k = j; k < NP; ++k) sdiag[k] = 0.0;
       sdiag[j] = diag[l];
       double qtbpj = 0.0;
+      LMG_UNROLL1
       for (int k = j; k < NP; ++k) {
         if (sdiag[k] == 0.0) continue;
         double c, s;
         if (fabs(LMG_R(k, k)) < fabs(sdiag[k])) {
-          const double cotan = LMG_R(k, k) / sdiag[k];
-          s = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+          const double cotan = ddiv(LMG_R(k, k), sdiag[k]);
+          s = ddiv(0.5, dsqrt(0.25 + 0.25 * (cotan * cotan)));
           c = s * cotan;
         } else {
-          const double tn = sdiag[k] / LMG_R(k, k);
-          c = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+          const double tn = ddiv(sdiag[k], LMG_R(k, k));
+          c = ddiv(0.5, dsqrt(0.25 + 0.25 * (tn * tn)));
           s = c * tn;
         }
         LMG_R(k, k) = c * LMG_R(k, k) + s * sdiag[k];
         const double temp = c * wa[k] + s * qtbpj;
         qtbpj = -s * wa[k] + c * qtbpj;
         wa[k] = temp;
+        LMG_UNROLL1
         for (int i = k + 1; i < NP; ++i) {
           const double t = c * LMG_R(i, k) + s * sdiag[i];
           sdiag[i] = -s * LMG_R(i, k) + c * sdiag[i];
@@ -150,16 +181,20 @@ LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const 
     LMG_R(j, j) = x[j];
   }
   int nsing = NP;
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
     if (sdiag[j] == 0.0 && nsing == NP) nsing = j;
     if (nsing < NP) wa[j] = 0.0;
   }
+  LMG_UNROLL1
   for (int k = 0; k < nsing; ++k) {
     const int j = nsing - 1 - k;
     double sum = 0.0;
+    LMG_UNROLL1
     for (int i = j + 1; i < nsing; ++i) sum += LMG_R(i, j) * wa[i];
-    wa[j] = (wa[j] - sum) / sdiag[j];
+    wa[j] = ddiv(wa[j] - sum, sdiag[j]);
   }
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa[j];
 }
 
@@ -168,19 +203,24 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
                              double delta, double* par, double* x, double* sdiag, double* wa1,
                              double* wa2) {
   int nsing = NP;
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
     wa1[j] = qtb[j];
     if (LMG_R(j, j) == 0.0 && nsing == NP) nsing = j;
     if (nsing < NP) wa1[j] = 0.0;
   }
+  LMG_UNROLL1
   for (int k = 0; k < nsing; ++k) {
     const int j = nsing - 1 - k;
-    wa1[j] /= LMG_R(j, j);
+    wa1[j] = ddiv(wa1[j], LMG_R(j, j));
     const double temp = wa1[j];
+    LMG_UNROLL1
     for (int i = 0; i < j; ++i) wa1[i] -= LMG_R(i, j) * temp;
   }
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa1[j];
   int iter = 0;
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
   double dxnorm = enorm<1>(wa2, NP);
   double fp = dxnorm - delta;
@@ -190,51 +230,62 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
   }
   double parl = 0.0;
   if (nsing >= NP) {
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) {
       const int l = ipvt[j];
-      wa1[j] = diag[l] * (wa2[l] / dxnorm);
+      wa1[j] = diag[l] * ddiv(wa2[l], dxnorm);
     }
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) {
       double sum = 0.0;
+      LMG_UNROLL1
       for (int i = 0; i < j; ++i) sum += LMG_R(i, j) * wa1[i];
-      wa1[j] = (wa1[j] - sum) / LMG_R(j, j);
+      wa1[j] = ddiv(wa1[j] - sum, LMG_R(j, j));
     }
     const double temp = enorm<1>(wa1, NP);
-    parl = ((fp / delta) / temp) / temp;
+    parl = ddiv(ddiv(ddiv(fp, delta), temp), temp);
   }
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
     double sum = 0.0;
+    LMG_UNROLL1
     for (int i = 0; i <= j; ++i) sum += LMG_R(i, j) * qtb[i];
-    wa1[j] = sum / diag[ipvt[j]];
+    wa1[j] = ddiv(sum, diag[ipvt[j]]);
   }
   const double gnorm = enorm<1>(wa1, NP);
-  double paru = gnorm / delta;
-  if (paru == 0.0) paru = DWARF / fmin(delta, 0.1);
+  double paru = ddiv(gnorm, delta);
+  if (paru == 0.0) paru = ddiv(DWARF, fmin(delta, 0.1));
   *par = fmax(*par, parl);
   *par = fmin(*par, paru);
-  if (*par == 0.0) *par = gnorm / dxnorm;
+  if (*par == 0.0) *par = ddiv(gnorm, dxnorm);
+  LMG_UNROLL1
   for (;;) {
     ++iter;
     if (*par == 0.0) *par = fmax(DWARF, 0.001 * paru);
-    double temp = sqrt(*par);
+    double temp = dsqrt(*par);
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
     qrsolv<ST>(r, ipvt, wa1, qtb, x, sdiag, wa2);
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = enorm<1>(wa2, NP);
     temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) {
       const int l = ipvt[j];
-      wa1[j] = diag[l] * (wa2[l] / dxnorm);
+      wa1[j] = diag[l] * ddiv(wa2[l], dxnorm);
     }
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) {
-      wa1[j] /= sdiag[j];
+      wa1[j] = ddiv(wa1[j], sdiag[j]);
       const double t = wa1[j];
+      LMG_UNROLL1
       for (int i = j + 1; i < NP; ++i) wa1[i] -= LMG_R(i, j) * t;
     }
     temp = enorm<1>(wa1, NP);
-    const double parc = ((fp / delta) / temp) / temp;
+    const double parc = ddiv(ddiv(ddiv(fp, delta), temp), temp);
     if (fp > 0.0) parl = fmax(parl, *par);
     if (fp < 0.0) paru = fmin(paru, *par);
     *par = fmax(parl, *par + parc);
@@ -268,6 +319,7 @@ struct LmSM {
     fvec = work;
     wa4 = work + MMAX * ST;
     a = work + 2 * MMAX * ST;
+    LMG_UNROLL1
     for (int j = 0; j < NP; ++j) p[j] = p0[j];
     par = delta = xnorm = fnorm = gnorm = pnorm = h = ptemp = 0.0;
     iter = 1;
@@ -278,7 +330,7 @@ struct LmSM {
   LMG_HD const double* eval_point() const { return phase == TRIAL ? wa2 : p; }
 
   LMG_HD void jac_setup(int j) {  // fdjac2: perturb p[j]
-    const double eps = sqrt(EPSMCH);  // sqrt(max(epsfcn, epsmch)), epsfcn = epsmch
+    const double eps = 1.4901161193847656e-08;  // sqrt(max(epsfcn, epsmch)) = sqrt(2^-52) = 2^-26
     ptemp = p[j];
     h = eps * fabs(ptemp);
     if (h == 0.0) h = eps;
@@ -291,6 +343,7 @@ struct LmSM {
     const int maxfev = 200 * (NP + 1);
     bool need_qr = false, need_step = false, need_jac = false;
     if (phase == INIT) {
+      LMG_UNROLL1
       for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
       nfev = 1;
       fnorm = enorm<ST>(fvec, m);
@@ -300,7 +353,8 @@ struct LmSM {
     } else if (phase < TRIAL) {
       const int j = phase - JAC0;
       p[j] = ptemp;
-      for (int i = 0; i < m; ++i) LMG_A(i, j) = (wa4[i * ST] - fvec[i * ST]) / h;
+      LMG_UNROLL1
+      for (int i = 0; i < m; ++i) LMG_A(i, j) = ddiv(wa4[i * ST] - fvec[i * ST], h);
       if (j + 1 < NP) {
         jac_setup(j + 1);
         phase = phase + 1;
@@ -313,36 +367,40 @@ struct LmSM {
       const double fnorm1 = enorm<ST>(wa4, m);
       double actred = -1.0;
       if (0.1 * fnorm1 < fnorm) {
-        const double q = fnorm1 / fnorm;
+        const double q = ddiv(fnorm1, fnorm);
         actred = 1.0 - q * q;
       }
+      LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
         wa3[j] = 0.0;
         const double temp = wa1[ipvt[j]];
+        LMG_UNROLL1
         for (int i = 0; i <= j; ++i) wa3[i] += LMG_A(i, j) * temp;
       }
-      const double temp1 = enorm<1>(wa3, NP) / fnorm;
-      const double temp2 = (sqrt(par) * pnorm) / fnorm;
+      const double temp1 = ddiv(enorm<1>(wa3, NP), fnorm);
+      const double temp2 = ddiv(dsqrt(par) * pnorm, fnorm);
       const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
       double ratio = 0.0;
-      if (prered != 0.0) ratio = actred / prered;
+      if (prered != 0.0) ratio = ddiv(actred, prered);
       if (ratio <= 0.25) {
         double temp;
         if (actred >= 0.0) temp = 0.5;
-        else temp = 0.5 * dirder / (dirder + 0.5 * actred);
+        else temp = ddiv(0.5 * dirder, dirder + 0.5 * actred);
         if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
         delta = temp * fmin(delta, pnorm / 0.1);
-        par /= temp;
+        par = ddiv(par, temp);
       } else if (par == 0.0 || ratio >= 0.75) {
         delta = pnorm / 0.5;
         par *= 0.5;
       }
       if (ratio >= 1e-4) {
+        LMG_UNROLL1
         for (int j = 0; j < NP; ++j) {
           p[j] = wa2[j];
           wa2[j] = diag[j] * p[j];
         }
+        LMG_UNROLL1
         for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
         xnorm = enorm<1>(wa2, NP);
         fnorm = fnorm1;
@@ -364,21 +422,27 @@ struct LmSM {
     if (need_qr) {
       qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
       if (iter == 1) {
+        LMG_UNROLL1
         for (int j = 0; j < NP; ++j) {
           diag[j] = wa2[j];
           if (wa2[j] == 0.0) diag[j] = 1.0;
         }
+        LMG_UNROLL1
         for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
         xnorm = enorm<1>(wa3, NP);
         delta = factor * xnorm;
         if (delta == 0.0) delta = factor;
       }
+      LMG_UNROLL1
       for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
+      LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
         if (LMG_A(j, j) != 0.0) {
           double sum = 0.0;
+          LMG_UNROLL1
           for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
-          const double temp = -sum / LMG_A(j, j);
+          const double temp = ddiv(-sum, LMG_A(j, j));
+          LMG_UNROLL1
           for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
         }
         LMG_A(j, j) = wa1[j];
@@ -386,12 +450,14 @@ struct LmSM {
       }
       gnorm = 0.0;
       if (fnorm != 0.0) {
+        LMG_UNROLL1
         for (int j = 0; j < NP; ++j) {
           const int l = ipvt[j];
           if (wa2[l] != 0.0) {
             double sum = 0.0;
-            for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * (qtf[i] / fnorm);
-            gnorm = fmax(gnorm, fabs(sum / wa2[l]));
+            LMG_UNROLL1
+            for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * ddiv(qtf[i], fnorm);
+            gnorm = fmax(gnorm, fabs(ddiv(sum, wa2[l])));
           }
         }
       }
@@ -399,12 +465,14 @@ struct LmSM {
         info = 4;
         phase = DONE;
       } else {
+        LMG_UNROLL1
         for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
         need_step = true;
       }
     }
     if (need_step) {
       lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+      LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = p[j] + wa1[j];
@@ -435,6 +503,7 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
     residuals<1>(pr, sm.eval_point(), sm.wa4);
     sm.advance(pr.m);
   }
+  LMG_UNROLL1
   for (int j = 0; j < NP; ++j) p[j] = sm.p[j];
   *nfev_out = sm.nfev;
   return sm.info;
