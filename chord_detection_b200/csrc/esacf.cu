@@ -207,9 +207,7 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
 // The LM state machine is a long dependent FP64 chain (warp IPC ~0.07): throughput comes from the
 // number of resident WARPS, not lanes.  Only kFitLanes lanes of each warp run fits, which shrinks the
 // per-warp shared-memory work area from 26.9 KB to 6.7 KB and lets 32 warps/SM stay resident.
-constexpr int kFitLanes = 8;
-constexpr int kFitWarps = 8;
-constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * kFitLanes * sizeof(double);
+constexpr int kFitThreads = 256;
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;
@@ -248,7 +246,9 @@ __global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kFitWarps * 32, 4) esacf_fit_kernel(const EsacfArgs a) {
+template <int kFitLanes>
+__global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs a) {
+  constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * kFitLanes * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = a.L;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kFitWarps * 32, 4) esacf_fit_kernel(const Esac
   const size_t per_frame = pad_l + 2 * pad_h;
   const int total = a.ws_counters[0];
   if (lane >= kFitLanes) return;  // (no block-wide barrier below)
-  constexpr unsigned kMask = (1u << kFitLanes) - 1u;
+  constexpr unsigned kMask = kFitLanes == 32 ? 0xffffffffu : ((1u << (kFitLanes & 31)) - 1u);
   double* lm_work = reinterpret_cast<double*>(smem + kLmWarpBytes * warp) + lane;
   lmg::Problem pr;
   lmg::LmSM<kFitLanes> sm;
@@ -514,12 +514,19 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
   if (half > 2048) return cdb_fail(h, CDB_E_UNSUPPORTED, "SACF too long for the task encoding");
-  const size_t fit_smem = kLmWarpBytes * kFitWarps;
-  CDB_CUDA(h, cudaFuncSetAttribute(esacf_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  int fit_lanes = 8;  // fit lanes per warp (see esacf_fit_kernel); CDB_ESACF_FIT_LANES overrides
+  if (const char* fl = std::getenv("CDB_ESACF_FIT_LANES")) fit_lanes = std::atoi(fl);
+  void (*fit_kernel)(const EsacfArgs) = fit_lanes >= 32   ? esacf_fit_kernel<32>
+                                        : fit_lanes >= 16 ? esacf_fit_kernel<16>
+                                        : fit_lanes >= 8  ? esacf_fit_kernel<8>
+                                                          : esacf_fit_kernel<4>;
+  fit_lanes = fit_lanes >= 32 ? 32 : fit_lanes >= 16 ? 16 : fit_lanes >= 8 ? 8 : 4;
+  const size_t fit_smem = (size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * (kFitThreads / 32);
+  CDB_CUDA(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)fit_smem));
   int fit_per_sm = 0;
-  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, esacf_fit_kernel,
-                                                            kFitWarps * 32, fit_smem));
+  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, fit_kernel, kFitThreads,
+                                                            fit_smem));
   if (fit_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "fit kernel does not fit");
   {
     const char* sf = std::getenv("CDB_ESACF_SKIP_FIT");
@@ -547,7 +554,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       h->launches += 1;
     }
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
-    esacf_fit_kernel<<<h->num_sms * fit_per_sm, kFitWarps * 32, fit_smem, st>>>(a);
+    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a);
     esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
     h->launches += 2;
     h->launches += 3;
