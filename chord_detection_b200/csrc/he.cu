@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 
 struct HeWin {
   int k0, k1, note, pad;
@@ -499,6 +500,264 @@ __global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
   if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Packed-FP32 version of the frame-2048 kernel (the one that is launched).  Same structure as
+// he2048_kernel above (one warp per frame, TMA-staged tile, radix-32 x radix-32 register FFT, one
+// transpose), but every complex value is one 64-bit register pair and all butterflies are
+// FFMA2 / FADD2 (f32x2.cuh): 3 instructions per twiddled butterfly instead of 6, 2 per complex
+// multiply instead of 4.  The two FFT passes are separate code instances so that pass 2 can be
+// output-pruned at compile time: KHI >= 0 means only Z[k1 + 32 k2] with k2 in [0, KHI] and their
+// mirror bins (k2 in [31-KHI, 31]) are consumed, and the dead half-butterflies are never emitted.
+// ------------------------------------------------------------------------------------------
+template <int m, bool NEED_A, bool NEED_B>
+__device__ __forceinline__ void bflyp(c64& a, c64& b) {
+  constexpr float C[16] = {1.0f,           0.980785280f,  0.923879533f,  0.831469612f,
+                           0.707106781f,   0.555570233f,  0.382683432f,  0.195090322f,
+                           0.0f,           -0.195090322f, -0.382683432f, -0.555570233f,
+                           -0.707106781f,  -0.831469612f, -0.923879533f, -0.980785280f};
+  constexpr float S[16] = {0.0f,          0.195090322f, 0.382683432f, 0.555570233f,
+                           0.707106781f,  0.831469612f, 0.923879533f, 0.980785280f,
+                           1.0f,          0.980785280f, 0.923879533f, 0.831469612f,
+                           0.707106781f,  0.555570233f, 0.382683432f, 0.195090322f};
+  const c64 t = a;
+  if (m == 0) {
+    if (NEED_A) a = add2(t, b);
+    if (NEED_B) b = sub2(t, b);
+  } else if (m == 8) {  // w = -i
+    const c64 r = mul_mi(b);
+    if (NEED_A) a = add2(t, r);
+    if (NEED_B) b = sub2(t, r);
+  } else if (NEED_A) {  // w b = C b + S (-i b)
+    const c64 o = fma2(bc(S[m]), mul_mi(b), fma2(bc(C[m]), b, t));
+    a = o;
+    if (NEED_B) b = fma2(bc(2.0f), t, neg2(o));
+  } else if (NEED_B) {
+    b = fma2(bc(-S[m]), mul_mi(b), fma2(bc(-C[m]), b, t));
+  }
+}
+
+template <int NP, int S_, int G, int J>
+struct PStageJ {
+  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
+    bflyp<J * (16 / S_), true, true>(v[G + J], v[G + J + S_]);
+    if constexpr (J + 1 < S_) PStageJ<NP, S_, G, J + 1>::run(v);
+  }
+};
+template <int NP, int S_, int G>
+struct PStageG {
+  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
+    PStageJ<NP, S_, G, 0>::run(v);
+    if constexpr (G + 2 * S_ < NP) PStageG<NP, S_, G + 2 * S_>::run(v);
+  }
+};
+// last (span-16) stage of the 32-point DFT, emitting only the outputs k2 in [0,KHI] u [31-KHI,31]
+template <int KHI, int J>
+struct PLastStage {
+  static __device__ __forceinline__ void run(c64 (&v)[32]) {
+    constexpr bool need_a = (KHI < 0) || (J <= KHI);
+    constexpr bool need_b = (KHI < 0) || (J + 16 >= 31 - KHI);
+    if constexpr (need_a || need_b) bflyp<J, need_a, need_b>(v[J], v[J + 16]);
+    if constexpr (J + 1 < 16) PLastStage<KHI, J + 1>::run(v);
+  }
+};
+template <int KHI>
+__device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
+  PStageG<32, 2, 0>::run(v);
+  PStageG<32, 4, 0>::run(v);
+  PStageG<32, 8, 0>::run(v);
+  PLastStage<KHI, 0>::run(v);
+}
+
+template <int W, int KHI>
+__global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  double* cta_acc = reinterpret_cast<double*>(smem + 16);  // [12]
+  float* inbuf = reinterpret_cast<float*>(smem + 128);
+  float* swin = inbuf + a.tile_cap;
+  float2* stw = reinterpret_cast<float2*>(swin + 2048);
+  float2* scr_all = stw + 1024;
+  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * kScr);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2048; i += W * 32) swin[i] = a.win[i];
+  for (int i = tid; i < 1024; i += W * 32) stw[i] = a.tw32[i];
+  for (int i = tid; i < a.n_windows; i += W * 32) swins[i] = a.wins[i];
+  if (tid < 12) cta_acc[tid] = 0.0;
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int64_t t_begin = (a.total_tiles * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t t_end = (a.total_tiles * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+
+  auto issue_load = [&](int64_t clip, int64_t f0) -> bool {
+    const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
+    const int64_t s0 = f0 * a.hop;
+    const int need = (int)((nf - 1) * a.hop + 2048);
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const bool full = (s0 + need <= a.clip_len);
+    const bool tma_ok =
+        full && ((need & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (tma_ok) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (uint32_t)need * 4u);
+        tma_load_1d(inbuf, src, (uint32_t)need * 4u, mbar);
+      }
+    } else {
+      const int64_t avail = a.clip_len - s0;  // may be <= 0
+      for (int i = tid; i < need; i += W * 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
+    }
+    return tma_ok;
+  };
+
+  float2* scr = scr_all + warp * kScr;
+  c64* scr64 = reinterpret_cast<c64*>(scr);
+  float* pw = reinterpret_cast<float*>(scr);          // [M+1] 4|X|^2 (aliases the scratch)
+  double* wv = reinterpret_cast<double*>(scr) + 520;  // [n_windows] (byte offset 4160)
+  const c64* w2 = reinterpret_cast<const c64*>(swin);
+  const c64* stw64 = reinterpret_cast<const c64*>(stw);
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+
+  bool cur_tma = false;
+  uint32_t phase = 0;
+  int64_t clip = t_begin / a.tiles_per_clip;
+  int64_t f0 = (t_begin - clip * a.tiles_per_clip) * W;
+  if (t_begin < t_end) cur_tma = issue_load(clip, f0);
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const int nf = (int)min((int64_t)W, a.frames_per_clip - f0);
+    int64_t nclip = clip, nf0 = f0 + W;  // coordinates of the next tile
+    if (nf0 >= a.frames_per_clip) {
+      nclip = clip + 1;
+      nf0 = 0;
+    }
+    if (cur_tma) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    } else {
+      __syncthreads();
+    }
+    const bool active = warp < nf;
+    if (active) {
+      // pass 1: n = 32*n1 + lane.  Window fused into the span-1 butterflies (pairs n1, n1+16):
+      // v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
+      c64 v[32];
+      const c64* fr2 = reinterpret_cast<const c64*>(inbuf + warp * a.hop);  // hop is even
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int na = br5(2 * p), nb = na + 16;
+        const c64 xa = fr2[32 * na + lane], wa = w2[32 * na + lane];
+        const c64 xb = fr2[32 * nb + lane], wb = w2[32 * nb + lane];
+        const c64 mb = mul2(xb, wb);
+        v[2 * p] = fma2(xa, wa, mb);
+        v[2 * p + 1] = fma2(xa, wa, neg2(mb));
+      }
+      fft32p_dit_tail<-1>(v);
+      // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1
+      scr64[lane] = v[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 32; ++k1) scr64[k1 * kRow + lane] = cmul2(v[k1], stw64[k1 * 32 + lane]);
+    }
+    __syncthreads();  // every warp is done reading the staged tile; transposes are visible
+    bool next_tma = false;
+    if (tile + 1 < t_end) next_tma = issue_load(nclip, nf0);  // overlaps pass 2 below
+
+    if (active) {
+      c64 v[32];
+      {
+        // pass 2: k1 = lane, n2 = 0..31 from this lane's transpose row (128-bit loads)
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(scr + lane * kRow);
+        c64 in[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const ulonglong2 q = row[i];
+          in[2 * i] = q.x;
+          in[2 * i + 1] = q.y;
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int na = br5(2 * p), nb = na + 16;
+          v[2 * p] = add2(in[na], in[nb]);
+          v[2 * p + 1] = sub2(in[na], in[nb]);
+        }
+      }
+      fft32p_dit_tail<KHI>(v);
+      // Z[lane + 32*k2] is in v[k2]
+      __syncwarp();  // scratch is re-used for the power spectrum below
+      // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2; pw = 4|X|^2
+      const int src_lane = (32 - lane) & 31;
+      const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;  // warp-uniform range of needed k2
+      constexpr int K2END = (KHI < 0) ? 32 : KHI + 1;
+#pragma unroll
+      for (int k2 = 0; k2 < K2END; ++k2) {
+        if (k2 >= k2a && k2 <= k2b) {
+          const int k = lane + 32 * k2;
+          float qr, qi;
+          upk(v[31 - k2], qr, qi);
+          float pr = __shfl_sync(0xffffffffu, qr, src_lane);
+          float pi = __shfl_sync(0xffffffffu, qi, src_lane);
+          c64 pz = pk(pr, pi);
+          if (lane == 0) pz = v[(32 - k2) & 31];  // partner of Z[32*k2] is Z[1024-32*k2]
+          const float2 cs = __ldg(&a.wsplit[k]);
+          const c64 pc = conj2(pz);
+          const c64 e = add2(v[k2], pc), d = sub2(v[k2], pc);
+          // 2 X = e + c (di, -dr) - s (dr, di)
+          const c64 x2 = fma2(bc(-cs.y), d, fma2(bc(cs.x), mul_mi(d), e));
+          float xr, xi;
+          upk(x2, xr, xi);
+          pw[k] = fmaf(xr, xr, xi * xi);
+        }
+      }
+      if (KHI < 0 && a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
+        float zr, zi;
+        upk(v[0], zr, zi);
+        const float xn = 2.0f * (zr - zi);
+        pw[1024] = xn * xn;
+      }
+      __syncwarp();
+      // ---- window maxima (harmonic_energy.py:58-64); max of 4|X|^2, then one 4th root
+      for (int wi = lane; wi < a.n_windows; wi += 32) {
+        const HeWin hw = swins[wi];
+        float m = pw[hw.k0];
+        for (int j = 1; j < a.max_width; ++j)  // uniform trip count, clamped index: no divergence
+          m = fmaxf(m, pw[min(hw.k0 + j, hw.k1 - 1)]);
+        wv[wi] = (double)sqrtf(sqrtf(0.25f * m)) * hw.weight;
+      }
+      __syncwarp();
+      if (lane < 12) {
+        double s = 0.0;
+        for (int j = 0; j < a.wins_per_note; ++j) s += wv[lane * a.wins_per_note + j];
+        if (a.clips) {
+          if (clip != my_clip) {
+            if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+            my_clip = clip;
+            acc_clip = 0.0;
+          }
+          acc_clip += s;
+        }
+        acc_total += s;
+        if (a.frames) a.frames[(clip * a.frames_per_clip + f0 + warp) * 12 + lane] = (float)s;
+      }
+      __syncwarp();
+    }
+    cur_tma = next_tma;
+    clip = nclip;
+    f0 = nf0;
+  }
+  if (lane < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+    if (a.total) atomicAdd(&cta_acc[lane], acc_total);
+  }
+  __syncthreads();
+  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
+}
+
 // ------------------------------------------------------------------------------------------
 // frame_size 8192 (the reference default, harmonic_energy.py:15): one CTA of 256 threads per
 // frame.  8192-pt real FFT = 4096-pt complex FFT = radix-16 x radix-16 x radix-16, every 16-pt
@@ -799,14 +1058,20 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
     a.tile_cap = (((kHeW - 1) * pl->hop + 2048) + 3) & ~3;
     const size_t smem = 128 + (size_t)a.tile_cap * 4 + 2048 * 4 + 1024 * 8 +
                         (size_t)kHeW * kScr * 8 + HE_MAX_WINDOWS * sizeof(HeWin);
-    CDB_CUDA(h, cudaFuncSetAttribute(he2048_kernel<kHeW>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // kernel variant: packed FP32x2 (default), pass 2 pruned to k2 <= 5 when the probed bins allow
+    // it (the metric shape probes bins 22..186); CDB_HE_SCALAR=1 selects the scalar-FP32 kernel.
+    const char* sc = std::getenv("CDB_HE_SCALAR");
+    void (*kern)(const HeArgs) = he2048p_kernel<kHeW, -1>;
+    if (sc && sc[0] == '1')
+      kern = he2048_kernel<kHeW>;
+    else if ((pl->kmax >> 5) <= 5)
+      kern = he2048p_kernel<kHeW, 5>;
+    CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he2048_kernel<kHeW>,
-                                                              kHeW * 32, smem));
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHeW * 32, smem));
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "tile does not fit in shared memory");
     int64_t grid = std::min<int64_t>(a.total_tiles, (int64_t)h->num_sms * per_sm);
-    he2048_kernel<kHeW><<<(unsigned)grid, kHeW * 32, smem, st>>>(a);
+    kern<<<(unsigned)grid, kHeW * 32, smem, st>>>(a);
   } else if (pl->N == 8192 && !pl->force_generic) {
     const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
