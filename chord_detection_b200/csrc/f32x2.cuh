@@ -68,3 +68,32 @@ __device__ __forceinline__ c64 cmul2(c64 z, c64 w) {
   upk(w, wr, wi);
   return fma2(mul_pi(z), bc(wi), mul2(z, bc(wr)));
 }
+
+// 64-bit shared-memory store of a packed value from its two halves: written this way ptxas stores
+// straight from the FFMA2 result registers (a plain 64-bit store of the asm result costs two MOVs).
+__device__ __forceinline__ void sts2(void* smem_ptr, c64 v) {
+  float x, y;
+  upk(v, x, y);
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr))),
+               "f"(x), "f"(y)
+               : "memory");
+}
+
+// MUFU.SQRT (relative error ~2^-22): the 4th root of the window maxima needs no IEEE rounding
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// 64-bit shared-memory load that keeps its program order relative to the other volatile
+// shared-memory accesses (used to software-pipeline table loads ahead of their use).
+__device__ __forceinline__ c64 lds2v(const void* smem_ptr) {
+  c64 r;
+  asm volatile("ld.shared.b64 %0, [%1];"
+               : "=l"(r)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr)))
+               : "memory");
+  return r;
+}

@@ -304,211 +304,15 @@ __host__ __device__ constexpr int br4(int k) {
 constexpr int kRow = 34;          // transpose row stride in float2 (16-byte aligned rows, conflict-free)
 constexpr int kScr = 32 * kRow;   // per-warp transpose scratch (float2)
 
-template <int W>
-__global__ void __launch_bounds__(W * 32, 2) he2048_kernel(const HeArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
-  double* cta_acc = reinterpret_cast<double*>(smem + 16);  // [12]
-  float* inbuf = reinterpret_cast<float*>(smem + 128);
-  float* swin = inbuf + a.tile_cap;
-  float2* stw = reinterpret_cast<float2*>(swin + 2048);
-  float2* scr_all = stw + 1024;
-  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * kScr);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2048; i += W * 32) swin[i] = a.win[i];
-  for (int i = tid; i < 1024; i += W * 32) stw[i] = a.tw32[i];
-  for (int i = tid; i < a.n_windows; i += W * 32) swins[i] = a.wins[i];
-  if (tid < 12) cta_acc[tid] = 0.0;
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int64_t t_begin = (a.total_tiles * (int64_t)blockIdx.x) / gridDim.x;
-  const int64_t t_end = (a.total_tiles * (int64_t)(blockIdx.x + 1)) / gridDim.x;
-
-  // stage one tile (clip `clip`, first frame `f0`); returns true when it went through the
-  // bulk-async (TMA) path
-  auto issue_load = [&](int64_t clip, int64_t f0) -> bool {
-    const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
-    const int64_t s0 = f0 * a.hop;
-    const int need = (int)((nf - 1) * a.hop + 2048);
-    const float* src = a.x + clip * a.clip_stride + s0;
-    const bool full = (s0 + need <= a.clip_len);
-    const bool tma_ok =
-        full && ((need & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    if (tma_ok) {
-      if (tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(mbar, (uint32_t)need * 4u);
-        tma_load_1d(inbuf, src, (uint32_t)need * 4u, mbar);
-      }
-    } else {
-      const int64_t avail = a.clip_len - s0;  // may be <= 0
-      for (int i = tid; i < need; i += W * 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
-    }
-    return tma_ok;
-  };
-
-  float2* scr = scr_all + warp * kScr;
-  float* pw = reinterpret_cast<float*>(scr);          // [M+1] power spectrum (aliases the scratch)
-  double* wv = reinterpret_cast<double*>(scr) + 520;  // [n_windows] (byte offset 4160)
-  double acc_total = 0.0, acc_clip = 0.0;
-  int64_t my_clip = -1;
-
-  bool cur_tma = false;
-  uint32_t phase = 0;
-  // running (clip, first frame) of the current tile: one division up front, none in the loop
-  int64_t clip = t_begin / a.tiles_per_clip;
-  int64_t f0 = (t_begin - clip * a.tiles_per_clip) * W;
-  if (t_begin < t_end) cur_tma = issue_load(clip, f0);
-
-  for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    const int nf = (int)min((int64_t)W, a.frames_per_clip - f0);
-    int64_t nclip = clip, nf0 = f0 + W;  // coordinates of the next tile
-    if (nf0 >= a.frames_per_clip) {
-      nclip = clip + 1;
-      nf0 = 0;
-    }
-    if (cur_tma) {
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-    } else {
-      __syncthreads();
-    }
-    float2 v[32];
-    const bool active = warp < nf;
-    bool next_tma = false;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {  // one shared instance of the 32-point FFT code
-      if (active) {
-        if (pass == 0) {
-          // pass 1: n = 32*n1 + lane.  Hamming window fused into the span-1 butterflies
-          // (pairs n1, n1+16): v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
-          const float2* fr2 = reinterpret_cast<const float2*>(inbuf + warp * a.hop);  // hop is even
-          const float2* w2 = reinterpret_cast<const float2*>(swin);
-#pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const int na = br5(2 * p), nb = na + 16;
-            const float2 xa = fr2[32 * na + lane], wa = w2[32 * na + lane];
-            const float2 xb = fr2[32 * nb + lane], wb = w2[32 * nb + lane];
-            const float mr = xb.x * wb.x, mi = xb.y * wb.y;
-            v[2 * p] = make_float2(fmaf(xa.x, wa.x, mr), fmaf(xa.y, wa.y, mi));
-            v[2 * p + 1] = make_float2(fmaf(xa.x, wa.x, -mr), fmaf(xa.y, wa.y, -mi));
-          }
-        } else {
-          // pass 2: k1 = lane, n2 = 0..31 from this lane's transpose row (128-bit loads)
-          const float4* row = reinterpret_cast<const float4*>(scr + lane * kRow);
-          float2 in[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 q = row[i];
-            in[2 * i] = make_float2(q.x, q.y);
-            in[2 * i + 1] = make_float2(q.z, q.w);
-          }
-#pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const int na = br5(2 * p), nb = na + 16;
-            v[2 * p] = make_float2(in[na].x + in[nb].x, in[na].y + in[nb].y);
-            v[2 * p + 1] = make_float2(in[na].x - in[nb].x, in[na].y - in[nb].y);
-          }
-        }
-        fft32_dit_tail(v);
-        if (pass == 0) {
-          // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1
-          scr[lane] = v[0];
-#pragma unroll
-          for (int k1 = 1; k1 < 32; ++k1) {
-            const float2 z = v[k1], w = stw[k1 * 32 + lane];
-            scr[k1 * kRow + lane] =
-                make_float2(fmaf(z.x, w.x, -z.y * w.y), fmaf(z.x, w.y, z.y * w.x));
-          }
-        }
-      }
-      if (pass == 0) {
-        __syncthreads();  // every warp is done reading the staged tile; transposes are visible
-        if (tile + 1 < t_end) next_tma = issue_load(nclip, nf0);  // overlaps pass 2 below
-      }
-    }
-
-    if (active) {
-      // Z[lane + 32*k2] is in v[k2]
-      __syncwarp();  // scratch is re-used for the power spectrum below
-      // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2
-      const int src_lane = (32 - lane) & 31;
-      const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;  // warp-uniform range of needed k2
-#pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        if (k2 > k2b) break;
-        if (k2 >= k2a) {
-          const int k = lane + 32 * k2;
-          const float2 z = v[k2];
-          float pr = __shfl_sync(0xffffffffu, v[31 - k2].x, src_lane);
-          float pi = __shfl_sync(0xffffffffu, v[31 - k2].y, src_lane);
-          if (lane == 0) {  // partner of Z[32*k2] is Z[1024-32*k2], held by lane 0 itself
-            pr = v[(32 - k2) & 31].x;
-            pi = v[(32 - k2) & 31].y;
-          }
-          const float2 cs = __ldg(&a.wsplit[k]);
-          const float er = z.x + pr, ei = z.y - pi, dr = z.x - pr, di = z.y + pi;
-          const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
-          const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
-          pw[k] = xr * xr + xi * xi;
-        }
-      }
-      if (a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
-        const float xn = v[0].x - v[0].y;
-        pw[1024] = xn * xn;
-      }
-      __syncwarp();
-      // ---- window maxima (harmonic_energy.py:58-64); max|X|^2 then one 4th root
-      for (int wi = lane; wi < a.n_windows; wi += 32) {
-        const HeWin hw = swins[wi];
-        float m = pw[hw.k0];
-        for (int j = 1; j < a.max_width; ++j)  // uniform trip count, clamped index: no divergence
-          m = fmaxf(m, pw[min(hw.k0 + j, hw.k1 - 1)]);
-        wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
-      }
-      __syncwarp();
-      if (lane < 12) {
-        double s = 0.0;
-        for (int j = 0; j < a.wins_per_note; ++j) s += wv[lane * a.wins_per_note + j];
-        if (a.clips) {
-          if (clip != my_clip) {
-            if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
-            my_clip = clip;
-            acc_clip = 0.0;
-          }
-          acc_clip += s;
-        }
-        acc_total += s;
-        if (a.frames) a.frames[(clip * a.frames_per_clip + f0 + warp) * 12 + lane] = (float)s;
-      }
-      __syncwarp();
-    }
-    cur_tma = next_tma;
-    clip = nclip;
-    f0 = nf0;
-  }
-  if (lane < 12) {
-    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
-    if (a.total) atomicAdd(&cta_acc[lane], acc_total);
-  }
-  __syncthreads();
-  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
-}
-
-
 // ------------------------------------------------------------------------------------------
-// Packed-FP32 version of the frame-2048 kernel (the one that is launched).  Same structure as
-// he2048_kernel above (one warp per frame, TMA-staged tile, radix-32 x radix-32 register FFT, one
-// transpose), but every complex value is one 64-bit register pair and all butterflies are
-// FFMA2 / FADD2 (f32x2.cuh): 3 instructions per twiddled butterfly instead of 6, 2 per complex
-// multiply instead of 4.  The two FFT passes are separate code instances so that pass 2 can be
-// output-pruned at compile time: KHI >= 0 means only Z[k1 + 32 k2] with k2 in [0, KHI] and their
-// mirror bins (k2 in [31-KHI, 31]) are consumed, and the dead half-butterflies are never emitted.
+// frame_size 2048 (the BASELINE metric shape): packed-FP32 register FFT.
+// Every complex value is one 64-bit register pair and all butterflies are FFMA2 / FADD2
+// (f32x2.cuh): 3 instructions per twiddled butterfly instead of 6, 2 per complex multiply instead
+// of 4 (same FP32 lane throughput as scalar code, half the issue slots; measured in
+// scripts/microbench/fp32_issue.cu).  The two FFT passes are separate code instances so that
+// pass 2 can be output-pruned at compile time: KHI >= 0 means only Z[k1 + 32 k2] with k2 in
+// [0, KHI] and their mirror bins (k2 in [31-KHI, 31]) are consumed, and the dead half-butterflies
+// are never emitted.
 // ------------------------------------------------------------------------------------------
 template <int m, bool NEED_A, bool NEED_B>
 __device__ __forceinline__ void bflyp(c64& a, c64& b) {
@@ -569,31 +373,45 @@ __device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
   PLastStage<KHI, 0>::run(v);
 }
 
-template <int W, int KHI>
-__global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
+// W warps (= W consecutive frames) form a GROUP that shares one staged tile, one mbarrier and one
+// named barrier; a CTA holds G independent groups (own tile buffers, shared window / twiddle
+// tables).  Groups drift apart in phase, so the shared-memory-heavy and the FMA-heavy parts of
+// different groups overlap on the SM.
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int W, int G, int KHI>
+__global__ void __launch_bounds__(W * G * 32, (W * G >= 16) ? 1 : 2) he2048p_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
-  double* cta_acc = reinterpret_cast<double*>(smem + 16);  // [12]
-  float* inbuf = reinterpret_cast<float*>(smem + 128);
-  float* swin = inbuf + a.tile_cap;
+  constexpr int NT = W * G * 32;                           // threads per CTA
+  constexpr int GT = W * 32;                               // threads per group
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem);  // [G] (G <= 8)
+  double* cta_acc = reinterpret_cast<double*>(smem + 64);  // [12]
+  float* inbuf_all = reinterpret_cast<float*>(smem + 256);
+  float* swin = inbuf_all + G * a.tile_cap;
   float2* stw = reinterpret_cast<float2*>(swin + 2048);
   float2* scr_all = stw + 1024;
-  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * kScr);
+  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * G * kScr);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2048; i += W * 32) swin[i] = a.win[i];
-  for (int i = tid; i < 1024; i += W * 32) stw[i] = a.tw32[i];
-  for (int i = tid; i < a.n_windows; i += W * 32) swins[i] = a.wins[i];
+  const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
+  const int grp = cwarp / W, warp = cwarp - grp * W, gtid = tid - grp * GT;
+  uint64_t* mbar = mbar_all + grp;
+  float* inbuf = inbuf_all + grp * a.tile_cap;
+  for (int i = tid; i < 2048; i += NT) swin[i] = a.win[i];
+  for (int i = tid; i < 1024; i += NT) stw[i] = a.tw32[i];
+  for (int i = tid; i < a.n_windows; i += NT) swins[i] = a.wins[i];
   if (tid < 12) cta_acc[tid] = 0.0;
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    fence_mbar_init();
-  }
+  if (tid < G) mbar_init(mbar_all + tid, 1);
+  if (tid == 0) fence_mbar_init();
   __syncthreads();
 
-  const int64_t t_begin = (a.total_tiles * (int64_t)blockIdx.x) / gridDim.x;
-  const int64_t t_end = (a.total_tiles * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+  const int64_t n_groups = (int64_t)gridDim.x * G, my_group = (int64_t)blockIdx.x * G + grp;
+  const int64_t t_begin = (a.total_tiles * my_group) / n_groups;
+  const int64_t t_end = (a.total_tiles * (my_group + 1)) / n_groups;
 
+  // stage one tile (clip `clip`, first frame `f0`); returns true when it went through the
+  // bulk-async (TMA) path
   auto issue_load = [&](int64_t clip, int64_t f0) -> bool {
     const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
     const int64_t s0 = f0 * a.hop;
@@ -603,19 +421,19 @@ __global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
     const bool tma_ok =
         full && ((need & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (tma_ok) {
-      if (tid == 0) {
+      if (gtid == 0) {
         fence_proxy_async();
         mbar_expect_tx(mbar, (uint32_t)need * 4u);
         tma_load_1d(inbuf, src, (uint32_t)need * 4u, mbar);
       }
     } else {
       const int64_t avail = a.clip_len - s0;  // may be <= 0
-      for (int i = tid; i < need; i += W * 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
+      for (int i = gtid; i < need; i += GT) inbuf[i] = (i < avail) ? src[i] : 0.0f;
     }
     return tma_ok;
   };
 
-  float2* scr = scr_all + warp * kScr;
+  float2* scr = scr_all + cwarp * kScr;
   c64* scr64 = reinterpret_cast<c64*>(scr);
   float* pw = reinterpret_cast<float*>(scr);          // [M+1] 4|X|^2 (aliases the scratch)
   double* wv = reinterpret_cast<double*>(scr) + 520;  // [n_windows] (byte offset 4160)
@@ -641,7 +459,7 @@ __global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
       mbar_wait(mbar, phase);
       phase ^= 1;
     } else {
-      __syncthreads();
+      group_sync(1 + grp, GT);
     }
     const bool active = warp < nf;
     if (active) {
@@ -659,12 +477,31 @@ __global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
         v[2 * p + 1] = fma2(xa, wa, neg2(mb));
       }
       fft32p_dit_tail<-1>(v);
-      // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1
-      scr64[lane] = v[0];
+      // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1.  The 31 table loads
+      // are software-pipelined in batches of 8, two batches ahead of their use (left to ptxas,
+      // every load sits right in front of its multiply and its latency is exposed 31 times).
+      {
+        c64 ta[8], tb[8];
 #pragma unroll
-      for (int k1 = 1; k1 < 32; ++k1) scr64[k1 * kRow + lane] = cmul2(v[k1], stw64[k1 * 32 + lane]);
+        for (int j = 0; j < 8; ++j) ta[j] = lds2v(&stw64[(1 + j) * 32 + lane]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tb[j] = lds2v(&stw64[(9 + j) * 32 + lane]);
+        sts2(&scr64[lane], v[0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts2(&scr64[(1 + j) * kRow + lane], cmul2(v[1 + j], ta[j]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ta[j] = lds2v(&stw64[(17 + j) * 32 + lane]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts2(&scr64[(9 + j) * kRow + lane], cmul2(v[9 + j], tb[j]));
+#pragma unroll
+        for (int j = 0; j < 7; ++j) tb[j] = lds2v(&stw64[(25 + j) * 32 + lane]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts2(&scr64[(17 + j) * kRow + lane], cmul2(v[17 + j], ta[j]));
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sts2(&scr64[(25 + j) * kRow + lane], cmul2(v[25 + j], tb[j]));
+      }
     }
-    __syncthreads();  // every warp is done reading the staged tile; transposes are visible
+    group_sync(1 + grp, GT);  // every warp of the group is done reading the staged tile
     bool next_tma = false;
     if (tile + 1 < t_end) next_tma = issue_load(nclip, nf0);  // overlaps pass 2 below
 
@@ -691,27 +528,28 @@ __global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
       // Z[lane + 32*k2] is in v[k2]
       __syncwarp();  // scratch is re-used for the power spectrum below
       // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2; pw = 4|X|^2
+      // (the pruned variant computes all KHI+1 rows: bins outside [kmin,kmax] are never read)
       const int src_lane = (32 - lane) & 31;
       const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;  // warp-uniform range of needed k2
       constexpr int K2END = (KHI < 0) ? 32 : KHI + 1;
+      const float2* csp = a.wsplit + lane;
 #pragma unroll
       for (int k2 = 0; k2 < K2END; ++k2) {
-        if (k2 >= k2a && k2 <= k2b) {
-          const int k = lane + 32 * k2;
+        if (KHI >= 0 || (k2 >= k2a && k2 <= k2b)) {
           float qr, qi;
           upk(v[31 - k2], qr, qi);
-          float pr = __shfl_sync(0xffffffffu, qr, src_lane);
-          float pi = __shfl_sync(0xffffffffu, qi, src_lane);
+          const float pr = __shfl_sync(0xffffffffu, qr, src_lane);
+          const float pi = __shfl_sync(0xffffffffu, qi, src_lane);
           c64 pz = pk(pr, pi);
           if (lane == 0) pz = v[(32 - k2) & 31];  // partner of Z[32*k2] is Z[1024-32*k2]
-          const float2 cs = __ldg(&a.wsplit[k]);
+          const float2 cs = __ldg(csp + 32 * k2);
           const c64 pc = conj2(pz);
           const c64 e = add2(v[k2], pc), d = sub2(v[k2], pc);
           // 2 X = e + c (di, -dr) - s (dr, di)
           const c64 x2 = fma2(bc(-cs.y), d, fma2(bc(cs.x), mul_mi(d), e));
           float xr, xi;
           upk(x2, xr, xi);
-          pw[k] = fmaf(xr, xr, xi * xi);
+          pw[lane + 32 * k2] = fmaf(xr, xr, xi * xi);
         }
       }
       if (KHI < 0 && a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
@@ -721,13 +559,18 @@ __global__ void __launch_bounds__(W * 32, 2) he2048p_kernel(const HeArgs a) {
         pw[1024] = xn * xn;
       }
       __syncwarp();
-      // ---- window maxima (harmonic_energy.py:58-64); max of 4|X|^2, then one 4th root
+      // ---- window maxima (harmonic_energy.py:58-64); max of 4|X|^2, then one 4th root.
+      // Blocks of 8 unconditional loads with the index clamped to the window's last bin.
       for (int wi = lane; wi < a.n_windows; wi += 32) {
         const HeWin hw = swins[wi];
-        float m = pw[hw.k0];
-        for (int j = 1; j < a.max_width; ++j)  // uniform trip count, clamped index: no divergence
-          m = fmaxf(m, pw[min(hw.k0 + j, hw.k1 - 1)]);
-        wv[wi] = (double)sqrtf(sqrtf(0.25f * m)) * hw.weight;
+        const float* p0 = pw + hw.k0;
+        const int last = hw.k1 - 1 - hw.k0;
+        float m = p0[0];
+        for (int j0 = 0; j0 < a.max_width; j0 += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fmaxf(m, p0[min(j0 + j, last)]);
+        }
+        wv[wi] = (double)sqrt_approx(sqrt_approx(0.25f * m)) * hw.weight;
       }
       __syncwarp();
       if (lane < 12) {
@@ -999,7 +842,6 @@ __global__ void __launch_bounds__(kGenThreads) he_generic_kernel(const HeArgs a)
 }
 
 // ------------------------------------------------------------------ C-ABI entry
-constexpr int kHeW = 8;  // warps (= frames) per tile in the fast path
 
 extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float* d_x,
                              int64_t n_clips, int64_t clip_len, int64_t clip_stride,
@@ -1053,25 +895,35 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.tile_cap = 0;
 
   if (pl->N == 2048 && !pl->force_generic && (pl->hop % 2) == 0) {
-    a.tiles_per_clip = (fpc + kHeW - 1) / kHeW;
+    // CTA shape: G groups of W warps.  Default 4 x 4 (one 512-thread CTA per SM: four tile
+    // pipelines in different phases); CDB_HE_GROUPS=1 selects 1 x 8 with two CTAs per SM.
+    const char* ge = std::getenv("CDB_HE_GROUPS");
+    int groups = (ge && ge[0] == '1') ? 1 : 4;
+    auto smem_for = [&](int g, int w) {
+      const size_t cap = (size_t)((((w - 1) * pl->hop + 2048) + 3) & ~3);
+      return 256 + (size_t)g * cap * 4 + 2048 * 4 + 1024 * 8 + (size_t)w * g * kScr * 8 +
+             (size_t)pl->n_windows * sizeof(HeWin);
+    };
+    if (groups == 4 && smem_for(4, 4) > (size_t)h->smem_optin) groups = 1;  // large hops: big tiles
+    const int W = (groups == 1) ? 8 : 4;
+    const bool pruned = (pl->kmax >> 5) <= 5;  // the metric shape probes bins 22..186
+    void (*kern)(const HeArgs);
+    if (groups == 1)
+      kern = pruned ? he2048p_kernel<8, 1, 5> : he2048p_kernel<8, 1, -1>;
+    else
+      kern = pruned ? he2048p_kernel<4, 4, 5> : he2048p_kernel<4, 4, -1>;
+    a.tiles_per_clip = (fpc + W - 1) / W;
     a.total_tiles = a.tiles_per_clip * n_clips;
-    a.tile_cap = (((kHeW - 1) * pl->hop + 2048) + 3) & ~3;
-    const size_t smem = 128 + (size_t)a.tile_cap * 4 + 2048 * 4 + 1024 * 8 +
-                        (size_t)kHeW * kScr * 8 + HE_MAX_WINDOWS * sizeof(HeWin);
-    // kernel variant: packed FP32x2 (default), pass 2 pruned to k2 <= 5 when the probed bins allow
-    // it (the metric shape probes bins 22..186); CDB_HE_SCALAR=1 selects the scalar-FP32 kernel.
-    const char* sc = std::getenv("CDB_HE_SCALAR");
-    void (*kern)(const HeArgs) = he2048p_kernel<kHeW, -1>;
-    if (sc && sc[0] == '1')
-      kern = he2048_kernel<kHeW>;
-    else if ((pl->kmax >> 5) <= 5)
-      kern = he2048p_kernel<kHeW, 5>;
+    a.tile_cap = (((W - 1) * pl->hop + 2048) + 3) & ~3;
+    const int threads = W * groups * 32;
+    const size_t smem = smem_for(groups, W);
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHeW * 32, smem));
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "tile does not fit in shared memory");
-    int64_t grid = std::min<int64_t>(a.total_tiles, (int64_t)h->num_sms * per_sm);
-    kern<<<(unsigned)grid, kHeW * 32, smem, st>>>(a);
+    const int64_t want = (a.total_tiles + groups - 1) / groups;
+    int64_t grid = std::min<int64_t>(want, (int64_t)h->num_sms * per_sm);
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
   } else if (pl->N == 8192 && !pl->force_generic) {
     const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
