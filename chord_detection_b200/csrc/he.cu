@@ -38,6 +38,8 @@ struct HePlan {
   int max_width;   // widest probe window
   bool force_generic;
   float* d_win = nullptr;      // [N]
+  float4* d_winlane = nullptr; // [32] per-lane window constants of the frame-2048 kernel
+  float win_a0 = 1.0f;
   float2* d_tw32 = nullptr;    // [32*32]: W_1024^(t*k1) at [k1*32+t]   (N == 2048)
   float2* d_tw8a = nullptr;    // [16*256]: W_4096^(t*k1) at [k1*256+t]  (N == 8192)
   float2* d_tw8b = nullptr;    // [16*16]:  W_256^(n3*k2) at [k2*16+n3]
@@ -182,6 +184,7 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
       }
   }
   std::vector<float2> tw8a, tw8b;
+  int rc;
   if (N == 8192) {
     tw8a.resize(16 * 256);
     tw8b.resize(16 * 16);
@@ -196,7 +199,19 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
         tw8b[k2 * 16 + n3] = make_float2((float)std::cos(a), (float)-std::sin(a));
       }
   }
-  int rc;
+  {
+    double a0 = 1.0, a1 = 0.0;
+    if (key.window_kind == CDB_WINDOW_HAMMING) a0 = 0.54, a1 = 0.46;
+    if (key.window_kind == CDB_WINDOW_HANN) a0 = 0.5, a1 = 0.5;
+    std::vector<float4> wl(32);
+    for (int l = 0; l < 32; ++l) {
+      const double b0 = 2.0 * kPi * (2 * l) / (double)(N - 1), b1 = 2.0 * kPi * (2 * l + 1) / (double)(N - 1);
+      wl[l] = make_float4((float)(-a1 * std::cos(b0)), (float)(-a1 * std::cos(b1)),
+                          (float)(a1 * std::sin(b0)), (float)(a1 * std::sin(b1)));
+    }
+    pl->win_a0 = (float)a0;
+    if ((rc = cdb_upload(h, wl, &pl->d_winlane))) return rc;
+  }
   if ((rc = cdb_upload(h, tw8a, &pl->d_tw8a))) return rc;
   if ((rc = cdb_upload(h, tw8b, &pl->d_tw8b))) return rc;
   if ((rc = cdb_upload(h, win, &pl->d_win))) return rc;
@@ -217,7 +232,10 @@ struct HeArgs {
   int hop, N, M, log2M;
   int n_windows, wins_per_note, kmin, kmax, max_width;
   int tile_cap;  // floats reserved for the staged tile (fast path)
+  int pw_floats, pw_bytes;  // per-warp power-spectrum buffer of the warp-autonomous kernel
   const float* win;
+  const float4* winlane;  // [32] (-a1 cos B0, -a1 cos B1, a1 sin B0, a1 sin B1), B_c = 2 pi (2 lane + c)/(N-1)
+  float win_a0;           // window = a0 - a1 cos(2 pi n / (N-1))
   const float2* tw32;
   const float2* tw8a;  // [16][256] W_4096^(t*k1)   (N == 8192)
   const float2* tw8b;  // [16][16]  W_256^(n3*k2)
@@ -602,6 +620,276 @@ __global__ void __launch_bounds__(W * G * 32, (W * G >= 16) ? 1 : 2) he2048p_ker
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-autonomous variant of the frame-2048 kernel: every warp owns ONE frame at a time and
+// never synchronises with another warp.  The frame (8 KB) is copied by the warp's own 1-D bulk
+// async copy into the warp's transpose scratch: the scratch is free from the moment pass 2 has
+// pulled its rows into registers until the next pass 1, so the copy of the warp's NEXT frame
+// overlaps pass 2 and the epilogue, and the power spectrum / window values live in a small
+// separate per-warp buffer.  Frames are dealt round-robin over all warps of the grid, so the 4
+// warps that share 75 % of their samples run at the same time: HBM still sees each sample once
+// (L2 absorbs the 4x re-read), there are no barriers, no tile hand-off and no tail imbalance
+// beyond one frame.
+// ------------------------------------------------------------------------------------------
+// Cosine-sum window w[n] = a0 - a1 cos(2 pi n / 2047) evaluated on the fly for the packed pair
+// n = 64 n1 + 2 lane + {0,1} by angle addition: cos(A + B) with A = 2 pi 64 n1 / 2047 (compile-time
+// immediates below) and B = 2 pi (2 lane + c) / 2047 (per-lane constants from the host, already
+// scaled: cb = -a1 cos B, sb = a1 sin B).  Two FFMA2 per pair instead of a 64-bit shared-memory
+// load: the kernel is bound by shared-memory wavefronts, not by the FMA pipe.
+template <int n1>
+__device__ __forceinline__ c64 win_pair(c64 a0, c64 cb, c64 sb) {
+  constexpr float CA[32] = {
+      1.000000000e+00f,  9.807665627e-01f,  9.238061010e-01f,  8.313097059e-01f,
+      7.068354246e-01f,  5.551713937e-01f,  3.821516543e-01f,  1.944317353e-01f,
+      -7.673650086e-04f, -1.959369471e-01f, -3.835694473e-01f, -5.564472296e-01f,
+      -7.079202262e-01f, -8.321617441e-01f, -9.243926006e-01f, -9.810649629e-01f,
+      -9.999988223e-01f, -9.804658524e-01f, -9.232174255e-01f, -8.304557097e-01f,
+      -7.057489582e-01f, -5.538942501e-01f, -3.807329613e-01f, -1.929260654e-01f,
+      2.302093218e-03f,  1.974416975e-01f,  3.849863368e-01f,  5.577217549e-01f,
+      7.090033603e-01f,  8.330118223e-01f,  9.249769230e-01f,  9.813610523e-01f};
+  constexpr float SA[32] = {
+      0.000000000e+00f,  1.951843987e-01f,  3.828606635e-01f,  5.558094753e-01f,
+      7.073780337e-01f,  8.317359699e-01f,  9.240996229e-01f,  9.809160516e-01f,
+      9.999997056e-01f,  9.806164963e-01f,  9.235120352e-01f,  8.308829524e-01f,
+      7.062923994e-01f,  5.545329851e-01f,  3.814424201e-01f,  1.936789574e-01f,
+      -1.534729565e-03f, -1.966893802e-01f, -3.842780052e-01f, -5.570846563e-01f,
+      -7.084620018e-01f, -8.325870283e-01f, -9.246850341e-01f, -9.812132965e-01f,
+      -9.999973502e-01f, -9.803146312e-01f, -9.229222722e-01f, -8.300279779e-01f,
+      -7.052051015e-01f, -5.532551888e-01f, -3.800232782e-01f, -1.921730599e-01f};
+  return fma2(sb, bc(SA[n1]), fma2(cb, bc(CA[n1]), a0));
+}
+// windowed span-1 butterflies of pass 1 for the pairs (na, na+16), na = br5(2p)
+template <int P>
+struct WinStage1 {
+  static __device__ __forceinline__ void run(c64 (&v)[32], const c64* fr2, int lane, c64 a0, c64 cb,
+                                             c64 sb) {
+    constexpr int na = br5(2 * P), nb = na + 16;
+    const c64 xa = fr2[32 * na + lane], xb = fr2[32 * nb + lane];
+    const c64 mb = mul2(xb, win_pair<nb>(a0, cb, sb));
+    const c64 wa = win_pair<na>(a0, cb, sb);
+    v[2 * P] = fma2(xa, wa, mb);
+    v[2 * P + 1] = fma2(xa, wa, neg2(mb));
+    if constexpr (P + 1 < 16) WinStage1<P + 1>::run(v, fr2, lane, a0, cb, sb);
+  }
+};
+// twiddle W_1024^(lane k1) = Ta[k1 >> 2] * Tb[k1 & 3] (10 table loads instead of 31), then the
+// transposed store of v[k1] * twiddle
+template <int K1>
+struct TwStore {
+  static __device__ __forceinline__ void run(const c64 (&v)[32], const c64 (&ta)[8], const c64 (&tb)[4],
+                                             c64* scr64, int lane) {
+    constexpr int A = K1 >> 2, B = K1 & 3;
+    c64 t;
+    if constexpr (B == 0)
+      t = ta[A];
+    else if constexpr (A == 0)
+      t = tb[B];
+    else
+      t = cmul2(ta[A], tb[B]);
+    sts2(&scr64[K1 * kRow + lane], cmul2(v[K1], t));
+    if constexpr (K1 + 1 < 32) TwStore<K1 + 1>::run(v, ta, tb, scr64, lane);
+  }
+};
+
+template <int NW, int KHI>
+__global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* cta_acc = reinterpret_cast<double*>(smem);          // [12]
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + 128);  // [NW] (NW <= 16)
+  float* swin = reinterpret_cast<float*>(smem + 256);
+  float2* stw = reinterpret_cast<float2*>(swin + 2048);
+  float2* scr_all = stw + 1024;
+  unsigned char* pwb_all = reinterpret_cast<unsigned char*>(scr_all + NW * kScr);
+  HeWin* swins = reinterpret_cast<HeWin*>(pwb_all + (size_t)NW * a.pw_bytes);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2048; i += NW * 32) swin[i] = a.win[i];
+  for (int i = tid; i < 1024; i += NW * 32) stw[i] = a.tw32[i];
+  for (int i = tid; i < a.n_windows; i += NW * 32) swins[i] = a.wins[i];
+  if (tid < 12) cta_acc[tid] = 0.0;
+  if (tid < NW) mbar_init(mbar_all + tid, 1);
+  if (tid == 0) fence_mbar_init();
+  __syncthreads();
+
+  uint64_t* mbar = mbar_all + warp;
+  float2* scr = scr_all + warp * kScr;
+  c64* scr64 = reinterpret_cast<c64*>(scr);
+  float* inbuf = reinterpret_cast<float*>(scr);  // the staged frame aliases the transpose scratch
+  float* pw = reinterpret_cast<float*>(pwb_all + (size_t)warp * a.pw_bytes);  // 4|X|^2
+  double* wv = reinterpret_cast<double*>(pw + a.pw_floats);                   // [n_windows]
+  const c64* stw64 = reinterpret_cast<const c64*>(stw);
+  const float4 wl = a.winlane[lane];
+  const c64 win_a0 = bc(a.win_a0), win_cb = pk(wl.x, wl.y), win_sb = pk(wl.z, wl.w);
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+
+  const int64_t total_frames = a.n_clips * a.frames_per_clip;
+  const int64_t stride_frames = (int64_t)gridDim.x * NW;
+  auto locate = [&](int64_t gf, int64_t& clip, int64_t& f) {
+    if (a.n_clips == 1) {
+      clip = 0;
+      f = gf;
+    } else if (total_frames < (1ll << 32)) {
+      const unsigned c = (unsigned)gf / (unsigned)a.frames_per_clip;
+      clip = c;
+      f = (int64_t)((unsigned)gf - c * (unsigned)a.frames_per_clip);
+    } else {
+      clip = gf / a.frames_per_clip;
+      f = gf - clip * a.frames_per_clip;
+    }
+  };
+  // stage frame (clip, f) into this warp's scratch; true when it went through the bulk copy
+  auto issue_load = [&](int64_t clip, int64_t f) -> bool {
+    const int64_t s0 = f * a.hop;
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const bool tma_ok =
+        (s0 + 2048 <= a.clip_len) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (tma_ok) {
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, 8192u);
+        tma_load_1d(inbuf, src, 8192u, mbar);
+      }
+    } else {
+      const int64_t avail = a.clip_len - s0;  // may be <= 0
+      for (int i = lane; i < 2048; i += 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
+    }
+    return tma_ok;
+  };
+
+  // deal frames so that the warps of one CTA take every (gridDim)-th frame: neighbouring frames
+  // go to neighbouring CTAs at the same time and share their samples in L2
+  int64_t gf = (int64_t)warp * gridDim.x + blockIdx.x;
+  int64_t clip = 0, f = 0;
+  bool cur_tma = false;
+  uint32_t phase = 0;
+  if (gf < total_frames) {
+    locate(gf, clip, f);
+    cur_tma = issue_load(clip, f);
+  }
+  while (gf < total_frames) {
+    if (cur_tma) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    } else {
+      __syncwarp();
+    }
+    c64 v[32];
+    {
+      // pass 1: n = 32*n1 + lane.  Window (computed on the fly) fused into the span-1
+      // butterflies (pairs n1, n1+16): v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
+      const c64* fr2 = reinterpret_cast<const c64*>(inbuf);
+      WinStage1<0>::run(v, fr2, lane, win_a0, win_cb, win_sb);
+      // the 10 twiddle factors are fetched while the butterflies run
+      c64 ta[8], tb[4];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) tb[j] = lds2v(&stw64[j * 32 + lane]);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) ta[j] = lds2v(&stw64[(4 * j) * 32 + lane]);
+      fft32p_dit_tail<-1>(v);
+      __syncwarp();  // every lane has read the staged frame: the transposes may overwrite it
+      sts2(&scr64[lane], v[0]);
+      TwStore<1>::run(v, ta, tb, scr64, lane);
+    }
+    __syncwarp();
+    {
+      // pass 2: k1 = lane, n2 = 0..31 from this lane's transpose row (128-bit loads)
+      const ulonglong2* row = reinterpret_cast<const ulonglong2*>(scr + lane * kRow);
+      c64 in[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const ulonglong2 q = row[i];
+        in[2 * i] = q.x;
+        in[2 * i + 1] = q.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int na = br5(2 * p), nb = na + 16;
+        v[2 * p] = add2(in[na], in[nb]);
+        v[2 * p + 1] = sub2(in[na], in[nb]);
+      }
+    }
+    __syncwarp();  // all rows are in registers: the scratch is free for the next frame
+    const int64_t ngf = gf + stride_frames;
+    int64_t nclip = 0, nf = 0;
+    bool next_tma = false;
+    if (ngf < total_frames) {
+      locate(ngf, nclip, nf);
+      next_tma = issue_load(nclip, nf);  // overlaps the rest of pass 2 and the epilogue
+    }
+    fft32p_dit_tail<KHI>(v);
+    {
+      // ---- real-FFT split for the probed bins: X[k], k = lane + 32*k2; pw = 4|X|^2
+      const int src_lane = (32 - lane) & 31;
+      const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;
+      constexpr int K2END = (KHI < 0) ? 32 : KHI + 1;
+      const float2* csp = a.wsplit + lane;
+#pragma unroll
+      for (int k2 = 0; k2 < K2END; ++k2) {
+        if (KHI >= 0 || (k2 >= k2a && k2 <= k2b)) {
+          float qr, qi;
+          upk(v[31 - k2], qr, qi);
+          const float pr = __shfl_sync(0xffffffffu, qr, src_lane);
+          const float pi = __shfl_sync(0xffffffffu, qi, src_lane);
+          c64 pz = pk(pr, pi);
+          if (lane == 0) pz = v[(32 - k2) & 31];
+          const float2 cs = __ldg(csp + 32 * k2);
+          const c64 pc = conj2(pz);
+          const c64 e = add2(v[k2], pc), d = sub2(v[k2], pc);
+          const c64 x2 = fma2(bc(-cs.y), d, fma2(bc(cs.x), mul_mi(d), e));
+          float xr, xi;
+          upk(x2, xr, xi);
+          pw[lane + 32 * k2] = fmaf(xr, xr, xi * xi);
+        }
+      }
+      if (KHI < 0 && a.kmax == 1024 && lane == 0) {
+        float zr, zi;
+        upk(v[0], zr, zi);
+        const float xn = 2.0f * (zr - zi);
+        pw[1024] = xn * xn;
+      }
+      __syncwarp();
+      for (int wi = lane; wi < a.n_windows; wi += 32) {
+        const HeWin hw = swins[wi];
+        const float* p0 = pw + hw.k0;
+        const int last = hw.k1 - 1 - hw.k0;
+        float m = p0[0];
+        for (int j0 = 0; j0 < a.max_width; j0 += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m = fmaxf(m, p0[min(j0 + j, last)]);
+        }
+        wv[wi] = (double)sqrt_approx(sqrt_approx(0.25f * m)) * hw.weight;
+      }
+      __syncwarp();
+      if (lane < 12) {
+        double sm = 0.0;
+        for (int j = 0; j < a.wins_per_note; ++j) sm += wv[lane * a.wins_per_note + j];
+        if (a.clips) {
+          if (clip != my_clip) {
+            if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+            my_clip = clip;
+            acc_clip = 0.0;
+          }
+          acc_clip += sm;
+        }
+        acc_total += sm;
+        if (a.frames) a.frames[gf * 12 + lane] = (float)sm;
+      }
+      __syncwarp();
+    }
+    gf = ngf;
+    clip = nclip;
+    f = nf;
+    cur_tma = next_tma;
+  }
+  if (lane < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
+    if (a.total) atomicAdd(&cta_acc[lane], acc_total);
+  }
+  __syncthreads();
+  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
+}
+
+// ------------------------------------------------------------------------------------------
 // frame_size 8192 (the reference default, harmonic_energy.py:15): one CTA of 256 threads per
 // frame.  8192-pt real FFT = 4096-pt complex FFT = radix-16 x radix-16 x radix-16, every 16-pt
 // DFT in registers, two shared-memory exchanges.  n = 256 n1 + 16 n2 + n3, k = k1 + 16 k2 + 256 k3.
@@ -882,6 +1170,8 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.kmax = pl->kmax;
   a.max_width = pl->max_width;
   a.win = pl->d_win;
+  a.winlane = pl->d_winlane;
+  a.win_a0 = pl->win_a0;
   a.tw32 = pl->d_tw32;
   a.tw8a = pl->d_tw8a;
   a.tw8b = pl->d_tw8b;
@@ -893,11 +1183,27 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.frames = d_chroma_frames;
   a.tiles_per_clip = a.total_tiles = 0;
   a.tile_cap = 0;
+  a.pw_floats = a.pw_bytes = 0;
 
   if (pl->N == 2048 && !pl->force_generic && (pl->hop % 2) == 0) {
+    const bool pruned = (pl->kmax >> 5) <= 5;  // the metric shape probes bins 22..186
+    const char* ge = std::getenv("CDB_HE_GROUPS");  // 1 / 4: tile kernel (A/B); default warp-autonomous
+    if (!ge) {
+      // warp-autonomous kernel: 16 warps per SM (12 when the full spectrum is probed: the
+      // per-warp power-spectrum buffer is 4 KB instead of 768 B)
+      const int nw = pruned ? 16 : 12;
+      a.pw_floats = pruned ? 192 : 1028;
+      a.pw_bytes = (a.pw_floats * 4 + pl->n_windows * 8 + 15) & ~15;
+      void (*kern)(const HeArgs) = pruned ? he2048w_kernel<16, 5> : he2048w_kernel<12, -1>;
+      const size_t smem = 256 + 2048 * 4 + 1024 * 8 + (size_t)nw * kScr * 8 +
+                          (size_t)nw * a.pw_bytes + (size_t)pl->n_windows * sizeof(HeWin);
+      CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int64_t total_frames = n_clips * fpc;
+      int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
+      kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
+    } else {
     // CTA shape: G groups of W warps.  Default 4 x 4 (one 512-thread CTA per SM: four tile
     // pipelines in different phases); CDB_HE_GROUPS=1 selects 1 x 8 with two CTAs per SM.
-    const char* ge = std::getenv("CDB_HE_GROUPS");
     int groups = (ge && ge[0] == '1') ? 1 : 4;
     auto smem_for = [&](int g, int w) {
       const size_t cap = (size_t)((((w - 1) * pl->hop + 2048) + 3) & ~3);
@@ -906,7 +1212,6 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
     };
     if (groups == 4 && smem_for(4, 4) > (size_t)h->smem_optin) groups = 1;  // large hops: big tiles
     const int W = (groups == 1) ? 8 : 4;
-    const bool pruned = (pl->kmax >> 5) <= 5;  // the metric shape probes bins 22..186
     void (*kern)(const HeArgs);
     if (groups == 1)
       kern = pruned ? he2048p_kernel<8, 1, 5> : he2048p_kernel<8, 1, -1>;
@@ -924,6 +1229,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
     const int64_t want = (a.total_tiles + groups - 1) / groups;
     int64_t grid = std::min<int64_t>(want, (int64_t)h->num_sms * per_sm);
     kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    }
   } else if (pl->N == 8192 && !pl->force_generic) {
     const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
