@@ -328,9 +328,12 @@ def main():
                             "overlapped with cdb_he_chroma on a compute stream -> 12 doubles D2H"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic(), "peak_source": peak_src,
-                         "kernel": "he2048_kernel<8>", "kernel_ms": kernel_ms,
+                         "kernel": "he2048w_kernel<16,5>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": nfr * ALG_BYTES_PER_FRAME,
-                         "binding_roof": "fp32 issue / shared memory, not HBM (29 flop/B, SURVEY.md 8d)",
+                         "binding_roof": "shared-memory wavefronts + FMA pipe, not HBM (29 flop/B, SURVEY.md "
+                                         "8d): ~333 wavefronts and ~570 packed FP32x2 instructions per frame "
+                                         "against 1 wavefront and 2 packed instructions per cycle per SM "
+                                         "(profiles/, DESIGN.md 3.1)",
                          "fp32_tflops": fps_kernel * ALG_FLOP_PER_FRAME / 1e12,
                          "fp32_frac_of_nominal": fps_kernel * ALG_FLOP_PER_FRAME / 1e12 / FP32_PEAK_TFLOPS},
         }

@@ -6,17 +6,18 @@
 // classes (:67) -> summed over frames (:69).  Everything is fused into one kernel: the only
 // HBM traffic is the fp32 samples (4*hop bytes per frame) and 12 doubles out.
 //
-// Two kernels:
-//   he2048_kernel  — frame_size 2048 (the BASELINE metric shape).  One warp per frame; a CTA
-//                    stages a tile of W consecutive frames ((W-1)*hop+2048 samples, overlap
-//                    shared) into shared memory with one 1-D bulk async copy (TMA engine,
-//                    mbarrier completion); 2048-pt real FFT = 1024-pt complex FFT done as
-//                    radix-32 x radix-32 entirely in registers with ONE shared-memory
-//                    transpose; split post-processing only for the probed bins; window maxima
-//                    and the 12 sums via shared memory + fp64 accumulators.
+// Three kernels:
+//   he2048w_kernel — frame_size 2048 (the BASELINE metric shape).  Warp-autonomous: one warp per
+//                    frame, the frame staged by the warp's own 1-D bulk async copy (TMA engine,
+//                    mbarrier completion) into the warp's transpose scratch; 2048-pt real FFT =
+//                    1024-pt complex FFT as radix-32 x radix-32 entirely in registers with packed
+//                    FP32x2 butterflies (FFMA2 / FADD2) and ONE shared-memory transpose; window
+//                    evaluated on the fly; pass 2 output-pruned; split post-processing only for
+//                    the probed bins; window maxima and the 12 sums via a small per-warp buffer
+//                    + fp64 accumulators.
+//   he8192_kernel  — frame_size 8192 (the reference default): one CTA per frame, radix-16^3.
 //   he_generic_kernel — any power-of-two frame_size in [64, 16384]; one CTA per frame,
-//                    shared-memory radix-2 FFT.  Correctness path for the other shapes
-//                    (reference default 8192).
+//                    shared-memory radix-2 FFT.  Correctness path for the other shapes.
 // No tensor cores: there is no dense contraction here (BASELINE.json north_star).
 #include <cmath>
 #include <cstdlib>
@@ -228,10 +229,8 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
 struct HeArgs {
   const float* x;
   int64_t n_clips, clip_len, clip_stride, frames_per_clip;
-  int64_t tiles_per_clip, total_tiles;  // fast path
   int hop, N, M, log2M;
   int n_windows, wins_per_note, kmin, kmax, max_width;
-  int tile_cap;  // floats reserved for the staged tile (fast path)
   int pw_floats, pw_bytes;  // per-warp power-spectrum buffer of the warp-autonomous kernel
   const float* win;
   const float4* winlane;  // [32] (-a1 cos B0, -a1 cos B1, a1 sin B0, a1 sin B1), B_c = 2 pi (2 lane + c)/(N-1)
@@ -391,237 +390,9 @@ __device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
   PLastStage<KHI, 0>::run(v);
 }
 
-// W warps (= W consecutive frames) form a GROUP that shares one staged tile, one mbarrier and one
-// named barrier; a CTA holds G independent groups (own tile buffers, shared window / twiddle
-// tables).  Groups drift apart in phase, so the shared-memory-heavy and the FMA-heavy parts of
-// different groups overlap on the SM.
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <int W, int G, int KHI>
-__global__ void __launch_bounds__(W * G * 32, (W * G >= 16) ? 1 : 2) he2048p_kernel(const HeArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int NT = W * G * 32;                           // threads per CTA
-  constexpr int GT = W * 32;                               // threads per group
-  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem);  // [G] (G <= 8)
-  double* cta_acc = reinterpret_cast<double*>(smem + 64);  // [12]
-  float* inbuf_all = reinterpret_cast<float*>(smem + 256);
-  float* swin = inbuf_all + G * a.tile_cap;
-  float2* stw = reinterpret_cast<float2*>(swin + 2048);
-  float2* scr_all = stw + 1024;
-  HeWin* swins = reinterpret_cast<HeWin*>(scr_all + W * G * kScr);
-
-  const int tid = threadIdx.x, lane = tid & 31, cwarp = tid >> 5;
-  const int grp = cwarp / W, warp = cwarp - grp * W, gtid = tid - grp * GT;
-  uint64_t* mbar = mbar_all + grp;
-  float* inbuf = inbuf_all + grp * a.tile_cap;
-  for (int i = tid; i < 2048; i += NT) swin[i] = a.win[i];
-  for (int i = tid; i < 1024; i += NT) stw[i] = a.tw32[i];
-  for (int i = tid; i < a.n_windows; i += NT) swins[i] = a.wins[i];
-  if (tid < 12) cta_acc[tid] = 0.0;
-  if (tid < G) mbar_init(mbar_all + tid, 1);
-  if (tid == 0) fence_mbar_init();
-  __syncthreads();
-
-  const int64_t n_groups = (int64_t)gridDim.x * G, my_group = (int64_t)blockIdx.x * G + grp;
-  const int64_t t_begin = (a.total_tiles * my_group) / n_groups;
-  const int64_t t_end = (a.total_tiles * (my_group + 1)) / n_groups;
-
-  // stage one tile (clip `clip`, first frame `f0`); returns true when it went through the
-  // bulk-async (TMA) path
-  auto issue_load = [&](int64_t clip, int64_t f0) -> bool {
-    const int64_t nf = min((int64_t)W, a.frames_per_clip - f0);
-    const int64_t s0 = f0 * a.hop;
-    const int need = (int)((nf - 1) * a.hop + 2048);
-    const float* src = a.x + clip * a.clip_stride + s0;
-    const bool full = (s0 + need <= a.clip_len);
-    const bool tma_ok =
-        full && ((need & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    if (tma_ok) {
-      if (gtid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(mbar, (uint32_t)need * 4u);
-        tma_load_1d(inbuf, src, (uint32_t)need * 4u, mbar);
-      }
-    } else {
-      const int64_t avail = a.clip_len - s0;  // may be <= 0
-      for (int i = gtid; i < need; i += GT) inbuf[i] = (i < avail) ? src[i] : 0.0f;
-    }
-    return tma_ok;
-  };
-
-  float2* scr = scr_all + cwarp * kScr;
-  c64* scr64 = reinterpret_cast<c64*>(scr);
-  float* pw = reinterpret_cast<float*>(scr);          // [M+1] 4|X|^2 (aliases the scratch)
-  double* wv = reinterpret_cast<double*>(scr) + 520;  // [n_windows] (byte offset 4160)
-  const c64* w2 = reinterpret_cast<const c64*>(swin);
-  const c64* stw64 = reinterpret_cast<const c64*>(stw);
-  double acc_total = 0.0, acc_clip = 0.0;
-  int64_t my_clip = -1;
-
-  bool cur_tma = false;
-  uint32_t phase = 0;
-  int64_t clip = t_begin / a.tiles_per_clip;
-  int64_t f0 = (t_begin - clip * a.tiles_per_clip) * W;
-  if (t_begin < t_end) cur_tma = issue_load(clip, f0);
-
-  for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    const int nf = (int)min((int64_t)W, a.frames_per_clip - f0);
-    int64_t nclip = clip, nf0 = f0 + W;  // coordinates of the next tile
-    if (nf0 >= a.frames_per_clip) {
-      nclip = clip + 1;
-      nf0 = 0;
-    }
-    if (cur_tma) {
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-    } else {
-      group_sync(1 + grp, GT);
-    }
-    const bool active = warp < nf;
-    if (active) {
-      // pass 1: n = 32*n1 + lane.  Window fused into the span-1 butterflies (pairs n1, n1+16):
-      // v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
-      c64 v[32];
-      const c64* fr2 = reinterpret_cast<const c64*>(inbuf + warp * a.hop);  // hop is even
-#pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        const int na = br5(2 * p), nb = na + 16;
-        const c64 xa = fr2[32 * na + lane], wa = w2[32 * na + lane];
-        const c64 xb = fr2[32 * nb + lane], wb = w2[32 * nb + lane];
-        const c64 mb = mul2(xb, wb);
-        v[2 * p] = fma2(xa, wa, mb);
-        v[2 * p + 1] = fma2(xa, wa, neg2(mb));
-      }
-      fft32p_dit_tail<-1>(v);
-      // twiddle W_1024^(lane*k1) and transpose: thread k1 will read row k1.  The 31 table loads
-      // are software-pipelined in batches of 8, two batches ahead of their use (left to ptxas,
-      // every load sits right in front of its multiply and its latency is exposed 31 times).
-      {
-        c64 ta[8], tb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ta[j] = lds2v(&stw64[(1 + j) * 32 + lane]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tb[j] = lds2v(&stw64[(9 + j) * 32 + lane]);
-        sts2(&scr64[lane], v[0]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sts2(&scr64[(1 + j) * kRow + lane], cmul2(v[1 + j], ta[j]));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ta[j] = lds2v(&stw64[(17 + j) * 32 + lane]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sts2(&scr64[(9 + j) * kRow + lane], cmul2(v[9 + j], tb[j]));
-#pragma unroll
-        for (int j = 0; j < 7; ++j) tb[j] = lds2v(&stw64[(25 + j) * 32 + lane]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sts2(&scr64[(17 + j) * kRow + lane], cmul2(v[17 + j], ta[j]));
-#pragma unroll
-        for (int j = 0; j < 7; ++j) sts2(&scr64[(25 + j) * kRow + lane], cmul2(v[25 + j], tb[j]));
-      }
-    }
-    group_sync(1 + grp, GT);  // every warp of the group is done reading the staged tile
-    bool next_tma = false;
-    if (tile + 1 < t_end) next_tma = issue_load(nclip, nf0);  // overlaps pass 2 below
-
-    if (active) {
-      c64 v[32];
-      {
-        // pass 2: k1 = lane, n2 = 0..31 from this lane's transpose row (128-bit loads)
-        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(scr + lane * kRow);
-        c64 in[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const ulonglong2 q = row[i];
-          in[2 * i] = q.x;
-          in[2 * i + 1] = q.y;
-        }
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int na = br5(2 * p), nb = na + 16;
-          v[2 * p] = add2(in[na], in[nb]);
-          v[2 * p + 1] = sub2(in[na], in[nb]);
-        }
-      }
-      fft32p_dit_tail<KHI>(v);
-      // Z[lane + 32*k2] is in v[k2]
-      __syncwarp();  // scratch is re-used for the power spectrum below
-      // ---- real-FFT split, only for the probed bins: X[k], k = lane + 32*k2; pw = 4|X|^2
-      // (the pruned variant computes all KHI+1 rows: bins outside [kmin,kmax] are never read)
-      const int src_lane = (32 - lane) & 31;
-      const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;  // warp-uniform range of needed k2
-      constexpr int K2END = (KHI < 0) ? 32 : KHI + 1;
-      const float2* csp = a.wsplit + lane;
-#pragma unroll
-      for (int k2 = 0; k2 < K2END; ++k2) {
-        if (KHI >= 0 || (k2 >= k2a && k2 <= k2b)) {
-          float qr, qi;
-          upk(v[31 - k2], qr, qi);
-          const float pr = __shfl_sync(0xffffffffu, qr, src_lane);
-          const float pi = __shfl_sync(0xffffffffu, qi, src_lane);
-          c64 pz = pk(pr, pi);
-          if (lane == 0) pz = v[(32 - k2) & 31];  // partner of Z[32*k2] is Z[1024-32*k2]
-          const float2 cs = __ldg(csp + 32 * k2);
-          const c64 pc = conj2(pz);
-          const c64 e = add2(v[k2], pc), d = sub2(v[k2], pc);
-          // 2 X = e + c (di, -dr) - s (dr, di)
-          const c64 x2 = fma2(bc(-cs.y), d, fma2(bc(cs.x), mul_mi(d), e));
-          float xr, xi;
-          upk(x2, xr, xi);
-          pw[lane + 32 * k2] = fmaf(xr, xr, xi * xi);
-        }
-      }
-      if (KHI < 0 && a.kmax == 1024 && lane == 0) {  // Nyquist bin: X[N/2] = Re Z[0] - Im Z[0]
-        float zr, zi;
-        upk(v[0], zr, zi);
-        const float xn = 2.0f * (zr - zi);
-        pw[1024] = xn * xn;
-      }
-      __syncwarp();
-      // ---- window maxima (harmonic_energy.py:58-64); max of 4|X|^2, then one 4th root.
-      // Blocks of 8 unconditional loads with the index clamped to the window's last bin.
-      for (int wi = lane; wi < a.n_windows; wi += 32) {
-        const HeWin hw = swins[wi];
-        const float* p0 = pw + hw.k0;
-        const int last = hw.k1 - 1 - hw.k0;
-        float m = p0[0];
-        for (int j0 = 0; j0 < a.max_width; j0 += 8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) m = fmaxf(m, p0[min(j0 + j, last)]);
-        }
-        wv[wi] = (double)sqrt_approx(sqrt_approx(0.25f * m)) * hw.weight;
-      }
-      __syncwarp();
-      if (lane < 12) {
-        double s = 0.0;
-        for (int j = 0; j < a.wins_per_note; ++j) s += wv[lane * a.wins_per_note + j];
-        if (a.clips) {
-          if (clip != my_clip) {
-            if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
-            my_clip = clip;
-            acc_clip = 0.0;
-          }
-          acc_clip += s;
-        }
-        acc_total += s;
-        if (a.frames) a.frames[(clip * a.frames_per_clip + f0 + warp) * 12 + lane] = (float)s;
-      }
-      __syncwarp();
-    }
-    cur_tma = next_tma;
-    clip = nclip;
-    f0 = nf0;
-  }
-  if (lane < 12) {
-    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
-    if (a.total) atomicAdd(&cta_acc[lane], acc_total);
-  }
-  __syncthreads();
-  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
-}
-
 // ------------------------------------------------------------------------------------------
-// Warp-autonomous variant of the frame-2048 kernel: every warp owns ONE frame at a time and
-// never synchronises with another warp.  The frame (8 KB) is copied by the warp's own 1-D bulk
+// The frame-2048 kernel is warp-autonomous: every warp owns ONE frame at a time and never
+// synchronises with another warp.  The frame (8 KB) is copied by the warp's own 1-D bulk
 // async copy into the warp's transpose scratch: the scratch is free from the moment pass 2 has
 // pulled its rows into registers until the next pass 1, so the copy of the warp's NEXT frame
 // overlaps pass 2 and the epilogue, and the power spectrum / window values live in a small
@@ -694,15 +465,13 @@ template <int NW, int KHI>
 __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* cta_acc = reinterpret_cast<double*>(smem);          // [12]
-  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + 128);  // [NW] (NW <= 16)
-  float* swin = reinterpret_cast<float*>(smem + 256);
-  float2* stw = reinterpret_cast<float2*>(swin + 2048);
+  uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + 128);  // [NW] (NW <= 32)
+  float2* stw = reinterpret_cast<float2*>(smem + 384);
   float2* scr_all = stw + 1024;
   unsigned char* pwb_all = reinterpret_cast<unsigned char*>(scr_all + NW * kScr);
   HeWin* swins = reinterpret_cast<HeWin*>(pwb_all + (size_t)NW * a.pw_bytes);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2048; i += NW * 32) swin[i] = a.win[i];
   for (int i = tid; i < 1024; i += NW * 32) stw[i] = a.tw32[i];
   for (int i = tid; i < a.n_windows; i += NW * 32) swins[i] = a.wins[i];
   if (tid < 12) cta_acc[tid] = 0.0;
@@ -1181,55 +950,23 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.total = d_chroma_total;
   a.clips = d_chroma_clips;
   a.frames = d_chroma_frames;
-  a.tiles_per_clip = a.total_tiles = 0;
-  a.tile_cap = 0;
   a.pw_floats = a.pw_bytes = 0;
 
-  if (pl->N == 2048 && !pl->force_generic && (pl->hop % 2) == 0) {
-    const bool pruned = (pl->kmax >> 5) <= 5;  // the metric shape probes bins 22..186
-    const char* ge = std::getenv("CDB_HE_GROUPS");  // 1 / 4: tile kernel (A/B); default warp-autonomous
-    if (!ge) {
-      // warp-autonomous kernel: 16 warps per SM (12 when the full spectrum is probed: the
-      // per-warp power-spectrum buffer is 4 KB instead of 768 B)
-      const int nw = pruned ? 16 : 12;
-      a.pw_floats = pruned ? 192 : 1028;
-      a.pw_bytes = (a.pw_floats * 4 + pl->n_windows * 8 + 15) & ~15;
-      void (*kern)(const HeArgs) = pruned ? he2048w_kernel<16, 5> : he2048w_kernel<12, -1>;
-      const size_t smem = 256 + 2048 * 4 + 1024 * 8 + (size_t)nw * kScr * 8 +
-                          (size_t)nw * a.pw_bytes + (size_t)pl->n_windows * sizeof(HeWin);
-      CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int64_t total_frames = n_clips * fpc;
-      int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
-      kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
-    } else {
-    // CTA shape: G groups of W warps.  Default 4 x 4 (one 512-thread CTA per SM: four tile
-    // pipelines in different phases); CDB_HE_GROUPS=1 selects 1 x 8 with two CTAs per SM.
-    int groups = (ge && ge[0] == '1') ? 1 : 4;
-    auto smem_for = [&](int g, int w) {
-      const size_t cap = (size_t)((((w - 1) * pl->hop + 2048) + 3) & ~3);
-      return 256 + (size_t)g * cap * 4 + 2048 * 4 + 1024 * 8 + (size_t)w * g * kScr * 8 +
-             (size_t)pl->n_windows * sizeof(HeWin);
-    };
-    if (groups == 4 && smem_for(4, 4) > (size_t)h->smem_optin) groups = 1;  // large hops: big tiles
-    const int W = (groups == 1) ? 8 : 4;
-    void (*kern)(const HeArgs);
-    if (groups == 1)
-      kern = pruned ? he2048p_kernel<8, 1, 5> : he2048p_kernel<8, 1, -1>;
-    else
-      kern = pruned ? he2048p_kernel<4, 4, 5> : he2048p_kernel<4, 4, -1>;
-    a.tiles_per_clip = (fpc + W - 1) / W;
-    a.total_tiles = a.tiles_per_clip * n_clips;
-    a.tile_cap = (((W - 1) * pl->hop + 2048) + 3) & ~3;
-    const int threads = W * groups * 32;
-    const size_t smem = smem_for(groups, W);
+  if (pl->N == 2048 && !pl->force_generic) {
+    // 16 warps per SM (12 when the whole spectrum is probed: the per-warp power-spectrum buffer is
+    // then 4 KB instead of 768 B).  Pass 2 is pruned to k2 <= 5 when the probed bins allow it (the
+    // metric shape probes bins 22..186).
+    const bool pruned = (pl->kmax >> 5) <= 5;
+    const int nw = pruned ? 16 : 12;
+    a.pw_floats = pruned ? 192 : 1028;
+    a.pw_bytes = (a.pw_floats * 4 + pl->n_windows * 8 + 15) & ~15;
+    void (*kern)(const HeArgs) = pruned ? he2048w_kernel<16, 5> : he2048w_kernel<12, -1>;
+    const size_t smem = 384 + 1024 * 8 + (size_t)nw * kScr * 8 + (size_t)nw * a.pw_bytes +
+                        (size_t)pl->n_windows * sizeof(HeWin);
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "tile does not fit in shared memory");
-    const int64_t want = (a.total_tiles + groups - 1) / groups;
-    int64_t grid = std::min<int64_t>(want, (int64_t)h->num_sms * per_sm);
-    kern<<<(unsigned)grid, threads, smem, st>>>(a);
-    }
+    const int64_t total_frames = n_clips * fpc;
+    int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
+    kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
   } else if (pl->N == 8192 && !pl->force_generic) {
     const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

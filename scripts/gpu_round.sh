@@ -16,7 +16,7 @@ cat gpurun_out/${TAG}_fp32_issue.jsonl
 timeout 300 python scripts/microbench/h2d_bw.py > gpurun_out/${TAG}_h2d.json 2>&1; cat gpurun_out/${TAG}_h2d.json
 CDB_PROFILE_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:he2048 -s 3 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:he2048 -s 3 -c 1 \
   -o gpurun_out/${TAG}_he2048 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 900 python scripts/bench_methods.py > gpurun_out/${TAG}_methods.json 2> gpurun_out/${TAG}_methods.err
 echo "methods exit $?"; cat gpurun_out/${TAG}_methods.json; tail -3 gpurun_out/${TAG}_methods.err

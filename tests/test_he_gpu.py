@@ -88,7 +88,7 @@ def test_he_per_frame_matches_oracle(frame_size, hop):
 @pytest.mark.parametrize("frame_size,hop,fs", [(2048, 512, 44100), (8192, None, 22050),
                                                (8192, 2048, 22050), (8192, 1001, 44100)])
 def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
-    """The register-FFT kernels (he2048_kernel, he8192_kernel) against the generic radix-2 kernel."""
+    """The register-FFT kernels (he2048w_kernel, he8192_kernel) against the generic radix-2 kernel."""
     x, fs = cases.make_input(dict(fn="s_poly_long", seed=2, fs=fs, n=200 * 512 + 77))
     a = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
     monkeypatch.setenv("CDB_HE_FORCE_GENERIC", "1")
