@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libchordb200.so")
 
 CDB_FLAG_ACCUMULATE = 1
+CDB_FLAG_PCM16 = 2
 WINDOW_KINDS = {"hamming": 0, "hann": 1, "rect": 2}
 STRETCH_MODES = {"truncate": 0, "none": 1}
 ITERF0_MAX_CHANNELS = 128
@@ -57,7 +58,7 @@ EXPORTS = [
     "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
     "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
-    "cdb_host_find_peaks",
+    "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32",
 ]
 
 
@@ -97,6 +98,7 @@ def lib():
         L.cdb_prime_chroma.argtypes = [vp, C.POINTER(PrimeParams), vp, i64, i64, i64, vp, vp, vp,
                                        C.c_int, vp]
         L.cdb_pack_and_key.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.cdb_pcm16_to_mono_f32.argtypes = [vp, vp, i64, C.c_int, vp, vp]
         L.cdb_esacf_debug_stride.argtypes = [C.c_int]
         L.cdb_esacf_debug_stride.restype = i64
         L.cdb_host_gauss_fit.argtypes = [C.c_int, dbl, C.POINTER(dbl), C.POINTER(dbl),

@@ -227,7 +227,7 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
 
 // ------------------------------------------------------------------ device code
 struct HeArgs {
-  const float* x;
+  const void* x;  // float32 samples, or int16 PCM with CDB_FLAG_PCM16 (frame-2048 kernel only)
   int64_t n_clips, clip_len, clip_stride, frames_per_clip;
   int hop, N, M, log2M;
   int n_windows, wins_per_note, kmin, kmax, max_width;
@@ -428,18 +428,34 @@ __device__ __forceinline__ c64 win_pair(c64 a0, c64 cb, c64 sb) {
       -7.052051015e-01f, -5.532551888e-01f, -3.800232782e-01f, -1.921730599e-01f};
   return fma2(sb, bc(SA[n1]), fma2(cb, bc(CA[n1]), a0));
 }
+// One packed pair of samples (2m, 2m+1) of the staged frame.  PCM16: the pair is one 32-bit word
+// of two int16; (s + 32768) is spliced into the mantissa of 1.5 * 2^23 (two PRMTs) and the offset
+// removed by one FADD2, giving the integers s exactly; the 1/32768 of soundfile's PCM_16 -> float32
+// convention is folded into the window constants (a power of two: results are bit-identical to
+// feeding the float32 samples).
+template <bool PCM16>
+__device__ __forceinline__ c64 load_pair(const void* frame, int m) {
+  if constexpr (PCM16) {
+    const uint32_t t = reinterpret_cast<const uint32_t*>(frame)[m] ^ 0x80008000u;
+    const float lo = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7610));
+    const float hi = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7632));
+    return add2(pk(lo, hi), bc(-(12582912.0f + 32768.0f)));
+  } else {
+    return reinterpret_cast<const c64*>(frame)[m];
+  }
+}
 // windowed span-1 butterflies of pass 1 for the pairs (na, na+16), na = br5(2p)
-template <int P>
+template <int P, bool PCM16>
 struct WinStage1 {
-  static __device__ __forceinline__ void run(c64 (&v)[32], const c64* fr2, int lane, c64 a0, c64 cb,
+  static __device__ __forceinline__ void run(c64 (&v)[32], const void* frame, int lane, c64 a0, c64 cb,
                                              c64 sb) {
     constexpr int na = br5(2 * P), nb = na + 16;
-    const c64 xa = fr2[32 * na + lane], xb = fr2[32 * nb + lane];
+    const c64 xa = load_pair<PCM16>(frame, 32 * na + lane), xb = load_pair<PCM16>(frame, 32 * nb + lane);
     const c64 mb = mul2(xb, win_pair<nb>(a0, cb, sb));
     const c64 wa = win_pair<na>(a0, cb, sb);
     v[2 * P] = fma2(xa, wa, mb);
     v[2 * P + 1] = fma2(xa, wa, neg2(mb));
-    if constexpr (P + 1 < 16) WinStage1<P + 1>::run(v, fr2, lane, a0, cb, sb);
+    if constexpr (P + 1 < 16) WinStage1<P + 1, PCM16>::run(v, frame, lane, a0, cb, sb);
   }
 };
 // twiddle W_1024^(lane k1) = Ta[k1 >> 2] * Tb[k1 & 3] (10 table loads instead of 31), then the
@@ -461,7 +477,7 @@ struct TwStore {
   }
 };
 
-template <int NW, int KHI>
+template <int NW, int KHI, bool PCM16>
 __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   double* cta_acc = reinterpret_cast<double*>(smem);          // [12]
@@ -487,7 +503,9 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
   double* wv = reinterpret_cast<double*>(pw + a.pw_floats);                   // [n_windows]
   const c64* stw64 = reinterpret_cast<const c64*>(stw);
   const float4 wl = a.winlane[lane];
-  const c64 win_a0 = bc(a.win_a0), win_cb = pk(wl.x, wl.y), win_sb = pk(wl.z, wl.w);
+  constexpr float kIn = PCM16 ? 1.0f / 32768.0f : 1.0f;  // exact power-of-two scaling
+  const c64 win_a0 = bc(a.win_a0 * kIn), win_cb = pk(wl.x * kIn, wl.y * kIn),
+            win_sb = pk(wl.z * kIn, wl.w * kIn);
   double acc_total = 0.0, acc_clip = 0.0;
   int64_t my_clip = -1;
 
@@ -508,19 +526,29 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
   };
   // stage frame (clip, f) into this warp's scratch; true when it went through the bulk copy
   auto issue_load = [&](int64_t clip, int64_t f) -> bool {
+    constexpr uint32_t kBytes = PCM16 ? 4096u : 8192u;
     const int64_t s0 = f * a.hop;
-    const float* src = a.x + clip * a.clip_stride + s0;
+    const int64_t first = clip * a.clip_stride + s0;
+    const void* src = PCM16 ? static_cast<const void*>(reinterpret_cast<const int16_t*>(a.x) + first)
+                            : static_cast<const void*>(reinterpret_cast<const float*>(a.x) + first);
     const bool tma_ok =
         (s0 + 2048 <= a.clip_len) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (tma_ok) {
       if (lane == 0) {
         fence_proxy_async();
-        mbar_expect_tx(mbar, 8192u);
-        tma_load_1d(inbuf, src, 8192u, mbar);
+        mbar_expect_tx(mbar, kBytes);
+        tma_load_1d(inbuf, src, kBytes, mbar);
       }
     } else {
       const int64_t avail = a.clip_len - s0;  // may be <= 0
-      for (int i = lane; i < 2048; i += 32) inbuf[i] = (i < avail) ? src[i] : 0.0f;
+      if constexpr (PCM16) {
+        const int16_t* sp = reinterpret_cast<const int16_t*>(src);
+        int16_t* dp = reinterpret_cast<int16_t*>(inbuf);
+        for (int i = lane; i < 2048; i += 32) dp[i] = (i < avail) ? sp[i] : (int16_t)0;
+      } else {
+        const float* sp = reinterpret_cast<const float*>(src);
+        for (int i = lane; i < 2048; i += 32) inbuf[i] = (i < avail) ? sp[i] : 0.0f;
+      }
     }
     return tma_ok;
   };
@@ -546,8 +574,7 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
     {
       // pass 1: n = 32*n1 + lane.  Window (computed on the fly) fused into the span-1
       // butterflies (pairs n1, n1+16): v[2p] = x_a w_a + x_b w_b, v[2p+1] = x_a w_a - x_b w_b.
-      const c64* fr2 = reinterpret_cast<const c64*>(inbuf);
-      WinStage1<0>::run(v, fr2, lane, win_a0, win_cb, win_sb);
+      WinStage1<0, PCM16>::run(v, inbuf, lane, win_a0, win_cb, win_sb);
       // the 10 twiddle factors are fetched while the butterflies run
       c64 ta[8], tb[4];
 #pragma unroll
@@ -687,7 +714,7 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
 
   for (int64_t gf = f_begin; gf < f_end; ++gf) {
     const int64_t s0 = f * a.hop;
-    const float* src = a.x + clip * a.clip_stride + s0;
+    const float* src = reinterpret_cast<const float*>(a.x) + clip * a.clip_stride + s0;
     const int64_t avail = a.clip_len - s0;
     float2 v[16];
     // ---- pass A: thread t holds z[256 n1 + t]; window fused into the span-1 butterflies
@@ -831,7 +858,7 @@ __global__ void __launch_bounds__(kGenThreads) he_generic_kernel(const HeArgs a)
     const int64_t clip = gf / a.frames_per_clip;
     const int64_t f = gf - clip * a.frames_per_clip;
     const int64_t s0 = f * a.hop;
-    const float* src = a.x + clip * a.clip_stride + s0;
+    const float* src = reinterpret_cast<const float*>(a.x) + clip * a.clip_stride + s0;
     const int64_t avail = a.clip_len - s0;
     for (int m = tid; m < M; m += kGenThreads) {
       const float x0 = (2 * m < avail) ? src[2 * m] : 0.0f;
@@ -900,7 +927,7 @@ __global__ void __launch_bounds__(kGenThreads) he_generic_kernel(const HeArgs a)
 
 // ------------------------------------------------------------------ C-ABI entry
 
-extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float* d_x,
+extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* d_x,
                              int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                              double* d_chroma_total, double* d_chroma_clips,
                              float* d_chroma_frames, int flags, void* stream) {
@@ -952,6 +979,10 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
   a.frames = d_chroma_frames;
   a.pw_floats = a.pw_bytes = 0;
 
+  if ((flags & CDB_FLAG_PCM16) && (pl->N != 2048 || pl->force_generic))
+    return cdb_fail(h, CDB_E_UNSUPPORTED,
+                    "CDB_FLAG_PCM16 is fused only into the frame-2048 kernel: convert with "
+                    "cdb_pcm16_to_mono_f32 first");
   if (pl->N == 2048 && !pl->force_generic) {
     // 16 warps per SM (12 when the whole spectrum is probed: the per-warp power-spectrum buffer is
     // then 4 KB instead of 768 B).  Pass 2 is pruned to k2 <= 5 when the probed bins allow it (the
@@ -960,7 +991,10 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float*
     const int nw = pruned ? 16 : 12;
     a.pw_floats = pruned ? 192 : 1028;
     a.pw_bytes = (a.pw_floats * 4 + pl->n_windows * 8 + 15) & ~15;
-    void (*kern)(const HeArgs) = pruned ? he2048w_kernel<16, 5> : he2048w_kernel<12, -1>;
+    const bool pcm = (flags & CDB_FLAG_PCM16) != 0;
+    void (*kern)(const HeArgs) =
+        pruned ? (pcm ? he2048w_kernel<16, 5, true> : he2048w_kernel<16, 5, false>)
+               : (pcm ? he2048w_kernel<12, -1, true> : he2048w_kernel<12, -1, false>);
     const size_t smem = 384 + 1024 * 8 + (size_t)nw * kScr * 8 + (size_t)nw * a.pw_bytes +
                         (size_t)pl->n_windows * sizeof(HeWin);
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -21,11 +21,11 @@ class ChromaResult:
         self.total, self.clips, self.frames, self.extra = total, clips, frames, extra
 
 
-def _batch_view(x):
+def _batch_view(x, allow_pcm16=False):
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise RuntimeError("expected a CUDA tensor: chord_detection_b200 has no CPU path")
-    if x.dtype != torch.float32:
-        raise ValueError("samples must be float32")
+    if x.dtype != torch.float32 and not (allow_pcm16 and x.dtype == torch.int16):
+        raise ValueError("samples must be float32" + (" or int16 PCM" if allow_pcm16 else ""))
     if x.dim() == 1:
         x = x.contiguous()
         return x, 1, x.shape[0], x.shape[0]
@@ -35,6 +35,24 @@ def _batch_view(x):
         stride = x.stride(0) if x.shape[0] > 1 else x.shape[1]
         return x, x.shape[0], x.shape[1], max(stride, x.shape[1])
     raise ValueError("Only 1D (clip) or 2D (batch of clips) inputs are supported")
+
+
+def pcm16_to_mono(pcm):
+    """Decode step of librosa.load (multipitch.py:25) on the device: int16 PCM [n] or interleaved
+    [n, channels] -> float32 [n] = mean over channels of s/32768 (exact).  SURVEY.md 8f-2."""
+    if not isinstance(pcm, torch.Tensor) or not pcm.is_cuda or pcm.dtype != torch.int16:
+        raise ValueError("expected an int16 CUDA tensor")
+    if pcm.dim() not in (1, 2):
+        raise ValueError("expected [n] or [n, channels]")
+    pcm = pcm.contiguous()
+    n = pcm.shape[0]
+    ch = 1 if pcm.dim() == 1 else pcm.shape[1]
+    out = torch.empty(n, dtype=torch.float32, device=pcm.device)
+    h = nat.Handle.get(pcm.device.index)
+    with torch.cuda.device(pcm.device):
+        rc = h.L.cdb_pcm16_to_mono_f32(h.ptr, _ptr(pcm), n, ch, _ptr(out), _stream_ptr(pcm))
+    h.check(rc, "cdb_pcm16_to_mono_f32")
+    return out
 
 
 def _stream_ptr(x):
@@ -50,8 +68,17 @@ def harmonic_energy(x, fs, frame_size=8192, num_harmonic=2, num_octave=2, num_bi
                     out_total=None, accumulate=False):
     """Harmonic-energy chromagram (reference harmonic_energy.py:31-73) -> ChromaResult.
 
-    hop=None reproduces the reference's non-overlapping frames."""
-    x, n_clips, clip_len, stride = _batch_view(x)
+    hop=None reproduces the reference's non-overlapping frames.  x may be int16
+    PCM (sample value s/32768): decoded inside the frame-2048 kernel, converted first otherwise."""
+    x, n_clips, clip_len, stride = _batch_view(x, allow_pcm16=True)
+    flags = nat.CDB_FLAG_ACCUMULATE if accumulate else 0
+    if x.dtype == torch.int16:
+        if int(frame_size) == 2048:
+            flags |= nat.CDB_FLAG_PCM16
+        else:
+            x = pcm16_to_mono(x.reshape(-1)).reshape(x.shape) if stride == clip_len else \
+                torch.stack([pcm16_to_mono(r) for r in x])
+            x, n_clips, clip_len, stride = _batch_view(x)
     h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
     hop_ = int(frame_size if hop is None else hop)
     p = nat.HeParams(float(fs), int(frame_size), hop_, nat.WINDOW_KINDS[window], int(num_harmonic),
@@ -62,8 +89,7 @@ def harmonic_energy(x, fs, frame_size=8192, num_harmonic=2, num_octave=2, num_bi
     frames = torch.empty((n_clips * fpc, 12), dtype=torch.float32, device=x.device) if per_frame else None
     with torch.cuda.device(x.device):
         rc = h.L.cdb_he_chroma(h.ptr, C.byref(p), _ptr(x), n_clips, clip_len, stride, _ptr(total),
-                               _ptr(clips), _ptr(frames), nat.CDB_FLAG_ACCUMULATE if accumulate else 0,
-                               _stream_ptr(x))
+                               _ptr(clips), _ptr(frames), flags, _stream_ptr(x))
     h.check(rc, "cdb_he_chroma")
     return ChromaResult(total, clips, frames)
 
@@ -83,14 +109,16 @@ class HostPipeline:
     read back to the host once.  This is the `e2e` path of bench.py.
     """
 
-    def __init__(self, device, fs, frame_size, hop=None, chunk_frames=16384, **he_kwargs):
+    def __init__(self, device, fs, frame_size, hop=None, chunk_frames=16384, dtype=torch.float32,
+                 **he_kwargs):
         self.device = torch.device(device)
         self.fs, self.frame_size = fs, int(frame_size)
         self.hop = int(frame_size if hop is None else hop)
         self.chunk_frames = int(chunk_frames)
         self.kw = he_kwargs
         self.chunk_samples = (self.chunk_frames - 1) * self.hop + self.frame_size
-        self.bufs = [torch.empty(self.chunk_samples, dtype=torch.float32, device=self.device)
+        self.dtype = dtype  # torch.float32, or torch.int16 for PCM16 on the wire (half the bytes)
+        self.bufs = [torch.empty(self.chunk_samples, dtype=dtype, device=self.device)
                      for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
@@ -101,7 +129,9 @@ class HostPipeline:
         self.h2d_bytes = 0
 
     def run(self, x_host):
-        """x_host: 1-D float32 CPU tensor (pinned for full PCIe speed) -> numpy [12] float64."""
+        """x_host: 1-D CPU tensor of self.dtype (pinned for full PCIe speed) -> numpy [12] float64."""
+        if x_host.dtype != self.dtype:
+            raise ValueError("HostPipeline was built for %s input" % self.dtype)
         n = x_host.shape[0]
         n_frames = nat.num_frames(n, self.frame_size, self.hop)
         self.h2d_bytes = 0
@@ -119,7 +149,7 @@ class HostPipeline:
                     self.copy_stream.wait_event(self.consumed[b])
                 buf[: s1 - s0].copy_(x_host[s0:s1], non_blocking=True)
                 self.copied[b].record(self.copy_stream)
-            self.h2d_bytes += (s1 - s0) * 4
+            self.h2d_bytes += (s1 - s0) * x_host.element_size()
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self.copied[b])
                 harmonic_energy(buf[: s1 - s0], self.fs, self.frame_size, hop=self.hop,

@@ -47,6 +47,7 @@ extern "C" {
 #define CDB_E_NOGPU (-4)       /* no CUDA device / wrong architecture */
 
 #define CDB_FLAG_ACCUMULATE 1 /* do not zero the outputs first */
+#define CDB_FLAG_PCM16 2      /* cdb_he_chroma, frame_size 2048: d_x is mono int16 PCM, sample value s/32768 */
 
 #define CDB_WINDOW_HAMMING 0 /* scipy.signal.hamming(N) symmetric (harmonic_energy.py:42) */
 #define CDB_WINDOW_HANN 1    /* symmetric Hann (north_star wording; not the reference) */
@@ -84,8 +85,9 @@ typedef struct {
  * or <0.  Needs no GPU (used by CPU tests of the host logic). */
 int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k1, double* weight);
 
-/* d_chroma_frames: [n_clips*frames_per_clip, 12] float32 or NULL */
-int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const float* d_x, int64_t n_clips,
+/* d_x: float32 samples; with CDB_FLAG_PCM16 (frame_size 2048 only) int16 PCM, decoded in the kernel
+ * exactly as s/32768.  d_chroma_frames: [n_clips*frames_per_clip, 12] float32 or NULL */
+int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* d_x, int64_t n_clips,
                   int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
                   double* d_chroma_clips, float* d_chroma_frames, int flags, void* stream);
 
@@ -176,6 +178,13 @@ int cdb_prime_window_sizes(const cdb_prime_params* p, int* sizes);
 int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x, int64_t n_clips,
                      int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
                      double* d_chroma_clips, double* d_chroma_cands, int flags, void* stream);
+
+/* ---------------- ingestion: the decode step of librosa.load (multipitch.py:25), SURVEY 8f-2 ---------------- */
+/* d_pcm: interleaved int16 [n_frames, channels] -> d_out[n_frames] float32 = mean over channels of
+ * s/32768 (soundfile PCM_16 -> float32, then librosa.to_mono); exact.  Halves the host->device
+ * bytes of a WAV payload.  Resampling stays on the host. */
+int cdb_pcm16_to_mono_f32(cdb_handle* h, const int16_t* d_pcm, int64_t n_frames, int channels,
+                          float* d_out, void* stream);
 
 /* ---------------- batched result post-processing (chromagram.py:50-126), SURVEY 8f-1 ---------------- */
 /* d_chroma [n,12] double -> d_digits [n,12] uint8 (the 12-digit string, chromagram.py:50-74) and
