@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "f32x2.cuh"
+#include "fft_packed.cuh"
 
 struct HeWin {
   int k0, k1, note, pad;
@@ -246,9 +247,6 @@ struct HeArgs {
   float* frames;
 };
 
-__host__ __device__ constexpr int br5(int k) {
-  return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
-}
 
 // One radix-2 DIT butterfly in registers: (a, b) -> (a + w b, a - w b), w = W_32^m = C[m] - i S[m].
 // FMA-fused: 6 instructions with a twiddle (second output as 2a - first), 4 without.
@@ -314,9 +312,6 @@ __device__ __forceinline__ void fft16_dit_tail(float2 (&v)[16]) {
   StageG<16, 4, 0>::run(v);
   StageG<16, 8, 0>::run(v);
 }
-__host__ __device__ constexpr int br4(int k) {
-  return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3);
-}
 
 constexpr int kRow = 34;          // transpose row stride in float2 (16-byte aligned rows, conflict-free)
 constexpr int kScr = 32 * kRow;   // per-warp transpose scratch (float2)
@@ -329,68 +324,8 @@ constexpr int kScr = 32 * kRow;   // per-warp transpose scratch (float2)
 // scripts/microbench/fp32_issue.cu).  The two FFT passes are separate code instances so that
 // pass 2 can be output-pruned at compile time: KHI >= 0 means only Z[k1 + 32 k2] with k2 in
 // [0, KHI] and their mirror bins (k2 in [31-KHI, 31]) are consumed, and the dead half-butterflies
-// are never emitted.
-// ------------------------------------------------------------------------------------------
-template <int m, bool NEED_A, bool NEED_B>
-__device__ __forceinline__ void bflyp(c64& a, c64& b) {
-  constexpr float C[16] = {1.0f,           0.980785280f,  0.923879533f,  0.831469612f,
-                           0.707106781f,   0.555570233f,  0.382683432f,  0.195090322f,
-                           0.0f,           -0.195090322f, -0.382683432f, -0.555570233f,
-                           -0.707106781f,  -0.831469612f, -0.923879533f, -0.980785280f};
-  constexpr float S[16] = {0.0f,          0.195090322f, 0.382683432f, 0.555570233f,
-                           0.707106781f,  0.831469612f, 0.923879533f, 0.980785280f,
-                           1.0f,          0.980785280f, 0.923879533f, 0.831469612f,
-                           0.707106781f,  0.555570233f, 0.382683432f, 0.195090322f};
-  const c64 t = a;
-  if (m == 0) {
-    if (NEED_A) a = add2(t, b);
-    if (NEED_B) b = sub2(t, b);
-  } else if (m == 8) {  // w = -i
-    const c64 r = mul_mi(b);
-    if (NEED_A) a = add2(t, r);
-    if (NEED_B) b = sub2(t, r);
-  } else if (NEED_A) {  // w b = C b + S (-i b)
-    const c64 o = fma2(bc(S[m]), mul_mi(b), fma2(bc(C[m]), b, t));
-    a = o;
-    if (NEED_B) b = fma2(bc(2.0f), t, neg2(o));
-  } else if (NEED_B) {
-    b = fma2(bc(-S[m]), mul_mi(b), fma2(bc(-C[m]), b, t));
-  }
-}
-
-template <int NP, int S_, int G, int J>
-struct PStageJ {
-  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
-    bflyp<J * (16 / S_), true, true>(v[G + J], v[G + J + S_]);
-    if constexpr (J + 1 < S_) PStageJ<NP, S_, G, J + 1>::run(v);
-  }
-};
-template <int NP, int S_, int G>
-struct PStageG {
-  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
-    PStageJ<NP, S_, G, 0>::run(v);
-    if constexpr (G + 2 * S_ < NP) PStageG<NP, S_, G + 2 * S_>::run(v);
-  }
-};
-// last (span-16) stage of the 32-point DFT, emitting only the outputs k2 in [0,KHI] u [31-KHI,31]
-template <int KHI, int J>
-struct PLastStage {
-  static __device__ __forceinline__ void run(c64 (&v)[32]) {
-    constexpr bool need_a = (KHI < 0) || (J <= KHI);
-    constexpr bool need_b = (KHI < 0) || (J + 16 >= 31 - KHI);
-    if constexpr (need_a || need_b) bflyp<J, need_a, need_b>(v[J], v[J + 16]);
-    if constexpr (J + 1 < 16) PLastStage<KHI, J + 1>::run(v);
-  }
-};
-template <int KHI>
-__device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
-  PStageG<32, 2, 0>::run(v);
-  PStageG<32, 4, 0>::run(v);
-  PStageG<32, 8, 0>::run(v);
-  PLastStage<KHI, 0>::run(v);
-}
-
-// ------------------------------------------------------------------------------------------
+// are never emitted.  (The butterflies themselves are in fft_packed.cuh.)
+//
 // The frame-2048 kernel is warp-autonomous: every warp owns ONE frame at a time and never
 // synchronises with another warp.  The frame (8 KB) is copied by the warp's own 1-D bulk
 // async copy into the warp's transpose scratch: the scratch is free from the moment pass 2 has
