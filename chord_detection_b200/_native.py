@@ -58,7 +58,7 @@ EXPORTS = [
     "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
     "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
-    "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32",
+    "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf",
 ]
 
 
@@ -105,6 +105,8 @@ def lib():
                                          C.POINTER(C.c_int)]
         L.cdb_host_find_peaks.argtypes = [C.POINTER(dbl), C.c_int, dbl, C.c_int,
                                           C.POINTER(C.c_int)]
+        L.cdb_host_esacf_acf.argtypes = [C.c_int, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(dbl),
+                                         C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
         _lib = L
         return _lib
 
@@ -186,6 +188,26 @@ def host_gauss_fit(x0, y):
     info = lib().cdb_host_gauss_fit(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
                                     C.byref(nfev))
     return info, [p[0], p[1], p[2]], nfev.value
+
+
+def host_esacf_acf(lo, hi, kexp=0.67, clip_pos=False, prefix=0):
+    """Host execution of the device FFT autocorrelation (test hook, no GPU).
+    lo, hi: [n_frames, N] float64 (n_frames 1 or 2) -> (enhanced [n_frames, L], raw [n_frames, L])"""
+    import numpy as np
+
+    lo = np.ascontiguousarray(np.atleast_2d(lo), dtype=np.float64)
+    hi = np.ascontiguousarray(np.atleast_2d(hi), dtype=np.float64)
+    nf, N = lo.shape
+    L = (N - 1) // 2
+    y = np.zeros((nf, L))
+    s = np.zeros((nf, L))
+    P = C.POINTER(C.c_double)
+    rc = lib().cdb_host_esacf_acf(N, float(kexp), int(bool(clip_pos)), int(prefix), nf,
+                                  lo.ctypes.data_as(P), hi.ctypes.data_as(P), y.ctypes.data_as(P),
+                                  s.ctypes.data_as(P))
+    if rc != 0:
+        raise ValueError("cdb_host_esacf_acf failed (%d)" % rc)
+    return y, s
 
 
 def host_find_peaks(y, thres, min_dist):

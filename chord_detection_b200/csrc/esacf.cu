@@ -3,25 +3,34 @@
 // esacf.py:93-134) for batches of frames.  All arithmetic is FP64 (B200 runs FP64 at 1/2 the
 // FP32 rate) because the output is decided by discrete peak picking.
 //
-// Three kernels per batch of B frames (workspace is per handle, grow-only):
+// Five kernels per batch of B frames (workspace is per handle, grow-only):
 //   esacf_filter_kernel : one thread per frame; warped-FIR whitening (12 cascaded first-order
 //                         all-passes + 13 taps, wfir.py:28-43) and the three Butterworth biquads
 //                         (esacf.py:47-51) as direct-form-II-transposed recurrences in the same
 //                         operation order as scipy.signal.lfilter (un-fused mul/add), zero state
 //                         per frame.  Output x_lo / x_hi, frame-minor so stores coalesce.
-//   esacf_acf_kernel    : one CTA per frame; |DFT_N(x_lo)|^k + |DFT_N(x_hi)|^k for the N-point
-//                         (N = 1023 / 2046, not a power of two, no padding: circular ACF,
-//                         esacf.py:98-105) via Goertzel recurrences, several bins per thread;
-//                         inverse real-even DFT for the first (N-1)/2 lags via Chebyshev
-//                         recurrences; clip + prefix-zero "enhancement" (esacf.py:108-129, see
-//                         SURVEY.md A.2).
-//   esacf_peaks_kernel  : one warp per frame; peakutils.indexes (peaks.cuh) by lane 0, one
-//                         Levenberg-Marquardt Gaussian fit per lane (lm_gauss.cuh), fs/tau ->
-//                         pitch class (librosa.hz_to_note), chroma += ESACF[peak] (esacf.py:65-71).
+//   esacf_acf_fft_kernel: one CTA per PAIR of frames; SACF = real(ifft(|fft(x_lo)|^k + |fft(x_hi)|^k))
+//                         for the N-point frame (N = 1023 / 2046: not a power of two, no padding,
+//                         circular ACF, esacf.py:98-105) as three Bluestein DFT_N per pair over a
+//                         register radix-16 FFT of 2048 / 4096 points in shared memory (acf_fft.cuh):
+//                         DFT(x_lo + i x_hi) per frame, Hermitian split, |.|^k, then ONE transform of
+//                         S_a + i S_b inverts both frames (S is real and even); clip + prefix-zero
+//                         "enhancement" (esacf.py:108-129) in its epilogue.
+//   esacf_acf_kernel    : the same by Goertzel / Chebyshev recurrences, O(N^2), one CTA per frame:
+//                         serves N <= 256 and N > 2048 (and CDB_ESACF_ACF=goertzel).
+//   esacf_pick_kernel   : one thread per frame; peakutils.indexes (peaks.cuh); every (frame, peak)
+//                         becomes a task of a batch-global list.
+//   esacf_fit_kernel    : persistent warps, one Levenberg-Marquardt Gaussian fit per lane
+//                         (lm_gauss.cuh), lanes phase-aligned in super-rounds.
+//   esacf_bin_kernel    : one thread per frame; fs/tau -> pitch class (librosa.hz_to_note),
+//                         chroma += ESACF[peak] (esacf.py:65-71).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 
+#include <complex>
+
+#include "acf_fft.cuh"
 #include "common.cuh"
 #include "lm_gauss.cuh"
 #include "peaks.cuh"
@@ -30,14 +39,65 @@ struct EsacfPlan {
   cdb_esacf_params p;
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // Bluestein tables of the FFT autocorrelation kernel (acf_fft.cuh), M = fft_r1 * 256
+  int fft_r1 = 0;
+  afft::cplx* d_tables = nullptr;  // chirp [N] | bhat [M] | tw [M]
 };
 
 void cdb_free_esacf_plans(cdb_handle* h) {
   for (auto& kv : h->esacf_plans) {
     if (kv.second->ws) cudaFree(kv.second->ws);
+    if (kv.second->d_tables) cudaFree(kv.second->d_tables);
     delete kv.second;
   }
   h->esacf_plans.clear();
+}
+
+// chirp [N] | chirp spectrum / M, digit-reversed [M] | FFT twiddles [M]; long double on the host
+static void build_acf_tables(int N, int R1, std::vector<afft::cplx>& out) {
+  typedef std::complex<long double> lc;
+  const int M = R1 * 256;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  out.assign((size_t)N + 2 * (size_t)M, afft::mk(0.0, 0.0));
+  std::vector<lc> b((size_t)M, lc(0.0L, 0.0L));
+  for (int n = 0; n < N; ++n) {
+    const long long e = ((long long)n * n) % (2LL * N);  // n^2 mod 2N keeps the angle exact
+    const long double ang = -pi * (long double)e / (long double)N;
+    out[n] = afft::mk((double)cosl(ang), (double)sinl(ang));
+    const lc cw(cosl(ang), -sinl(ang));  // conj chirp
+    b[n] = cw;
+    if (n) b[M - n] = cw;
+  }
+  // iterative radix-2 FFT of b (decimation in time)
+  for (int i = 1, j = 0; i < M; ++i) {
+    int bit = M >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(b[i], b[j]);
+  }
+  for (int len = 2; len <= M; len <<= 1) {
+    for (int i = 0; i < M; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const long double ang = -2.0L * pi * (long double)k / (long double)len;
+        const lc w(cosl(ang), sinl(ang));
+        const lc u = b[i + k], v = b[i + k + len / 2] * w;
+        b[i + k] = u + v;
+        b[i + k + len / 2] = u - v;
+      }
+  }
+  for (int k = 0; k < M; ++k) {
+    const lc v = b[k] / (long double)M;
+    out[(size_t)N + afft::digit_pos(k, R1)] = afft::mk((double)v.real(), (double)v.imag());
+    const long double ang = -2.0L * pi * (long double)k / (long double)M;
+    out[(size_t)N + M + k] = afft::mk((double)cosl(ang), (double)sinl(ang));
+  }
+}
+
+// smallest supported FFT size for the Bluestein convolution of an N-point DFT (0: none)
+static int acf_fft_r1(int N) {
+  if (2 * N - 1 <= 2048) return 8;
+  if (2 * N - 1 <= 4096) return 16;
+  return 0;
 }
 
 constexpr int kMaxN = 4096;      // ham_samples limit (shared-memory staging of one frame)
@@ -72,6 +132,7 @@ struct EsacfArgs {
   double* frames;  // [n_frames, 12]
   double* debug;
   int64_t debug_stride;
+  const afft::cplx* acf_tables;  // chirp [N] | bhat [M] | tw [M]
 };
 
 // scipy.signal.lfilter second-order section, direct form II transposed, un-fused (sigtools
@@ -204,6 +265,51 @@ __global__ void __launch_bounds__(kAcfThreads) esacf_acf_kernel(const EsacfArgs 
   }
 }
 
+// FFT autocorrelation: one CTA per PAIR of frames, R1*16 threads, three Bluestein DFTs per pair
+// (acf_fft.cuh).  ~3 x 2 FFT_M per pair instead of O(N^2) Goertzel recurrences per frame.
+struct AcfExecDev {
+  template <class F>
+  __host__ __device__ __forceinline__ void for_units(int n, F f) {
+#ifdef __CUDA_ARCH__
+    for (int u = threadIdx.x; u < n; u += blockDim.x) f(u);
+#endif
+  }
+  __host__ __device__ __forceinline__ void sync() {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+  }
+};
+template <int R1>
+__global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kernel(const EsacfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int M = R1 * 256;
+  afft::AcfCtx c;
+  c.N = a.N;
+  c.L = a.L;
+  c.B = a.B;
+  c.K = a.K;
+  c.fa = 2 * blockIdx.x;
+  c.fb = (c.fa + 1 < a.B) ? c.fa + 1 : -1;
+  c.lo = a.ws_lo;
+  c.hi = a.ws_hi;
+  c.chirp = a.acf_tables;
+  c.bhat = a.acf_tables + a.N;
+  c.tw = a.acf_tables + a.N + M;
+  c.buf = reinterpret_cast<afft::cplx*>(smem);
+  c.Sa = reinterpret_cast<double*>(c.buf + afft::padded_size(M));
+  c.Sb = c.Sa + a.K;
+  c.live = reinterpret_cast<int*>(c.Sb + a.K);
+  if (threadIdx.x < 2) c.live[threadIdx.x] = 0;  // (published by the barriers of the first DFT)
+  c.half_kexp = 0.5 * a.kexp;
+  c.clip_pos = a.clip_pos;
+  c.prefix = a.prefix;
+  c.y = a.ws_y;
+  c.s = a.ws_s;
+  AcfExecDev ex;
+  afft::acf_pair<R1>(ex, c);
+}
+
 // kFitLanes lanes of each warp run fits; fewer lanes shrink the per-warp shared-memory work area
 // (26.9 KB at 32 lanes) and allow more resident warps.  Measured flat (228-244 ms per 62 592 frames for
 // 4..32 lanes): the stage is bound by lanes of one warp sitting in different LM phases.
@@ -222,7 +328,8 @@ __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sg
 //                      pulls its next task from a global counter the moment its fit finishes.  Fits
 //                      take 30..800 evaluations (heavy tail): any static assignment, or a queue per
 //                      CTA, left ~5-8 of 32 lanes busy.  All lanes of a warp advance in lock-step
-//                      rounds (one residual evaluation = 21 exp per round).
+//                      super-rounds (lmg::super_round: Jacobian + QR for the lanes whose last step
+//                      was accepted, then lmpar + trial evaluation for every lane).
 //   esacf_bin_kernel   one thread per frame: pairs the surviving centres with the peak list BY
 //                      POSITION (failed fits are dropped: the latent misalignment of
 //                      esacf.py:65-69 is reproduced), fs/tau -> pitch class (librosa.hz_to_note),
@@ -289,17 +396,16 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
           }
           const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
           sm.init(lm_work, p0);
+          lmg::residuals<kFitLanes>(pr, sm.p, sm.wa4);
+          sm.begin(pr.m);
         }
       }
-      if (fitting) {
-        lmg::residuals<kFitLanes>(pr, sm.eval_point(), sm.wa4);
-        sm.advance(pr.m);
-        if (sm.phase == lmg::LmSM<kFitLanes>::DONE) {
-          const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
-                          isfinite(sm.p[2]);
-          a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
-          fitting = false;
-        }
+      lmg::super_round<kFitLanes>(pr, sm, fitting);
+      if (fitting && sm.phase == lmg::LmSM<kFitLanes>::DONE) {
+        const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
+                        isfinite(sm.p[2]);
+        a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
+        fitting = false;
       }
       if (!fitting) {  // fetch the next task
         task = atomicAdd(&a.ws_counters[1], 1);
@@ -382,6 +488,15 @@ __global__ void esacf_debug_copy_kernel(const EsacfArgs a) {
   }
 }
 
+// SACF + enhancement of one or two frames through the SAME code as esacf_acf_fft_kernel, units
+// executed sequentially on the host (CPU tests; no GPU).  lo/hi: [N] per frame; y/s: [L] per frame.
+struct AcfExecHost {
+  template <class F>
+  __host__ __device__ void for_units(int n, F f) {
+    for (int u = 0; u < n; ++u) f(u);
+  }
+  __host__ __device__ void sync() {}
+};
 extern "C" {
 
 // host-only test hooks (no GPU): the same code the kernels run, callable from CPU tests
@@ -412,6 +527,48 @@ int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int*
   const int n = pk::find_peaks(y, L, thres, min_dist, sgn.data(), cand.data(), order.data());
   for (int i = 0; i < n; ++i) peaks_out[i] = cand[i];
   return n;
+}
+
+int cdb_host_esacf_acf(int N, double kexp, int clip_pos, int prefix, int n_frames, const double* lo,
+                       const double* hi, double* y, double* s) {
+  const int R1 = acf_fft_r1(N);
+  if (N < 3 || !R1 || n_frames < 1 || n_frames > 2 || !lo || !hi || !y) return -1;
+  const int M = R1 * 256, L = (N - 1) / 2, K = N / 2 + 1;
+  std::vector<afft::cplx> tables;
+  build_acf_tables(N, R1, tables);
+  std::vector<double> wl((size_t)N * n_frames), wh((size_t)N * n_frames), S(2 * (size_t)K);
+  for (int f = 0; f < n_frames; ++f)
+    for (int n = 0; n < N; ++n) {
+      wl[(size_t)n * n_frames + f] = lo[(size_t)f * N + n];
+      wh[(size_t)n * n_frames + f] = hi[(size_t)f * N + n];
+    }
+  std::vector<afft::cplx> buf(afft::padded_size(M));
+  afft::AcfCtx c;
+  c.N = N;
+  c.L = L;
+  c.B = n_frames;
+  c.K = K;
+  c.fa = 0;
+  c.fb = n_frames > 1 ? 1 : -1;
+  c.lo = wl.data();
+  c.hi = wh.data();
+  c.chirp = tables.data();
+  c.bhat = tables.data() + N;
+  c.tw = tables.data() + N + M;
+  c.buf = buf.data();
+  c.Sa = S.data();
+  c.Sb = S.data() + K;
+  int live[2] = {0, 0};
+  c.live = live;
+  c.half_kexp = 0.5 * (kexp ? kexp : 0.67);
+  c.clip_pos = clip_pos;
+  c.prefix = prefix;
+  c.y = y;
+  c.s = s;
+  AcfExecHost ex;
+  if (R1 == 8) afft::acf_pair<8>(ex, c);
+  else afft::acf_pair<16>(ex, c);
+  return 0;
 }
 
 int64_t cdb_esacf_debug_stride(int ham_samples) {
@@ -451,6 +608,19 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     } else {
       pl = it->second;
     }
+  }
+  // FFT autocorrelation for frames of more than 256 samples that fit a 4096-point convolution;
+  // the Goertzel kernel serves tiny and > 2048-sample frames (CDB_ESACF_ACF=goertzel forces it)
+  int fft_r1 = N > 256 ? acf_fft_r1(N) : 0;
+  if (const char* am = std::getenv("CDB_ESACF_ACF"))
+    if (am[0] == 'g') fft_r1 = 0;
+  if (fft_r1 && !pl->d_tables) {
+    std::vector<afft::cplx> tables;
+    build_acf_tables(N, fft_r1, tables);
+    CDB_CUDA(h, cudaMalloc(&pl->d_tables, tables.size() * sizeof(afft::cplx)));
+    CDB_CUDA(h, cudaMemcpy(pl->d_tables, tables.data(), tables.size() * sizeof(afft::cplx),
+                           cudaMemcpyHostToDevice));
+    pl->fft_r1 = fft_r1;
   }
   const int64_t fpc = cdb_num_frames(clip_len, N, N);  // dsp/frame.py: non-overlapping
   const int64_t n_frames = fpc * n_clips;
@@ -504,6 +674,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   a.frames = d_chroma_frames;
   a.debug = d_debug;
   a.debug_stride = cdb_esacf_debug_stride(N);
+  a.acf_tables = pl->d_tables;
 
   const size_t acf_smem = (size_t)N * 16 + (size_t)a.K * 8;
   int bins = (a.K + kAcfThreads - 1) / kAcfThreads;
@@ -513,6 +684,13 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
+  const size_t acf_fft_smem =
+      (size_t)afft::padded_size(fft_r1 * 256) * sizeof(afft::cplx) + 2 * (size_t)a.K * sizeof(double) + 16;
+  void (*acf_fft_kernel)(const EsacfArgs) =
+      fft_r1 == 8 ? esacf_acf_fft_kernel<8> : esacf_acf_fft_kernel<16>;
+  if (fft_r1)
+    CDB_CUDA(h, cudaFuncSetAttribute(acf_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)acf_fft_smem));
   if (half > 2048) return cdb_fail(h, CDB_E_UNSUPPORTED, "SACF too long for the task encoding");
   int fit_lanes = 32;  // fit lanes per warp (4/8/16/32 measured within 7 %); CDB_ESACF_FIT_LANES overrides
   if (const char* fl = std::getenv("CDB_ESACF_FIT_LANES")) fit_lanes = std::atoi(fl);
@@ -548,7 +726,8 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.ws_counters = a.ws_np + B;
     CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 2 * sizeof(int), st));
     esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
-    acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
+    if (fft_r1) acf_fft_kernel<<<(B + 1) / 2, fft_r1 * 16, acf_fft_smem, st>>>(a);
+    else acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
     if (d_debug) {
       esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);
       h->launches += 1;

@@ -295,18 +295,25 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
 // work: (MMAX + MMAX + MMAX*NP) doubles with element stride ST (fvec | wa4 | fjac)
 constexpr int WORK_DOUBLES = MMAX * (2 + NP);
 
-// lmdif as an explicit state machine: the caller alternates
-//     residuals<ST>(pr, sm.eval_point(), sm.wa4);   sm.advance(m);
-// until sm.phase == DONE.  One residual evaluation per step, so that on the GPU 32 independent fits
-// (one per lane) advance in LOCK-STEP: every lane evaluates its 21 exponentials together, and lanes
-// that need the same follow-up (store a Jacobian column / QR / trust-region step) execute it
-// together.  (A plain per-lane lmdif loop lets lanes drift into different loop phases; the warp then
-// serialises them -- measured 4.4 active lanes of 32.)  Arithmetic and control flow are those of
-// MINPACK's lmdif: phases 1..3 = fdjac2 columns, QR block = qrfac + (Q^T)fvec + gnorm test,
-// step block = lmpar + trial point, phase 4 = the ratio / acceptance / convergence logic.
+// lmdif as an explicit state machine in PHASE-ALIGNED blocks.  A fit alternates between two states:
+//   JAC  : needs a new Jacobian (3 evaluations, one per perturbed parameter: fdjac2), then the QR
+//          block (qrfac + (Q^T)fvec + gnorm test), then falls into STEP;
+//   STEP : lmpar + trial point, ONE evaluation at the trial point, then the ratio / acceptance /
+//          convergence logic, which ends in JAC (step accepted), STEP (rejected: MINPACK's inner
+//          loop, a new lmpar with the shrunk region) or DONE.
+// The driver loop is therefore
+//     residuals(p) -> begin();
+//     while (!DONE) { if (JAC) { 3x (jac_setup, residuals, jac_col); qr_block(); }
+//                     if (STEP) { step_block(); residuals(wa2); trial_block(); } }
+// On the GPU 32 independent fits (one per lane) run this loop in lock-step "super-rounds": every
+// lane that is in JAC executes the Jacobian + QR block together, and EVERY active lane executes the
+// lmpar / trial block together.  (History: a plain per-lane lmdif loop ran 4.4 active lanes of 32;
+// a state machine stepping ONE evaluation per round kept the 4 phases of different lanes mixed, so
+// QR and lmpar -- 90 % of the instructions -- ran at ~25 % lane occupancy every round.)
+// Arithmetic and control flow are those of MINPACK's lmdif, evaluation for evaluation.
 template <int ST>
 struct LmSM {
-  enum { INIT = 0, JAC0 = 1, TRIAL = 4, DONE = 5 };
+  enum { JAC = 1, STEP = 2, DONE = 5 };
   double p[NP], diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
   int ipvt[NP];
   double par, delta, xnorm, fnorm, gnorm, pnorm, h, ptemp;
@@ -325,9 +332,19 @@ struct LmSM {
     iter = 1;
     nfev = 0;
     info = 0;
-    phase = INIT;
+    phase = JAC;
   }
-  LMG_HD const double* eval_point() const { return phase == TRIAL ? wa2 : p; }
+
+  // residuals at the start point are in wa4
+  LMG_HD void begin(int m) {
+    LMG_UNROLL1
+    for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
+    nfev = 1;
+    fnorm = enorm<ST>(fvec, m);
+    par = 0.0;
+    iter = 1;
+    phase = JAC;
+  }
 
   LMG_HD void jac_setup(int j) {  // fdjac2: perturb p[j]
     const double eps = 1.4901161193847656e-08;  // sqrt(max(epsfcn, epsmch)) = sqrt(2^-52) = 2^-26
@@ -337,160 +354,166 @@ struct LmSM {
     p[j] = ptemp + h;
   }
 
-  // to be called right after the residuals at eval_point() were written to wa4
-  LMG_HD void advance(int m) {
-    const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
-    const int maxfev = 200 * (NP + 1);
-    bool need_qr = false, need_step = false, need_jac = false;
-    if (phase == INIT) {
-      LMG_UNROLL1
-      for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
-      nfev = 1;
-      fnorm = enorm<ST>(fvec, m);
-      par = 0.0;
-      iter = 1;
-      need_jac = true;
-    } else if (phase < TRIAL) {
-      const int j = phase - JAC0;
-      p[j] = ptemp;
-      LMG_UNROLL1
-      for (int i = 0; i < m; ++i) LMG_A(i, j) = ddiv(wa4[i * ST] - fvec[i * ST], h);
-      if (j + 1 < NP) {
-        jac_setup(j + 1);
-        phase = phase + 1;
-      } else {
-        nfev += NP;
-        need_qr = true;
-      }
-    } else {  // TRIAL: residuals at wa2 are in wa4
-      ++nfev;
-      const double fnorm1 = enorm<ST>(wa4, m);
-      double actred = -1.0;
-      if (0.1 * fnorm1 < fnorm) {
-        const double q = ddiv(fnorm1, fnorm);
-        actred = 1.0 - q * q;
-      }
+  // residuals at the perturbed point are in wa4: column j of the forward-difference Jacobian
+  LMG_HD void jac_col(int m, int j) {
+    p[j] = ptemp;
+    LMG_UNROLL1
+    for (int i = 0; i < m; ++i) LMG_A(i, j) = ddiv(wa4[i * ST] - fvec[i * ST], h);
+  }
+
+  // after the NP columns: QR factorisation, (Q^T) fvec, scaled-gradient norm.  -> STEP or DONE
+  LMG_HD void qr_block(int m) {
+    const double gtol = 0.0, factor = 100.0;
+    nfev += NP;
+    qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
+    if (iter == 1) {
       LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
-        wa3[j] = 0.0;
-        const double temp = wa1[ipvt[j]];
-        LMG_UNROLL1
-        for (int i = 0; i <= j; ++i) wa3[i] += LMG_A(i, j) * temp;
+        diag[j] = wa2[j];
+        if (wa2[j] == 0.0) diag[j] = 1.0;
       }
-      const double temp1 = ddiv(enorm<1>(wa3, NP), fnorm);
-      const double temp2 = ddiv(dsqrt(par) * pnorm, fnorm);
-      const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
-      const double dirder = -(temp1 * temp1 + temp2 * temp2);
-      double ratio = 0.0;
-      if (prered != 0.0) ratio = ddiv(actred, prered);
-      if (ratio <= 0.25) {
-        double temp;
-        if (actred >= 0.0) temp = 0.5;
-        else temp = ddiv(0.5 * dirder, dirder + 0.5 * actred);
-        if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-        delta = temp * fmin(delta, pnorm / 0.1);
-        par = ddiv(par, temp);
-      } else if (par == 0.0 || ratio >= 0.75) {
-        delta = pnorm / 0.5;
-        par *= 0.5;
-      }
-      if (ratio >= 1e-4) {
-        LMG_UNROLL1
-        for (int j = 0; j < NP; ++j) {
-          p[j] = wa2[j];
-          wa2[j] = diag[j] * p[j];
-        }
-        LMG_UNROLL1
-        for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
-        xnorm = enorm<1>(wa2, NP);
-        fnorm = fnorm1;
-        ++iter;
-      }
-      if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
-      if (delta <= xtol * xnorm) info = 2;
-      if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
-      if (info == 0) {
-        if (nfev >= maxfev) info = 5;
-        if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) info = 6;
-        if (delta <= EPSMCH * xnorm) info = 7;
-        if (gnorm <= EPSMCH) info = 8;
-      }
-      if (info != 0) phase = DONE;
-      else if (ratio < 1e-4) need_step = true;  // inner loop: new lmpar with the shrunk region
-      else need_jac = true;                     // outer loop: new Jacobian
+      LMG_UNROLL1
+      for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
+      xnorm = enorm<1>(wa3, NP);
+      delta = factor * xnorm;
+      if (delta == 0.0) delta = factor;
     }
-    if (need_qr) {
-      qrfac<ST>(m, a, ipvt, wa1, wa2, wa3);
-      if (iter == 1) {
+    LMG_UNROLL1
+    for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      if (LMG_A(j, j) != 0.0) {
+        double sum = 0.0;
         LMG_UNROLL1
-        for (int j = 0; j < NP; ++j) {
-          diag[j] = wa2[j];
-          if (wa2[j] == 0.0) diag[j] = 1.0;
-        }
+        for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
+        const double temp = ddiv(-sum, LMG_A(j, j));
         LMG_UNROLL1
-        for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
-        xnorm = enorm<1>(wa3, NP);
-        delta = factor * xnorm;
-        if (delta == 0.0) delta = factor;
+        for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
       }
-      LMG_UNROLL1
-      for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
+      LMG_A(j, j) = wa1[j];
+      qtf[j] = wa4[j * ST];
+    }
+    gnorm = 0.0;
+    if (fnorm != 0.0) {
       LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
-        if (LMG_A(j, j) != 0.0) {
+        const int l = ipvt[j];
+        if (wa2[l] != 0.0) {
           double sum = 0.0;
           LMG_UNROLL1
-          for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
-          const double temp = ddiv(-sum, LMG_A(j, j));
-          LMG_UNROLL1
-          for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
+          for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * ddiv(qtf[i], fnorm);
+          gnorm = fmax(gnorm, fabs(ddiv(sum, wa2[l])));
         }
-        LMG_A(j, j) = wa1[j];
-        qtf[j] = wa4[j * ST];
-      }
-      gnorm = 0.0;
-      if (fnorm != 0.0) {
-        LMG_UNROLL1
-        for (int j = 0; j < NP; ++j) {
-          const int l = ipvt[j];
-          if (wa2[l] != 0.0) {
-            double sum = 0.0;
-            LMG_UNROLL1
-            for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * ddiv(qtf[i], fnorm);
-            gnorm = fmax(gnorm, fabs(ddiv(sum, wa2[l])));
-          }
-        }
-      }
-      if (gnorm <= gtol) {
-        info = 4;
-        phase = DONE;
-      } else {
-        LMG_UNROLL1
-        for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
-        need_step = true;
       }
     }
-    if (need_step) {
-      lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+    if (gnorm <= gtol) {
+      info = 4;
+      phase = DONE;
+    } else {
+      LMG_UNROLL1
+      for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
+      phase = STEP;
+    }
+  }
+
+  // trust-region step: leaves the trial point in wa2
+  LMG_HD void step_block() {
+    lmpar<ST>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      wa1[j] = -wa1[j];
+      wa2[j] = p[j] + wa1[j];
+      wa3[j] = diag[j] * wa1[j];
+    }
+    pnorm = enorm<1>(wa3, NP);
+    if (iter == 1) delta = fmin(delta, pnorm);
+  }
+
+  // residuals at the trial point wa2 are in wa4.  -> JAC (accepted), STEP (rejected) or DONE
+  LMG_HD void trial_block(int m) {
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8;
+    const int maxfev = 200 * (NP + 1);
+    ++nfev;
+    const double fnorm1 = enorm<ST>(wa4, m);
+    double actred = -1.0;
+    if (0.1 * fnorm1 < fnorm) {
+      const double q = ddiv(fnorm1, fnorm);
+      actred = 1.0 - q * q;
+    }
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      wa3[j] = 0.0;
+      const double temp = wa1[ipvt[j]];
+      LMG_UNROLL1
+      for (int i = 0; i <= j; ++i) wa3[i] += LMG_A(i, j) * temp;
+    }
+    const double temp1 = ddiv(enorm<1>(wa3, NP), fnorm);
+    const double temp2 = ddiv(dsqrt(par) * pnorm, fnorm);
+    const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
+    const double dirder = -(temp1 * temp1 + temp2 * temp2);
+    double ratio = 0.0;
+    if (prered != 0.0) ratio = ddiv(actred, prered);
+    if (ratio <= 0.25) {
+      double temp;
+      if (actred >= 0.0) temp = 0.5;
+      else temp = ddiv(0.5 * dirder, dirder + 0.5 * actred);
+      if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+      delta = temp * fmin(delta, pnorm / 0.1);
+      par = ddiv(par, temp);
+    } else if (par == 0.0 || ratio >= 0.75) {
+      delta = pnorm / 0.5;
+      par *= 0.5;
+    }
+    if (ratio >= 1e-4) {
       LMG_UNROLL1
       for (int j = 0; j < NP; ++j) {
-        wa1[j] = -wa1[j];
-        wa2[j] = p[j] + wa1[j];
-        wa3[j] = diag[j] * wa1[j];
+        p[j] = wa2[j];
+        wa2[j] = diag[j] * p[j];
       }
-      pnorm = enorm<1>(wa3, NP);
-      if (iter == 1) delta = fmin(delta, pnorm);
-      phase = TRIAL;
+      LMG_UNROLL1
+      for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
+      xnorm = enorm<1>(wa2, NP);
+      fnorm = fnorm1;
+      ++iter;
     }
-    if (need_jac) {
-      jac_setup(0);
-      phase = JAC0;
+    if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
+    if (delta <= xtol * xnorm) info = 2;
+    if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
+    if (info == 0) {
+      if (nfev >= maxfev) info = 5;
+      if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) info = 6;
+      if (delta <= EPSMCH * xnorm) info = 7;
+      if (gnorm <= EPSMCH) info = 8;
     }
+    if (info != 0) phase = DONE;
+    else if (ratio < 1e-4) phase = STEP;  // inner loop: new lmpar with the shrunk region
+    else phase = JAC;                     // outer loop: new Jacobian
   }
 };
 
+// One super-round of a fit that is not DONE: the Jacobian + QR block if the fit needs one, then the
+// trust-region step and its trial evaluation.  All lanes of a warp call this together.
+template <int ST>
+LMG_HD inline void super_round(const Problem& pr, LmSM<ST>& sm, bool active) {
+  if (active && sm.phase == LmSM<ST>::JAC) {
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      sm.jac_setup(j);
+      residuals<ST>(pr, sm.p, sm.wa4);
+      sm.jac_col(pr.m, j);
+    }
+    sm.qr_block(pr.m);
+  }
+  if (active && sm.phase == LmSM<ST>::STEP) {
+    sm.step_block();
+    residuals<ST>(pr, sm.wa2, sm.wa4);
+    sm.trial_block(pr.m);
+  }
+}
+
 // p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).  Single-fit driver
-// (host tests, simple callers); the GPU kernel steps 32 LmSM<32> instances in lock-step instead.
+// (host tests, simple callers); the GPU kernel runs 32 LmSM<32> instances through the same
+// super_round() in lock-step.
 LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
   if (pr.m < NP) {
     *nfev_out = 0;
@@ -499,10 +522,9 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
   double work[WORK_DOUBLES];
   LmSM<1> sm;
   sm.init(work, p);
-  while (sm.phase != LmSM<1>::DONE) {
-    residuals<1>(pr, sm.eval_point(), sm.wa4);
-    sm.advance(pr.m);
-  }
+  residuals<1>(pr, sm.p, sm.wa4);
+  sm.begin(pr.m);
+  while (sm.phase != LmSM<1>::DONE) super_round<1>(pr, sm, true);
   LMG_UNROLL1
   for (int j = 0; j < NP; ++j) p[j] = sm.p[j];
   *nfev_out = sm.nfev;

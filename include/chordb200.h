@@ -129,6 +129,12 @@ int64_t cdb_esacf_debug_stride(int ham_samples);
  * MINPACK info code (1..4 = converged). */
 int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev);
 int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out);
+/* cdb_host_esacf_acf: host execution (CPU tests, no GPU) of the device FFT autocorrelation
+ * (esacf.py:93-129: sum over the two channels of |DFT_N|^k, real inverse DFT, first (N-1)/2 lags,
+ * clip / prefix-zero enhancement) for n_frames = 1 or 2 frames of N in [3, 2048] samples.
+ * lo, hi: [n_frames][N]; y (enhanced), s (raw, may be NULL): [n_frames][(N-1)/2]. */
+int cdb_host_esacf_acf(int N, double kexp, int clip_pos, int prefix, int n_frames, const double* lo,
+                       const double* hi, double* y, double* s);
 
 /* ---------------- method 3: iterative F0 (iterative_f0.py, periodicity.py) ---------------- */
 #define CDB_ITERF0_MAX_CHANNELS 128

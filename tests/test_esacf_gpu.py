@@ -94,11 +94,15 @@ def test_esacf_golden_exact_fraction():
     assert frac >= 0.97
 
 
+@pytest.mark.parametrize("acf", ["fft", "goertzel"])
 @pytest.mark.parametrize("fs", [22050, 44100])
-def test_esacf_stages_match_oracle(fs):
-    """x_lo/x_hi (IIR chain), SACF, ESACF, peak indices, fitted centres and per-frame chroma."""
+def test_esacf_stages_match_oracle(fs, acf, monkeypatch):
+    """x_lo/x_hi (IIR chain), SACF, ESACF, peak indices, fitted centres and per-frame chroma, with
+    the FFT autocorrelation kernel (default for these frame lengths) and with the Goertzel kernel
+    that serves frames <= 256 or > 2048 samples."""
     from chord_detection_b200 import _native as nat
 
+    monkeypatch.setenv("CDB_ESACF_ACF", acf)
     x, _ = cases.make_input(dict(fn="s_poly", seed=77, fs=fs, n=int(fs * 0.5) + 123))
     N = int(fs * 46.4 / 1000)
     L = (N - 1) // 2
@@ -126,6 +130,31 @@ def test_esacf_stages_match_oracle(fs):
         got_c = r[o + 1 + 64:o + 1 + 64 + min(nfit, 64)]
         assert np.allclose(got_c, d["interp"][:64], rtol=5e-5, atol=0)
         _close(res.frames[f].cpu().numpy(), c)
+
+
+def test_esacf_silent_frames_stay_exactly_zero():
+    """A silent frame next to a live one (they share one inverse transform in the FFT
+    autocorrelation kernel) must give exactly zero chroma, as numpy does."""
+    fs = 22050
+    N = int(fs * 46.4 / 1000)
+    x, _ = cases.make_input(dict(fn="s_poly", seed=3, fs=fs, n=6 * N))
+    x = x.copy()
+    x[N:2 * N] = 0.0
+    x[4 * N:6 * N] = 0.0
+    res = _run(x, fs, per_frame=True)
+    fr = res.frames.cpu().numpy()
+    assert fr.shape[0] == 6
+    for f in (1, 4, 5):
+        assert np.all(fr[f] == 0.0), (f, fr[f])
+    for f in (0, 2, 3):
+        assert fr[f].sum() > 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, want, loose = rn.esacf(x, fs, sensitivity=True)
+    assert np.all(want[[1, 4, 5]] == 0.0)
+    for f in (0, 2, 3):
+        if loose[f] == 0.0:
+            _close(fr[f], want[f])
 
 
 def test_esacf_stretch_none_and_params():

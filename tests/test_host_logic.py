@@ -93,6 +93,40 @@ def test_host_peak_picker_matches_peakutils_semantics():
     assert nat.host_find_peaks(np.ones(1), 0.1, 10) == []
 
 
+def test_host_fft_autocorrelation_matches_numpy_sacf():
+    """The device FFT autocorrelation (Bluestein DFT_N over a radix-16 FFT, frame pairs sharing the
+    inverse transform), executed on the host, against the oracle's numpy sacf + enhancement."""
+    n = 0
+    for d in _esacf_frames(2):
+        N = d["x_lo"].shape[0]
+        L = (N - 1) // 2
+        y, s = nat.host_esacf_acf(d["x_lo"], d["x_hi"], clip_pos=True, prefix=int(np.round(L / 2.0)))
+        # |X|^0.67 magnifies the rounding floor of the near-empty bins of the low-passed channel
+        # (d/dx x^0.67 ~ x^-0.33), so two correct FFTs agree to ~1e-13 of the SACF peak, not 1e-16
+        scale = np.max(np.abs(d["sacf"]))
+        assert np.max(np.abs(s[0] - d["sacf"])) <= 1e-12 * scale
+        assert np.max(np.abs(y[0] - d["esacf"])) <= 1e-12 * scale
+        assert np.array_equal(y[0] == 0.0, d["esacf"] == 0.0)
+        n += 1
+    assert n > 20
+    rng = np.random.default_rng(5)
+    for N in (3, 4, 7, 257, 300, 1023, 1024, 1025, 1500, 2046, 2047, 2048):
+        lo = rng.standard_normal((2, N))
+        hi = np.clip(rng.standard_normal((2, N)), 0, None)
+        if N == 300:
+            lo[1] = 0.0
+            hi[1] = 0.0  # silence next to a live frame: exact zeros must stay exact
+        y, s = nat.host_esacf_acf(lo, hi)
+        for f in range(2):
+            want = rn.sacf([lo[f], hi[f]])
+            assert np.max(np.abs(s[f] - want)) <= 1e-13 * max(np.max(np.abs(want)), 1e-300), (N, f)
+            assert np.array_equal(y[f], s[f])  # no enhancement requested
+        y1, s1 = nat.host_esacf_acf(lo[:1], hi[:1])  # odd batch tail: a pair with one frame
+        assert np.max(np.abs(s1[0] - s[0])) <= 1e-13 * np.max(np.abs(s[0]))
+    with pytest.raises(ValueError):
+        nat.host_esacf_acf(np.zeros((1, 2049)), np.zeros((1, 2049)))
+
+
 def test_host_gaussian_fit_matches_scipy_curve_fit():
     n, worst = 0, 0.0
     for d in _esacf_frames():
