@@ -58,7 +58,8 @@ EXPORTS = [
     "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
     "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
-    "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf",
+    "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
+    "cdb_host_iterf0_spectrum8k",
 ]
 
 
@@ -103,8 +104,11 @@ def lib():
         L.cdb_esacf_debug_stride.restype = i64
         L.cdb_host_gauss_fit.argtypes = [C.c_int, dbl, C.POINTER(dbl), C.POINTER(dbl),
                                          C.POINTER(C.c_int)]
+        L.cdb_host_gauss_fit2.argtypes = [C.c_int, dbl, C.POINTER(dbl), C.POINTER(dbl),
+                                          C.POINTER(C.c_int), C.c_int]
         L.cdb_host_find_peaks.argtypes = [C.POINTER(dbl), C.c_int, dbl, C.c_int,
                                           C.POINTER(C.c_int)]
+        L.cdb_host_iterf0_spectrum8k.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(dbl)]
         L.cdb_host_esacf_acf.argtypes = [C.c_int, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(dbl),
                                          C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
         _lib = L
@@ -177,7 +181,7 @@ def num_frames(clip_len, frame_size, hop=0):
     return int(lib().cdb_num_frames(int(clip_len), int(frame_size), int(hop)))
 
 
-def host_gauss_fit(x0, y):
+def host_gauss_fit(x0, y, suspend_after=0):
     """Host build of the device Levenberg-Marquardt Gaussian fit (test hook, no GPU).
     -> (info, [ampl, centre, dev], nfev)"""
     import numpy as np
@@ -185,9 +189,25 @@ def host_gauss_fit(x0, y):
     y = np.ascontiguousarray(y, dtype=np.float64)
     p = (C.c_double * 3)()
     nfev = C.c_int(0)
-    info = lib().cdb_host_gauss_fit(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
-                                    C.byref(nfev))
+    info = lib().cdb_host_gauss_fit2(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
+                                     C.byref(nfev), int(suspend_after))
     return info, [p[0], p[1], p[2]], nfev.value
+
+
+def host_iterf0_spectrum8k(yc):
+    """Host execution of the frame-8192 summary-spectrum kernel (test hook, no GPU).
+    yc: [C, 8192] float32 filtered channels -> U[8193] float64."""
+    import numpy as np
+
+    yc = np.ascontiguousarray(np.atleast_2d(yc), dtype=np.float32)
+    if yc.shape[1] != 8192:
+        raise ValueError("frame size must be 8192")
+    U = np.zeros(8193)
+    rc = lib().cdb_host_iterf0_spectrum8k(yc.ctypes.data_as(C.POINTER(C.c_float)), yc.shape[0],
+                                          U.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise ValueError("cdb_host_iterf0_spectrum8k failed (%d)" % rc)
+    return U
 
 
 def host_esacf_acf(lo, hi, kexp=0.67, clip_pos=False, prefix=0):

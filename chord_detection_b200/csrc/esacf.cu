@@ -104,6 +104,17 @@ constexpr int kMaxN = 4096;      // ham_samples limit (shared-memory staging of 
 constexpr int kAcfThreads = 256;
 constexpr int kMaxPeaksDbg = 64;
 
+// A fit that is still running after kEvictRounds super-rounds (~4 evaluations each) is a runaway
+// (converging fits take < 200 evaluations; the others hit maxfev = 800 and are dropped, ~1 % of all
+// fits but 10 % of the evaluations and a 200-round dependency chain): pass 0 parks it, pass 1
+// runs all parked fits together, so the latency tail of the batch is ONE long chain rather than
+// a long chain that started when the queue was almost empty.
+constexpr int kEvictRounds = 48;
+struct LongFit {
+  int task, pad;
+  lmg::LmSaved st;
+};
+
 struct EsacfArgs {
   const float* x;
   int64_t clip_len, clip_stride, frames_per_clip;
@@ -125,7 +136,9 @@ struct EsacfArgs {
   double* ws_res;    // [B][L/2+2] fitted centre per peak (NaN = fit failed / dropped)
   int* ws_np;        // [B] peaks per frame
   int* ws_tasks;     // [B*(L/2+2)] (frame << 11) | peak
-  int* ws_counters;  // [0] tasks appended, [1] tasks handed out
+  int* ws_counters;  // [0] tasks appended, [1] handed out, [2] long fits parked, [3] handed out
+  struct LongFit* ws_long;  // [long_cap] fits suspended by pass 0, finished by pass 1
+  int long_cap;
   int skip_fit;      // debug (CDB_ESACF_SKIP_FIT=1): time the peak picking alone
   double* total;
   double* clips;
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
 }
 
 template <int kFitLanes>
-__global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs a) {
+__global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs a, const int pass) {
   constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * kFitLanes * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -362,23 +375,25 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
   const int half = L / 2 + 2;
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h;
-  const int total = a.ws_counters[0];
+  const int total = pass == 0 ? a.ws_counters[0] : min(a.ws_counters[2], a.long_cap);
+  int* next = &a.ws_counters[pass == 0 ? 1 : 3];
   if (lane >= kFitLanes) return;  // (no block-wide barrier below)
   constexpr unsigned kMask = kFitLanes == 32 ? 0xffffffffu : ((1u << (kFitLanes & 31)) - 1u);
   double* lm_work = reinterpret_cast<double*>(smem + kLmWarpBytes * warp) + lane;
   lmg::Problem pr;
   lmg::LmSM<kFitLanes> sm;
-  int task = atomicAdd(&a.ws_counters[1], 1);
-  int fb = 0, pi = 0;
+  int task = atomicAdd(next, 1);
+  int fb = 0, pi = 0, rounds = 0, tcode = 0;
   bool need_init = true;
   while (__any_sync(kMask, task < total)) {
     if (task < total) {
       bool fitting = true;
       if (need_init) {
         need_init = false;
-        const int t = a.ws_tasks[task];
-        fb = t >> 11;
-        pi = t & 2047;
+        rounds = 0;
+        tcode = pass == 0 ? a.ws_tasks[task] : a.ws_long[task].task;
+        fb = tcode >> 11;
+        pi = tcode & 2047;
         const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + per_frame * (size_t)fb + pad_l);
         const int idx = cand[pi];
         const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
@@ -394,21 +409,37 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
             pr.y[i] = __ldg(y + lo + i);
             ymax = fmax(ymax, pr.y[i]);
           }
-          const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
-          sm.init(lm_work, p0);
-          lmg::residuals<kFitLanes>(pr, sm.p, sm.wa4);
-          sm.begin(pr.m);
+          if (pass == 0) {
+            const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
+            sm.init(lm_work, p0);
+            lmg::residuals<kFitLanes>(pr, sm.p, sm.wa4);
+            sm.begin(pr.m);
+          } else {
+            const lmg::LmSaved& sv = a.ws_long[task].st;
+            sm.init(lm_work, sv.p);
+            lmg::residuals<kFitLanes>(pr, sm.p, sm.wa4);
+            sm.resume(pr.m, sv);
+          }
         }
       }
       lmg::super_round<kFitLanes>(pr, sm, fitting);
+      ++rounds;
       if (fitting && sm.phase == lmg::LmSM<kFitLanes>::DONE) {
         const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
                         isfinite(sm.p[2]);
         a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
         fitting = false;
+      } else if (fitting && pass == 0 && rounds >= kEvictRounds &&
+                 sm.phase == lmg::LmSM<kFitLanes>::JAC) {
+        const int slot = atomicAdd(&a.ws_counters[2], 1);
+        if (slot < a.long_cap) {  // (a full queue keeps the fit here)
+          a.ws_long[slot].task = tcode;
+          sm.save(a.ws_long[slot].st);
+          fitting = false;
+        }
       }
       if (!fitting) {  // fetch the next task
-        task = atomicAdd(&a.ws_counters[1], 1);
+        task = atomicAdd(next, 1);
         need_init = true;
       }
     }
@@ -500,7 +531,13 @@ struct AcfExecHost {
 extern "C" {
 
 // host-only test hooks (no GPU): the same code the kernels run, callable from CPU tests
+int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* nfev,
+                        int suspend_after);
 int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev) {
+  return cdb_host_gauss_fit2(m, x0, y, p_out, nfev, 0);
+}
+int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* nfev,
+                        int suspend_after) {
   if (m > lmg::MMAX || m < 0 || !y || !p_out) return -1;
   lmg::Problem pr;
   pr.m = m;
@@ -512,7 +549,7 @@ int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nf
   }
   double p[3] = {ymax, x0, 5.0};
   int nf = 0;
-  const int info = lmg::lmdif(pr, p, &nf);
+  const int info = lmg::lmdif(pr, p, &nf, suspend_after);
   p_out[0] = p[0];
   p_out[1] = p[1];
   p_out[2] = p[2];
@@ -636,8 +673,10 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   const int64_t Bmax = std::min<int64_t>(n_frames, 65536);
   const size_t half = (size_t)L / 2 + 2;
   const size_t scratch_pf = (peaks_scratch_bytes(L) + 15) & ~(size_t)15;
+  const size_t long_cap = (size_t)Bmax * 4 + 4096;  // ~0.1 long fits per frame measured
   const size_t need = (size_t)Bmax * ((2 * (size_t)N + 2 * (size_t)L + half) * sizeof(double) +
-                                      scratch_pf + half * sizeof(int) + sizeof(int)) + 64;
+                                      scratch_pf + half * sizeof(int) + sizeof(int)) + 64 +
+                      long_cap * sizeof(LongFit) + 16;
   if (pl->ws_bytes < need) {
     CDB_CUDA(h, cudaStreamSynchronize(st));
     if (pl->ws) cudaFree(pl->ws);
@@ -694,7 +733,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   if (half > 2048) return cdb_fail(h, CDB_E_UNSUPPORTED, "SACF too long for the task encoding");
   int fit_lanes = 32;  // fit lanes per warp (4/8/16/32 measured within 7 %); CDB_ESACF_FIT_LANES overrides
   if (const char* fl = std::getenv("CDB_ESACF_FIT_LANES")) fit_lanes = std::atoi(fl);
-  void (*fit_kernel)(const EsacfArgs) = fit_lanes >= 32   ? esacf_fit_kernel<32>
+  void (*fit_kernel)(const EsacfArgs, const int) = fit_lanes >= 32   ? esacf_fit_kernel<32>
                                         : fit_lanes >= 16 ? esacf_fit_kernel<16>
                                         : fit_lanes >= 8  ? esacf_fit_kernel<8>
                                                           : esacf_fit_kernel<4>;
@@ -724,7 +763,10 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.ws_tasks = reinterpret_cast<int*>(a.ws_scratch + scratch_pf * (size_t)B);
     a.ws_np = a.ws_tasks + half * (size_t)B;
     a.ws_counters = a.ws_np + B;
-    CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 2 * sizeof(int), st));
+    a.ws_long = reinterpret_cast<LongFit*>(
+        (reinterpret_cast<uintptr_t>(a.ws_counters + 4) + 15) & ~(uintptr_t)15);
+    a.long_cap = (int)long_cap;
+    CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 4 * sizeof(int), st));
     esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
     if (fft_r1) acf_fft_kernel<<<(B + 1) / 2, fft_r1 * 16, acf_fft_smem, st>>>(a);
     else acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
@@ -733,10 +775,10 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       h->launches += 1;
     }
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
-    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a);
+    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a, 0);
+    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a, 1);  // parked runaways
     esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
-    h->launches += 2;
-    h->launches += 3;
+    h->launches += 6;
     CDB_CUDA(h, cudaGetLastError());
   }
   return 0;

@@ -14,7 +14,7 @@ __host__ __device__ constexpr int br4(int k) {
 // One radix-2 DIT butterfly (a, b) -> (a + w b, a - w b), w = W_32^m = C[m] - i S[m]: 3 FFMA2 with
 // a twiddle (second output as 2a - first), 2 FADD2 without.  NEED_A / NEED_B prune dead outputs.
 template <int m, bool NEED_A, bool NEED_B>
-__device__ __forceinline__ void bflyp(c64& a, c64& b) {
+F32X2_HD void bflyp(c64& a, c64& b) {
   constexpr float C[16] = {1.0f,           0.980785280f,  0.923879533f,  0.831469612f,
                            0.707106781f,   0.555570233f,  0.382683432f,  0.195090322f,
                            0.0f,           -0.195090322f, -0.382683432f, -0.555570233f,
@@ -42,14 +42,14 @@ __device__ __forceinline__ void bflyp(c64& a, c64& b) {
 
 template <int NP, int S_, int G, int J>
 struct PStageJ {
-  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
+  static F32X2_HD void run(c64 (&v)[NP]) {
     bflyp<J * (16 / S_), true, true>(v[G + J], v[G + J + S_]);
     if constexpr (J + 1 < S_) PStageJ<NP, S_, G, J + 1>::run(v);
   }
 };
 template <int NP, int S_, int G>
 struct PStageG {
-  static __device__ __forceinline__ void run(c64 (&v)[NP]) {
+  static F32X2_HD void run(c64 (&v)[NP]) {
     PStageJ<NP, S_, G, 0>::run(v);
     if constexpr (G + 2 * S_ < NP) PStageG<NP, S_, G + 2 * S_>::run(v);
   }
@@ -57,7 +57,7 @@ struct PStageG {
 // last (span-16) stage of the 32-point DFT, emitting only the outputs k2 in [0,KHI] u [31-KHI,31]
 template <int KHI, int J>
 struct PLastStage {
-  static __device__ __forceinline__ void run(c64 (&v)[32]) {
+  static F32X2_HD void run(c64 (&v)[32]) {
     constexpr bool need_a = (KHI < 0) || (J <= KHI);
     constexpr bool need_b = (KHI < 0) || (J + 16 >= 31 - KHI);
     if constexpr (need_a || need_b) bflyp<J, need_a, need_b>(v[J], v[J + 16]);
@@ -65,7 +65,7 @@ struct PLastStage {
   }
 };
 template <int KHI>
-__device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
+F32X2_HD void fft32p_dit_tail(c64 (&v)[32]) {
   PStageG<32, 2, 0>::run(v);
   PStageG<32, 4, 0>::run(v);
   PStageG<32, 8, 0>::run(v);
@@ -73,7 +73,7 @@ __device__ __forceinline__ void fft32p_dit_tail(c64 (&v)[32]) {
 }
 
 // 16-point version (W_16^j = W_32^(2j): the same twiddle indexing works unchanged)
-__device__ __forceinline__ void fft16p_dit_tail(c64 (&v)[16]) {
+F32X2_HD void fft16p_dit_tail(c64 (&v)[16]) {
   PStageG<16, 2, 0>::run(v);
   PStageG<16, 4, 0>::run(v);
   PStageG<16, 8, 0>::run(v);

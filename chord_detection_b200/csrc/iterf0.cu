@@ -18,7 +18,10 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "iterf0_spec8k.cuh"
 
 struct IterF0Plan {
   cdb_iterf0_params p;
@@ -27,6 +30,8 @@ struct IterF0Plan {
   float2* d_tw = nullptr;      // [M/2] W_M^q
   float2* d_wsplit = nullptr;  // [M+1] (cos, sin)(2*pi*k/(2M))
   double* d_coef = nullptr;    // [channels][30]: res1 b,a | res2 b,a | lp b,a (each 3) ... see below
+  // frame_size 8192 (iterf0_spec8k.cuh): W_8192^(t k1) [32][256] | W_256^(n k2) [16][16] | split [8192]
+  float2* d_s8k = nullptr;
 };
 
 void cdb_free_iterf0_plans(cdb_handle* h) {
@@ -51,6 +56,7 @@ struct IterArgs {
   const float* win;
   const float2* tw;
   const float2* wsplit;
+  s8k::Tables s8;
   float* yc;    // [n_batch_clips][C][n_pad]
   double* Ut;   // [n_batch_clips*fpc][M+1]
   double* Ud;   // [grid][2M] cancellation scratch
@@ -186,6 +192,65 @@ __global__ void __launch_bounds__(kSpecThreads) iterf0_spectrum_kernel(const Ite
     const int k = tid + j * kSpecThreads;
     if (k <= M) out[k] = U[j];
   }
+}
+
+// ---- frame_size 8192, power 1: register radix-32/16/16 FFT (iterf0_spec8k.cuh) -----------------
+static void s8k_build_tables(std::vector<float2>& t) {
+  const double pi = 3.14159265358979323846;
+  t.assign(32 * 256 + 256 + 8192, make_float2(0.f, 0.f));
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int q = 0; q < 256; ++q) {
+      const double ang = -2.0 * pi * (double)((k1 * q) % 8192) / 8192.0;
+      t[k1 * 256 + q] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  for (int k2 = 0; k2 < 16; ++k2)
+    for (int n = 0; n < 16; ++n) {
+      const double ang = -2.0 * pi * (double)(k2 * n) / 256.0;
+      t[8192 + k2 * 16 + n] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  for (int k = 0; k < 8192; ++k) {
+    const int k1 = k & 31, k2 = (k >> 5) & 15, k3 = k >> 9;
+    const double th = pi * (double)k / 8192.0;
+    t[8192 + 256 + k1 * 256 + k2 * 16 + k3] = make_float2((float)-std::sin(th), (float)-std::cos(th));
+  }
+}
+static s8k::Tables s8k_tables(const float* win, const float2* t) {
+  s8k::Tables T;
+  T.win2 = reinterpret_cast<const c64*>(win);
+  T.tw1 = reinterpret_cast<const c64*>(t);
+  T.tw2 = reinterpret_cast<const c64*>(t + 8192);
+  T.csd = reinterpret_cast<const c64*>(t + 8192 + 256);
+  return T;
+}
+
+__global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(const IterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  c64* buf = reinterpret_cast<c64*>(smem);
+  const int t = threadIdx.x;
+  const int64_t gf = blockIdx.x;  // frame within this batch
+  const int64_t lc = gf / a.fpc, f = gf - lc * a.fpc;
+  float U[2][16], Unyq = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) U[h][j] = 0.f;
+  const float* src = a.yc + (int64_t)lc * a.C * a.n_pad + f * s8k::kM;
+  for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
+    s8k::p1(t, src, a.s8, buf);
+    __syncthreads();
+    s8k::p2(t, a.s8, buf);
+    __syncthreads();
+    s8k::p3(t, buf);
+    __syncthreads();
+    s8k::mag(t, buf, a.s8, U, Unyq);
+    __syncthreads();
+  }
+  double* out = a.Ut + gf * (int64_t)(s8k::kM + 1);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[s8k::bin_of(t, h, j)] = (double)U[h][j];
+  if (t == 0) out[s8k::kM] = (double)Unyq;
 }
 
 __constant__ double kHW9[9] = {0.0011244659258033, 0.11559343551383, 0.42817348241183,
@@ -398,6 +463,14 @@ static int iterf0_get_plan(cdb_handle* h, const cdb_iterf0_params* p, IterF0Plan
     }
   }
   int rc;
+  if (F == s8k::kM) {
+    std::vector<float2> t8;
+    s8k_build_tables(t8);
+    if ((rc = cdb_upload(h, t8, &pl->d_s8k))) {
+      delete pl;
+      return rc;
+    }
+  }
   if ((rc = cdb_upload(h, win, &pl->d_win)) || (rc = cdb_upload(h, tw, &pl->d_tw)) ||
       (rc = cdb_upload(h, ws, &pl->d_wsplit)) || (rc = cdb_upload(h, coef, &pl->d_coef))) {
     delete pl;
@@ -419,6 +492,38 @@ static int64_t ud_bytes(const cdb_iterf0_params* p, int num_sms) {
 }
 
 extern "C" {
+
+// Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
+// channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.
+int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U) {
+  if (!yc || !U || C < 1) return -1;
+  const int F = s8k::kM;
+  const double pi = 3.14159265358979323846;
+  std::vector<float> win(F);
+  for (int n = 0; n < F; ++n) win[n] = (float)(0.54 - 0.46 * std::cos(2.0 * pi * n / (double)(F - 1)));
+  std::vector<float2> t8;
+  s8k_build_tables(t8);
+  const s8k::Tables T = s8k_tables(win.data(), t8.data());
+  std::vector<c64> buf(s8k::kBufLen, 0);
+  struct Acc {
+    float U[2][16];
+    float nyq;
+  };
+  std::vector<Acc> acc(s8k::kThreads);
+  std::memset(acc.data(), 0, acc.size() * sizeof(Acc));
+  for (int ch = 0; ch < C; ++ch) {
+    const float* src = yc + (size_t)ch * F;
+    for (int t = 0; t < s8k::kThreads; ++t) s8k::p1(t, src, T, buf.data());
+    for (int t = 0; t < s8k::kThreads; ++t) s8k::p2(t, T, buf.data());
+    for (int t = 0; t < s8k::kThreads; ++t) s8k::p3(t, buf.data());
+    for (int t = 0; t < s8k::kThreads; ++t) s8k::mag(t, buf.data(), T, acc[t].U, acc[t].nyq);
+  }
+  for (int t = 0; t < s8k::kThreads; ++t)
+    for (int h = 0; h < 2; ++h)
+      for (int j = 0; j < 16; ++j) U[s8k::bin_of(t, h, j)] = (double)acc[t].U[h][j];
+  U[F] = (double)acc[0].nyq;
+  return 0;
+}
 
 int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params* p, int64_t n_clips, int64_t clip_len) {
   if (!p || n_clips < 0 || clip_len < 0) return -1;
@@ -479,6 +584,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   a.win = pl->d_win;
   a.tw = pl->d_tw;
   a.wsplit = pl->d_wsplit;
+  bool use_s8k = pl->d_s8k != nullptr && p->power == 1.0;
+  if (const char* sm = std::getenv("CDB_ITERF0_SPEC"))
+    if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
+  if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   a.fs = p->fs;
   a.K = (double)F / p->fs;  // periodicity.py:31
   a.tau_min = p->tau_min;
@@ -502,6 +611,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   const size_t spec_smem = (size_t)pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
+  const size_t s8k_smem = (size_t)s8k::kBufLen * sizeof(c64);
+  if (use_s8k)
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   const size_t per_smem = (size_t)2 * pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_smem));
@@ -515,7 +628,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     const int threads = nb * a.C;
     iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
     const int64_t nframes = (int64_t)nb * fpc;
-    iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
+    if (use_s8k)
+      iterf0_spectrum8k_kernel<<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    else
+      iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     const int pgrid = (int)std::min<int64_t>(nframes, pgrid_max);
     iterf0_periodicity_kernel<<<pgrid, 32 * p->M, per_smem, st>>>(a);
     h->launches += 3;

@@ -1,0 +1,168 @@
+// Summary-spectrum transform of the iterative-F0 method at the reference frame size (8192):
+// for every auditory channel, Hamming window, zero-pad x2, 16384-point real FFT, |X[k]| for
+// k = 0..8192 (/root/reference/chord_detection/iterative_f0.py:75-85), summed over channels.
+//
+// The 16384-point real FFT is one 8192-point complex FFT of z[m] = x[2m] + i x[2m+1] (the upper
+// half of z is the zero padding) + a Hermitian split.  8192 = 32 x 16 x 16: three passes of
+// register-resident DFTs in packed FP32x2 arithmetic (fft_packed.cuh) over ONE shared-memory
+// buffer, 256 threads:
+//   P1  thread t:      32-point DFT over n1 of z[256 n1 + t] (only n1 < 16 is non-zero: the first
+//                      butterfly stage is a copy), times W_8192^(t k1), stored at [k1][t]
+//   P2  2 units/thread (k1, n''): 16-point DFT over n2 of [k1][16 n2 + n''], times W_256^(n'' k2)
+//   P3  2 units/thread (k1, k2): 16-point DFT of 16 CONTIGUOUS elements -> Z[k1 + 32 k2 + 512 k3]
+//   MAG the Hermitian partner Z[8192 - k] of a unit's 16 outputs is one other contiguous row (in
+//       reverse order): |X[k]| accumulates in 32 + 1 per-thread registers over the channels.
+// Index i of the buffer lives at i + 2*(i >> 4): rows of 16 elements start 144 bytes apart, so the
+// 128-bit row reads of P3 / MAG and the strided 64-bit accesses of P1 / P2 are all conflict-free.
+// (The radix-2 kernel this replaces ran 13 barrier-separated passes with 44 % bank conflicts.)
+//
+// Every phase is a function of the thread index so that CPU tests can run the kernel thread by
+// thread (f32x2.cuh emulates the packed instructions on the host).
+#pragma once
+#include "f32x2.cuh"
+#include "fft_packed.cuh"
+
+namespace s8k {
+
+constexpr int kM = 8192;               // complex FFT size = frame size
+constexpr int kThreads = 256;
+constexpr int kBufLen = kM + kM / 8;   // padded
+F32X2_HD int pad(int i) { return i + ((i >> 4) << 1); }
+
+struct Tables {
+  const c64* win2;  // [4096]  (w[2m], w[2m+1])
+  const c64* tw1;   // [32][256]  W_8192^(t k1) at [k1][t]
+  const c64* tw2;   // [16][16]   W_256^(n'' k2) at [k2][n'']
+  const c64* csd;   // [8192]  -i conj(e^{i pi k / 8192}) = (-sin, -cos)(pi k / 8192) at the buffer
+                    //         position (k1*256 + k2*16 + k3) of bin k = k1 + 32 k2 + 512 k3
+};
+
+struct Pair {
+  c64 a, b;
+};
+F32X2_HD Pair ld_pair(const c64* p) {  // 128-bit load of two packed values
+#ifdef __CUDA_ARCH__
+  const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p);
+  return Pair{q.x, q.y};
+#else
+  return Pair{p[0], p[1]};
+#endif
+}
+F32X2_HD void st_pair(c64* p, c64 a, c64 b) {
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b);
+#else
+  p[0] = a;
+  p[1] = b;
+#endif
+}
+
+// 16-point DFT of in[0..15] (natural order) -> v[0..15] (natural order)
+F32X2_HD void dft16(const c64 (&in)[16], c64 (&v)[16]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int na = br4(2 * p), nb = na + 8;
+    v[2 * p] = add2(in[na], in[nb]);
+    v[2 * p + 1] = sub2(in[na], in[nb]);
+  }
+  fft16p_dit_tail(v);
+}
+
+// src: the 8192 filtered samples of this (frame, channel)
+F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
+  const c64* s2 = reinterpret_cast<const c64*>(src);  // (x[2m], x[2m+1]) pairs, 8-byte aligned
+  c64 v[32];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const int n1 = br5(2 * p);  // < 16; its butterfly partner n1 + 16 is zero padding
+    const int m = 256 * n1 + t;
+    const c64 x = mul2(s2[m], T.win2[m]);
+    v[2 * p] = x;
+    v[2 * p + 1] = x;
+  }
+  fft32p_dit_tail<-1>(v);
+  buf[pad(t)] = v[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
+}
+
+F32X2_HD void p2(int t, const Tables& T, c64* buf) {
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int u = t + h * kThreads;
+    const int npp = u & 15, base = (u >> 4) * 256 + npp;
+    c64 in[16], v[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) in[n2] = buf[pad(base + 16 * n2)];
+    dft16(in, v);
+    buf[pad(base)] = v[0];
+#pragma unroll
+    for (int k2 = 1; k2 < 16; ++k2) buf[pad(base + 16 * k2)] = cmul2(v[k2], T.tw2[k2 * 16 + npp]);
+  }
+}
+
+F32X2_HD void p3(int t, c64* buf) {
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    c64* row = buf + (t + h * kThreads) * 18;
+    c64 in[16], v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const Pair q = ld_pair(row + 2 * i);
+      in[2 * i] = q.a;
+      in[2 * i + 1] = q.b;
+    }
+    dft16(in, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_pair(row + 2 * i, v[2 * i], v[2 * i + 1]);
+  }
+}
+
+// U[h][k3] += |X[k]| for k = k1 + 32 k2 + 512 k3 of unit u = 16 k1 + k2 = t + 256 h; Unyq += |X[8192]|
+// (thread 0 only).  X[k] = (Z[k] + conj Z[M-k])/2 - i e^{-i pi k/M} (Z[k] - conj Z[M-k])/2.
+F32X2_HD void mag(int t, const c64* buf, const Tables& T, float (&U)[2][16], float& Unyq) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int u = t + h * kThreads;
+    const int k1 = u >> 4, k2 = u & 15;
+    // partner row: (32 - k1, 15 - k2) for k1 != 0, else (0, (16 - k2) & 15); elements reversed
+    const int pu = k1 ? ((32 - k1) << 4) + (15 - k2) : ((16 - k2) & 15);
+    const c64* row = buf + u * 18;
+    const c64* prow = buf + pu * 18;
+    const c64* cs = T.csd + u * 16;
+    c64 z[16], pz[16], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const Pair q = ld_pair(row + 2 * i), r = ld_pair(prow + 2 * i), c = ld_pair(cs + 2 * i);
+      z[2 * i] = q.a;
+      z[2 * i + 1] = q.b;
+      pz[2 * i] = r.a;
+      pz[2 * i + 1] = r.b;
+      w[2 * i] = c.a;
+      w[2 * i + 1] = c.b;
+    }
+#pragma unroll
+    for (int k3 = 0; k3 < 16; ++k3) {
+      // row 0 pairs k3 with (16 - k3) & 15 (bin 0 with itself); every other row with 15 - k3
+      const c64 pc = conj2(u == 0 ? pz[(16 - k3) & 15] : pz[15 - k3]);
+      const c64 s = add2(z[k3], pc), d = sub2(z[k3], pc);
+      const c64 x2 = add2(s, cmul2(d, w[k3]));  // 2 X[k]
+      float xr, xi;
+      upk(mul2(x2, x2), xr, xi);
+      U[h][k3] += 0.5f * sqrt_approx(xr + xi);
+    }
+    if (u == 0) {  // X[8192] = Re Z[0] - Im Z[0]
+      float zr, zi;
+      upk(z[0], zr, zi);
+      Unyq += fabsf(zr - zi);
+    }
+  }
+}
+
+// bin handled by accumulator U[h][k3] of thread t
+F32X2_HD int bin_of(int t, int h, int k3) {
+  const int u = t + h * kThreads;
+  return (u >> 4) + 32 * (u & 15) + 512 * k3;
+}
+
+}  // namespace s8k

@@ -105,8 +105,9 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
     double ajnorm = enorm<ST>(a + (j + j * MMAX) * ST, m - j);
     if (ajnorm != 0.0) {
       if (LMG_A(j, j) < 0.0) ajnorm = -ajnorm;
+      const double rnorm = ddiv(1.0, ajnorm);  // (MINPACK divides every element: <= 1 ulp apart)
       LMG_UNROLL1
-      for (int i = j; i < m; ++i) LMG_A(i, j) = ddiv(LMG_A(i, j), ajnorm);
+      for (int i = j; i < m; ++i) LMG_A(i, j) *= rnorm;
       LMG_A(j, j) += 1.0;
       LMG_UNROLL1
       for (int k = j + 1; k < NP; ++k) {
@@ -311,6 +312,13 @@ constexpr int WORK_DOUBLES = MMAX * (2 + NP);
 // a state machine stepping ONE evaluation per round kept the 4 phases of different lanes mixed, so
 // QR and lmpar -- 90 % of the instructions -- ran at ~25 % lane occupancy every round.)
 // Arithmetic and control flow are those of MINPACK's lmdif, evaluation for evaluation.
+// A fit can be suspended whenever it is in JAC (a step was just accepted, or right after begin):
+// everything lmdif carries across that point is in LmSaved; fvec is recomputed from p.
+struct LmSaved {
+  double p[NP], diag[NP], par, delta, xnorm, fnorm;
+  int iter, nfev;
+};
+
 template <int ST>
 struct LmSM {
   enum { JAC = 1, STEP = 2, DONE = 5 };
@@ -346,6 +354,34 @@ struct LmSM {
     phase = JAC;
   }
 
+  LMG_HD void save(LmSaved& s) const {
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      s.p[j] = p[j];
+      s.diag[j] = diag[j];
+    }
+    s.par = par;
+    s.delta = delta;
+    s.xnorm = xnorm;
+    s.fnorm = fnorm;
+    s.iter = iter;
+    s.nfev = nfev;
+  }
+  // after init(work, s.p) and residuals at p in wa4
+  LMG_HD void resume(int m, const LmSaved& s) {
+    LMG_UNROLL1
+    for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) diag[j] = s.diag[j];
+    par = s.par;
+    delta = s.delta;
+    xnorm = s.xnorm;
+    fnorm = s.fnorm;
+    iter = s.iter;
+    nfev = s.nfev;
+    phase = JAC;
+  }
+
   LMG_HD void jac_setup(int j) {  // fdjac2: perturb p[j]
     const double eps = 1.4901161193847656e-08;  // sqrt(max(epsfcn, epsmch)) = sqrt(2^-52) = 2^-26
     ptemp = p[j];
@@ -357,8 +393,11 @@ struct LmSM {
   // residuals at the perturbed point are in wa4: column j of the forward-difference Jacobian
   LMG_HD void jac_col(int m, int j) {
     p[j] = ptemp;
+    // one reciprocal per column instead of m divisions (<= 1 ulp from MINPACK's quotient, on a
+    // forward difference that is itself accurate to ~1e-8)
+    const double rh = ddiv(1.0, h);
     LMG_UNROLL1
-    for (int i = 0; i < m; ++i) LMG_A(i, j) = ddiv(wa4[i * ST] - fvec[i * ST], h);
+    for (int i = 0; i < m; ++i) LMG_A(i, j) = (wa4[i * ST] - fvec[i * ST]) * rh;
   }
 
   // after the NP columns: QR factorisation, (Q^T) fvec, scaled-gradient norm.  -> STEP or DONE
@@ -514,7 +553,10 @@ LMG_HD inline void super_round(const Problem& pr, LmSM<ST>& sm, bool active) {
 // p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).  Single-fit driver
 // (host tests, simple callers); the GPU kernel runs 32 LmSM<32> instances through the same
 // super_round() in lock-step.
-LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
+// suspend_after > 0: every suspend_after super-rounds a fit that is in JAC is saved, torn down and
+// resumed from the saved state (what the GPU does once for long-running fits); results are
+// bit-identical to an uninterrupted run.
+LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out, int suspend_after = 0) {
   if (pr.m < NP) {
     *nfev_out = 0;
     return 0;
@@ -524,7 +566,21 @@ LMG_HD inline int lmdif(const Problem& pr, double* p, int* nfev_out) {
   sm.init(work, p);
   residuals<1>(pr, sm.p, sm.wa4);
   sm.begin(pr.m);
-  while (sm.phase != LmSM<1>::DONE) super_round<1>(pr, sm, true);
+  int rounds = 0;
+  while (sm.phase != LmSM<1>::DONE) {
+    super_round<1>(pr, sm, true);
+    if (suspend_after > 0 && ++rounds >= suspend_after && sm.phase == LmSM<1>::JAC) {
+      LmSaved sv;
+      sm.save(sv);
+      for (int i = 0; i < WORK_DOUBLES; ++i) work[i] = -1.0;
+      LmSM<1> fresh;
+      fresh.init(work, sv.p);
+      residuals<1>(pr, fresh.p, fresh.wa4);
+      fresh.resume(pr.m, sv);
+      sm = fresh;
+      rounds = 0;
+    }
+  }
   LMG_UNROLL1
   for (int j = 0; j < NP; ++j) p[j] = sm.p[j];
   *nfev_out = sm.nfev;

@@ -128,7 +128,15 @@ int64_t cdb_esacf_debug_stride(int ham_samples);
  * cdb_host_gauss_fit: abscissae x0..x0+m-1, m <= 21; p_out[3] = (ampl, centre, dev); returns the
  * MINPACK info code (1..4 = converged). */
 int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev);
+/* the same fit, suspended and resumed from its saved state every suspend_after super-rounds (the
+ * device parks long-running fits this way); bit-identical to cdb_host_gauss_fit */
+int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* nfev,
+                        int suspend_after);
 int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out);
+/* cdb_host_iterf0_spectrum8k: host execution (CPU tests, no GPU) of the frame-8192 summary-spectrum
+ * kernel for one frame (iterative_f0.py:75-85): yc = filtered channels [C][8192] fp32,
+ * U[8193] = sum_c |rfft(hamming(8192) * yc[c], 16384)|. */
+int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U);
 /* cdb_host_esacf_acf: host execution (CPU tests, no GPU) of the device FFT autocorrelation
  * (esacf.py:93-129: sum over the two channels of |DFT_N|^k, real inverse DFT, first (N-1)/2 lags,
  * clip / prefix-zero enhancement) for n_frames = 1 or 2 frames of N in [3, 2048] samples.

@@ -127,6 +127,30 @@ def test_host_fft_autocorrelation_matches_numpy_sacf():
         nat.host_esacf_acf(np.zeros((1, 2049)), np.zeros((1, 2049)))
 
 
+def test_host_iterf0_spectrum8k_matches_numpy_rfft():
+    """The frame-8192 summary-spectrum kernel (radix 32/16/16 packed-FP32 FFT + Hermitian split,
+    fp32 accumulation over channels) executed thread by thread on the host."""
+    import scipy.signal.windows as sw
+
+    rng = np.random.default_rng(11)
+    win = sw.hamming(8192)
+    x, _ = cases.make_input(dict(fn="s_poly", seed=5, fs=22050, n=8192))
+    chans = [rn.auditory_channel(x.astype(np.float64), 22050, fc) for fc in rn.iterf0_channels(6)]
+    inputs = [np.abs(rng.standard_normal((1, 8192))), np.abs(rng.standard_normal((5, 8192))),
+              np.asarray(chans), np.zeros((2, 8192))]
+    imp = np.zeros((1, 8192))
+    imp[0, 4095] = 1.0
+    inputs.append(imp)
+    for yc in inputs:
+        yc32 = yc.astype(np.float32)
+        got = nat.host_iterf0_spectrum8k(yc32)
+        want = np.abs(np.fft.rfft(yc32.astype(np.float64) * win, 16384, axis=1)).sum(axis=0)
+        assert got.shape == want.shape == (8193,)
+        assert np.max(np.abs(got - want)) <= 2e-6 * max(np.max(want), 1e-30)
+    with pytest.raises(ValueError):
+        nat.host_iterf0_spectrum8k(np.zeros((1, 4096), dtype=np.float32))
+
+
 def test_host_gaussian_fit_matches_scipy_curve_fit():
     n, worst = 0, 0.0
     for d in _esacf_frames():
@@ -136,7 +160,12 @@ def test_host_gaussian_fit_matches_scipy_curve_fit():
             lo, hi = i - 10, min(i + 11, len(y))
             if lo < 0:
                 continue
-            info, p, _ = nat.host_gauss_fit(lo, y[lo:hi])
+            info, p, nfev = nat.host_gauss_fit(lo, y[lo:hi])
+            # parking a long-running fit and resuming it from its saved state (what the device
+            # does after 48 super-rounds) must not change a single bit
+            for every in (1, 3, 48):
+                info2, p2, nfev2 = nat.host_gauss_fit(lo, y[lo:hi], suspend_after=every)
+                assert (info2, nfev2) == (info, nfev) and p2 == p, (i, every)
             try:
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")

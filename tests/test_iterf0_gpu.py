@@ -46,10 +46,13 @@ def test_iterf0_matches_reference_golden(golden, cid):
     assert rn.pack_chroma(got) == g["digits"]
 
 
-def test_iterf0_voices_match_oracle():
-    """Per frame: the (salience, period) of every voice slot, i.e. the whole tau search."""
+@pytest.mark.parametrize("spec", ["s8k", "generic"])
+def test_iterf0_voices_match_oracle(spec, monkeypatch):
+    """Per frame: the (salience, period) of every voice slot, i.e. the whole tau search; with the
+    frame-8192 register-FFT summary-spectrum kernel (default) and the generic radix-2 one."""
     from chord_detection_b200 import ops
 
+    monkeypatch.setenv("CDB_ITERF0_SPEC", spec)
     x, fs = cases.make_input(dict(fn="s_poly", seed=210, fs=22050, n=3 * 8192 + 1000))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
