@@ -98,6 +98,9 @@ class ClockSampler(threading.Thread):
                 "reasons": [k for k, v in names.items() if bits & v], "samples": len(mhz)}
 
 
+REF_FRAMES_PER_CORE = 20000  # reference arm: ~2 s of the per-frame Python loop per core and step
+
+
 def _cpu_worker(args):
     """Reference-style per-frame loop (oracle port of harmonic_energy.py:31-73) on one core."""
     seed, n_frames = args
@@ -120,7 +123,7 @@ def _cpu_pool(cores):
     return pool
 
 
-def cpu_baseline(frames_per_core=3000, cores=None, pool=None):
+def cpu_baseline(frames_per_core=40000, cores=None, pool=None):
     """Oracle port timed on all host cores: each worker runs the reference's Python per-frame
     loop on its own shard of `frames_per_core` frames (same frame shape as the workload)."""
     cores = cores or os.cpu_count() or 1
@@ -128,9 +131,9 @@ def cpu_baseline(frames_per_core=3000, cores=None, pool=None):
     if own:
         pool = _cpu_pool(cores)
     try:
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(100 + i, frames_per_core) for i in range(cores)])
-        dt = time.perf_counter() - t0
+        # every worker times its own loop (input synthesis excluded); the job time is the slowest
+        res = pool.map(_cpu_worker, [(100 + i, frames_per_core) for i in range(cores)])
+        dt = max(r[0] for r in res)
     finally:
         if own:
             pool.close()
@@ -154,7 +157,7 @@ def run_reference(args):
             cpu_baseline(frames_per_core=200, cores=cores, pool=pool)
         steps = max(1, min(args.steps, 5))
         for _ in range(steps):
-            cb, dt = cpu_baseline(frames_per_core=1500, cores=cores, pool=pool)
+            cb, dt = cpu_baseline(frames_per_core=REF_FRAMES_PER_CORE, cores=cores, pool=pool)
             vals.append(cb["value"])
             secs.append(dt)
     finally:
@@ -169,7 +172,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "harmonic-energy chromagram, 44.1 kHz mono, 2048-pt frames hop 512 "
                                "(BASELINE configs[1]); bounded sample per step on host cores",
-                   "frames_per_step": 1500 * cores},
+                   "frames_per_step": REF_FRAMES_PER_CORE * cores},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
