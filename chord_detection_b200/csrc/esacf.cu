@@ -136,7 +136,11 @@ struct EsacfArgs {
   double* ws_res;    // [B][L/2+2] fitted centre per peak (NaN = fit failed / dropped)
   int* ws_np;        // [B] peaks per frame
   int* ws_tasks;     // [B*(L/2+2)] (frame << 11) | peak
-  int* ws_counters;  // [0] tasks appended, [1] handed out, [2] long fits parked, [3] handed out
+  int* ws_counters;  // [0] suspect tasks, [1] handed out, [2] long fits parked, [3] handed out,
+                     // [4] ordinary tasks
+  int task_cap;      // ws_tasks: suspects grow from the front, ordinary tasks from the back
+  int evict_rounds;  // park a fit after this many super-rounds (0: never)
+  int prioritise;    // 1: suspects first
   struct LongFit* ws_long;  // [long_cap] fits suspended by pass 0, finished by pass 1
   int long_cap;
   int skip_fit;      // debug (CDB_ESACF_SKIP_FIT=1): time the peak picking alone
@@ -326,7 +330,8 @@ __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kerne
 // kFitLanes lanes of each warp run fits; fewer lanes shrink the per-warp shared-memory work area
 // (26.9 KB at 32 lanes) and allow more resident warps.  Measured flat (228-244 ms per 62 592 frames for
 // 4..32 lanes): the stage is bound by lanes of one warp sitting in different LM phases.
-constexpr int kFitThreads = 256;
+constexpr int kFitThreads = 256;  // upper bound; kFitWarpsDefault of them are launched
+constexpr int kFitWarpsDefault = 6;
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;
@@ -361,8 +366,33 @@ __global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
                                 cand, order);
   a.ws_np[fb] = np;
   if (np > 0) {
-    const int start = atomicAdd(&a.ws_counters[0], np);
-    for (int i = 0; i < np; ++i) a.ws_tasks[start + i] = (fb << 11) | i;
+    // A peak that is not the maximum of its own +-10 window (it rides on the slope of a larger
+    // one) is where 96 % of the runaway fits come from (15 % of all fits, measured on the host):
+    // those tasks go to the front of the queue so that their 200-round chains overlap the bulk of
+    // the work instead of forming its tail.  Ordering only: every fit is computed the same way.
+    const double* y = a.ws_y + (int64_t)fb * L;
+    unsigned suspect = 0;  // np <= L/11 + 1 < 32 * ... : one bit per peak for the first 32
+    int ns = 0;
+    for (int i = 0; i < np; ++i) {
+      const int idx = cand[i];
+      const int lo = max(idx - 10, 0), hi = min(idx + 11, L);
+      const double v = y[idx];
+      bool sus = false;
+      for (int j = lo; j < hi; ++j) sus |= y[j] > v;
+      sus = sus && a.prioritise && i < 32;
+      if (sus) {
+        suspect |= 1u << i;
+        ++ns;
+      }
+    }
+    const int s0 = ns ? atomicAdd(&a.ws_counters[0], ns) : 0;
+    const int n0 = (np - ns) ? atomicAdd(&a.ws_counters[4], np - ns) : 0;
+    int si = 0, ni = 0;
+    for (int i = 0; i < np; ++i) {
+      const int code = (fb << 11) | i;
+      if (i < 32 && ((suspect >> i) & 1u)) a.ws_tasks[s0 + si++] = code;
+      else a.ws_tasks[a.task_cap - 1 - (n0 + ni++)] = code;
+    }
   }
 }
 
@@ -375,7 +405,8 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
   const int half = L / 2 + 2;
   const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
   const size_t per_frame = pad_l + 2 * pad_h;
-  const int total = pass == 0 ? a.ws_counters[0] : min(a.ws_counters[2], a.long_cap);
+  const int n_suspect = a.ws_counters[0];
+  const int total = pass == 0 ? n_suspect + a.ws_counters[4] : min(a.ws_counters[2], a.long_cap);
   int* next = &a.ws_counters[pass == 0 ? 1 : 3];
   if (lane >= kFitLanes) return;  // (no block-wide barrier below)
   constexpr unsigned kMask = kFitLanes == 32 ? 0xffffffffu : ((1u << (kFitLanes & 31)) - 1u);
@@ -391,7 +422,9 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
       if (need_init) {
         need_init = false;
         rounds = 0;
-        tcode = pass == 0 ? a.ws_tasks[task] : a.ws_long[task].task;
+        tcode = pass != 0          ? a.ws_long[task].task
+                : task < n_suspect ? a.ws_tasks[task]
+                                   : a.ws_tasks[a.task_cap - 1 - (task - n_suspect)];
         fb = tcode >> 11;
         pi = tcode & 2047;
         const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + per_frame * (size_t)fb + pad_l);
@@ -401,14 +434,11 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
           fitting = false;  // empty slice -> RuntimeError in peakutils -> peak dropped
           a.ws_res[(int64_t)fb * half + pi] = NAN;
         } else {
-          const double* y = a.ws_y + (int64_t)fb * L;
+          pr.y = a.ws_y + (int64_t)fb * L + lo;
           pr.m = hi - lo;
           pr.x0 = (double)lo;
-          double ymax = __ldg(y + lo);
-          for (int i = 0; i < pr.m; ++i) {
-            pr.y[i] = __ldg(y + lo + i);
-            ymax = fmax(ymax, pr.y[i]);
-          }
+          double ymax = __ldg(pr.y);
+          for (int i = 1; i < pr.m; ++i) ymax = fmax(ymax, __ldg(pr.y + i));
           if (pass == 0) {
             const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
             sm.init(lm_work, p0);
@@ -429,7 +459,7 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
                         isfinite(sm.p[2]);
         a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
         fitting = false;
-      } else if (fitting && pass == 0 && rounds >= kEvictRounds &&
+      } else if (fitting && pass == 0 && a.evict_rounds > 0 && rounds >= a.evict_rounds &&
                  sm.phase == lmg::LmSM<kFitLanes>::JAC) {
         const int slot = atomicAdd(&a.ws_counters[2], 1);
         if (slot < a.long_cap) {  // (a full queue keeps the fit here)
@@ -542,11 +572,9 @@ int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* n
   lmg::Problem pr;
   pr.m = m;
   pr.x0 = x0;
+  pr.y = y;
   double ymax = m ? y[0] : 0.0;
-  for (int i = 0; i < m; ++i) {
-    pr.y[i] = y[i];
-    ymax = std::fmax(ymax, y[i]);
-  }
+  for (int i = 0; i < m; ++i) ymax = std::fmax(ymax, y[i]);
   double p[3] = {ymax, x0, 5.0};
   int nf = 0;
   const int info = lmg::lmdif(pr, p, &nf, suspend_after);
@@ -676,7 +704,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   const size_t long_cap = (size_t)Bmax * 4 + 4096;  // ~0.1 long fits per frame measured
   const size_t need = (size_t)Bmax * ((2 * (size_t)N + 2 * (size_t)L + half) * sizeof(double) +
                                       scratch_pf + half * sizeof(int) + sizeof(int)) + 64 +
-                      long_cap * sizeof(LongFit) + 16;
+                      long_cap * sizeof(LongFit) + 64;
   if (pl->ws_bytes < need) {
     CDB_CUDA(h, cudaStreamSynchronize(st));
     if (pl->ws) cudaFree(pl->ws);
@@ -738,16 +766,28 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
                                         : fit_lanes >= 8  ? esacf_fit_kernel<8>
                                                           : esacf_fit_kernel<4>;
   fit_lanes = fit_lanes >= 32 ? 32 : fit_lanes >= 16 ? 16 : fit_lanes >= 8 ? 8 : 4;
-  const size_t fit_smem = (size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * (kFitThreads / 32);
-  CDB_CUDA(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)fit_smem));
+  CDB_CUDA(h, cudaFuncSetAttribute(
+                  fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                  (int)((size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * (kFitThreads / 32))));
+  // warps per CTA (one CTA per SM): fewer warps leave more of the 256 KB to L1, which holds the
+  // fits' 3-vectors (local memory); CDB_ESACF_FIT_WARPS overrides
+  int fit_warps = kFitWarpsDefault;  // measured (15 648 frames): 8 warps 35.7 ms, 7: 29.3, 6: 26.4, 5: 26.2, 4: 38.8
+  if (const char* fw = std::getenv("CDB_ESACF_FIT_WARPS")) fit_warps = std::atoi(fw);
+  fit_warps = fit_warps < 1 ? 1 : fit_warps > kFitThreads / 32 ? kFitThreads / 32 : fit_warps;
+  const int fit_threads = fit_warps * 32;
+  const size_t fit_smem = (size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * fit_warps;
   int fit_per_sm = 0;
-  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, fit_kernel, kFitThreads,
+  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, fit_kernel, fit_threads,
                                                             fit_smem));
   if (fit_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "fit kernel does not fit");
+  if (fit_lanes == 32) fit_per_sm = 1;  // one persistent CTA per SM (the rest of the SM's memory is L1)
   {
     const char* sf = std::getenv("CDB_ESACF_SKIP_FIT");
     a.skip_fit = (sf && sf[0] == '1') ? 1 : 0;
+    const char* ev = std::getenv("CDB_ESACF_PARK");  // super-rounds before a fit is parked (0: never)
+    a.evict_rounds = ev ? std::atoi(ev) : kEvictRounds;
+    const char* pr = std::getenv("CDB_ESACF_PRIO");
+    a.prioritise = (pr && pr[0] == '0') ? 0 : 1;
   }
   for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {
     const int B = (int)std::min<int64_t>(Bmax, n_frames - f0);
@@ -764,9 +804,10 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.ws_np = a.ws_tasks + half * (size_t)B;
     a.ws_counters = a.ws_np + B;
     a.ws_long = reinterpret_cast<LongFit*>(
-        (reinterpret_cast<uintptr_t>(a.ws_counters + 4) + 15) & ~(uintptr_t)15);
+        (reinterpret_cast<uintptr_t>(a.ws_counters + 8) + 15) & ~(uintptr_t)15);
     a.long_cap = (int)long_cap;
-    CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 4 * sizeof(int), st));
+    a.task_cap = (int)(half * (size_t)B);
+    CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 8 * sizeof(int), st));
     esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
     if (fft_r1) acf_fft_kernel<<<(B + 1) / 2, fft_r1 * 16, acf_fft_smem, st>>>(a);
     else acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
@@ -775,8 +816,9 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       h->launches += 1;
     }
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
-    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a, 0);
-    fit_kernel<<<h->num_sms * fit_per_sm, kFitThreads, fit_smem, st>>>(a, 1);  // parked runaways
+    fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 0);
+    if (a.evict_rounds > 0)
+      fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 1);  // parked runaways
     esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
     h->launches += 6;
     CDB_CUDA(h, cudaGetLastError());

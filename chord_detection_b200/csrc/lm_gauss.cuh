@@ -18,10 +18,22 @@
 #define LMG_HD
 #endif
 
+// LMG_UNROLL1 keeps the 3x3 logic compact (the fit kernel was instruction-cache bound at 145 KB of
+// SASS); the loops over the m <= 21 samples are unrolled by 3 so that the shared-memory load ->
+// FP64 -> store chains of neighbouring samples overlap (the fits are latency-bound).
 #ifdef __CUDA_ARCH__
 #define LMG_UNROLL1 _Pragma("unroll 1")
+#ifndef LMG_UNROLLM
+#define LMG_UNROLLM _Pragma("unroll 3")
+#endif
 #else
 #define LMG_UNROLL1
+#define LMG_UNROLLM
+#endif
+#ifdef __CUDA_ARCH__
+#define LMG_UNROLLY _Pragma("unroll 7")
+#else
+#define LMG_UNROLLY
 #endif
 
 namespace lmg {
@@ -49,15 +61,25 @@ constexpr double DWARF = 2.2250738585072014e-308;
 template <int ST = 1>
 LMG_HD inline double enorm(const double* v, int n) {
   double s = 0.0;
+  LMG_UNROLLM
   for (int i = 0; i < n; ++i) s += v[i * ST] * v[i * ST];
   return dsqrt(s);
 }
 
 struct Problem {
   int m;
-  double x0;  // abscissae are x0, x0+1, ..., x0+m-1 (numpy.arange slice)
-  double y[MMAX];
+  double x0;        // abscissae are x0, x0+1, ..., x0+m-1 (numpy.arange slice)
+  const double* y;  // the m samples (read-only; on the GPU they stay in global memory / L2: a
+                    // per-thread copy would sit in local memory and thrash the L1 left over by the
+                    // shared-memory work arrays)
 };
+LMG_HD inline double ldy(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 
 // model values on the integer grid by recurrence outward from the sample nearest the centre:
 //   E_i = exp(ninv (d0 + i)^2),  E_{i+1} = E_i r_i,  r_i = exp(ninv (2 (d0 + i) + 1)),  r_{i+1} = r_i q,
@@ -74,7 +96,7 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
 #ifdef LMG_DIRECT_EXP
   for (int i = 0; i < pr.m; ++i) {
     const double d = (pr.x0 + (double)i) - p[1];
-    f[i * ST] = p[0] * exp((d * d) * ninv) - pr.y[i];
+    f[i * ST] = p[0] * exp((d * d) * ninv) - ldy(pr.y + i);
   }
 #else
   const double d0 = pr.x0 - p[1];
@@ -85,20 +107,24 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
   const double dc = d0 + ic;
   const double e0 = p[0] * exp((dc * dc) * ninv);
   const double q = exp(2.0 * ninv);
-  f[i0 * ST] = e0 - pr.y[i0];
+  f[i0 * ST] = e0;
   double e = e0, r = exp(ninv * (2.0 * dc + 1.0));
   for (int i = i0 + 1; i < pr.m; ++i) {
     e *= r;
     r *= q;
-    f[i * ST] = e - pr.y[i];
+    f[i * ST] = e;
   }
   e = e0;
   r = exp(ninv * (1.0 - 2.0 * dc));
   for (int i = i0 - 1; i >= 0; --i) {
     e *= r;
     r *= q;
-    f[i * ST] = e - pr.y[i];
+    f[i * ST] = e;
   }
+  // second pass so that the loads of y overlap each other instead of sitting one by one in the
+  // dependency chain of the recurrence
+  LMG_UNROLLY
+  for (int i = 0; i < pr.m; ++i) f[i * ST] -= ldy(pr.y + i);
 #endif
 }
 
@@ -122,7 +148,7 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
     for (int k = j; k < NP; ++k)
       if (rdiag[k] > rdiag[kmax]) kmax = k;
     if (kmax != j) {
-      LMG_UNROLL1
+      LMG_UNROLLM
       for (int i = 0; i < m; ++i) {
         const double t = LMG_A(i, j);
         LMG_A(i, j) = LMG_A(i, kmax);
@@ -138,16 +164,16 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
     if (ajnorm != 0.0) {
       if (LMG_A(j, j) < 0.0) ajnorm = -ajnorm;
       const double rnorm = ddiv(1.0, ajnorm);  // (MINPACK divides every element: <= 1 ulp apart)
-      LMG_UNROLL1
+      LMG_UNROLLM
       for (int i = j; i < m; ++i) LMG_A(i, j) *= rnorm;
       LMG_A(j, j) += 1.0;
       LMG_UNROLL1
       for (int k = j + 1; k < NP; ++k) {
         double sum = 0.0;
-        LMG_UNROLL1
+        LMG_UNROLLM
         for (int i = j; i < m; ++i) sum += LMG_A(i, j) * LMG_A(i, k);
         const double temp = ddiv(sum, LMG_A(j, j));
-        LMG_UNROLL1
+        LMG_UNROLLM
         for (int i = j; i < m; ++i) LMG_A(i, k) -= temp * LMG_A(i, j);
         if (rdiag[k] != 0.0) {
           double t = ddiv(LMG_A(j, k), rdiag[k]);
@@ -377,7 +403,7 @@ struct LmSM {
 
   // residuals at the start point are in wa4
   LMG_HD void begin(int m) {
-    LMG_UNROLL1
+    LMG_UNROLLM
     for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
     nfev = 1;
     fnorm = enorm<ST>(fvec, m);
@@ -401,7 +427,7 @@ struct LmSM {
   }
   // after init(work, s.p) and residuals at p in wa4
   LMG_HD void resume(int m, const LmSaved& s) {
-    LMG_UNROLL1
+    LMG_UNROLLM
     for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
     LMG_UNROLL1
     for (int j = 0; j < NP; ++j) diag[j] = s.diag[j];
@@ -428,7 +454,7 @@ struct LmSM {
     // one reciprocal per column instead of m divisions (<= 1 ulp from MINPACK's quotient, on a
     // forward difference that is itself accurate to ~1e-8)
     const double rh = ddiv(1.0, h);
-    LMG_UNROLL1
+    LMG_UNROLLM
     for (int i = 0; i < m; ++i) LMG_A(i, j) = (wa4[i * ST] - fvec[i * ST]) * rh;
   }
 
@@ -449,16 +475,16 @@ struct LmSM {
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
-    LMG_UNROLL1
+    LMG_UNROLLM
     for (int i = 0; i < m; ++i) wa4[i * ST] = fvec[i * ST];
     LMG_UNROLL1
     for (int j = 0; j < NP; ++j) {
       if (LMG_A(j, j) != 0.0) {
         double sum = 0.0;
-        LMG_UNROLL1
+        LMG_UNROLLM
         for (int i = j; i < m; ++i) sum += LMG_A(i, j) * wa4[i * ST];
         const double temp = ddiv(-sum, LMG_A(j, j));
-        LMG_UNROLL1
+        LMG_UNROLLM
         for (int i = j; i < m; ++i) wa4[i * ST] += LMG_A(i, j) * temp;
       }
       LMG_A(j, j) = wa1[j];
@@ -541,7 +567,7 @@ struct LmSM {
         p[j] = wa2[j];
         wa2[j] = diag[j] * p[j];
       }
-      LMG_UNROLL1
+      LMG_UNROLLM
       for (int i = 0; i < m; ++i) fvec[i * ST] = wa4[i * ST];
       xnorm = enorm<1>(wa2, NP);
       fnorm = fnorm1;

@@ -10,7 +10,7 @@ tail -6 gpurun_out/${TAG}_pytest.log
 timeout 600 python scripts/bench_methods.py > gpurun_out/${TAG}_methods.json 2> gpurun_out/${TAG}_methods.err
 echo "methods exit $?"; cat gpurun_out/${TAG}_methods.json; tail -3 gpurun_out/${TAG}_methods.err
 for alt in $CDB_ALT_ENVS; do
-  env $alt NC=32 timeout 300 python scripts/esacf_time.py > gpurun_out/${TAG}_esacf_$alt.json 2>&1
+  env ${alt//,/ } NC=${CDB_ALT_NC:-32} timeout 300 python scripts/esacf_time.py > gpurun_out/${TAG}_esacf_$alt.json 2>&1
   echo "$alt:"; cat gpurun_out/${TAG}_esacf_$alt.json
 done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"esacf_|iterf0_|prime_" -c 600 --csv \
