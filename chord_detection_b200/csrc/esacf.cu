@@ -109,7 +109,7 @@ constexpr int kMaxPeaksDbg = 64;
 // fits but 10 % of the evaluations and a 200-round dependency chain): pass 0 parks it, pass 1
 // runs all parked fits together, so the latency tail of the batch is ONE long chain rather than
 // a long chain that started when the queue was almost empty.
-constexpr int kEvictRounds = 48;
+constexpr int kEvictRounds = 0;  // default: never (see below); CDB_ESACF_PARK=48 enables it
 struct LongFit {
   int task, pad;
   lmg::LmSaved st;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kerne
 // (26.9 KB at 32 lanes) and allow more resident warps.  Measured flat (228-244 ms per 62 592 frames for
 // 4..32 lanes): the stage is bound by lanes of one warp sitting in different LM phases.
 constexpr int kFitThreads = 256;  // upper bound; kFitWarpsDefault of them are launched
-constexpr int kFitWarpsDefault = 6;
+constexpr int kFitWarpsDefault = 5;
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(32) esacf_pick_kernel(const EsacfArgs a) {
 
 template <int kFitLanes>
 __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs a, const int pass) {
-  constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES * kFitLanes * sizeof(double);
+  constexpr size_t kLmWarpBytes = (size_t)lmg::WORK_DOUBLES_Y * kFitLanes * sizeof(double);
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = a.L;
@@ -434,11 +434,17 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
           fitting = false;  // empty slice -> RuntimeError in peakutils -> peak dropped
           a.ws_res[(int64_t)fb * half + pi] = NAN;
         } else {
-          pr.y = a.ws_y + (int64_t)fb * L + lo;
+          const double* yg = a.ws_y + (int64_t)fb * L + lo;
+          double* ys = lm_work + lmg::WORK_DOUBLES * kFitLanes;
+          pr.y = ys;
           pr.m = hi - lo;
           pr.x0 = (double)lo;
-          double ymax = __ldg(pr.y);
-          for (int i = 1; i < pr.m; ++i) ymax = fmax(ymax, __ldg(pr.y + i));
+          double ymax = __ldg(yg);
+          for (int i = 0; i < pr.m; ++i) {
+            const double v = __ldg(yg + i);
+            ys[i * kFitLanes] = v;
+            ymax = fmax(ymax, v);
+          }
           if (pass == 0) {
             const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
             sm.init(lm_work, p0);
@@ -766,16 +772,17 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
                                         : fit_lanes >= 8  ? esacf_fit_kernel<8>
                                                           : esacf_fit_kernel<4>;
   fit_lanes = fit_lanes >= 32 ? 32 : fit_lanes >= 16 ? 16 : fit_lanes >= 8 ? 8 : 4;
-  CDB_CUDA(h, cudaFuncSetAttribute(
-                  fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                  (int)((size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * (kFitThreads / 32))));
   // warps per CTA (one CTA per SM): fewer warps leave more of the 256 KB to L1, which holds the
   // fits' 3-vectors (local memory); CDB_ESACF_FIT_WARPS overrides
   int fit_warps = kFitWarpsDefault;  // measured (15 648 frames): 8 warps 35.7 ms, 7: 29.3, 6: 26.4, 5: 26.2, 4: 38.8
   if (const char* fw = std::getenv("CDB_ESACF_FIT_WARPS")) fit_warps = std::atoi(fw);
-  fit_warps = fit_warps < 1 ? 1 : fit_warps > kFitThreads / 32 ? kFitThreads / 32 : fit_warps;
+  const size_t fit_warp_smem = (size_t)lmg::WORK_DOUBLES_Y * fit_lanes * sizeof(double);
+  const int fit_warps_max = std::min<int>(kFitThreads / 32, (int)((size_t)h->smem_optin / fit_warp_smem));
+  fit_warps = fit_warps < 1 ? 1 : fit_warps > fit_warps_max ? fit_warps_max : fit_warps;
   const int fit_threads = fit_warps * 32;
-  const size_t fit_smem = (size_t)lmg::WORK_DOUBLES * fit_lanes * sizeof(double) * fit_warps;
+  const size_t fit_smem = fit_warp_smem * fit_warps;
+  CDB_CUDA(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)fit_smem));
   int fit_per_sm = 0;
   CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit_per_sm, fit_kernel, fit_threads,
                                                             fit_smem));

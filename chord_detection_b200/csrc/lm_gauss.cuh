@@ -69,17 +69,10 @@ LMG_HD inline double enorm(const double* v, int n) {
 struct Problem {
   int m;
   double x0;        // abscissae are x0, x0+1, ..., x0+m-1 (numpy.arange slice)
-  const double* y;  // the m samples (read-only; on the GPU they stay in global memory / L2: a
-                    // per-thread copy would sit in local memory and thrash the L1 left over by the
-                    // shared-memory work arrays)
+  const double* y;  // the m samples, element stride ST like the work arrays (on the GPU: a
+                    // lane-interleaved shared-memory copy; a per-thread array would sit in local
+                    // memory and thrash the L1 left over by the shared-memory work arrays)
 };
-LMG_HD inline double ldy(const double* p) {
-#ifdef __CUDA_ARCH__
-  return __ldg(p);
-#else
-  return *p;
-#endif
-}
 
 // model values on the integer grid by recurrence outward from the sample nearest the centre:
 //   E_i = exp(ninv (d0 + i)^2),  E_{i+1} = E_i r_i,  r_i = exp(ninv (2 (d0 + i) + 1)),  r_{i+1} = r_i q,
@@ -96,7 +89,7 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
 #ifdef LMG_DIRECT_EXP
   for (int i = 0; i < pr.m; ++i) {
     const double d = (pr.x0 + (double)i) - p[1];
-    f[i * ST] = p[0] * exp((d * d) * ninv) - ldy(pr.y + i);
+    f[i * ST] = p[0] * exp((d * d) * ninv) - pr.y[i * ST];
   }
 #else
   const double d0 = pr.x0 - p[1];
@@ -124,7 +117,7 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
   // second pass so that the loads of y overlap each other instead of sitting one by one in the
   // dependency chain of the recurrence
   LMG_UNROLLY
-  for (int i = 0; i < pr.m; ++i) f[i * ST] -= ldy(pr.y + i);
+  for (int i = 0; i < pr.m; ++i) f[i * ST] -= pr.y[i * ST];
 #endif
 }
 
@@ -351,8 +344,10 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
   }
 }
 
-// work: (MMAX + MMAX + MMAX*NP) doubles with element stride ST (fvec | wa4 | fjac)
+// work: (MMAX + MMAX + MMAX*NP) doubles with element stride ST (fvec | wa4 | fjac); the GPU kernel
+// appends the MMAX samples y
 constexpr int WORK_DOUBLES = MMAX * (2 + NP);
+constexpr int WORK_DOUBLES_Y = WORK_DOUBLES + MMAX;
 
 // lmdif as an explicit state machine in PHASE-ALIGNED blocks.  A fit alternates between two states:
 //   JAC  : needs a new Jacobian (3 evaluations, one per perturbed parameter: fdjac2), then the QR

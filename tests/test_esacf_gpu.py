@@ -157,6 +157,24 @@ def test_esacf_silent_frames_stay_exactly_zero():
             _close(fr[f], want[f])
 
 
+def test_esacf_scheduling_variants_are_bit_identical(monkeypatch):
+    """Task order (suspect peaks first), parking of long-running fits (suspend / resume from the
+    saved state in a second pass) and warps per SM only change WHEN a fit runs, never its result."""
+    fs = 44100
+    x, _ = cases.make_input(dict(fn="s_poly", seed=91, fs=fs, n=int(fs * 1.2)))
+    base = _run(x, fs, per_frame=True).frames.cpu().numpy()
+    assert base.sum() > 0
+    for env in (dict(CDB_ESACF_PARK="4"), dict(CDB_ESACF_PARK="48"), dict(CDB_ESACF_PRIO="0"),
+                dict(CDB_ESACF_PARK="3", CDB_ESACF_PRIO="0", CDB_ESACF_FIT_WARPS="2"),
+                dict(CDB_ESACF_FIT_WARPS="7")):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = _run(x, fs, per_frame=True).frames.cpu().numpy()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(got, base), env
+
+
 def test_esacf_stretch_none_and_params():
     x, fs = cases.make_input(dict(fn="s_poly", seed=78, fs=22050, n=9000))
     for kw in (dict(stretch_mode="none"), dict(peak_thresh=0.3, peak_min_dist=4),
