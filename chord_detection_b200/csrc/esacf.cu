@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kerne
 // (26.9 KB at 32 lanes) and allow more resident warps.  Measured flat (228-244 ms per 62 592 frames for
 // 4..32 lanes): the stage is bound by lanes of one warp sitting in different LM phases.
 constexpr int kFitThreads = 256;  // upper bound; kFitWarpsDefault of them are launched
-constexpr int kFitWarpsDefault = 5;
+constexpr int kFitWarpsDefault = 6;  // y in shared memory (15 648 frames): 4 warps 24.7 ms, 5: 22.5, 6: 21.6, 7: 25.8
 
 __host__ __device__ inline size_t peaks_scratch_bytes(int L) {  // per frame: sgn | cand | order
   const size_t half = (size_t)L / 2 + 2;

@@ -527,10 +527,12 @@ int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U) {
 
 int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params* p, int64_t n_clips, int64_t clip_len) {
   if (!p || n_clips < 0 || clip_len < 0) return -1;
-  // enough for min(n_clips, 1024) clips per batch, capped at 8 GiB of per-clip scratch
+  // enough for min(n_clips, 2048) clips per batch, capped at 40 GiB of per-clip scratch (a B200
+  // has 180 GB; the thread-per-(clip, channel) filter kernel wants >= 30 warps per SM, i.e.
+  // >= 2000 clips of 70 channels; any workspace that holds one clip is accepted)
   int64_t per = per_clip_bytes(p, clip_len);
-  int64_t b = std::min<int64_t>(n_clips, 1024);
-  const int64_t cap = (int64_t)8 << 30;
+  int64_t b = std::min<int64_t>(n_clips, 2048);
+  const int64_t cap = (int64_t)40 << 30;
   if (per > 0 && b * per > cap) b = std::max<int64_t>(1, cap / per);
   return b * per + ud_bytes(p, 1024) + 1024;
 }

@@ -96,3 +96,29 @@ def test_iterf0_class_api():
     assert repr(c) == "090000000000"  # SURVEY.md Appendix B / golden
     assert c.key() == "C#maj"
     assert cd.METHODS[3] is cd.MultipitchIterativeF0
+
+
+def test_iterf0_c4_full_size_properties():
+    """Config C4 at full size (8192 clips x 65 536 samples @22.05 kHz = 65 536 frames of 8192):
+    frames sum to clips sum to the total, duplicated clips are identical, sampled clips equal the
+    oracle."""
+    from chord_detection_b200 import ops, synth
+
+    fs, n, n_clips = 22050, 65536, 8192
+    dev = torch.device("cuda:0") if torch.cuda.is_available() else pytest.skip("no CUDA device")
+    base_np = np.stack([synth.s_poly(400 + i, fs, n) for i in range(16)])
+    x = torch.from_numpy(base_np).to(dev).repeat(n_clips // 16, 1).contiguous()
+    res = ops.iterative_f0(x, fs, per_clip=True, per_frame=True)
+    torch.cuda.synchronize()
+    assert res.frames.shape == (n_clips * 8, 12)
+    clips = res.clips.cpu().numpy()
+    frames = res.frames.cpu().numpy().reshape(n_clips, 8, 12)
+    _close(clips.sum(axis=0), res.total.cpu().numpy(), tol=1e-10)
+    _close(frames.sum(axis=1), clips, tol=1e-10)
+    assert np.array_equal(frames[16:32], frames[0:16])          # next repetition of the 16 bases
+    assert np.array_equal(frames[n_clips - 16:], frames[0:16])  # last batch of the workspace loop
+    for c in (0, 7):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = rn.iterf0(base_np[c], fs)
+        _close(clips[c], want)
