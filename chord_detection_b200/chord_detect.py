@@ -1,5 +1,9 @@
 """`chord-detect` CLI — same flags and output lines as
-/root/reference/chord_detection/chord_detect.py:11-63 (--key, --displayplots N, --method, input_path)."""
+/root/reference/chord_detection/chord_detect.py:11-63 (--key, --displayplots N, --method, input_path).
+
+Batch mode: several inputs, a directory, or a manifest (*.txt / *.lst, one path
+per line) run through the batched device ops (chord_detection_b200/batch.py); under torchrun the
+clip list is sharded over the GPUs.  A single WAV path behaves exactly like the reference CLI."""
 import argparse
 
 from chord_detection_b200 import METHODS
@@ -33,8 +37,25 @@ def main_cli(argv=None):
         help=method_nums_help_string,
         default=next(iter(METHODS.keys())),
     )
-    parser.add_argument("input_path", help="Path to WAV audio clip")
+    parser.add_argument("--batch", action="store_true",
+                        help="force batch mode for a single input (per-clip lines + corpus sums)")
+    parser.add_argument("input_path", nargs="+",
+                        help="Path to WAV audio clip (or several, a directory, a *.txt manifest)")
     args = parser.parse_args(argv)
+
+    import os
+
+    first = args.input_path[0]
+    if (args.batch or len(args.input_path) > 1 or os.path.isdir(first)
+            or first.lower().endswith((".txt", ".lst"))):
+        from chord_detection_b200 import batch
+
+        methods = list(METHODS.keys()) if args.method == -1 else [args.method]
+        if any(m not in METHODS for m in methods):
+            raise ValueError("valid methods: {0}".format(method_nums_help_string))
+        batch.main_batch(args.input_path, methods, key=args.key)
+        return
+    args.input_path = first
 
     compute_objs = []
     if args.method == -1:

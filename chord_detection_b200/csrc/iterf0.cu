@@ -257,11 +257,19 @@ __constant__ double kHW9[9] = {0.0011244659258033, 0.11559343551383, 0.428173482
                                0.81822361914331,   1.0,              0.81822361914331,
                                0.42817348241183,   0.11559343551383, 0.0011244659258033};
 
+constexpr int kPerBlock = 64;                      // bins per block-maximum entry
+constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 16384
+
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* Ur = reinterpret_cast<double*>(smem);  // [nb]
   __shared__ double lo[32], up[32], smax[32], part[2][32];
   __shared__ double sal[8], per[8], chroma[12];
+  // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
+  // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
+  // thousands of bins per harmonic; with the table a range costs its two ragged ends plus one
+  // entry per whole block (max is exact in any order: bit-identical to the plain scan)
+  __shared__ double bmax[kPerBlocksMax];
   __shared__ int s_q, s_qb;
   __shared__ double s_tau, s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
@@ -276,6 +284,18 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     }
     if (tid < 8) sal[tid] = per[tid] = 0.0;
     if (tid < 12) chroma[tid] = 0.0;
+    __syncthreads();
+    auto build_bmax = [&]() {  // one warp per block, two bins per lane
+      for (int b = warp; b * kPerBlock < nb; b += nthr >> 5) {
+        const int i0 = b * kPerBlock + lane;
+        double mx = i0 < nb ? Ur[i0] : -INFINITY;
+        if (i0 + 32 < nb) mx = fmax(mx, Ur[i0 + 32]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) bmax[b] = mx;
+      }
+    };
+    build_bmax();
     __syncthreads();
     int nv = 0;
     double prev = 0.0, mix = 0.0;
@@ -313,7 +333,14 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
             int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
             if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
             double mx = -INFINITY;
-            for (int i = lowk + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
+            const int b0 = (lowk + kPerBlock - 1) / kPerBlock, b1 = (highk + 1) / kPerBlock;  // whole blocks [b0, b1)
+            if (lowk < 0 || b1 <= b0) {
+              for (int i = lowk + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
+            } else {
+              for (int i = lowk + lane; i < b0 * kPerBlock; i += 32) mx = fmax(mx, Ur[i]);
+              for (int b = b0 + lane; b < b1; b += 32) mx = fmax(mx, bmax[b]);
+              for (int i = b1 * kPerBlock + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             if (lane == 0) part[which][m] = ((double)m * a.fs / up[qq] + a.e2) * mx;
@@ -381,6 +408,8 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
         const double d = Uk[i <= M ? i : nb - i] - __ldcg(&Ud[i]);
         Ur[i] = d > 0.0 ? d : 0.0;
       }
+      __syncthreads();
+      build_bmax();
       __syncthreads();
     }
     __syncthreads();

@@ -83,3 +83,57 @@ def test_gloo_world2_frame_and_clip_sharding_sum_to_whole():
         wc[0] += rn.harmonic_energy_fast(xi, 22050)
         wc[1] += rn.prime(xi, 22050)
     assert np.allclose(ret["clips"], wc, rtol=1e-12)
+
+
+def test_batch_expand_inputs(tmp_path):
+    from chord_detection_b200 import batch
+
+    d = tmp_path / "clips"
+    (d / "sub").mkdir(parents=True)
+    for name in ("b.wav", "a.wav", "sub/c.WAV", "notes.md"):
+        (d / name).write_bytes(b"")
+    man = tmp_path / "list.txt"
+    man.write_text("# corpus\nclips/a.wav\n\n%s\n" % (d / "b.wav"))
+    got = batch.expand_inputs([str(d), str(man), "x.wav"])
+    assert [q.name for q in got] == ["a.wav", "b.wav", "c.WAV", "a.wav", "b.wav", "x.wav"]
+    assert got[3] == tmp_path / "clips" / "a.wav"
+
+
+def _batch_worker(rank, world, port, paths, ret):
+    import io
+
+    from chord_detection_b200 import batch
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+
+    def fake_run(ps, methods, key=False, device=None, **kw):  # stands in for the device ops
+        lines = [(str(q), [(m, "M%d" % m, "%012d" % (int(Path(q).stem) * 10 + m), "Cmaj" if key else None)
+                           for m in methods]) for q in ps]
+        sums = {m: np.full(12, float(sum(int(Path(q).stem) for q in ps) * m)) for m in methods}
+        return lines, sums
+
+    from pathlib import Path
+
+    batch.run_batch = fake_run
+    real_init = D.init
+    D.init = lambda backend=None: real_init(backend="gloo")
+    buf = io.StringIO()
+    lines, sums = batch.main_batch(paths, [2, 4], key=True, out=buf)
+    ret[rank] = (buf.getvalue(), [ln[0] for ln in lines], {m: v.tolist() for m, v in sums.items()})
+
+
+def test_batch_front_end_two_ranks_gloo():
+    """Sharding of the clip list, gather of the per-clip lines in order, ONE all-reduce of the
+    corpus sums (the device ops are replaced by a stub: this is the plumbing)."""
+    paths = ["%d.wav" % i for i in range(1, 8)]
+    ret = mp.Manager().dict()
+    mp.spawn(_batch_worker, args=(2, _free_port(), paths, ret), nprocs=2, join=True)
+    out0, order0, sums0 = ret[0]
+    out1, order1, sums1 = ret[1]
+    assert order0 == order1 == paths
+    assert out1 == ""  # only rank 0 prints
+    assert sums0 == sums1 and sums0[2][0] == 2.0 * sum(range(1, 8)) and sums0[4][0] == 4.0 * sum(range(1, 8))
+    rows = out0.strip().splitlines()
+    assert rows[0] == "1.wav" and rows[1] == "2 - M2" and rows[2] == "%012d" % 12 and rows[3] == "Cmaj"
+    assert "== corpus (7 clips)" in rows

@@ -126,3 +126,42 @@ def test_cli_on_wav_file(tmp_path):
     assert all(len(lines[i]) == 12 and lines[i].isdigit() for i in (1, 4, 7, 10))
     with pytest.raises(ValueError):
         chord_detect.main_cli(["--method", "9", path])
+
+
+def test_cli_batch_mode_matches_single_clip_cli(tmp_path):
+    """a directory of clips (two different lengths) through the batched ops gives,
+    per clip, the lines the single-clip CLI prints; plus the corpus sums."""
+    import scipy.io.wavfile as wavfile
+
+    from chord_detection_b200 import chord_detect
+
+    _dev()
+    names = []
+    for i, n in enumerate((22050, 30000, 22050, 22050, 30000)):
+        x, fs = cases.make_input(dict(fn="s_poly", seed=600 + i, fs=22050, n=n))
+        path = os.path.join(tmp_path, "clip%d.wav" % i)
+        wavfile.write(path, fs, np.round(np.clip(x, -1, 1 - 2 ** -15) * 32768.0).astype(np.int16))
+        names.append(path)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        chord_detect.main_cli(["--method", "-1", "--key", str(tmp_path)])
+    rows = buf.getvalue().strip().splitlines()
+    per_clip = 1 + 4 * 3
+    assert rows[5 * per_clip] == "== corpus (5 clips)"
+    n_same = 0
+    for i, path in enumerate(names):
+        blk = rows[i * per_clip:(i + 1) * per_clip]
+        assert blk[0] == path
+        one = io.StringIO()
+        with contextlib.redirect_stdout(one):
+            chord_detect.main_cli(["--method", "-1", "--key", path])
+        single = one.getvalue().strip().splitlines()
+        assert [blk[1 + 3 * j] for j in range(4)] == [single[3 * j] for j in range(4)]  # headers
+        # HE / IterF0 / Prime are deterministic per clip; ESACF (method 1) shares paired
+        # transforms between neighbouring frames of a batch, so compare it loosely
+        for j in (1, 2, 3):
+            assert blk[2 + 3 * j] == single[1 + 3 * j] and blk[3 + 3 * j] == single[2 + 3 * j], (i, j)
+        n_same += blk[2] == single[1]
+    assert n_same >= 4
+    with pytest.raises(ValueError):
+        chord_detect.main_cli(["--method", "7", str(tmp_path)])
