@@ -207,7 +207,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a mismatched collective must fail loudly, not hang the driver
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     nfr = args.frames
     n = nfr * HOP  # ceil(n/hop) = nfr frames, the last three zero-padded (dsp/frame.py tail rule)
@@ -256,14 +259,16 @@ def main():
     launches = ops.launch_count(local_rank) - launches0
     clock_note = "sampled during the timed region"
     if len(sampler.samples) < 8:
-        # the timed region was shorter than a few NVML polls: keep the same step loop running
-        # (untimed) for ~0.3 s so that the clocks / throttle reasons are sampled under this load
-        clock_note = "timed region too short for NVML polling; sampled under the same step loop right after it"
+        # the timed region was shorter than a few NVML polls: keep the same kernel running
+        # (untimed) for ~0.3 s so that the clocks / throttle reasons are sampled under this load.
+        # LOCAL work only: this branch and its trip count differ between ranks, so it must not
+        # contain a collective (a mismatched all-reduce here deadlocked the N = 2 run of r01B).
+        clock_note = "timed region too short for NVML polling; sampled under the same kernel loop right after it"
         t_end = time.perf_counter() + 0.3
         i = 0
         while time.perf_counter() < t_end:
             for _ in range(20):
-                step(i)
+                ops.harmonic_energy(bufs[i % N_ROTATING], FS, frame_size=FRAME, hop=HOP, out_total=total)
                 i += 1
             torch.cuda.synchronize()
     sampler.stop_flag = True
