@@ -28,6 +28,11 @@ def main():
     c0, c1 = D.shard_range(args.clips, rank, world)
     base = torch.from_numpy(np.stack([synth.s_poly(1000 + i, 22050, 44100) for i in range(16)])).to(dev)
     sums = torch.zeros((4, 12), dtype=torch.float64, device=dev)
+    # untimed warm-up at the timed chunk shape: plan tables, workspaces (cudaMalloc of several GB),
+    # NCCL communicator
+    wn = min(args.chunk, max(1, c1 - c0))
+    D.all_methods_sharded(base[torch.arange(wn, device=dev) % 16], 22050, reduce=False)
+    D.all_reduce_chroma(torch.zeros((4, 12), dtype=torch.float64, device=dev))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
