@@ -3,8 +3,11 @@ sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from chord_detection_b200 import ops, synth
 dev=torch.device('cuda:0')
-base = torch.from_numpy(np.stack([synth.s_poly(1 + i, 44100, 1_000_000) for i in range(8)])).to(dev)
 import os
+FS=int(os.environ.get('FS','44100'))
+N=int(FS*46.4/1000); L=(N-1)//2
+NS=1_000_000 if FS==44100 else N*489
+base = torch.from_numpy(np.stack([synth.s_poly(1 + i, FS, NS) for i in range(8)])).to(dev)
 NC=int(os.environ.get('NC','32'))
 x = base.repeat((NC+7)//8,1)[:NC].contiguous()
 g=torch.Generator(device=dev).manual_seed(0)
@@ -15,8 +18,8 @@ def t(fn, reps=3):
         e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts)//2]
-ms=t(lambda: ops.esacf(x,44100))
-r=ops.esacf(x[:2],44100,debug=True)
-d=r.extra.cpu().numpy(); N=2046; L=1022; o=2*N+2*L
+ms=t(lambda: ops.esacf(x,FS))
+r=ops.esacf(x[:2],FS,debug=True)
+d=r.extra.cpu().numpy(); o=2*N+2*L
 npk=d[:,o]; nfit=d[:,o+1+128]
-print(json.dumps({"skip":os.environ.get("CDB_ESACF_SKIP_FIT"),"frames":NC*489,"ms":ms,"peaks_per_frame_mean":float(npk.mean()),"peaks_max":float(npk.max()),"fit_mean":float(nfit.mean())}))
+print(json.dumps({"fs":FS,"skip":os.environ.get("CDB_ESACF_SKIP_FIT"),"frames":NC*489,"ms":ms,"peaks_per_frame_mean":float(npk.mean()),"peaks_max":float(npk.max()),"fit_mean":float(nfit.mean())}))
