@@ -59,7 +59,7 @@ EXPORTS = [
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
     "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
     "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
-    "cdb_host_iterf0_spectrum8k",
+    "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
 ]
 
 
@@ -108,6 +108,8 @@ def lib():
                                           C.POINTER(C.c_int), C.c_int]
         L.cdb_host_find_peaks.argtypes = [C.POINTER(dbl), C.c_int, dbl, C.c_int,
                                           C.POINTER(C.c_int)]
+        L.cdb_host_iterf0_filter.argtypes = [C.POINTER(C.c_float), C.c_int64, C.POINTER(dbl), dbl,
+                                             C.POINTER(dbl), C.c_int, C.POINTER(C.c_float)]
         L.cdb_host_iterf0_spectrum8k.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(dbl)]
         L.cdb_host_esacf_acf.argtypes = [C.c_int, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(dbl),
                                          C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
@@ -192,6 +194,27 @@ def host_gauss_fit(x0, y, suspend_after=0):
     info = lib().cdb_host_gauss_fit2(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
                                      C.byref(nfev), int(suspend_after))
     return info, [p[0], p[1], p[2]], nfev.value
+
+
+def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
+    """Host execution of the device auditory-channel filter (test hook, no GPU).
+    x float32 [n]; coef float64 [18] (res1 b,a | res2 b,a | lp b,a); taps float64 [13] -> float32 [n]"""
+    import numpy as np
+
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    taps = np.ascontiguousarray(taps, dtype=np.float64)
+    if coef.shape != (18,) or taps.shape != (13,):
+        raise ValueError("coef must have 18 entries, taps 13")
+    y = np.zeros(x.shape[0], dtype=np.float32)
+    P = C.POINTER(C.c_double)
+    F = C.POINTER(C.c_float)
+    rc = lib().cdb_host_iterf0_filter(x.ctypes.data_as(F), x.shape[0], coef.ctypes.data_as(P),
+                                      float(lam), taps.ctypes.data_as(P), int(bool(pipelined)),
+                                      y.ctypes.data_as(F))
+    if rc != 0:
+        raise ValueError("cdb_host_iterf0_filter failed (%d)" % rc)
+    return y
 
 
 def host_iterf0_spectrum8k(yc):

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "iterf0_filter.cuh"
 #include "iterf0_spec8k.cuh"
 
 struct IterF0Plan {
@@ -69,61 +70,13 @@ struct IterArgs {
   double* voices;
 };
 
-struct Sos {
-  double b0, b1, b2, a1, a2, z0, z1;
-  __device__ __forceinline__ void init(const double* c) {  // c = b[3], a[3]
-    const double a0 = c[3];
-    b0 = c[0] / a0;
-    b1 = c[1] / a0;
-    b2 = c[2] / a0;
-    a1 = c[4] / a0;
-    a2 = c[5] / a0;
-    z0 = z1 = 0.0;
-  }
-  __device__ __forceinline__ double step(double x) {  // scipy lfilter, direct form II transposed
-    const double y = z0 + b0 * x;
-    z0 = (z1 + x * b1) - y * a1;
-    z1 = x * b2 - y * a2;
-    return y;
-  }
-};
-
 __global__ void __launch_bounds__(32) iterf0_filter_kernel(const IterArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_batch_clips * a.C) return;
   const int lc = t / a.C, ch = t - lc * a.C;
   const float* src = a.x + (a.clip0 + lc) * a.clip_stride;
   float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
-  const double* cf = a.coef + ch * kCoefStride;
-  Sos r1a, r1b, r2a, r2b, lp;
-  r1a.init(cf);
-  r1b.init(cf);
-  r2a.init(cf + 6);
-  r2b.init(cf + 6);
-  lp.init(cf + 12);
-  double z[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) z[i] = 0.0;
-  const double mlam = -a.lam;
-  for (int64_t n = 0; n < a.clip_len; ++n) {
-    double v = (double)__ldg(src + n);
-    v = r1a.step(v);  // iterative_f0.py:188-191
-    v = r1b.step(v);
-    v = r2a.step(v);
-    v = r2b.step(v);
-    double u = v, xhat = a.taps[0] * v;  // wfir.py:28-43
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const double y = z[i] + mlam * u;
-      z[i] = u - y * mlam;
-      xhat += a.taps[i + 1] * y;
-      u = y;
-    }
-    double y = fabs(v - xhat);       // iterative_f0.py:60
-    y = (y + lp.step(y)) / 2.0;      // :61-63
-    dst[n] = (float)y;
-  }
-  for (int64_t n = a.clip_len; n < a.n_pad; ++n) dst[n] = 0.0f;  // frame_cutter pads the FILTERED signal
+  iff::filter_channel<true>(src, a.clip_len, a.n_pad, a.coef + ch * kCoefStride, a.lam, a.taps, dst);
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -521,6 +474,17 @@ static int64_t ud_bytes(const cdb_iterf0_params* p, int num_sms) {
 }
 
 extern "C" {
+
+// Host execution (CPU tests, no GPU) of the auditory-channel filter of iterf0_filter_kernel:
+// coef = res1 b[3] a[3] | res2 b[3] a[3] | lp b[3] a[3]; pipelined != 0 runs the software-pipelined
+// schedule the kernel uses, 0 the straight per-sample loop (bit-identical by construction).
+int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double lam,
+                           const double* taps, int pipelined, float* y) {
+  if (!x || !coef || !taps || !y || n < 0) return -1;
+  if (pipelined) iff::filter_channel<true>(x, n, n, coef, lam, taps, y);
+  else iff::filter_channel<false>(x, n, n, coef, lam, taps, y);
+  return 0;
+}
 
 // Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
 // channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.

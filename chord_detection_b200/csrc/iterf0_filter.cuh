@@ -1,0 +1,115 @@
+// One auditory channel of the iterative-F0 front end over a whole clip
+// (/root/reference/chord_detection/iterative_f0.py:57-65, :171-193; dsp/wfir.py:25-43;
+// dsp/lowpass.py:6-8): 2+2 resonator biquads, the warped FIR whitener (12 first-order all-passes +
+// 13 taps, residual), |.|, (y + lowpass(y)) / 2.  FP64 recurrences in scipy.signal.lfilter's
+// direct-form-II-transposed operation order, output fp32.
+//
+// The chain is 17 stages deep and every stage depends on the previous one, so a sample takes ~20
+// dependent FP64 operations (~360 cycles measured) and a thread per (clip, channel) is latency-bound
+// unless there are >= 30 warps per SM.  Here the stages are SOFTWARE-PIPELINED across samples: in
+// iteration t stage s works on sample t - s, reading what stage s-1 left in the previous iteration,
+// so the 17 stage bodies of one iteration are independent of each other (stages run in reverse
+// order, updating the pipeline registers in place).  Every sample still goes through exactly the
+// same operations in the same order: results are bit-identical to the straight loop.  Pipeline
+// fill needs no predication: a zero-state IIR section fed with zeros produces zeros.
+#pragma once
+#include <math.h>
+#ifdef __CUDACC__
+#define IFF_HD __host__ __device__ __forceinline__
+#else
+#define IFF_HD inline
+#endif
+
+namespace iff {
+
+constexpr int kSections = 12;
+constexpr int kDepth = 4 + kSections;  // stages ahead of the final one
+
+struct Sos {  // y = z0 + b0 x; z0 = z1 + b1 x - a1 y; z1 = b2 x - a2 y   (explicit FMAs)
+  double b0, b1, b2, a1, a2, z0, z1;
+  IFF_HD void init(const double* c) {  // c = b[3], a[3]
+    const double a0 = c[3];
+    b0 = c[0] / a0;
+    b1 = c[1] / a0;
+    b2 = c[2] / a0;
+    a1 = c[4] / a0;
+    a2 = c[5] / a0;
+    z0 = z1 = 0.0;
+  }
+  IFF_HD double step(double x) {
+    const double y = fma(b0, x, z0);
+    z0 = fma(-a1, y, fma(b1, x, z1));
+    z1 = fma(-a2, y, b2 * x);
+    return y;
+  }
+};
+
+// coef: res1 b[3] a[3] | res2 b[3] a[3] | lp b[3] a[3];  dst[n .. n_pad) is zero-filled
+// (frame_cutter pads the FILTERED signal, iterative_f0.py:66 / dsp/frame.py:12)
+template <bool PIPELINED>
+IFF_HD void filter_channel(const float* src, long long n, long long n_pad, const double* coef,
+                           double lam, const double* taps, float* dst) {
+  Sos r1a, r1b, r2a, r2b, lp;
+  r1a.init(coef);
+  r1b.init(coef);
+  r2a.init(coef + 6);
+  r2b.init(coef + 6);
+  lp.init(coef + 12);
+  double z[kSections];
+#pragma unroll
+  for (int i = 0; i < kSections; ++i) z[i] = 0.0;
+  const double mlam = -lam;
+  if (!PIPELINED) {
+    for (long long t = 0; t < n; ++t) {
+      double v = (double)src[t];
+      v = r1a.step(v);  // iterative_f0.py:188-191
+      v = r1b.step(v);
+      v = r2a.step(v);
+      v = r2b.step(v);
+      double u = v, xhat = taps[0] * v;  // wfir.py:28-43
+#pragma unroll
+      for (int i = 0; i < kSections; ++i) {
+        const double y = fma(mlam, u, z[i]);
+        z[i] = fma(-mlam, y, u);
+        xhat = fma(taps[i + 1], y, xhat);
+        u = y;
+      }
+      double y = fabs(v - xhat);     // iterative_f0.py:60
+      y = (y + lp.step(y)) / 2.0;    // :61-63
+      dst[t] = (float)y;
+    }
+  } else {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;  // inputs of the biquad stages 1..3
+    double u[kSections + 1], P[kSections + 1], vv[kSections + 1];  // inputs of section i / the final stage
+#pragma unroll
+    for (int i = 0; i <= kSections; ++i) u[i] = P[i] = vv[i] = 0.0;
+    for (long long t = 0; t < n + kDepth; ++t) {
+      // final stage: sample t - 16
+      {
+        double y = fabs(vv[kSections] - P[kSections]);
+        y = (y + lp.step(y)) / 2.0;
+        if (t >= kDepth) dst[t - kDepth] = (float)y;
+      }
+      // all-pass sections, last first: section i works on sample t - 4 - i
+#pragma unroll
+      for (int i = kSections - 1; i >= 0; --i) {
+        const double y = fma(mlam, u[i], z[i]);
+        z[i] = fma(-mlam, y, u[i]);
+        P[i + 1] = fma(taps[i + 1], y, P[i]);
+        vv[i + 1] = vv[i];
+        u[i + 1] = y;
+      }
+      // resonators: sample t - 3 .. t
+      const double v = r2b.step(s3);
+      u[0] = v;
+      P[0] = taps[0] * v;
+      vv[0] = v;
+      s3 = r2a.step(s2);
+      s2 = r1b.step(s1);
+      s1 = r1a.step(t < n ? (double)src[t] : 0.0);
+    }
+  }
+  for (long long t = n; t < n_pad; ++t) dst[t] = 0.0f;
+}
+
+}  // namespace iff

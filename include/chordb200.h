@@ -133,6 +133,11 @@ int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nf
 int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* nfev,
                         int suspend_after);
 int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out);
+/* cdb_host_iterf0_filter: host execution (CPU tests, no GPU) of one auditory channel
+ * (iterative_f0.py:57-65): x[n] fp32 -> y[n] fp32; coef = res1 b[3] a[3] | res2 b[3] a[3] |
+ * lp b[3] a[3] (float64), lam / taps[13] = warped-FIR design (dsp/wfir.py). */
+int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double lam,
+                           const double* taps, int pipelined, float* y);
 /* cdb_host_iterf0_spectrum8k: host execution (CPU tests, no GPU) of the frame-8192 summary-spectrum
  * kernel for one frame (iterative_f0.py:75-85): yc = filtered channels [C][8192] fp32,
  * U[8193] = sum_c |rfft(hamming(8192) * yc[c], 16384)|. */

@@ -127,6 +127,29 @@ def test_host_fft_autocorrelation_matches_numpy_sacf():
         nat.host_esacf_acf(np.zeros((1, 2049)), np.zeros((1, 2049)))
 
 
+def test_host_iterf0_filter_pipelined_schedule_is_exact():
+    """The auditory-channel filter of iterf0_filter_kernel on the host: the software-pipelined
+    schedule (stage s on sample t - s) equals the straight per-sample loop bit for bit, and both
+    match scipy's lfilter chain (oracle) to the fp32 rounding of the output."""
+    from chord_detection_b200 import ops
+
+    fs = 22050
+    lam, taps = ops.wfir_design(fs)
+    fcs = rn.iterf0_channels(70)
+    for seed, n in ((5, 20000), (6, 17), (7, 1), (8, 5000)):
+        x, _ = cases.make_input(dict(fn="s_poly", seed=seed, fs=fs, n=n))
+        for fc in (fcs[0], fcs[33], fcs[69]):
+            r1, r2 = rn.auditory_filterbank_coefs(fs, fc)
+            lb, la = rn.butter2(fs, fc, "low")
+            coef = np.array(list(r1[0]) + list(r1[1]) + [r2[0][0], 0.0, 0.0] + list(r2[1]) + list(lb) + list(la))
+            yp = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=True)
+            ys = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=False)
+            assert np.array_equal(yp, ys)
+            want = rn.auditory_channel(x.astype(np.float64), fs, fc)
+            assert np.max(np.abs(yp - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
+    assert nat.host_iterf0_filter(np.zeros(0, dtype=np.float32), np.ones(18), lam, taps).shape == (0,)
+
+
 def test_host_iterf0_spectrum8k_matches_numpy_rfft():
     """The frame-8192 summary-spectrum kernel (radix 32/16/16 packed-FP32 FFT + Hermitian split,
     fp32 accumulation over channels) executed thread by thread on the host."""
