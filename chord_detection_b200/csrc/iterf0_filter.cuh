@@ -79,34 +79,54 @@ IFF_HD void filter_channel(const float* src, long long n, long long n_pad, const
       dst[t] = (float)y;
     }
   } else {
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;  // inputs of the biquad stages 1..3
-    double u[kSections + 1], P[kSections + 1], vv[kSections + 1];  // inputs of section i / the final stage
+    // Pipeline registers: s1..s3 = inputs of the biquad stages 1..3; u[i], P[i] = input and partial
+    // tap sum entering all-pass section i (i = 12: the final stage).  They are written by one stage
+    // and read by the next in the following iteration, so nothing is shifted.  Only v itself rides
+    // along unchanged for kRing = 13 iterations: a ring buffer whose index is static because the
+    // time loop is unrolled by kRing.  The kRing input samples of the NEXT block are loaded at the
+    // top of each block (their latency hides behind ~800 FP64 instructions).
+    constexpr int kRing = kSections + 1;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double u[kSections + 1], P[kSections + 1], vring[kRing];
+    float xcur[kRing], xnext[kRing];
 #pragma unroll
-    for (int i = 0; i <= kSections; ++i) u[i] = P[i] = vv[i] = 0.0;
-    for (long long t = 0; t < n + kDepth; ++t) {
-      // final stage: sample t - 16
-      {
-        double y = fabs(vv[kSections] - P[kSections]);
-        y = (y + lp.step(y)) / 2.0;
-        if (t >= kDepth) dst[t - kDepth] = (float)y;
-      }
-      // all-pass sections, last first: section i works on sample t - 4 - i
+    for (int i = 0; i <= kSections; ++i) u[i] = P[i] = vring[i] = 0.0;
 #pragma unroll
-      for (int i = kSections - 1; i >= 0; --i) {
-        const double y = fma(mlam, u[i], z[i]);
-        z[i] = fma(-mlam, y, u[i]);
-        P[i + 1] = fma(taps[i + 1], y, P[i]);
-        vv[i + 1] = vv[i];
-        u[i + 1] = y;
+    for (int j = 0; j < kRing; ++j) xcur[j] = j < n ? src[j] : 0.0f;
+    for (long long base = 0; base < n + kDepth; base += kRing) {
+#pragma unroll
+      for (int j = 0; j < kRing; ++j) {
+        const long long tn = base + kRing + j;
+        xnext[j] = tn < n ? src[tn] : 0.0f;
       }
-      // resonators: sample t - 3 .. t
-      const double v = r2b.step(s3);
-      u[0] = v;
-      P[0] = taps[0] * v;
-      vv[0] = v;
-      s3 = r2a.step(s2);
-      s2 = r1b.step(s1);
-      s1 = r1a.step(t < n ? (double)src[t] : 0.0);
+#pragma unroll
+      for (int j = 0; j < kRing; ++j) {
+        const long long t = base + j;
+        // final stage: sample t - 16 (its v was put into vring[j] kRing iterations ago)
+        {
+          double y = fabs(vring[j] - P[kSections]);
+          y = (y + lp.step(y)) / 2.0;
+          if (t >= kDepth && t - kDepth < n) dst[t - kDepth] = (float)y;
+        }
+        // all-pass sections, last first: section i works on sample t - 4 - i
+#pragma unroll
+        for (int i = kSections - 1; i >= 0; --i) {
+          const double y = fma(mlam, u[i], z[i]);
+          z[i] = fma(-mlam, y, u[i]);
+          P[i + 1] = fma(taps[i + 1], y, P[i]);
+          u[i + 1] = y;
+        }
+        // resonators: samples t - 3 .. t
+        const double v = r2b.step(s3);
+        u[0] = v;
+        P[0] = taps[0] * v;
+        vring[j] = v;
+        s3 = r2a.step(s2);
+        s2 = r1b.step(s1);
+        s1 = r1a.step((double)xcur[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kRing; ++j) xcur[j] = xnext[j];
     }
   }
   for (long long t = n; t < n_pad; ++t) dst[t] = 0.0f;
