@@ -773,6 +773,191 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// frame_size 8192, second generation (he8192p_kernel): the same radix-16^3 decomposition with
+//  * packed FP32x2 butterflies (fft_packed.cuh: half the FMA-pipe issue slots of the scalar form),
+//  * the NEXT frame of the CTA staged by ONE 32 KB bulk async copy (TMA engine, mbarrier
+//    completion) that is issued as soon as pass A has pulled the current frame into registers,
+//    so the HBM read of frame i+1 runs under passes B, C and the epilogue of frame i.  At this
+//    frame size (hop = frame in the reference) the kernel is HBM-heavy: 32 KB per frame against
+//    ~7 flop/B.  Frames that are short (clip tails) or not 16-byte aligned are read directly.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ c64 ldg_c64(const float2* p) {
+  return __ldg(reinterpret_cast<const unsigned long long*>(p));
+}
+
+__global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  c64* stage = reinterpret_cast<c64*>(smem);              // [4096] the staged frame (x[2m], x[2m+1])
+  c64* bufA = stage + 4096;                               // [16][256]; later Z[4096]
+  c64* bufB = bufA + 4096;                                // [256 rows][18]; later the power spectrum
+  double* wv = reinterpret_cast<double*>(bufB + 256 * k8RowB);  // [n_windows]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wv + HE_MAX_WINDOWS);
+  float* pw = reinterpret_cast<float*>(bufB);             // [4097]
+  const float2* zA = reinterpret_cast<const float2*>(bufA);
+  const int tid = threadIdx.x;
+  const int M = 4096;
+  const int64_t total_frames = a.n_clips * a.frames_per_clip;
+  const int64_t f_begin = (total_frames * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t f_end = (total_frames * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+  int64_t clip = f_begin / a.frames_per_clip;
+  int64_t f = f_begin - clip * a.frames_per_clip;
+  const float2* win2 = reinterpret_cast<const float2*>(a.win);
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // stage frame (c, fr) if it is a whole, 16-byte aligned frame; every thread evaluates the same
+  // predicate, thread 0 issues the copy
+  auto stageable = [&](int64_t c, int64_t fr) -> bool {
+    const int64_t s0 = fr * a.hop;
+    const float* src = reinterpret_cast<const float*>(a.x) + c * a.clip_stride + s0;
+    return (a.clip_len - s0 >= 8192) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  };
+  auto issue = [&](int64_t c, int64_t fr) {
+    const float* src = reinterpret_cast<const float*>(a.x) + c * a.clip_stride + fr * a.hop;
+    fence_proxy_async();
+    mbar_expect_tx(mbar, 32768u);
+    tma_load_1d(stage, src, 32768u, mbar);
+  };
+  bool staged = f_begin < f_end && stageable(clip, f);
+  if (staged && tid == 0) issue(clip, f);
+  uint32_t phase = 0;
+
+  for (int64_t gf = f_begin; gf < f_end; ++gf) {
+    const int64_t s0 = f * a.hop;
+    const float* src = reinterpret_cast<const float*>(a.x) + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    int64_t nclip = clip, nf = f + 1;
+    if (nf >= a.frames_per_clip) {
+      nf = 0;
+      ++nclip;
+    }
+    const bool next_staged = (gf + 1 < f_end) && stageable(nclip, nf);
+    c64 v[16];
+    // ---- pass A: thread t holds z[256 n1 + t]; window fused into the span-1 butterflies
+    {
+      if (staged) {
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+      }
+      const bool vec = (avail >= 8192) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+      auto ld = [&](int m) -> c64 {  // complex point m = (x[2m], x[2m+1])
+        if (staged) return stage[m];
+        if (vec) return ldg_c64(reinterpret_cast<const float2*>(src) + m);
+        const int64_t i = 2 * (int64_t)m;
+        return pk(i < avail ? __ldg(src + i) : 0.0f, i + 1 < avail ? __ldg(src + i + 1) : 0.0f);
+      };
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        const c64 xa = ld(256 * na + tid), wa = ldg_c64(win2 + 256 * na + tid);
+        const c64 xb = ld(256 * nb + tid), wb = ldg_c64(win2 + 256 * nb + tid);
+        const c64 m2 = mul2(xb, wb);
+        v[2 * p] = fma2(xa, wa, m2);
+        v[2 * p + 1] = fma2(xa, wa, neg2(m2));
+      }
+      fft16p_dit_tail(v);
+      bufA[tid] = v[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1)  // twiddle W_4096^(t*k1), table laid out [k1][t]
+        bufA[k1 * 256 + tid] = cmul2(v[k1], ldg_c64(&a.tw8a[k1 * 256 + tid]));
+    }
+    __syncthreads();  // the staged frame is in registers everywhere: the stage may be refilled
+    if (next_staged && tid == 0) issue(nclip, nf);
+    // ---- pass B: thread (k1 = t>>4, n3 = t&15): DFT over n2, twiddle W_256^(n3*k2)
+    {
+      const int k1 = tid >> 4, n3 = tid & 15;
+      c64 in[16];
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) in[n2] = bufA[k1 * 256 + 16 * n2 + n3];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        v[2 * p] = add2(in[na], in[nb]);
+        v[2 * p + 1] = sub2(in[na], in[nb]);
+      }
+      fft16p_dit_tail(v);
+      bufB[(0 * 16 + k1) * k8RowB + n3] = v[0];
+#pragma unroll
+      for (int k2 = 1; k2 < 16; ++k2)
+        bufB[(k2 * 16 + k1) * k8RowB + n3] = cmul2(v[k2], ldg_c64(&a.tw8b[k2 * 16 + n3]));
+    }
+    __syncthreads();
+    // ---- pass C: thread (k2 = t>>4, k1 = t&15): DFT over n3 -> Z[k1 + 16 k2 + 256 k3]
+    {
+      const int k2 = tid >> 4, k1 = tid & 15;
+      const ulonglong2* row = reinterpret_cast<const ulonglong2*>(bufB + (k2 * 16 + k1) * k8RowB);
+      c64 in[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const ulonglong2 q = row[i];
+        in[2 * i] = q.x;
+        in[2 * i + 1] = q.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int na = br4(2 * p), nb = na + 8;
+        v[2 * p] = add2(in[na], in[nb]);
+        v[2 * p + 1] = sub2(in[na], in[nb]);
+      }
+      fft16p_dit_tail(v);
+#pragma unroll
+      for (int k3 = 0; k3 < 16; ++k3) bufA[k1 + 16 * k2 + 256 * k3] = v[k3];
+    }
+    __syncthreads();
+    // ---- real-FFT split for the probed bins only, |X|^2 into pw (aliases bufB)
+    for (int k = a.kmin + tid; k <= a.kmax; k += k8Threads) {
+      float pwr;
+      if (k == M) {
+        const float xn = zA[0].x - zA[0].y;
+        pwr = xn * xn;
+      } else {
+        const float2 z = zA[k], pz = zA[(M - k) & (M - 1)];
+        const float2 cs = __ldg(&a.wsplit[k]);
+        const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+        const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+        const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+        pwr = xr * xr + xi * xi;
+      }
+      pw[k] = pwr;
+    }
+    __syncthreads();
+    for (int wi = tid; wi < a.n_windows; wi += k8Threads) {
+      const HeWin hw = a.wins[wi];
+      float m = pw[hw.k0];
+      for (int k = hw.k0 + 1; k < hw.k1; ++k) m = fmaxf(m, pw[k]);
+      wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double sum = 0.0;
+      for (int j = 0; j < a.wins_per_note; ++j) sum += wv[tid * a.wins_per_note + j];
+      if (a.clips) {
+        if (clip != my_clip) {
+          if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+          my_clip = clip;
+          acc_clip = 0.0;
+        }
+        acc_clip += sum;
+      }
+      acc_total += sum;
+      if (a.frames) a.frames[gf * 12 + tid] = (float)sum;
+    }
+    staged = next_staged;
+    clip = nclip;
+    f = nf;
+  }
+  if (tid < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+    if (a.total) atomicAdd(&a.total[tid], acc_total);
+  }
+}
+
 // Generic power-of-two path: one CTA per frame at a time, in-place radix-2 DIT in shared memory.
 constexpr int kGenThreads = 256;
 
@@ -937,15 +1122,18 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
     kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
   } else if (pl->N == 8192 && !pl->force_generic) {
-    const size_t smem = (size_t)4096 * 8 + (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
-    CDB_CUDA(h, cudaFuncSetAttribute(he8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+    // CDB_HE8192=scalar selects the first-generation kernel (scalar butterflies, direct loads)
+    const char* k8 = std::getenv("CDB_HE8192");
+    const bool packed = !(k8 && k8[0] == 's');
+    void (*kern)(const HeArgs) = packed ? he8192p_kernel : he8192_kernel;
+    const size_t smem = (packed ? (size_t)4096 * 8 + 16 : 0) + (size_t)4096 * 8 +
+                        (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
+    CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he8192_kernel, k8Threads,
-                                                              smem));
+    CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, k8Threads, smem));
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
     int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
-    he8192_kernel<<<(unsigned)grid, k8Threads, smem, st>>>(a);
+    kern<<<(unsigned)grid, k8Threads, smem, st>>>(a);
   } else {
     const size_t smem = (size_t)pl->M * 8 + (size_t)(pl->M + 2) * 4 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he_generic_kernel,
