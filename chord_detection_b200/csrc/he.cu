@@ -205,8 +205,9 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
     double a0 = 1.0, a1 = 0.0;
     if (key.window_kind == CDB_WINDOW_HAMMING) a0 = 0.54, a1 = 0.46;
     if (key.window_kind == CDB_WINDOW_HANN) a0 = 0.5, a1 = 0.5;
-    std::vector<float4> wl(32);
-    for (int l = 0; l < 32; ++l) {
+    const int n_wl = N == 8192 ? 256 : 32;  // per-lane (frame 2048) / per-thread (frame 8192) constants
+    std::vector<float4> wl(n_wl);
+    for (int l = 0; l < n_wl; ++l) {
       const double b0 = 2.0 * kPi * (2 * l) / (double)(N - 1), b1 = 2.0 * kPi * (2 * l + 1) / (double)(N - 1);
       wl[l] = make_float4((float)(-a1 * std::cos(b0)), (float)(-a1 * std::cos(b1)),
                           (float)(a1 * std::sin(b0)), (float)(a1 * std::sin(b1)));
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
 // overlap at this size); window and twiddle tables are read through L1.
 // ------------------------------------------------------------------------------------------
 constexpr int k8Threads = 256;
+static const char* const kHe8192Default = "scalar";  // scalar | packed | staged (see the dispatch)
 constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
 
 __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
@@ -785,11 +787,35 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
 __device__ __forceinline__ c64 ldg_c64(const float2* p) {
   return __ldg(reinterpret_cast<const unsigned long long*>(p));
 }
+// window pair (w[512 n1 + 2t], w[512 n1 + 2t + 1]) = a0 - a1 cos(A + B), A = 2 pi 512 n1 / 8191
+// (immediates), B = 2 pi (2t + c) / 8191 (per-thread constants cb = -a1 cos B, sb = a1 sin B):
+// 2 FFMA2 instead of an 8-byte table load per pair (the 32 KB window table competes with the
+// twiddle tables for the L1 that two 70-104 KB CTAs leave)
+template <int n1>
+__device__ __forceinline__ c64 win8_pair(c64 a0, c64 cb, c64 sb) {
+  constexpr float CA[16] = {1.000000000e+00f, 9.238611846e-01f, 7.070389766e-01f, 3.825505484e-01f, -1.917710069e-04f, -3.829048880e-01f, -7.073101558e-01f, -9.240079088e-01f, -9.999999264e-01f, -9.237143244e-01f, -7.067676935e-01f, -3.821961526e-01f, 5.753129924e-04f, 3.832591713e-01f, 7.075812309e-01f, 9.241544970e-01f};
+  constexpr float SA[16] = {0.000000000e+00f, 3.827277253e-01f, 7.071745792e-01f, 9.239345636e-01f, 9.999999816e-01f, 9.237877715e-01f, 7.069033481e-01f, 3.823733575e-01f, -3.835420067e-04f, -3.830820367e-01f, -7.074457064e-01f, -9.240812199e-01f, -9.999998345e-01f, -9.236408434e-01f, -7.066320129e-01f, -3.820189336e-01f};
+  return fma2(bc(SA[n1]), sb, fma2(bc(CA[n1]), cb, a0));
+}
+template <int P>
+struct Win8Stage {
+  template <class LD>
+  static __device__ __forceinline__ void run(c64 (&v)[16], LD ld, int tid, c64 a0, c64 cb, c64 sb) {
+    constexpr int na = br4(2 * P), nb = na + 8;
+    const c64 xa = ld(256 * na + tid), xb = ld(256 * nb + tid);
+    const c64 m2 = mul2(xb, win8_pair<nb>(a0, cb, sb));
+    const c64 wa = win8_pair<na>(a0, cb, sb);
+    v[2 * P] = fma2(xa, wa, m2);
+    v[2 * P + 1] = fma2(xa, wa, neg2(m2));
+    if constexpr (P + 1 < 8) Win8Stage<P + 1>::run(v, ld, tid, a0, cb, sb);
+  }
+};
 
+template <bool STAGE>
 __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   c64* stage = reinterpret_cast<c64*>(smem);              // [4096] the staged frame (x[2m], x[2m+1])
-  c64* bufA = stage + 4096;                               // [16][256]; later Z[4096]
+  c64* bufA = stage + (STAGE ? 4096 : 0);                 // [16][256]; later Z[4096]
   c64* bufB = bufA + 4096;                                // [256 rows][18]; later the power spectrum
   double* wv = reinterpret_cast<double*>(bufB + 256 * k8RowB);  // [n_windows]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(wv + HE_MAX_WINDOWS);
@@ -804,7 +830,8 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
   int64_t my_clip = -1;
   int64_t clip = f_begin / a.frames_per_clip;
   int64_t f = f_begin - clip * a.frames_per_clip;
-  const float2* win2 = reinterpret_cast<const float2*>(a.win);
+  const float4 wl = a.winlane[tid];  // [256] for frame 8192
+  const c64 win_a0 = bc(a.win_a0), win_cb = pk(wl.x, wl.y), win_sb = pk(wl.z, wl.w);
 
   if (tid == 0) {
     mbar_init(mbar, 1);
@@ -814,6 +841,7 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
   // stage frame (c, fr) if it is a whole, 16-byte aligned frame; every thread evaluates the same
   // predicate, thread 0 issues the copy
   auto stageable = [&](int64_t c, int64_t fr) -> bool {
+    if (!STAGE) return false;
     const int64_t s0 = fr * a.hop;
     const float* src = reinterpret_cast<const float*>(a.x) + c * a.clip_stride + s0;
     return (a.clip_len - s0 >= 8192) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -852,15 +880,7 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
         const int64_t i = 2 * (int64_t)m;
         return pk(i < avail ? __ldg(src + i) : 0.0f, i + 1 < avail ? __ldg(src + i + 1) : 0.0f);
       };
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int na = br4(2 * p), nb = na + 8;
-        const c64 xa = ld(256 * na + tid), wa = ldg_c64(win2 + 256 * na + tid);
-        const c64 xb = ld(256 * nb + tid), wb = ldg_c64(win2 + 256 * nb + tid);
-        const c64 m2 = mul2(xb, wb);
-        v[2 * p] = fma2(xa, wa, m2);
-        v[2 * p + 1] = fma2(xa, wa, neg2(m2));
-      }
+      Win8Stage<0>::run(v, ld, tid, win_a0, win_cb, win_sb);
       fft16p_dit_tail(v);
       bufA[tid] = v[0];
 #pragma unroll
@@ -1122,11 +1142,15 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
     kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
   } else if (pl->N == 8192 && !pl->force_generic) {
-    // CDB_HE8192=scalar selects the first-generation kernel (scalar butterflies, direct loads)
+    // CDB_HE8192 = scalar (first generation: scalar butterflies, direct loads) | packed (packed
+    // butterflies, direct loads) | staged (packed butterflies + bulk-async staging of the next frame)
     const char* k8 = std::getenv("CDB_HE8192");
-    const bool packed = !(k8 && k8[0] == 's');
-    void (*kern)(const HeArgs) = packed ? he8192p_kernel : he8192_kernel;
-    const size_t smem = (packed ? (size_t)4096 * 8 + 16 : 0) + (size_t)4096 * 8 +
+    std::string mode = k8 ? k8 : kHe8192Default;
+    void (*kern)(const HeArgs) = mode == "packed"   ? he8192p_kernel<false>
+                                 : mode == "staged" ? he8192p_kernel<true>
+                                                    : he8192_kernel;
+    const bool staged_k = mode == "staged";
+    const size_t smem = (staged_k ? (size_t)4096 * 8 : 0) + 16 + (size_t)4096 * 8 +
                         (size_t)256 * k8RowB * 8 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -73,16 +73,13 @@ def main():
                            "alg_GBps": nf * 32768 / ms / 1e6, "note": "frame 8192, hop 8192 (reference default), one long signal"}
     xbig = xl.repeat(8)  # 2.9 GB: far beyond L2
     nfb = xbig.numel() // 8192
-    ms = timed(lambda: ops.harmonic_energy(xbig, 22050))
-    out["he_8192_big"] = {"frames": nfb, "ms": ms, "frames_per_s": nfb / ms * 1e3,
-                          "alg_GBps": nfb * 32768 / ms / 1e6,
-                          "note": "frame 8192, hop 8192, 2.9 GB signal: packed FFT + bulk-async staging"}
-    os.environ["CDB_HE8192"] = "scalar"
-    ms = timed(lambda: ops.harmonic_energy(xbig, 22050))
-    del os.environ["CDB_HE8192"]
-    out["he_8192_big_scalar"] = {"frames": nfb, "ms": ms, "frames_per_s": nfb / ms * 1e3,
-                                 "alg_GBps": nfb * 32768 / ms / 1e6,
-                                 "note": "first-generation kernel (scalar butterflies, direct loads)"}
+    for mode in ("scalar", "packed", "staged"):
+        os.environ["CDB_HE8192"] = mode
+        ms = timed(lambda: ops.harmonic_energy(xbig, 22050))
+        del os.environ["CDB_HE8192"]
+        out["he_8192_big_" + mode] = {"frames": nfb, "ms": ms, "frames_per_s": nfb / ms * 1e3,
+                                      "alg_GBps": nfb * 32768 / ms / 1e6,
+                                      "note": "frame 8192, hop 8192, 2.9 GB signal; kernel variant " + mode}
     del xbig
     x2 = xl[: 25000 * 2048]
     ms = timed(lambda: ops.harmonic_energy(x2, 44100, frame_size=2048))

@@ -96,13 +96,14 @@ def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
     _assert_close(a.total.cpu().numpy(), b.total.cpu().numpy(), tol=1e-5)
     _assert_close(a.frames.cpu().numpy(), b.frames.cpu().numpy(), tol=1e-4)
     if frame_size == 8192:
-        # first-generation frame-8192 kernel (scalar butterflies, direct loads); the default one
-        # stages whole aligned frames by bulk async copy and reads ragged / unaligned ones directly
-        # (hop 1001 and the clip tail exercise that path)
+        # the three frame-8192 kernels: scalar butterflies / packed butterflies / packed + the next
+        # frame staged by bulk async copy (ragged and unaligned frames are read directly: hop 1001
+        # and the clip tail exercise that path)
         monkeypatch.delenv("CDB_HE_FORCE_GENERIC")
-        monkeypatch.setenv("CDB_HE8192", "scalar")
-        c = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
-        _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(), tol=1e-5)
+        for mode in ("scalar", "packed", "staged"):
+            monkeypatch.setenv("CDB_HE8192", mode)
+            c = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
+            _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(), tol=1e-5)
         monkeypatch.delenv("CDB_HE8192")
         xo = np.concatenate([np.zeros(1, dtype=np.float32), x])  # 4-byte-aligned view
         xd = torch.from_numpy(xo).to(_dev())[1:]
