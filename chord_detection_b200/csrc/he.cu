@@ -629,7 +629,10 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
 // overlap at this size); window and twiddle tables are read through L1.
 // ------------------------------------------------------------------------------------------
 constexpr int k8Threads = 256;
-static const char* const kHe8192Default = "scalar";  // scalar | packed | staged (see the dispatch)
+// scalar | packed | staged (see the dispatch).  88 200 frames, hop = frame, 2.9 GB (r01H):
+// scalar 60.8 M frames/s (1.99 TB/s), packed 41.0 M (direct global loads end up exposed between the
+// window computations: long-scoreboard stalls x5), staged 63.7 M (2.09 TB/s, 23 % fewer instructions).
+static const char* const kHe8192Default = "staged";
 constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
 
 __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
