@@ -60,6 +60,7 @@ EXPORTS = [
     "cdb_prime_chroma", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
     "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
     "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
+    "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
 ]
 
 
@@ -108,6 +109,11 @@ def lib():
                                           C.POINTER(C.c_int), C.c_int]
         L.cdb_host_find_peaks.argtypes = [C.POINTER(dbl), C.c_int, dbl, C.c_int,
                                           C.POINTER(C.c_int)]
+        L.cdb_resample_poly_f32.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+                                            C.c_int, vp, i64, vp]
+        L.cdb_host_resample_poly_f32.argtypes = [C.POINTER(C.c_float), i64, C.c_int, C.c_int,
+                                                 C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
+                                                 C.POINTER(C.c_float), i64]
         L.cdb_host_iterf0_filter.argtypes = [C.POINTER(C.c_float), C.c_int64, C.POINTER(dbl), dbl,
                                              C.POINTER(dbl), C.c_int, C.POINTER(C.c_float)]
         L.cdb_host_iterf0_spectrum8k.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(dbl)]
@@ -194,6 +200,22 @@ def host_gauss_fit(x0, y, suspend_after=0):
     info = lib().cdb_host_gauss_fit2(len(y), float(x0), y.ctypes.data_as(C.POINTER(C.c_double)), p,
                                      C.byref(nfev), int(suspend_after))
     return info, [p[0], p[1], p[2]], nfev.value
+
+
+def host_resample_poly(x, up, down, taps, n_pre_pad, n_pre_remove, n_out):
+    """Host execution of the device polyphase resampler (test hook, no GPU) -> float32 [n_out]."""
+    import numpy as np
+
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    y = np.zeros(int(n_out), dtype=np.float32)
+    F = C.POINTER(C.c_float)
+    rc = lib().cdb_host_resample_poly_f32(x.ctypes.data_as(F), x.shape[0], int(up), int(down),
+                                          taps.ctypes.data_as(F), taps.shape[0], int(n_pre_pad),
+                                          int(n_pre_remove), y.ctypes.data_as(F), int(n_out))
+    if rc != 0:
+        raise ValueError("cdb_host_resample_poly_f32 failed (%d)" % rc)
+    return y
 
 
 def host_iterf0_filter(x, coef, lam, taps, pipelined=True):

@@ -44,8 +44,10 @@ def run_batch(paths, methods, key=False, device=None, max_batch_bytes=1 << 30, l
 
     from . import METHODS, audio, ops
 
-    load = loader or audio.load
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    # librosa.load on the device (decode / down-mix / resample); clips come back as
+    # CUDA tensors and are stacked on the device
+    load = loader or (lambda p: audio.load_device(p, dev))
     fn = {1: ops.esacf, 2: ops.harmonic_energy, 3: ops.iterative_f0, 4: ops.prime_multif0}
     for m in methods:
         if m not in fn:
@@ -53,7 +55,9 @@ def run_batch(paths, methods, key=False, device=None, max_batch_bytes=1 << 30, l
     clips, groups = [], OrderedDict()
     for i, p in enumerate(paths):
         x, fs = load(p)
-        if x.ndim != 1:
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        if x.dim() != 1:
             raise ValueError("Only 1D numpy ndarrays are supported")  # dsp/frame.py:6-7
         clips.append(x)
         groups.setdefault((int(fs), int(x.shape[0])), []).append(i)
@@ -68,8 +72,7 @@ def run_batch(paths, methods, key=False, device=None, max_batch_bytes=1 << 30, l
         per = max(1, int(max_batch_bytes // (4 * n)))
         for s in range(0, len(idxs), per):
             part = idxs[s:s + per]
-            host = torch.from_numpy(np.stack([clips[i] for i in part]).astype(np.float32, copy=False))
-            xd = host.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else host
+            xd = torch.stack([clips[i].to(dev) for i in part])
             for m in methods:
                 r = fn[m](xd, fs, per_clip=True)
                 digits, keys = ops.pack_and_key(r.clips)

@@ -28,7 +28,7 @@ class MultipitchIterativeF0(Multipitch):
     ):
         super().__init__(audio_path, fs=fs, device=device)
         self.frame_size = frame_size
-        n = self.x.shape[0] if self.x is not None else self._x_dev.shape[0]
+        n = self._x_dev.shape[0] if self._x_dev is not None else self.x.shape[0]
         self.num_frames = math.ceil(n / self.frame_size)
         self.power = power
         self.channels = [

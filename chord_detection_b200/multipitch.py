@@ -34,10 +34,23 @@ class Multipitch(object):
     @abstractmethod
     def __init__(self, audio_path, fs=None, device=None):
         self._x_dev = None
+        self._x_host = None
         self.device = device
         if isinstance(audio_path, (str, Path)):
-            self.x, self.fs = audio.load(audio_path)
             self.clip_name = Path(audio_path).name
+            try:
+                import torch
+                have_gpu = torch.cuda.is_available()
+            except ImportError:  # pragma: no cover
+                have_gpu = False
+            if have_gpu:
+                # librosa.load on the device: PCM16 stays int16 on the wire, mono
+                # down-mix and resampling to 22 050 Hz run on the GPU; x is fetched on demand
+                dev = torch.device("cuda" if device is None else device)
+                self._x_dev, self.fs = audio.load_device(audio_path, dev)
+                self.device = self._x_dev.device
+            else:
+                self.x, self.fs = audio.load(audio_path)
         else:
             if fs is None:
                 raise ValueError("fs= is required when passing samples instead of a path")
@@ -54,7 +67,6 @@ class Multipitch(object):
                 if t.is_cuda:
                     self._x_dev = t.to(torch.float32).contiguous()
                     self.device = t.device
-                    self.x = None  # fetched lazily
                 else:
                     self.x = t.detach().to(torch.float32).numpy()
             else:
@@ -62,6 +74,19 @@ class Multipitch(object):
                 if len(x.shape) != 1:
                     raise ValueError("Only 1D numpy ndarrays are supported")
                 self.x = x.astype(numpy.float32)
+
+    @property
+    def x(self):
+        """The clip as a float32 numpy array (reference attribute, multipitch.py:25); copied back
+        from the device on first use when the clip was loaded / passed in as a CUDA tensor."""
+        if self._x_host is None and self._x_dev is not None:
+            self._x_host = self._x_dev.detach().cpu().numpy()
+        return self._x_host
+
+    @x.setter
+    def x(self, value):
+        self._x_host = value
+        self._x_dev = None  # re-uploaded on the next compute_pitches()
 
     # -- device plumbing ---------------------------------------------------
     def _device_samples(self):

@@ -55,6 +55,27 @@ def pcm16_to_mono(pcm):
     return out
 
 
+def resample_poly(x, fs_in, fs_out):
+    """Polyphase resampling of a 1-D CUDA float32 signal, scipy.signal.resample_poly semantics
+    (audio.resample_plan designs the filter on the host once per rate pair)."""
+    from . import audio
+
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 1:
+        raise ValueError("expected a 1-D CUDA float32 tensor")
+    x = x.contiguous()
+    up, down, taps, n_pre_pad, n_pre_remove, n_out = audio.resample_plan(x.numel(), fs_in, fs_out)
+    if up == down:
+        return x.clone()
+    h = nat.Handle.get(x.device.index)
+    td = torch.from_numpy(taps).to(x.device)
+    y = torch.empty(n_out, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = h.L.cdb_resample_poly_f32(h.ptr, _ptr(x), x.numel(), up, down, _ptr(td), td.numel(),
+                                       n_pre_pad, n_pre_remove, _ptr(y), n_out, _stream_ptr(x))
+    h.check(rc, "cdb_resample_poly_f32")
+    return y
+
+
 def _stream_ptr(x):
     return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
 

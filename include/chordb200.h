@@ -201,9 +201,20 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
 /* ---------------- ingestion: the decode step of librosa.load (multipitch.py:25), SURVEY 8f-2 ---------------- */
 /* d_pcm: interleaved int16 [n_frames, channels] -> d_out[n_frames] float32 = mean over channels of
  * s/32768 (soundfile PCM_16 -> float32, then librosa.to_mono); exact.  Halves the host->device
- * bytes of a WAV payload.  Resampling stays on the host. */
+ * bytes of a WAV payload. */
 int cdb_pcm16_to_mono_f32(cdb_handle* h, const int16_t* d_pcm, int64_t n_frames, int channels,
                           float* d_out, void* stream);
+
+/* Polyphase resampling on the device with scipy.signal.resample_poly's semantics (the resampling
+ * half of librosa.load, multipitch.py:25).  d_taps[n_taps] = the low-pass FIR times `up` (float32),
+ * n_pre_pad / n_pre_remove / n_out exactly as resample_poly derives them
+ * (chord_detection_b200/audio.py: resample_plan); d_y[n_out]. */
+int cdb_resample_poly_f32(cdb_handle* h, const float* d_x, int64_t n_in, int up, int down,
+                          const float* d_taps, int n_taps, int n_pre_pad, int n_pre_remove,
+                          float* d_y, int64_t n_out, void* stream);
+/* host execution of the same per-sample code (CPU tests, no GPU) */
+int cdb_host_resample_poly_f32(const float* x, int64_t n_in, int up, int down, const float* taps,
+                               int n_taps, int n_pre_pad, int n_pre_remove, float* y, int64_t n_out);
 
 /* ---------------- batched result post-processing (chromagram.py:50-126), SURVEY 8f-1 ---------------- */
 /* d_chroma [n,12] double -> d_digits [n,12] uint8 (the 12-digit string, chromagram.py:50-74) and

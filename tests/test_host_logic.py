@@ -127,6 +127,28 @@ def test_host_fft_autocorrelation_matches_numpy_sacf():
         nat.host_esacf_acf(np.zeros((1, 2049)), np.zeros((1, 2049)))
 
 
+def test_host_resampler_matches_scipy_resample_poly():
+    """The device polyphase resampler (ingestion), executed on the host, against
+    scipy.signal.resample_poly -- the resampling half of audio.load()."""
+    import scipy.signal
+    from math import gcd
+
+    from chord_detection_b200 import audio
+
+    rng = np.random.default_rng(3)
+    for fs_in, n in ((44100, 50001), (48000, 30000), (16000, 9999), (8000, 5000), (11025, 7777),
+                     (96000, 40000), (44100, 1), (44100, 3), (32000, 2)):
+        x = rng.standard_normal(n).astype(np.float32)
+        up, down, taps, npp, npr, n_out = audio.resample_plan(n, fs_in, 22050)
+        g = gcd(22050, fs_in)
+        assert (up, down) == (22050 // g, fs_in // g)
+        got = nat.host_resample_poly(x, up, down, taps, npp, npr, n_out)
+        want = scipy.signal.resample_poly(x, up, down).astype(np.float32)
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= 1e-6 * max(np.max(np.abs(want)), 1e-30), (fs_in, n)
+    assert audio.resample_plan(10, 22050, 22050)[:2] == (1, 1)
+
+
 def test_host_iterf0_filter_pipelined_schedule_is_exact():
     """The auditory-channel filter of iterf0_filter_kernel on the host: the software-pipelined
     schedule (stage s on sample t - s) equals the straight per-sample loop bit for bit, and both

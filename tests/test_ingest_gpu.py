@@ -112,3 +112,30 @@ def test_host_pipeline_pcm16_wire():
     assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-9
     with pytest.raises(ValueError):
         pipe.run(torch.from_numpy(x))
+
+
+def test_device_load_matches_host_load(tmp_path):
+    """audio.load_device (int16 on the wire, mono down-mix and polyphase resampling on the GPU)
+    against audio.load (scipy on the host) for mono / stereo clips at several sample rates."""
+    import scipy.io.wavfile as wavfile
+
+    from chord_detection_b200 import audio
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    for i, (fs, ch, n) in enumerate(((44100, 1, 30011), (48000, 2, 20000), (22050, 1, 5000),
+                                     (16000, 2, 7001), (8000, 1, 999))):
+        pcm = rng.integers(-20000, 20000, size=(n, ch) if ch > 1 else n).astype(np.int16)
+        path = os.path.join(tmp_path, "c%d.wav" % i)
+        wavfile.write(path, fs, pcm)
+        want, fs_w = audio.load(path)
+        got, fs_g = audio.load_device(path, dev)
+        assert fs_w == fs_g == 22050
+        got = got.cpu().numpy()
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert np.max(np.abs(got - want)) <= 1e-6 * max(np.max(np.abs(want)), 1e-30), (fs, ch)
+    with pytest.raises(ValueError):
+        from chord_detection_b200 import ops
+        ops.resample_poly(torch.zeros(4), 44100, 22050)  # CPU tensor: no fallback
