@@ -224,3 +224,25 @@ def test_host_gaussian_fit_matches_scipy_curve_fit():
                 n += 1
     assert n > 200
     assert worst < 5e-5  # xtol = 1.49e-8 on ill-conditioned fits: termination point differs slightly
+
+
+def test_audio_load_host_path(tmp_path):
+    """audio.load (the host twin of audio.load_device): decode, float32 mean over channels,
+    resample_poly to 22 050 Hz; read_wav keeps 16-bit PCM as stored."""
+    import scipy.io.wavfile as wavfile
+    import scipy.signal
+
+    from chord_detection_b200 import audio
+
+    rng = np.random.default_rng(4)
+    pcm = rng.integers(-30000, 30000, size=(4410, 2)).astype(np.int16)
+    path = os.path.join(tmp_path, "s.wav")
+    wavfile.write(path, 44100, pcm)
+    raw, fs = audio.read_wav(path)
+    assert fs == 44100 and raw.dtype == np.int16 and raw.shape == (4410, 2)
+    x, fs2 = audio.load(path)
+    mono = (pcm.astype(np.float32) / 32768.0).mean(axis=1)
+    want = scipy.signal.resample_poly(mono, 1, 2).astype(np.float32)
+    assert fs2 == 22050 and x.dtype == np.float32 and np.array_equal(x, want)
+    x0, fs0 = audio.load(path, sr=None)
+    assert fs0 == 44100 and np.array_equal(x0, mono)
