@@ -375,7 +375,7 @@ def main():
                                   "kernel, bit-identical chroma); informational, not the headline"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic(), "peak_source": peak_src,
-                         "kernel": "he2048w_kernel<16,5>", "kernel_ms": kernel_ms,
+                         "kernel": "he2048w_kernel<16,5,false>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": nfr * ALG_BYTES_PER_FRAME,
                          "binding_roof": "shared-memory wavefronts + FMA pipe, not HBM (29 flop/B, SURVEY.md "
                                          "8d): ~333 wavefronts and ~570 packed FP32x2 instructions per frame "
