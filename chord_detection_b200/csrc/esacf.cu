@@ -327,9 +327,11 @@ __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kerne
   afft::acf_pair<R1>(ex, c);
 }
 
-// kFitLanes lanes of each warp run fits; fewer lanes shrink the per-warp shared-memory work area
-// (26.9 KB at 32 lanes) and allow more resident warps.  Measured flat (228-244 ms per 62 592 frames for
-// 4..32 lanes): the stage is bound by lanes of one warp sitting in different LM phases.
+// kFitLanes lanes of each warp run fits (32 by default; the 4 / 8 / 16-lane instances shrink the
+// per-warp shared-memory work area, 31.5 KB at 32 lanes, and were measured within 7 % of each other
+// before the lanes were phase-aligned).  Resident fits per SM = lanes x warps is what matters: the
+// stage is latency-bound, and the work area plus the local-memory 3-vectors of every fit must fit
+// in the SM's 256 KB of shared memory + L1.
 constexpr int kFitThreads = 256;  // upper bound; kFitWarpsDefault of them are launched
 constexpr int kFitWarpsDefault = 6;  // y in shared memory (15 648 frames): 4 warps 24.7 ms, 5: 22.5, 6: 21.6, 7: 25.8
 

@@ -65,7 +65,7 @@ def main():
                        "samples_per_s": nc * 44100 / ms * 1e3}
     ms = timed(lambda: ops.harmonic_energy(x, 22050, per_clip=True))
     out["he_default_c5"] = {"clips": nc, "frames": nc * 6, "ms": ms, "frames_per_s": nc * 6 / ms * 1e3,
-                            "note": "reference defaults (frame 8192, generic kernel)"}
+                            "note": "reference defaults (frame 8192, 6 frames per clip)"}
     xl = x.reshape(-1)[: (x.numel() // 8192) * 8192]
     ms = timed(lambda: ops.harmonic_energy(xl, 22050))
     nf = xl.numel() // 8192
