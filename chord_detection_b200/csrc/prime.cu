@@ -168,6 +168,39 @@ struct PrimeArgs {
   double* cands;  // [n_clips, n_cand, 12]
 };
 
+// Goertzel recurrences for the J consecutive bins k0 + tid * J + j, j < J, over the W windowed
+// samples (broadcast from shared memory): s[n] = x[n] + c s[n-1] - s[n-2];
+// |X_k|^2 = s1^2 + s2^2 - c s1 s2.  Consecutive bins per thread keep the active threads contiguous,
+// so whole warps beyond the last bin skip the pass.
+template <int J>
+__device__ __forceinline__ void prime_goertzel(const double* xw, int W, int H, int k0, int tid,
+                                               double invW, double invsum, double* s) {
+  double cc[J], s1[J], s2[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    cc[j] = 2.0 * cospi(2.0 * (double)(k0 + tid * J + j) * invW);
+    s1[j] = s2[j] = 0.0;
+  }
+  for (int n = 0; n < W; ++n) {
+    const double v = xw[n];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const double t = fma(cc[j], s1[j], v) - s2[j];
+      s2[j] = s1[j];
+      s1[j] = t;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int k = k0 + tid * J + j;
+    if (k < H) {
+      double p = s1[j] * s1[j] + s2[j] * s2[j] - cc[j] * s1[j] * s2[j];
+      p = p > 0.0 ? p : 0.0;
+      s[k] = sqrt(p) * invsum;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* xw = reinterpret_cast<double*>(smem);  // [maxW]
@@ -196,31 +229,19 @@ __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a)
     __syncthreads();
     const double invW = 1.0 / (double)W;
     const double invsum = a.invsum[c];
-    for (int k0 = 0; k0 < H; k0 += kPrimeThreads * 4) {
-      double cc[4], s1[4], s2[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        cc[j] = 2.0 * cospi(2.0 * (double)(k0 + tid + j * kPrimeThreads) * invW);
-        s1[j] = s2[j] = 0.0;
-      }
-      for (int n = 0; n < W; ++n) {
-        const double v = xw[n];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double t = fma(cc[j], s1[j], v) - s2[j];
-          s2[j] = s1[j];
-          s1[j] = t;
+    // J = bins per thread for this pass: ceil(remaining bins / threads), at most 4.  (A fixed J = 4
+    // spent 2/3 of the FP64 work on bins >= H: H is 89..337 at 22 050 Hz against 512 slots.)
+    for (int k0 = 0; k0 < H;) {
+      const int J = min(4, (H - k0 + kPrimeThreads - 1) / kPrimeThreads);
+      if (k0 + (tid & ~31) * J < H) {  // warps whose bins all lie beyond H skip the pass
+        switch (J) {
+          case 1: prime_goertzel<1>(xw, W, H, k0, tid, invW, invsum, s); break;
+          case 2: prime_goertzel<2>(xw, W, H, k0, tid, invW, invsum, s); break;
+          case 3: prime_goertzel<3>(xw, W, H, k0, tid, invW, invsum, s); break;
+          default: prime_goertzel<4>(xw, W, H, k0, tid, invW, invsum, s); break;
         }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + tid + j * kPrimeThreads;
-        if (k < H) {
-          double p = s1[j] * s1[j] + s2[j] * s2[j] - cc[j] * s1[j] * s2[j];
-          p = p > 0.0 ? p : 0.0;
-          s[k] = sqrt(p) * invsum;
-        }
-      }
+      k0 += kPrimeThreads * J;
     }
     __syncthreads();
     const int8_t* note = a.note + a.offh[c];
