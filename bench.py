@@ -224,28 +224,18 @@ def main():
         x = seg.repeat(reps)[:n] * (0.75 + 0.5 * torch.rand(n, device=dev, generator=g))
         bufs.append(x.contiguous())
     total = torch.zeros(12, dtype=torch.float64, device=dev)
-    totals = [torch.zeros(12, dtype=torch.float64, device=dev) for _ in range(2)]
-    pending = [None, None]
 
     def step(i):
-        # one 12-double NCCL all-reduce over NVLink per step.  Steps are independent,
-        # so the collective of step i runs on NCCL's stream under the kernel of step i+1 (two result
-        # buffers); drain() makes the launching stream wait for every outstanding collective, and
-        # the timed region ends after it.
-        if world == 1:
-            ops.harmonic_energy(bufs[i % N_ROTATING], FS, frame_size=FRAME, hop=HOP, out_total=total)
-            return
-        b = i & 1
-        if pending[b] is not None:
-            pending[b].wait()
-        ops.harmonic_energy(bufs[i % N_ROTATING], FS, frame_size=FRAME, hop=HOP, out_total=totals[b])
-        pending[b] = dist.all_reduce(totals[b], async_op=True)
+        ops.harmonic_energy(bufs[i % N_ROTATING], FS, frame_size=FRAME, hop=HOP, out_total=total)
+        if world > 1:
+            # one 12-double NCCL all-reduce over NVLink per step.  Issuing it
+            # asynchronously under the next step's kernel was measured SLOWER on 2 GPUs (0.186 vs
+            # 0.175 ms per step, r01I vs r01C: the extra stream hand-offs cost more than the ~11 us
+            # the collective takes), so it stays in stream order.
+            dist.all_reduce(total)
 
     def drain():
-        for b in range(2):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+        pass
 
     def barrier():
         if world > 1:
@@ -358,7 +348,7 @@ def main():
                        "window": "hamming (reference harmonic_energy.py:42)",
                        "accumulate": "fp64", "parallelism": "frames sharded, dp%d" % world,
                        "collective": "none (1 GPU)" if world == 1 else
-                                     "one 12-double NCCL all-reduce per step, overlapped with the next step's kernel",
+                                     "one 12-double NCCL all-reduce per step, in stream order",
                        "l2": "%d rotating %.1f MB inputs (> 126 MB L2): every step reads cold data"
                              % (N_ROTATING, n * 4 / 1e6)},
             "gpu_launches": int(launches),
