@@ -181,25 +181,15 @@ __device__ __forceinline__ void prime_goertzel(const double* xw, int W, int H, i
     cc[j] = 2.0 * cospi(2.0 * (double)(k0 + tid * J + j) * invW);
     s1[j] = s2[j] = 0.0;
   }
-  auto step = [&](double v) {
+  for (int n = 0; n < W; ++n) {
+    const double v = xw[n];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const double t = fma(cc[j], s1[j], v) - s2[j];
       s2[j] = s1[j];
       s1[j] = t;
     }
-  };
-  // two samples per 128-bit broadcast load: with 1-3 bins per thread the sample loads were 21 % of
-  // the LSU slots next to a 62 % busy FP64 pipe (ncu r01K)
-  const double2* xw2 = reinterpret_cast<const double2*>(xw);
-  int n = 0;
-#pragma unroll 2
-  for (; n + 1 < W; n += 2) {
-    const double2 v = xw2[n >> 1];
-    step(v.x);
-    step(v.y);
   }
-  if (n < W) step(xw[n]);
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int k = k0 + tid * J + j;
