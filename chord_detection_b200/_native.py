@@ -191,6 +191,7 @@ def num_frames(clip_len, frame_size, hop=0):
 
 def host_gauss_fit(x0, y, suspend_after=0):
     """Host build of the device Levenberg-Marquardt Gaussian fit (test hook, no GPU).
+    suspend_after > 0: park / resume every so many super-rounds; -1: the array-free LmStream variant.
     -> (info, [ampl, centre, dev], nfev)"""
     import numpy as np
 

@@ -585,7 +585,9 @@ int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* n
   for (int i = 0; i < m; ++i) ymax = std::fmax(ymax, y[i]);
   double p[3] = {ymax, x0, 5.0};
   int nf = 0;
-  const int info = lmg::lmdif(pr, p, &nf, suspend_after);
+  // suspend_after == -1: the array-free LmStream variant (row-wise Givens QR)
+  const int info = suspend_after == -1 ? lmg::lmdif_stream(pr, p, &nf)
+                                       : lmg::lmdif(pr, p, &nf, suspend_after);
   p_out[0] = p[0];
   p_out[1] = p[1];
   p_out[2] = p[2];

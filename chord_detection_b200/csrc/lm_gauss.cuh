@@ -121,14 +121,15 @@ LMG_HD inline void residuals(const Problem& pr, const double* p, double* f) {
 #endif
 }
 
-// a is column-major: element (i, j) at a[(i + j*MMAX)*ST], i < m, j < NP
-#define LMG_A(i, j) a[((i) + (j)*MMAX) * ST]
-template <int ST>
+// a is column-major: element (i, j) at a[(i + j*LD)*ST], i < m, j < NP (LD = MMAX for the m x 3
+// Jacobian of LmSM, 3 for the 3 x 3 triangle of LmStream)
+#define LMG_A(i, j) a[((i) + (j)*LD) * ST]
+template <int ST, int LD = MMAX>
 LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm,
                              double* wa) {
   LMG_UNROLL1
   for (int j = 0; j < NP; ++j) {
-    acnorm[j] = enorm<ST>(a + (j * MMAX) * ST, m);
+    acnorm[j] = enorm<ST>(a + (j * LD) * ST, m);
     rdiag[j] = acnorm[j];
     wa[j] = rdiag[j];
     ipvt[j] = j;
@@ -153,7 +154,7 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
       ipvt[j] = ipvt[kmax];
       ipvt[kmax] = k;
     }
-    double ajnorm = enorm<ST>(a + (j + j * MMAX) * ST, m - j);
+    double ajnorm = enorm<ST>(a + (j + j * LD) * ST, m - j);
     if (ajnorm != 0.0) {
       if (LMG_A(j, j) < 0.0) ajnorm = -ajnorm;
       const double rnorm = ddiv(1.0, ajnorm);  // (MINPACK divides every element: <= 1 ulp apart)
@@ -175,7 +176,7 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
           rdiag[k] *= dsqrt(d);
           const double q = ddiv(rdiag[k], wa[k]);
           if (0.05 * (q * q) <= EPSMCH) {
-            rdiag[k] = enorm<ST>(a + ((j + 1) + k * MMAX) * ST, m - j - 1);
+            rdiag[k] = enorm<ST>(a + ((j + 1) + k * LD) * ST, m - j - 1);
             wa[k] = rdiag[k];
           }
         }
@@ -185,8 +186,8 @@ LMG_HD inline void qrfac(int m, double* a, int* ipvt, double* rdiag, double* acn
   }
 }
 
-#define LMG_R(i, j) r[((i) + (j)*MMAX) * ST]
-template <int ST>
+#define LMG_R(i, j) r[((i) + (j)*LD) * ST]
+template <int ST, int LD = MMAX>
 LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const double* qtb,
                               double* x, double* sdiag, double* wa) {
   LMG_UNROLL1
@@ -250,7 +251,7 @@ LMG_HD inline void qrsolv(double* r, const int* ipvt, const double* diag, const 
   for (int j = 0; j < NP; ++j) x[ipvt[j]] = wa[j];
 }
 
-template <int ST>
+template <int ST, int LD = MMAX>
 LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const double* qtb,
                              double delta, double* par, double* x, double* sdiag, double* wa1,
                              double* wa2) {
@@ -317,7 +318,7 @@ LMG_HD inline void lmpar(double* r, const int* ipvt, const double* diag, const d
     double temp = dsqrt(*par);
     LMG_UNROLL1
     for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
-    qrsolv<ST>(r, ipvt, wa1, qtb, x, sdiag, wa2);
+    qrsolv<ST, LD>(r, ipvt, wa1, qtb, x, sdiag, wa2);
     LMG_UNROLL1
     for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = enorm<1>(wa2, NP);
@@ -374,6 +375,7 @@ struct LmSaved {
 
 template <int ST>
 struct LmSM {
+  static constexpr int LD = MMAX;
   enum { JAC = 1, STEP = 2, DONE = 5 };
   double p[NP], diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
   int ipvt[NP];
@@ -601,6 +603,302 @@ LMG_HD inline void super_round(const Problem& pr, LmSM<ST>& sm, bool active) {
     residuals<ST>(pr, sm.wa2, sm.wa4);
     sm.trial_block(pr.m);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LmStream: the same algorithm with NO per-fit arrays.  The m x 3 Jacobian is never stored: its rows
+// (forward differences of the model at p and at the three perturbed points, all four Gaussians
+// advanced together by the outward recurrence) are rotated one by one into a 3 x 3 triangle and
+// Q^T f by Givens rotations (what MINPACK's lmstr / rwupdt do); the 3 x 3 triangle is then
+// column-pivoted by qrfac like lmdif's Jacobian, and lmpar / the acceptance logic are shared.
+// Residual vectors are not kept either: their norms are accumulated on the fly and f(p) is
+// recomputed with the next Jacobian.  State = ~45 doubles in registers instead of 126 in shared
+// memory, i.e. several times more fits resident per SM on the GPU.  Mathematically identical to
+// lmdif (R is unique up to signs), numerically different at rounding level: see the host
+// comparison against SciPy in tests/test_host_logic.py before switching the device kernel over.
+struct LmStream {
+  static constexpr int LD = NP;
+  static constexpr int ST = 1;
+  enum { JAC = 1, STEP = 2, DONE = 5 };
+  double p[NP], diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
+  double a[NP * NP];  // R factor, element (i, j) at a[i + 3 j]
+  int ipvt[NP];
+  double par, delta, xnorm, fnorm, gnorm, pnorm;
+  int iter, nfev, info, phase;
+
+  // K Gaussians a_k exp(-(x - c_k)^2 / (2 s_k^2 + eps)) on the grid x0 + i, advanced together
+  // outward from the sample nearest the centre of parameter set 0
+  template <int K>
+  struct Rows {
+    double e[K], r[K], q[K], e0[K], rdn[K];
+    int i0;
+    LMG_HD void init(const Problem& pr, const double (*P)[NP]) {
+      const double d0c = pr.x0 - P[0][1];
+      double ic = nearbyint(-d0c);
+      ic = ic > 0.0 ? ic : 0.0;
+      ic = ic < (double)(pr.m - 1) ? ic : (double)(pr.m - 1);
+      i0 = (int)ic;
+      LMG_UNROLL1
+      for (int k = 0; k < K; ++k) {
+        const double ninv = ddiv(-1.0, 2.0 * P[k][2] * P[k][2] + EPSMCH);
+        const double dc = (pr.x0 - P[k][1]) + ic;
+        e0[k] = P[k][0] * exp((dc * dc) * ninv);
+        q[k] = exp(2.0 * ninv);
+        r[k] = exp(ninv * (2.0 * dc + 1.0));
+        rdn[k] = exp(ninv * (1.0 - 2.0 * dc));
+        e[k] = e0[k];
+      }
+    }
+    LMG_HD void turn_down() {
+      for (int k = 0; k < K; ++k) {
+        e[k] = e0[k];
+        r[k] = rdn[k];
+      }
+    }
+    LMG_HD void next() {
+      for (int k = 0; k < K; ++k) {
+        e[k] *= r[k];
+        r[k] *= q[k];
+      }
+    }
+  };
+
+  LMG_HD void init(const double* p0) {
+    for (int j = 0; j < NP; ++j) p[j] = p0[j];
+    par = delta = xnorm = fnorm = gnorm = pnorm = 0.0;
+    iter = 1;
+    nfev = 0;
+    info = 0;
+    phase = JAC;
+  }
+
+  // ||f(q)|| with the rows visited centre-outward
+  LMG_HD double resid_norm(const Problem& pr, const double* q) const {
+    double P[1][NP];
+    for (int j = 0; j < NP; ++j) P[0][j] = q[j];
+    Rows<1> g;
+    g.init(pr, P);
+    double ss = 0.0;
+    {
+      const double f = g.e[0] - pr.y[g.i0];
+      ss += f * f;
+    }
+    for (int i = g.i0 + 1; i < pr.m; ++i) {
+      g.next();
+      const double f = g.e[0] - pr.y[i];
+      ss += f * f;
+    }
+    g.turn_down();
+    for (int i = g.i0 - 1; i >= 0; --i) {
+      g.next();
+      const double f = g.e[0] - pr.y[i];
+      ss += f * f;
+    }
+    return dsqrt(ss);
+  }
+
+  LMG_HD void begin(const Problem& pr) {
+    fnorm = resid_norm(pr, p);
+    nfev = 1;
+    par = 0.0;
+    iter = 1;
+    phase = JAC;
+  }
+
+  // one row (w[0..2] | alpha) rotated into the triangle a and qtf (MINPACK rwupdt)
+  LMG_HD void rotate_row(double* w, double alpha) {
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      if (w[j] == 0.0) continue;
+      double c, sn;
+      if (fabs(LMG_A(j, j)) < fabs(w[j])) {
+        const double cotan = ddiv(LMG_A(j, j), w[j]);
+        sn = ddiv(0.5, dsqrt(0.25 + 0.25 * (cotan * cotan)));
+        c = sn * cotan;
+      } else {
+        const double tn = ddiv(w[j], LMG_A(j, j));
+        c = ddiv(0.5, dsqrt(0.25 + 0.25 * (tn * tn)));
+        sn = c * tn;
+      }
+      LMG_A(j, j) = c * LMG_A(j, j) + sn * w[j];
+      LMG_UNROLL1
+      for (int k = j + 1; k < NP; ++k) {
+        const double t = c * LMG_A(j, k) + sn * w[k];
+        w[k] = -sn * LMG_A(j, k) + c * w[k];
+        LMG_A(j, k) = t;
+      }
+      const double t = c * qtf[j] + sn * alpha;
+      alpha = -sn * qtf[j] + c * alpha;
+      qtf[j] = t;
+    }
+  }
+
+  // fdjac2 + QR + gnorm test in one pass over the rows.  -> STEP or DONE
+  LMG_HD void jac_block(const Problem& pr) {
+    const double gtol = 0.0, factor = 100.0, eps = 1.4901161193847656e-08;
+    double P[NP + 1][NP], rh[NP];
+    for (int k = 0; k <= NP; ++k)
+      for (int j = 0; j < NP; ++j) P[k][j] = p[j];
+    for (int j = 0; j < NP; ++j) {
+      double h = eps * fabs(p[j]);
+      if (h == 0.0) h = eps;
+      P[j + 1][j] = p[j] + h;
+      rh[j] = ddiv(1.0, h);
+    }
+    for (int i = 0; i < NP * NP; ++i) a[i] = 0.0;
+    for (int j = 0; j < NP; ++j) qtf[j] = 0.0;
+    Rows<NP + 1> g;
+    g.init(pr, P);
+    auto row = [&](int i) {
+      const double yi = pr.y[i];
+      const double f0 = g.e[0] - yi;
+      double w[NP];
+      for (int j = 0; j < NP; ++j) w[j] = ((g.e[j + 1] - yi) - f0) * rh[j];
+      rotate_row(w, f0);
+    };
+    row(g.i0);
+    for (int i = g.i0 + 1; i < pr.m; ++i) {
+      g.next();
+      row(i);
+    }
+    g.turn_down();
+    for (int i = g.i0 - 1; i >= 0; --i) {
+      g.next();
+      row(i);
+    }
+    nfev += NP;
+    // column pivoting on the 3 x 3 triangle, as lmdif's qrfac does on the Jacobian
+    qrfac<1, NP>(NP, a, ipvt, wa1, wa2, wa3);
+    if (iter == 1) {
+      for (int j = 0; j < NP; ++j) {
+        diag[j] = wa2[j];
+        if (wa2[j] == 0.0) diag[j] = 1.0;
+      }
+      for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
+      xnorm = enorm<1>(wa3, NP);
+      delta = factor * xnorm;
+      if (delta == 0.0) delta = factor;
+    }
+    double w4[NP];
+    for (int j = 0; j < NP; ++j) w4[j] = qtf[j];
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      if (LMG_A(j, j) != 0.0) {
+        double sum = 0.0;
+        for (int i = j; i < NP; ++i) sum += LMG_A(i, j) * w4[i];
+        const double temp = ddiv(-sum, LMG_A(j, j));
+        for (int i = j; i < NP; ++i) w4[i] += LMG_A(i, j) * temp;
+      }
+      LMG_A(j, j) = wa1[j];
+      qtf[j] = w4[j];
+    }
+    gnorm = 0.0;
+    if (fnorm != 0.0) {
+      LMG_UNROLL1
+      for (int j = 0; j < NP; ++j) {
+        const int l = ipvt[j];
+        if (wa2[l] != 0.0) {
+          double sum = 0.0;
+          for (int i = 0; i <= j; ++i) sum += LMG_A(i, j) * ddiv(qtf[i], fnorm);
+          gnorm = fmax(gnorm, fabs(ddiv(sum, wa2[l])));
+        }
+      }
+    }
+    if (gnorm <= gtol) {
+      info = 4;
+      phase = DONE;
+    } else {
+      for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
+      phase = STEP;
+    }
+  }
+
+  LMG_HD void step_block() {
+    lmpar<1, NP>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+    for (int j = 0; j < NP; ++j) {
+      wa1[j] = -wa1[j];
+      wa2[j] = p[j] + wa1[j];
+      wa3[j] = diag[j] * wa1[j];
+    }
+    pnorm = enorm<1>(wa3, NP);
+    if (iter == 1) delta = fmin(delta, pnorm);
+  }
+
+  LMG_HD void trial_block(const Problem& pr) {
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8;
+    const int maxfev = 200 * (NP + 1);
+    ++nfev;
+    const double fnorm1 = resid_norm(pr, wa2);
+    double actred = -1.0;
+    if (0.1 * fnorm1 < fnorm) {
+      const double q = ddiv(fnorm1, fnorm);
+      actred = 1.0 - q * q;
+    }
+    for (int j = 0; j < NP; ++j) {
+      wa3[j] = 0.0;
+      const double temp = wa1[ipvt[j]];
+      for (int i = 0; i <= j; ++i) wa3[i] += LMG_A(i, j) * temp;
+    }
+    const double temp1 = ddiv(enorm<1>(wa3, NP), fnorm);
+    const double temp2 = ddiv(dsqrt(par) * pnorm, fnorm);
+    const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
+    const double dirder = -(temp1 * temp1 + temp2 * temp2);
+    double ratio = 0.0;
+    if (prered != 0.0) ratio = ddiv(actred, prered);
+    if (ratio <= 0.25) {
+      double temp;
+      if (actred >= 0.0) temp = 0.5;
+      else temp = ddiv(0.5 * dirder, dirder + 0.5 * actred);
+      if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+      delta = temp * fmin(delta, pnorm / 0.1);
+      par = ddiv(par, temp);
+    } else if (par == 0.0 || ratio >= 0.75) {
+      delta = pnorm / 0.5;
+      par *= 0.5;
+    }
+    if (ratio >= 1e-4) {
+      for (int j = 0; j < NP; ++j) {
+        p[j] = wa2[j];
+        wa2[j] = diag[j] * p[j];
+      }
+      xnorm = enorm<1>(wa2, NP);
+      fnorm = fnorm1;
+      ++iter;
+    }
+    if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
+    if (delta <= xtol * xnorm) info = 2;
+    if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
+    if (info == 0) {
+      if (nfev >= maxfev) info = 5;
+      if (fabs(actred) <= EPSMCH && prered <= EPSMCH && 0.5 * ratio <= 1.0) info = 6;
+      if (delta <= EPSMCH * xnorm) info = 7;
+      if (gnorm <= EPSMCH) info = 8;
+    }
+    if (info != 0) phase = DONE;
+    else if (ratio < 1e-4) phase = STEP;
+    else phase = JAC;
+  }
+};
+
+// lmdif through LmStream (pr.y with element stride 1)
+LMG_HD inline int lmdif_stream(const Problem& pr, double* p, int* nfev_out) {
+  if (pr.m < NP) {
+    *nfev_out = 0;
+    return 0;
+  }
+  LmStream sm;
+  sm.init(p);
+  sm.begin(pr);
+  while (sm.phase != LmStream::DONE) {
+    if (sm.phase == LmStream::JAC) sm.jac_block(pr);
+    if (sm.phase == LmStream::STEP) {
+      sm.step_block();
+      sm.trial_block(pr);
+    }
+  }
+  for (int j = 0; j < NP; ++j) p[j] = sm.p[j];
+  *nfev_out = sm.nfev;
+  return sm.info;
 }
 
 // p: in = start, out = solution.  Returns MINPACK info (1..4 = converged).  Single-fit driver

@@ -129,7 +129,8 @@ int64_t cdb_esacf_debug_stride(int ham_samples);
  * MINPACK info code (1..4 = converged). */
 int cdb_host_gauss_fit(int m, double x0, const double* y, double* p_out, int* nfev);
 /* the same fit, suspended and resumed from its saved state every suspend_after super-rounds (the
- * device parks long-running fits this way); bit-identical to cdb_host_gauss_fit */
+ * device parks long-running fits this way); bit-identical to cdb_host_gauss_fit.
+ * suspend_after == -1: the array-free variant (lmg::LmStream, row-wise Givens QR). */
 int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* nfev,
                         int suspend_after);
 int cdb_host_find_peaks(const double* y, int L, double thres, int min_dist, int* peaks_out);
