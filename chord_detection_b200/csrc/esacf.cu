@@ -585,9 +585,12 @@ int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* n
   for (int i = 0; i < m; ++i) ymax = std::fmax(ymax, y[i]);
   double p[3] = {ymax, x0, 5.0};
   int nf = 0;
-  // suspend_after == -1: the array-free LmStream variant (row-wise Givens QR)
-  const int info = suspend_after == -1 ? lmg::lmdif_stream(pr, p, &nf)
-                                       : lmg::lmdif(pr, p, &nf, suspend_after);
+  // suspend_after < 0: the array-free LmStream variants: -1 row-wise Givens QR, -4 / -7 Householder
+  // reduction of blocks of 4 / 7 rows
+  const int info = suspend_after == -1   ? lmg::lmdif_stream<0>(pr, p, &nf)
+                   : suspend_after == -4 ? lmg::lmdif_stream<4>(pr, p, &nf)
+                   : suspend_after == -7 ? lmg::lmdif_stream<7>(pr, p, &nf)
+                                         : lmg::lmdif(pr, p, &nf, suspend_after);
   p_out[0] = p[0];
   p_out[1] = p[1];
   p_out[2] = p[2];

@@ -733,7 +733,40 @@ struct LmStream {
     }
   }
 
+  // Householder reduction of a block: W is (NP + B) x (NP + 1), column-major with leading dimension
+  // NP + B; rows 0..2 hold the running triangle (columns 0..2) and Q^T f (column 3), rows 3.. the
+  // new Jacobian rows | residuals.  MINPACK qrfac without pivoting; 3 square roots and ~6 divisions
+  // per block instead of 3 rotations (sqrt + 2 divisions each) per row.
+  template <int B>
+  LMG_HD void reduce_block(double* W, int nrows) {
+    constexpr int L = NP + B;
+    LMG_UNROLL1
+    for (int j = 0; j < NP; ++j) {
+      double ss = 0.0;
+      for (int i = j; i < nrows; ++i) ss += W[i + j * L] * W[i + j * L];
+      double nrm = dsqrt(ss);
+      if (nrm == 0.0) continue;
+      if (W[j + j * L] < 0.0) nrm = -nrm;
+      const double rn = ddiv(1.0, nrm);
+      for (int i = j; i < nrows; ++i) W[i + j * L] *= rn;
+      W[j + j * L] += 1.0;
+      const double rv = ddiv(1.0, W[j + j * L]);
+      LMG_UNROLL1
+      for (int k = j + 1; k <= NP; ++k) {
+        double sum = 0.0;
+        for (int i = j; i < nrows; ++i) sum += W[i + j * L] * W[i + k * L];
+        const double temp = sum * rv;
+        for (int i = j; i < nrows; ++i) W[i + k * L] -= temp * W[i + j * L];
+      }
+      W[j + j * L] = -nrm;
+      for (int i = j + 1; i < nrows; ++i) W[i + j * L] = 0.0;  // the next block sees a clean triangle
+    }
+  }
+
   // fdjac2 + QR + gnorm test in one pass over the rows.  -> STEP or DONE
+  // B = 0: every row is rotated into the triangle (Givens, lmstr-style); B > 0: rows are collected
+  // in blocks of B and reduced by Householder reflections.
+  template <int B = 0>
   LMG_HD void jac_block(const Problem& pr) {
     const double gtol = 0.0, factor = 100.0, eps = 1.4901161193847656e-08;
     double P[NP + 1][NP], rh[NP];
@@ -747,6 +780,11 @@ struct LmStream {
     }
     for (int i = 0; i < NP * NP; ++i) a[i] = 0.0;
     for (int j = 0; j < NP; ++j) qtf[j] = 0.0;
+    constexpr int L = NP + (B > 0 ? B : 1);
+    double W[L * (NP + 1)];
+    int fill = 0;
+    if (B > 0)
+      for (int i = 0; i < L * (NP + 1); ++i) W[i] = 0.0;
     Rows<NP + 1> g;
     g.init(pr, P);
     auto row = [&](int i) {
@@ -754,7 +792,17 @@ struct LmStream {
       const double f0 = g.e[0] - yi;
       double w[NP];
       for (int j = 0; j < NP; ++j) w[j] = ((g.e[j + 1] - yi) - f0) * rh[j];
-      rotate_row(w, f0);
+      if (B == 0) {
+        rotate_row(w, f0);
+      } else {
+        for (int j = 0; j < NP; ++j) W[(NP + fill) + j * L] = w[j];
+        W[(NP + fill) + NP * L] = f0;
+        if (++fill == B) {
+          reduce_block<(B > 0 ? B : 1)>(W, NP + fill);
+          for (int r = NP; r < L; ++r) W[r + NP * L] = 0.0;
+          fill = 0;
+        }
+      }
     };
     row(g.i0);
     for (int i = g.i0 + 1; i < pr.m; ++i) {
@@ -765,6 +813,13 @@ struct LmStream {
     for (int i = g.i0 - 1; i >= 0; --i) {
       g.next();
       row(i);
+    }
+    if (B > 0) {
+      if (fill > 0) reduce_block<(B > 0 ? B : 1)>(W, NP + fill);
+      for (int j = 0; j < NP; ++j) {
+        for (int i = 0; i <= j; ++i) LMG_A(i, j) = W[i + j * L];
+        qtf[j] = W[j + NP * L];
+      }
     }
     nfev += NP;
     // column pivoting on the 3 x 3 triangle, as lmdif's qrfac does on the Jacobian
@@ -881,6 +936,7 @@ struct LmStream {
 };
 
 // lmdif through LmStream (pr.y with element stride 1)
+template <int B = 0>
 LMG_HD inline int lmdif_stream(const Problem& pr, double* p, int* nfev_out) {
   if (pr.m < NP) {
     *nfev_out = 0;
@@ -890,7 +946,7 @@ LMG_HD inline int lmdif_stream(const Problem& pr, double* p, int* nfev_out) {
   sm.init(p);
   sm.begin(pr);
   while (sm.phase != LmStream::DONE) {
-    if (sm.phase == LmStream::JAC) sm.jac_block(pr);
+    if (sm.phase == LmStream::JAC) sm.template jac_block<B>(pr);
     if (sm.phase == LmStream::STEP) {
       sm.step_block();
       sm.trial_block(pr);

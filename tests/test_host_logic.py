@@ -226,10 +226,12 @@ def test_host_gaussian_fit_matches_scipy_curve_fit():
     assert worst < 5e-5  # xtol = 1.49e-8 on ill-conditioned fits: termination point differs slightly
 
 
-def test_host_streaming_lm_matches_scipy_curve_fit():
-    """lmg::LmStream (no stored Jacobian / residual vectors: rows rotated into a 3 x 3 triangle by
-    Givens rotations, all per-fit state in registers) -- the candidate for the next generation of the
-    device fit kernel -- has the same success / failure pattern as SciPy and the same centres."""
+@pytest.mark.parametrize("variant", [-1, -4, -7])
+def test_host_streaming_lm_matches_scipy_curve_fit(variant):
+    """lmg::LmStream (no stored Jacobian / residual vectors: rows folded into a 3 x 3 triangle by
+    Givens rotations (-1) or by Householder reflections over blocks of 4 / 7 rows (-4 / -7), all
+    per-fit state in registers) -- the candidate for the next generation of the device fit kernel --
+    has the same success / failure pattern as SciPy and the same centres."""
     n, worst, same_nfev = 0, 0.0, 0
     for d in _esacf_frames():
         y = d["esacf"]
@@ -238,7 +240,7 @@ def test_host_streaming_lm_matches_scipy_curve_fit():
             lo, hi = i - 10, min(i + 11, len(y))
             if lo < 0:
                 continue
-            info, p, nfev = nat.host_gauss_fit(lo, y[lo:hi], suspend_after=-1)
+            info, p, nfev = nat.host_gauss_fit(lo, y[lo:hi], suspend_after=variant)
             log = []
             try:
                 with warnings.catch_warnings():
