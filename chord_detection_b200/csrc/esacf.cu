@@ -485,6 +485,71 @@ __global__ void __launch_bounds__(kFitThreads) esacf_fit_kernel(const EsacfArgs 
   }
 }
 
+// Fit kernel, second design (experimental, CDB_ESACF_LM=stream | stream4 | givens): lmg::LmStream
+// keeps a whole fit in registers / L1-resident local memory (no shared-memory work area: the
+// Jacobian rows are folded into a 3 x 3 triangle as they are produced), so the number of resident
+// fits is limited by registers, not by 1 KB of shared memory each.  Same task queue and lock-step
+// super-rounds as esacf_fit_kernel.  Host parity study: DESIGN.md 9 / tests/test_host_logic.py.
+constexpr int kStreamThreads = 128;
+template <int B>
+__global__ void __launch_bounds__(kStreamThreads) esacf_fit_stream_kernel(const EsacfArgs a) {
+  const int L = a.L;
+  const int half = L / 2 + 2;
+  const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
+  const size_t per_frame = pad_l + 2 * pad_h;
+  const int n_suspect = a.ws_counters[0];
+  const int total = n_suspect + a.ws_counters[4];
+  lmg::Problem pr;
+  lmg::LmStream sm;
+  int task = atomicAdd(&a.ws_counters[1], 1);
+  int fb = 0, pi = 0;
+  bool need_init = true;
+  while (__any_sync(0xffffffffu, task < total)) {
+    if (task < total) {
+      bool fitting = true;
+      if (need_init) {
+        need_init = false;
+        const int tcode = task < n_suspect ? a.ws_tasks[task]
+                                           : a.ws_tasks[a.task_cap - 1 - (task - n_suspect)];
+        fb = tcode >> 11;
+        pi = tcode & 2047;
+        const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + per_frame * (size_t)fb + pad_l);
+        const int idx = cand[pi];
+        const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
+        if (a.skip_fit || lo < 0 || hi - lo < 3) {
+          fitting = false;
+          a.ws_res[(int64_t)fb * half + pi] = NAN;
+        } else {
+          pr.y = a.ws_y + (int64_t)fb * L + lo;  // read through L1 / L2 (element stride 1)
+          pr.m = hi - lo;
+          pr.x0 = (double)lo;
+          double ymax = __ldg(pr.y);
+          for (int i = 1; i < pr.m; ++i) ymax = fmax(ymax, __ldg(pr.y + i));
+          const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
+          sm.init(p0);
+          sm.begin(pr);
+        }
+      }
+      if (fitting && sm.phase == lmg::LmStream::JAC) sm.template jac_block<B>(pr);
+      if (fitting && sm.phase == lmg::LmStream::STEP) {
+        sm.step_block();
+        sm.trial_block(pr);
+      }
+      if (fitting && sm.phase == lmg::LmStream::DONE) {
+        const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
+                        isfinite(sm.p[2]);
+        a.ws_res[(int64_t)fb * half + pi] = ok ? sm.p[1] : NAN;
+        fitting = false;
+      }
+      if (!fitting) {
+        task = atomicAdd(&a.ws_counters[1], 1);
+        need_init = true;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(64) esacf_bin_kernel(const EsacfArgs a) {
   __shared__ double cta_total[12];
   if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
@@ -803,6 +868,22 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     const char* pr = std::getenv("CDB_ESACF_PRIO");
     a.prioritise = (pr && pr[0] == '0') ? 0 : 1;
   }
+  // experimental register-resident fit kernel (see esacf_fit_stream_kernel)
+  void (*stream_kernel)(const EsacfArgs) = nullptr;
+  int stream_per_sm = 0;
+  if (const char* lm = std::getenv("CDB_ESACF_LM")) {
+    const std::string m = lm;
+    stream_kernel = m == "stream"    ? esacf_fit_stream_kernel<7>
+                    : m == "stream4" ? esacf_fit_stream_kernel<4>
+                    : m == "givens"  ? esacf_fit_stream_kernel<0>
+                                     : nullptr;
+    if (stream_kernel) {
+      CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stream_per_sm, stream_kernel,
+                                                                kStreamThreads, 0));
+      if (stream_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "stream fit kernel does not fit");
+      a.evict_rounds = 0;
+    }
+  }
   for (int64_t f0 = 0; f0 < n_frames; f0 += Bmax) {
     const int B = (int)std::min<int64_t>(Bmax, n_frames - f0);
     a.frame0 = f0;
@@ -830,9 +911,13 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       h->launches += 1;
     }
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
-    fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 0);
-    if (a.evict_rounds > 0)
-      fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 1);  // parked runaways
+    if (stream_kernel) {
+      stream_kernel<<<h->num_sms * stream_per_sm, kStreamThreads, 0, st>>>(a);
+    } else {
+      fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 0);
+      if (a.evict_rounds > 0)
+        fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 1);  // parked runaways
+    }
     esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
     h->launches += 6;
     CDB_CUDA(h, cudaGetLastError());

@@ -175,6 +175,23 @@ def test_esacf_scheduling_variants_are_bit_identical(monkeypatch):
         assert np.array_equal(got, base), env
 
 
+def test_esacf_experimental_stream_fit_kernels_agree(monkeypatch):
+    """CDB_ESACF_LM = givens / stream4 / stream: the register-resident Levenberg-Marquardt kernels
+    (lmg::LmStream; slower than the default so far, DESIGN.md 9).  The chroma depends on a fit only
+    through its pitch class, so agreeing fits give bit-identical frames; rounding-sensitive fits may
+    land elsewhere."""
+    fs = 44100
+    x, _ = cases.make_input(dict(fn="s_poly", seed=92, fs=fs, n=int(fs * 2.0)))
+    base = _run(x, fs, per_frame=True).frames.cpu().numpy()
+    for mode in ("givens", "stream4", "stream"):
+        monkeypatch.setenv("CDB_ESACF_LM", mode)
+        got = _run(x, fs, per_frame=True).frames.cpu().numpy()
+        monkeypatch.delenv("CDB_ESACF_LM")
+        same = np.all(got == base, axis=1).mean()
+        assert same >= 0.9, (mode, same)
+        assert abs(got.sum() - base.sum()) <= 0.1 * base.sum()
+
+
 def test_esacf_stretch_none_and_params():
     x, fs = cases.make_input(dict(fn="s_poly", seed=78, fs=22050, n=9000))
     for kw in (dict(stretch_mode="none"), dict(peak_thresh=0.3, peak_min_dist=4),
