@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libchordb200.so")
 
 CDB_FLAG_ACCUMULATE = 1
 CDB_FLAG_PCM16 = 2
+CDB_KEY_AMBIGUOUS = -1
 WINDOW_KINDS = {"hamming": 0, "hann": 1, "rect": 2}
 STRETCH_MODES = {"truncate": 0, "none": 1}
 ITERF0_MAX_CHANNELS = 128
@@ -61,6 +62,7 @@ EXPORTS = [
     "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
     "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
     "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
+    "cdb_host_pack_and_key", "cdb_host_py_round3",
 ]
 
 
@@ -100,6 +102,10 @@ def lib():
         L.cdb_prime_chroma.argtypes = [vp, C.POINTER(PrimeParams), vp, i64, i64, i64, vp, vp, vp,
                                        C.c_int, vp]
         L.cdb_pack_and_key.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.cdb_host_pack_and_key.argtypes = [C.POINTER(dbl), i64, C.POINTER(C.c_uint8),
+                                            C.POINTER(C.c_int32)]
+        L.cdb_host_py_round3.argtypes = [dbl]
+        L.cdb_host_py_round3.restype = dbl
         L.cdb_pcm16_to_mono_f32.argtypes = [vp, vp, i64, C.c_int, vp, vp]
         L.cdb_esacf_debug_stride.argtypes = [C.c_int]
         L.cdb_esacf_debug_stride.restype = i64
@@ -287,3 +293,21 @@ def host_find_peaks(y, thres, min_dist):
     if n < 0:
         raise ValueError("cdb_host_find_peaks failed")
     return [out[i] for i in range(n)]
+
+
+def host_pack_and_key(chroma):
+    """Host execution of the device pack / key row code (test hook, no GPU).
+    chroma [n, 12] float64 -> (digits uint8 [n, 12], key codes int32 [n], -1 = ambiguous)."""
+    import numpy as np
+
+    a = np.ascontiguousarray(np.atleast_2d(chroma), dtype=np.float64)
+    if a.shape[1] != 12:
+        raise ValueError("expected [n, 12]")
+    digits = np.zeros((a.shape[0], 12), dtype=np.uint8)
+    keys = np.zeros(a.shape[0], dtype=np.int32)
+    rc = lib().cdb_host_pack_and_key(a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0],
+                                     digits.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                     keys.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise ValueError("cdb_host_pack_and_key failed (%d)" % rc)
+    return digits, keys

@@ -75,12 +75,11 @@ def run_batch(paths, methods, key=False, device=None, max_batch_bytes=1 << 30, l
             xd = torch.stack([clips[i].to(dev) for i in part])
             for m in methods:
                 r = fn[m](xd, fs, per_clip=True)
-                digits, keys = ops.pack_and_key(r.clips)
+                digits, keys = ops.pack_and_key(r.clips, resolve=key)
                 sums[m] += r.total.cpu().numpy()
                 dg = digits.cpu().numpy()
-                kc = keys.cpu().numpy()
                 for j, i in enumerate(part):
-                    ks = ops.key_code_to_str(int(kc[j])) if key else None
+                    ks = keys[j] if key else None
                     results[i].append((m, METHODS[m].display_name(), "".join(str(int(d)) for d in dg[j]), ks))
     return [(str(p), results[i]) for i, p in enumerate(paths)], sums
 

@@ -88,19 +88,19 @@ _MAJOR = [6.35, 2.23, 3.48, 2.33, 4.38, 4.09, 2.52, 5.19, 2.39, 3.66, 2.29, 2.88
 _MINOR = [6.33, 2.68, 3.52, 5.38, 2.60, 3.53, 2.54, 4.75, 3.98, 2.69, 3.34, 3.17]
 
 
-def _zscore(v):
-    v = numpy.asarray(v, dtype=numpy.float64)
-    with numpy.errstate(divide="ignore", invalid="ignore"):
-        return (v - v.mean()) / v.std()
-
-
 def key_scores(X):
-    """Correlation of the z-scored chroma with all 12 rotations of the Krumhansl-Schmuckler
-    major / minor profiles (chromagram.py:90-109): scores[r] = sum_i profile[(i-r)%12]*X[i]."""
-    X = _zscore(X)
-    major, minor = _zscore(_MAJOR), _zscore(_MINOR)
-    idx = (numpy.arange(12)[None, :] - numpy.arange(12)[:, None]) % 12  # [r, i]
-    return major[idx].dot(X), minor[idx].dot(X)
+    """Scores of the 12 rotations of the Krumhansl-Schmuckler major / minor profiles against the
+    z-scored chroma, formed with the reference's own operations (chromagram.py:90-109:
+    scipy.stats.zscore, scipy.linalg.circulant(profile).T.dot(X)) so that rounding-level decisions
+    (flat or silent chroma, exact ties) come out exactly as the reference's do."""
+    import scipy.linalg
+    import scipy.stats
+
+    with numpy.errstate(divide="ignore", invalid="ignore"):
+        X = scipy.stats.zscore(numpy.asarray(X))
+        major = scipy.linalg.circulant(scipy.stats.zscore(numpy.asarray(_MAJOR))).T.dot(X)
+        minor = scipy.linalg.circulant(scipy.stats.zscore(numpy.asarray(_MINOR))).T.dot(X)
+    return major, minor
 
 
 def detect_key(X):
@@ -119,3 +119,14 @@ def detect_key(X):
     elif major_winner == minor_winner:
         return "{0}majmin".format(_note_names[major_winner])
     return "{0}maj OR {1}min".format(_note_names[major_winner], _note_names[minor_winner])
+
+
+def key_code_to_str(code):
+    """cdb_pack_and_key key code -> the reference's result string (chromagram.py:114-126).
+    0..11 "<note>maj", 12..23 "<note>min"; the tie strings exist only on the host path."""
+    code = int(code)
+    if 0 <= code < 12:
+        return "%smaj" % _note_names[code]
+    if 12 <= code < 24:
+        return "%smin" % _note_names[code - 12]
+    raise ValueError("key code %d is not a decided key (CDB_KEY_AMBIGUOUS = -1)" % code)

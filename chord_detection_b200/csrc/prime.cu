@@ -296,79 +296,6 @@ __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a)
   if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// batched Chromagram._pack (chromagram.py:50-74) and detect_key (:84-126): one thread per chroma
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double py_round3(double v) {
-  // Python round(v, 3) for |v| < 2^52/1000: correctly rounded decimal rounding is approximated by
-  // round-half-even of v*1000 (exact for the representable cases that occur: v/min ratios)
-  return nearbyint(v * 1000.0) / 1000.0;
-}
-
-__global__ void pack_key_kernel(const double* chroma, int64_t n, uint8_t* digits, int32_t* key) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double c[12];
-  for (int j = 0; j < 12; ++j) c[j] = chroma[i * 12 + j];
-  if (digits) {
-    double d[12];
-    double cmin = c[0];
-    for (int j = 1; j < 12; ++j) cmin = fmin(cmin, c[j]);
-    for (int j = 0; j < 12; ++j) d[j] = (cmin != 0.0) ? py_round3(c[j] / cmin) : c[j];
-    double cmax = d[0];
-    for (int j = 1; j < 12; ++j) cmax = fmax(cmax, d[j]);
-    if (cmax > 9.0) {
-      const double f = 9.0 / cmax;
-      for (int j = 0; j < 12; ++j) d[j] *= f;
-    }
-    for (int j = 0; j < 12; ++j) {
-      const double r = nearbyint(d[j]);  // Python round(): half to even
-      digits[i * 12 + j] = (uint8_t)(r < 0.0 ? 0 : (r > 255.0 ? 255 : (int)r));
-    }
-  }
-  if (key) {
-    const double MAJ[12] = {6.35, 2.23, 3.48, 2.33, 4.38, 4.09, 2.52, 5.19, 2.39, 3.66, 2.29, 2.88};
-    const double MIN[12] = {6.33, 2.68, 3.52, 5.38, 2.60, 3.53, 2.54, 4.75, 3.98, 2.69, 3.34, 3.17};
-    double z[12], zm[12], zn[12];
-    auto zscore = [](const double* v, double* o) {
-      double mean = 0.0;
-      for (int j = 0; j < 12; ++j) mean += v[j];
-      mean /= 12.0;
-      double var = 0.0;
-      for (int j = 0; j < 12; ++j) var += (v[j] - mean) * (v[j] - mean);
-      const double sd = sqrt(var / 12.0);
-      for (int j = 0; j < 12; ++j) o[j] = (v[j] - mean) / sd;
-    };
-    zscore(c, z);
-    zscore(MAJ, zm);
-    zscore(MIN, zn);
-    double bmaj = 0.0, bmin = 0.0;
-    int imaj = 0, imin = 0;
-    for (int r = 0; r < 12; ++r) {  // circulant(profile).T.dot(X): score[r] = sum_i p[(i-r)%12] X[i]
-      double sm = 0.0, sn = 0.0;
-      for (int j = 0; j < 12; ++j) {
-        const int q = (j - r + 12) % 12;
-        sm += zm[q] * z[j];
-        sn += zn[q] * z[j];
-      }
-      if (r == 0 || sm > bmaj) {  // numpy.argmax: first maximum; all-NaN scores keep index 0
-        bmaj = sm;
-        imaj = r;
-      }
-      if (r == 0 || sn > bmin) {
-        bmin = sn;
-        imin = r;
-      }
-    }
-    int code;
-    if (bmaj > bmin) code = imaj;                  // "<note>maj"
-    else if (bmaj < bmin) code = 12 + imin;        // "<note>min"
-    else if (imaj == imin) code = 24 + imaj;       // "<note>majmin"
-    else code = 36 + imaj * 12 + imin;             // "<a>maj OR <b>min"
-    key[i] = code;
-  }
-}
-
 extern "C" {
 
 int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x, int64_t n_clips,
@@ -440,19 +367,6 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "window does not fit in shared memory");
   const int64_t grid = std::min<int64_t>(a.total_items, (int64_t)h->num_sms * per_sm);
   prime_kernel<<<(unsigned)grid, kPrimeThreads, smem, st>>>(a);
-  h->launches += 1;
-  CDB_CUDA(h, cudaGetLastError());
-  return 0;
-}
-
-int cdb_pack_and_key(cdb_handle* h, const double* d_chroma, int64_t n, uint8_t* d_digits,
-                     int32_t* d_key, void* stream) {
-  if (!h) return CDB_E_NULL;
-  if (!d_chroma || n < 0) return cdb_fail(h, CDB_E_INVALID, "bad arguments");
-  if (n == 0) return 0;
-  CDB_CUDA(h, cudaSetDevice(h->device));
-  pack_key_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_chroma, n,
-                                                                                 d_digits, d_key);
   h->launches += 1;
   CDB_CUDA(h, cudaGetLastError());
   return 0;

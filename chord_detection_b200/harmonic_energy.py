@@ -39,6 +39,8 @@ class MultipitchHarmonicEnergy(Multipitch):
             x, self.fs, self.frame_size, self.num_harmonic, self.num_octave, self.num_bins,
             hop=self.hop, window=self.window, per_frame=display_plot_frame >= 0)
         self.frame_chroma = None
+        self.frame_data = None
         if res.frames is not None and display_plot_frame < res.frames.shape[0]:
             self.frame_chroma = res.frames[display_plot_frame].cpu().numpy()
+            self.frame_data = {"frame": display_plot_frame, "chroma": self.frame_chroma}
         return Chromagram(res.total.cpu().numpy())

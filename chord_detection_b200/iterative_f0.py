@@ -48,7 +48,21 @@ class MultipitchIterativeF0(Multipitch):
         return 3
 
     def compute_pitches(self, display_plot_frame=-1):
+        """-> Chromagram (sum over frames).  Plots are out of scope, but for
+        ``display_plot_frame >= 0`` that frame's periodicity results (what iterative_f0.py:93-94
+        hands to its plot routine: the detected voices' saliences and periods) and its chroma are
+        kept in ``self.frame_data``.  SURVEY.md 8f-3."""
         x = self._device_samples()
+        want = display_plot_frame >= 0
         res = ops.iterative_f0(x, self.fs, frame_size=self.frame_size, power=self.power,
-                               channel_freqs=self.channels)
+                               channel_freqs=self.channels, per_frame=want, voices=want)
+        self.frame_data = None
+        if want and display_plot_frame < res.frames.shape[0]:
+            v = res.extra[display_plot_frame].cpu().numpy()
+            nv = v.shape[0] // 2
+            self.frame_data = {
+                "frame": display_plot_frame,
+                "voice_saliences": v[:nv], "voice_periods": v[nv:],
+                "chroma": res.frames[display_plot_frame].cpu().numpy(),
+            }
         return Chromagram(res.total.cpu().numpy())

@@ -216,6 +216,9 @@ def butter2(fs, band, btype):
     return _design_cache[key]
 
 
+ESACF_DEBUG_MAX_PEAKS = 64  # peak / centre slots per frame in the debug record (csrc/esacf.cu)
+
+
 def esacf_params(fs, ham_samples, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
                  stretch_mode="truncate"):
     p = nat.EsacfParams()
@@ -289,25 +292,21 @@ def prime_window_sizes(fs, num_harmonic=1, num_octave=2):
     return [out[i] for i in range(rc)]
 
 
-_NOTE = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
-
-
 def key_code_to_str(code):
-    """Inverse of cdb_pack_and_key's key code (chromagram.py:114-126 result strings)."""
-    code = int(code)
-    if code < 12:
-        return "%smaj" % _NOTE[code]
-    if code < 24:
-        return "%smin" % _NOTE[code - 12]
-    if code < 36:
-        return "%smajmin" % _NOTE[code - 24]
-    code -= 36
-    return "%smaj OR %smin" % (_NOTE[code // 12], _NOTE[code % 12])
+    from .chromagram import key_code_to_str as f
+
+    return f(code)
 
 
-def pack_and_key(chroma):
+def pack_and_key(chroma, resolve=True):
     """Batched Chromagram._pack + detect_key on the device.
-    chroma: CUDA float64 [n, 12] -> (digits uint8 [n, 12], key codes int32 [n])."""
+    chroma: CUDA float64 [n, 12] -> (digits uint8 [n, 12] on the device, keys).
+
+    resolve=True (default): keys is a list of n strings, identical to what the reference's
+    detect_key returns for each row: rows the kernel decides come from its key code, rows it
+    reports as CDB_KEY_AMBIGUOUS (decision inside fp64 rounding noise: silent / flat chroma, exact
+    ties) are settled by chromagram.detect_key, i.e. with the reference's own scipy calls.
+    resolve=False: keys is the raw int32 CUDA tensor of key codes (no synchronisation)."""
     if not chroma.is_cuda or chroma.dtype != torch.float64 or chroma.dim() != 2 or chroma.shape[1] != 12:
         raise ValueError("expected a CUDA float64 tensor of shape [n, 12]")
     chroma = chroma.contiguous()
@@ -318,7 +317,20 @@ def pack_and_key(chroma):
     with torch.cuda.device(chroma.device):
         rc = h.L.cdb_pack_and_key(h.ptr, _ptr(chroma), n, _ptr(digits), _ptr(keys), _stream_ptr(chroma))
     h.check(rc, "cdb_pack_and_key")
-    return digits, keys
+    if not resolve:
+        return digits, keys
+    from . import chromagram as cg
+
+    codes = keys.cpu().numpy()
+    out = [None] * n
+    amb = np.nonzero(codes < 0)[0]
+    if amb.size:
+        rows = chroma[torch.from_numpy(amb).to(chroma.device)].cpu().numpy()
+        for i, r in zip(amb, rows):
+            out[int(i)] = cg.detect_key(r)
+    for i in np.nonzero(codes >= 0)[0]:
+        out[int(i)] = cg.key_code_to_str(codes[i])
+    return digits, out
 
 
 def iterf0_channel_freqs(channels=70, zeta0=2.3, zeta1=0.39):

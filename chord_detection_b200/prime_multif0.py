@@ -35,9 +35,26 @@ class MultipitchPrimeMultiF0(Multipitch):
         return 4
 
     def compute_pitches(self, display_plot_frame=-1):
+        """-> Chromagram (sum over candidates and frames).  Plots are out of scope; for
+        ``display_plot_frame >= 0`` the reference plots the FIRST candidate pass that reaches that
+        frame index and then stops (prime_multif0.py:84-87): the chroma that this frame of the
+        first candidate contributes (its two picked peaks) is kept in ``self.frame_data``.
+        SURVEY.md 8f-3."""
         x = self._device_samples()
-        res = ops.prime_multif0(
-            x, self.fs, num_harmonic=self.num_harmonic, num_octave=self.num_octave,
-            harmonic_multiples_elim=self.harmonic_multiples_elim,
-            harmonic_elim_runs=self.harmonic_elim_runs)
+        kw = dict(num_harmonic=self.num_harmonic, num_octave=self.num_octave,
+                  harmonic_multiples_elim=self.harmonic_multiples_elim,
+                  harmonic_elim_runs=self.harmonic_elim_runs)
+        res = ops.prime_multif0(x, self.fs, **kw)
+        self.frame_data = None
+        if display_plot_frame >= 0:
+            sizes = ops.prime_window_sizes(self.fs, self.num_harmonic, self.num_octave)
+            for cand, W in enumerate(sizes):  # candidates in loop order; frames never span clips
+                if display_plot_frame * W < x.shape[0]:
+                    f = display_plot_frame
+                    one = ops.prime_multif0(x[f * W:(f + 1) * W], self.fs, per_candidate=True, **kw)
+                    self.frame_data = {
+                        "frame": f, "candidate": cand, "window_size": W,
+                        "chroma": one.extra[0, cand].cpu().numpy(),
+                    }
+                    break
         return Chromagram(res.total.cpu().numpy())

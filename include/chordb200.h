@@ -218,10 +218,19 @@ int cdb_host_resample_poly_f32(const float* x, int64_t n_in, int up, int down, c
                                int n_taps, int n_pre_pad, int n_pre_remove, float* y, int64_t n_out);
 
 /* ---------------- batched result post-processing (chromagram.py:50-126), SURVEY 8f-1 ---------------- */
-/* d_chroma [n,12] double -> d_digits [n,12] uint8 (the 12-digit string, chromagram.py:50-74) and
- * d_key [n] int32: 0..11 = <note>maj, 12..23 = <note>min, 24+12*a+b... see DESIGN.md.  Either output may be NULL. */
+/* d_chroma [n,12] double -> d_digits [n,12] uint8 (the 12-digit string, chromagram.py:50-74:
+ * bit-exact, including Python's decimal round(v, 3)) and d_key [n] int32 (chromagram.py:84-126):
+ * 0..11 = "<note>maj", 12..23 = "<note>min", CDB_KEY_AMBIGUOUS = the decision margin of this row is
+ * inside fp64 rounding noise (flat / silent chroma, exact ties: the reference's own answer then
+ * depends on scipy's summation order) -- the caller settles such rows with the reference's scipy
+ * operations (chord_detection_b200.chromagram.detect_key does; ops.pack_and_key(resolve=True)).
+ * Either output may be NULL. */
+#define CDB_KEY_AMBIGUOUS (-1)
 int cdb_pack_and_key(cdb_handle* h, const double* d_chroma, int64_t n, uint8_t* d_digits,
                      int32_t* d_key, void* stream);
+/* host execution of the same per-row code (CPU tests, no GPU) */
+int cdb_host_pack_and_key(const double* chroma, int64_t n, uint8_t* digits, int32_t* key);
+double cdb_host_py_round3(double v);
 
 #ifdef __cplusplus
 }

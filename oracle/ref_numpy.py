@@ -312,11 +312,11 @@ def esacf_peak_is_sensitive(fs, peak_index, tau, nfev):
 
 
 def esacf(x, fs, ham_ms=46.4, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
-          stretch_mode="truncate", per_frame=False, sensitivity=False):
+          stretch_mode="truncate", per_frame=False, sensitivity=False, stats=None):
     """sensitivity=True (oracle-only extra) also returns, per frame, the summed height of the
     rounding-sensitive peaks (esacf_peak_is_sensitive) plus the whole frame's mass when a fit
     failed (a dropped fit shifts the peak/centre pairing of esacf.py:65-69 for the rest of
-    the frame)."""
+    the frame).  stats (dict, optional) accumulates 'peaks', 'sensitive_peaks', 'failed_fits'."""
     ham_samples = int(fs * ham_ms / 1000.0)  # :27
     total = np.zeros(12)
     outs, loose = [], []
@@ -325,12 +325,18 @@ def esacf(x, fs, ham_ms=46.4, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_min_
             c, d = esacf_frame(xf, fs, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode,
                                detail=True)
             lm = 0.0
+            n_sens = 0
             if len(d["interp"]) != len(d["peaks"]):
                 lm = float(np.sum(np.abs(d["esacf"][d["peaks"]])))
             else:
                 for j, nf in enumerate(d["nfev"]):
                     if esacf_peak_is_sensitive(fs, int(d["peaks"][j]), d["interp"][j], nf):
                         lm += abs(d["esacf"][int(d["peaks"][j])])
+                        n_sens += 1
+            if stats is not None:
+                stats["peaks"] = stats.get("peaks", 0) + len(d["peaks"])
+                stats["sensitive_peaks"] = stats.get("sensitive_peaks", 0) + n_sens
+                stats["failed_fits"] = stats.get("failed_fits", 0) + len(d["peaks"]) - len(d["interp"])
             loose.append(lm)
         else:
             c = esacf_frame(xf, fs, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode)

@@ -46,7 +46,7 @@ def main():
         part, per_clip = D.all_methods_sharded(clips, 22050, reduce=False)
         sums += part
         for m, pc in per_clip.items():
-            digits, keys = ops.pack_and_key(pc)
+            digits, keys = ops.pack_and_key(pc, resolve=False)
             n_keys += keys.numel()
     D.all_reduce_chroma(sums)  # the single collective of the run: [4, 12] doubles
     torch.cuda.synchronize()

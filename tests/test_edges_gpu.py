@@ -102,7 +102,7 @@ def test_strided_batch_rows_all_methods():
     _close(e.clips.cpu().numpy(), e2.clips.cpu().numpy(), tol=1e-12)
 
 
-def test_cli_on_wav_file(tmp_path):
+def test_cli_on_wav_file(tmp_path, golden):
     """chord-detect --method -1 --key <wav>: same output lines as chord_detect.py:56-63."""
     import scipy.io.wavfile as wavfile
 
@@ -123,6 +123,11 @@ def test_cli_on_wav_file(tmp_path):
     # golden strings of the PCM16-clipped clip (tests/golden, made by the unmodified reference)
     assert lines[4] == "234416722312" and lines[7] == "000000000090" and lines[10] == "000001343193"
     assert lines[5] == "F#min" and lines[8] == "A#maj" and lines[11] == "A#min"
+    g1 = golden["cases"]["clips_pcm16/test_2_notes_G3_Asharp4/m1"]  # ESACF: string and key identical too
+    assert lines[1] == g1["digits"] and lines[2] == g1["key"]
+    for m, row in ((2, 4), (3, 7), (4, 10)):
+        gm = golden["cases"]["clips_pcm16/test_2_notes_G3_Asharp4/m%d" % m]
+        assert lines[row] == gm["digits"] and lines[row + 1] == gm["key"]
     assert all(len(lines[i]) == 12 and lines[i].isdigit() for i in (1, 4, 7, 10))
     with pytest.raises(ValueError):
         chord_detect.main_cli(["--method", "9", path])
@@ -165,3 +170,54 @@ def test_cli_batch_mode_matches_single_clip_cli(tmp_path):
     assert n_same >= 4
     with pytest.raises(ValueError):
         chord_detect.main_cli(["--method", "7", str(tmp_path)])
+
+
+def test_display_plot_frame_keeps_that_frames_intermediates():
+    """compute_pitches(display_plot_frame=f) keeps what the reference hands to its
+    plot routine for frame f (esacf.py:74-88, harmonic_energy.py:71-72, iterative_f0.py:93-94,
+    prime_multif0.py:84-87) in .frame_data; the result itself is unchanged."""
+    import chord_detection_b200 as cd
+
+    _dev()
+    fs = 22050
+    x, _ = cases.make_input(dict(fn="s_poly", seed=810, fs=fs, n=3 * 8192 + 100))
+    f = 2
+    # method 1
+    m1 = cd.MultipitchESACF(x, fs=fs)
+    c_plain = repr(m1.compute_pitches())
+    assert m1.frame_data is None
+    c = m1.compute_pitches(display_plot_frame=f)
+    assert repr(c) == c_plain
+    N = m1.ham_samples
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wc, d = rn.esacf_frame(rn.cut_frames(x, N)[f], fs, detail=True)
+    fd = m1.frame_data
+    assert fd["frame"] == f
+    assert np.allclose(fd["x_lo"], d["x_lo"], rtol=0, atol=1e-12 * np.abs(d["x_lo"]).max())
+    assert np.allclose(fd["x_hi"], d["x_hi"], rtol=0, atol=1e-12 * np.abs(d["x_hi"]).max())
+    assert np.allclose(fd["x_sacf"], d["sacf"], rtol=0, atol=1e-9 * np.abs(d["sacf"]).max())
+    assert np.allclose(fd["x_esacf"], d["esacf"], rtol=0, atol=1e-9 * np.abs(d["sacf"]).max())
+    assert list(fd["peak_indices"]) == [int(v) for v in d["peaks"]]
+    assert np.allclose(fd["peak_indices_interp"], d["interp"], rtol=5e-5)
+    assert m1.compute_pitches(display_plot_frame=10 ** 6) is not None and m1.frame_data is None
+    # method 2
+    m2 = cd.MultipitchHarmonicEnergy(x, fs=fs)
+    m2.compute_pitches(display_plot_frame=f)
+    want = rn.harmonic_energy_fast(rn.cut_frames(x, 8192)[f], fs)
+    _close(m2.frame_data["chroma"], want)
+    # method 3
+    m3 = cd.MultipitchIterativeF0(x, fs=fs)
+    c3 = m3.compute_pitches(display_plot_frame=f)
+    wt, wU, det = rn.iterf0(x, fs, detail=True)
+    _close(c3.asarray(), wt)
+    assert np.allclose(m3.frame_data["voice_saliences"], det[f][0], rtol=1e-5)
+    assert np.allclose(m3.frame_data["voice_periods"], det[f][1], rtol=1e-9)
+    # method 4: first candidate whose frame f exists (candidate 0 here), that frame alone
+    m4 = cd.MultipitchPrimeMultiF0(x, fs=fs)
+    c4 = m4.compute_pitches(display_plot_frame=f)
+    _close(c4.asarray(), rn.prime(x, fs))
+    W = rn.prime_candidates(fs)[0]
+    assert m4.frame_data["candidate"] == 0 and m4.frame_data["window_size"] == W
+    _, wc4 = rn.prime(x[f * W:(f + 1) * W], fs, per_candidate=True)
+    _close(m4.frame_data["chroma"], wc4[0])
