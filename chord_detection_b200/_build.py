@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libchordb200.so")
-SOURCES = ["api.cu", "he.cu", "esacf.cu", "iterf0.cu", "prime.cu", "ingest.cu", "chroma.cu"]
+SOURCES = ["api.cu", "he.cu", "esacf.cu", "iterf0.cu", "prime.cu", "ingest.cu", "chroma.cu", "comm.cu"]
 # esacf.cu: the Levenberg-Marquardt fit and the lfilter recurrences mirror host (scipy) arithmetic,
 # which has no fused multiply-add; the DFT loops there call fma() explicitly.
 NO_FMAD = {"esacf.cu", "chroma.cu"}  # chroma.cu: exact decimal rounding, no contraction

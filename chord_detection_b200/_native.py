@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libchordb200.so")
 
 CDB_FLAG_ACCUMULATE = 1
 CDB_FLAG_PCM16 = 2
+CDB_FLAG_ALLREDUCE = 4
+CDB_IPC_HANDLE_BYTES = 64
 CDB_KEY_AMBIGUOUS = -1
 WINDOW_KINDS = {"hamming": 0, "hann": 1, "rect": 2}
 STRETCH_MODES = {"truncate": 0, "none": 1}
@@ -63,6 +65,8 @@ EXPORTS = [
     "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
     "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
     "cdb_host_pack_and_key", "cdb_host_py_round3",
+    "cdb_profile_enable", "cdb_profile_report",
+    "cdb_comm_alloc", "cdb_comm_connect", "cdb_comm_status", "cdb_comm_destroy",
 ]
 
 
@@ -102,6 +106,13 @@ def lib():
         L.cdb_prime_chroma.argtypes = [vp, C.POINTER(PrimeParams), vp, i64, i64, i64, vp, vp, vp,
                                        C.c_int, vp]
         L.cdb_pack_and_key.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.cdb_profile_enable.argtypes = [vp, C.c_int]
+        L.cdb_profile_report.argtypes = [vp, C.c_char_p, i64]
+        L.cdb_profile_report.restype = i64
+        L.cdb_comm_alloc.argtypes = [vp, C.c_int, C.c_char_p]
+        L.cdb_comm_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+        L.cdb_comm_status.argtypes = [vp]
+        L.cdb_comm_destroy.argtypes = [vp]
         L.cdb_host_pack_and_key.argtypes = [C.POINTER(dbl), i64, C.POINTER(C.c_uint8),
                                             C.POINTER(C.c_int32)]
         L.cdb_host_py_round3.argtypes = [dbl]
@@ -167,6 +178,42 @@ class Handle:
     @property
     def launches(self):
         return int(self.L.cdb_launch_count(self.ptr))
+
+    # -- per-kernel timing (cdb_profile_enable / cdb_profile_report) -----------
+    def profile_start(self):
+        self.check(self.L.cdb_profile_enable(self.ptr, 1), "cdb_profile_enable")
+
+    def profile_stop(self):
+        """-> {kernel name: milliseconds summed over the recording}; waits for the device."""
+        buf = C.create_string_buffer(8192)
+        n = self.L.cdb_profile_report(self.ptr, buf, len(buf))
+        self.L.cdb_profile_enable(self.ptr, 0)
+        if n < 0:
+            raise RuntimeError("cdb_profile_report failed (%d)" % n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(" ", 1)
+            out[name] = float(ms)
+        return out
+
+    # -- fused all-reduce over peer memory (cdb_comm_*) ------------------------
+    def comm_init(self, rank, world, exchange):
+        """exchange(bytes) -> list of every rank's bytes in rank order (e.g. an all_gather_object)."""
+        mine = C.create_string_buffer(CDB_IPC_HANDLE_BYTES)
+        self.check(self.L.cdb_comm_alloc(self.ptr, int(world), mine), "cdb_comm_alloc")
+        handles = exchange(mine.raw)
+        if len(handles) != world or any(len(b) != CDB_IPC_HANDLE_BYTES for b in handles):
+            raise ValueError("exchange() must return one %d-byte handle per rank" % CDB_IPC_HANDLE_BYTES)
+        self.check(self.L.cdb_comm_connect(self.ptr, int(rank), int(world), b"".join(handles)),
+                   "cdb_comm_connect")
+        self.comm_world = int(world)
+
+    def comm_status(self):
+        return int(self.L.cdb_comm_status(self.ptr))
+
+    def comm_destroy(self):
+        self.L.cdb_comm_destroy(self.ptr)
+        self.comm_world = 0
 
     def __del__(self):
         try:

@@ -1,6 +1,7 @@
 // libchordb200: handle management and shared C-ABI glue (include/chordb200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -14,7 +15,61 @@ int cdb_fail(cdb_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
+void cdb_mark(cdb_handle* h, cudaStream_t st, const char* name) {
+  if (!h || !h->prof_on) return;
+  cudaEvent_t e = nullptr;
+  if (!h->prof_pool.empty()) {
+    e = h->prof_pool.back();
+    h->prof_pool.pop_back();
+  } else if (cudaEventCreate(&e) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(e, st);
+  h->prof_marks.emplace_back(name, e);
+}
+
 extern "C" {
+
+int cdb_profile_enable(cdb_handle* h, int on) {
+  if (!h) return CDB_E_NULL;
+  for (auto& m : h->prof_marks) h->prof_pool.push_back(m.second);
+  h->prof_marks.clear();
+  h->prof_on = on != 0;
+  return 0;
+}
+
+// "name ms\n" per distinct stage, summed over everything recorded since cdb_profile_enable(h, 1);
+// a stage's time is the gap between its mark and the previous mark on the stream ("begin" marks
+// open a call and are not reported).  Waits for the recorded events.
+int64_t cdb_profile_report(cdb_handle* h, char* buf, int64_t buf_len) {
+  if (!h || !buf || buf_len < 1) return CDB_E_NULL;
+  std::vector<std::pair<std::string, double>> acc;
+  for (size_t i = 1; i < h->prof_marks.size(); ++i) {
+    const std::string name = h->prof_marks[i].first;
+    if (name == "begin") continue;
+    if (cudaEventSynchronize(h->prof_marks[i].second) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_marks[i - 1].second, h->prof_marks[i].second) !=
+        cudaSuccess)
+      continue;
+    bool found = false;
+    for (auto& kv : acc)
+      if (kv.first == name) {
+        kv.second += ms;
+        found = true;
+      }
+    if (!found) acc.emplace_back(name, (double)ms);
+  }
+  std::string out;
+  char line[160];
+  for (auto& kv : acc) {
+    snprintf(line, sizeof(line), "%s %.6f\n", kv.first.c_str(), kv.second);
+    out += line;
+  }
+  if ((int64_t)out.size() + 1 > buf_len) return CDB_E_INVALID;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int64_t)out.size();
+}
 
 int cdb_version(void) { return CDB_VERSION; }
 
@@ -32,6 +87,13 @@ int cdb_create(cdb_handle** out, int device) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  // finalisation scratch of the harmonic-energy kernel: must be zero before the first launch
+  if (cudaMalloc(&h->he_scratch, 16 * sizeof(double)) != cudaSuccess ||
+      cudaMemset(h->he_scratch, 0, 16 * sizeof(double)) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    delete h;
+    return CDB_E_NOGPU;
+  }
   *out = h;
   return 0;
 }
@@ -43,7 +105,12 @@ int cdb_destroy(cdb_handle* h) {
   cdb_free_esacf_plans(h);
   cdb_free_iterf0_plans(h);
   cdb_free_prime_plans(h);
+  cdb_comm_destroy(h);
+  if (h->he_scratch) cudaFree(h->he_scratch);
   for (void* p : h->owned) cudaFree(p);
+  if (h->ws) cudaFree(h->ws);
+  for (auto& m : h->prof_marks) cudaEventDestroy(m.second);
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   delete h;
   return 0;
 }

@@ -37,8 +37,6 @@
 
 struct EsacfPlan {
   cdb_esacf_params p;
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
   // Bluestein tables of the FFT autocorrelation kernel (acf_fft.cuh), M = fft_r1 * 256
   int fft_r1 = 0;
   afft::cplx* d_tables = nullptr;  // chirp [N] | bhat [M] | tw [M]
@@ -46,7 +44,6 @@ struct EsacfPlan {
 
 void cdb_free_esacf_plans(cdb_handle* h) {
   for (auto& kv : h->esacf_plans) {
-    if (kv.second->ws) cudaFree(kv.second->ws);
     if (kv.second->d_tables) cudaFree(kv.second->d_tables);
     delete kv.second;
   }
@@ -742,7 +739,9 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   cudaStream_t st = (cudaStream_t)stream;
   EsacfPlan* pl;
   {
-    std::string key = pod_key(*p);
+    std::string key = cdb_key(p->fs, p->ham_samples, p->k, p->n_peaks_elim, p->peak_thresh,
+                              p->peak_min_dist, p->stretch_mode, p->wfir_lambda, p->wfir_taps,
+                              p->lp_b, p->lp_a, p->hp_b, p->hp_a);
     auto it = h->esacf_plans.find(key);
     if (it == h->esacf_plans.end()) {
       pl = new EsacfPlan();
@@ -763,6 +762,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     CDB_CUDA(h, cudaMalloc(&pl->d_tables, tables.size() * sizeof(afft::cplx)));
     CDB_CUDA(h, cudaMemcpy(pl->d_tables, tables.data(), tables.size() * sizeof(afft::cplx),
                            cudaMemcpyHostToDevice));
+    CDB_CUDA(h, cudaDeviceSynchronize());  // pageable upload vs. the caller's non-blocking stream
     pl->fft_r1 = fft_r1;
   }
   const int64_t fpc = cdb_num_frames(clip_len, N, N);  // dsp/frame.py: non-overlapping
@@ -783,13 +783,14 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   const size_t need = (size_t)Bmax * ((2 * (size_t)N + 2 * (size_t)L + half) * sizeof(double) +
                                       scratch_pf + half * sizeof(int) + sizeof(int)) + 64 +
                       long_cap * sizeof(LongFit) + 64;
-  if (pl->ws_bytes < need) {
-    CDB_CUDA(h, cudaStreamSynchronize(st));
-    if (pl->ws) cudaFree(pl->ws);
-    pl->ws = nullptr;
-    pl->ws_bytes = 0;
-    CDB_CUDA(h, cudaMalloc(&pl->ws, need));
-    pl->ws_bytes = need;
+  if (h->ws_bytes < need) {
+    // earlier calls on this handle (any stream) may still be using the old buffer
+    CDB_CUDA(h, cudaDeviceSynchronize());
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    CDB_CUDA(h, cudaMalloc(&h->ws, need));
+    h->ws_bytes = need;
   }
 
   EsacfArgs a;
@@ -888,7 +889,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     const int B = (int)std::min<int64_t>(Bmax, n_frames - f0);
     a.frame0 = f0;
     a.B = B;
-    double* w = reinterpret_cast<double*>(pl->ws);
+    double* w = reinterpret_cast<double*>(h->ws);
     a.ws_lo = w;
     a.ws_hi = w + (size_t)N * B;
     a.ws_y = w + 2 * (size_t)N * B;
@@ -903,14 +904,19 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     a.long_cap = (int)long_cap;
     a.task_cap = (int)(half * (size_t)B);
     CDB_CUDA(h, cudaMemsetAsync(a.ws_counters, 0, 8 * sizeof(int), st));
+    cdb_mark(h, st, "begin");
     esacf_filter_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
+    cdb_mark(h, st, "esacf_filter_kernel");
     if (fft_r1) acf_fft_kernel<<<(B + 1) / 2, fft_r1 * 16, acf_fft_smem, st>>>(a);
     else acf_kernel<<<B, kAcfThreads, acf_smem, st>>>(a);
+    cdb_mark(h, st, fft_r1 ? "esacf_acf_fft_kernel" : "esacf_acf_kernel");
     if (d_debug) {
       esacf_debug_copy_kernel<<<B, 128, 0, st>>>(a);
       h->launches += 1;
+      cdb_mark(h, st, "esacf_debug_copy_kernel");
     }
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
+    cdb_mark(h, st, "esacf_pick_kernel");
     if (stream_kernel) {
       stream_kernel<<<h->num_sms * stream_per_sm, kStreamThreads, 0, st>>>(a);
     } else {
@@ -918,7 +924,9 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       if (a.evict_rounds > 0)
         fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 1);  // parked runaways
     }
+    cdb_mark(h, st, "esacf_fit_kernel");
     esacf_bin_kernel<<<(B + 63) / 64, 64, 0, st>>>(a);
+    cdb_mark(h, st, "esacf_bin_kernel");
     h->launches += 6;
     CDB_CUDA(h, cudaGetLastError());
   }

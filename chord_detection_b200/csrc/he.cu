@@ -113,7 +113,9 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
   key.frames_per_clip = 0;  // not part of the tables
   const char* fg = std::getenv("CDB_HE_FORCE_GENERIC");
   const bool force_generic = fg && fg[0] == '1';
-  std::string ks = pod_key(key) + (force_generic ? "g" : "f");
+  std::string ks = cdb_key(key.fs, key.frame_size, key.hop, key.window_kind, key.num_harmonic,
+                           key.num_octave, key.num_bins) +
+                   (force_generic ? "g" : "f");
   auto it = h->he_plans.find(ks);
   if (it != h->he_plans.end()) {
     *out = it->second;
@@ -246,6 +248,11 @@ struct HeArgs {
   double* total;
   double* clips;
   float* frames;
+  // frame-2048 kernel: grid-wide accumulators + CTA ticket (handle-owned, zero between launches),
+  // whether `total` is overwritten or added to, and the optional fused all-reduce
+  double* scratch;
+  int accumulate;
+  CommArgs comm;
 };
 
 
@@ -617,8 +624,36 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
     if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
     if (a.total) atomicAdd(&cta_acc[lane], acc_total);
   }
+  if (!a.total) return;
   __syncthreads();
-  if (a.total && tid < 12) atomicAdd(&a.total[tid], cta_acc[tid]);
+  // grid-wide sum in the handle's scratch; the LAST CTA to arrive finalises: it reads the 12 sums,
+  // leaves the scratch zeroed for the next launch (no memset node per call), optionally all-reduces
+  // them with the peer GPUs through NVLink mailboxes (one kernel = compute + collective), and
+  // writes / accumulates `total` once.
+  __shared__ int s_last;
+  if (tid < 12) {
+    atomicAdd(&a.scratch[tid], cta_acc[tid]);
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(a.scratch + 12), 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  __threadfence();
+  double v = 0.0;
+  if (lane < 12) {
+    v = __ldcg(&a.scratch[lane]);
+    __stcg(&a.scratch[lane], 0.0);
+  }
+  if (lane == 12) *reinterpret_cast<unsigned*>(a.scratch + 12) = 0u;
+  // CDB_FLAG_ACCUMULATE: total <- total + this launch; with CDB_FLAG_ALLREDUCE on top:
+  // total <- sum over ranks of (total + this launch), i.e. the running local sums are combined
+  if (lane < 12 && a.accumulate) v += a.total[lane];
+  if (a.comm.seq) v = comm_allreduce12(a.comm, v, lane);
+  if (lane < 12) a.total[lane] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1086,12 +1121,19 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t fpc =
       p->frames_per_clip > 0 ? p->frames_per_clip : cdb_num_frames(clip_len, pl->N, pl->hop);
+  // the frame-2048 kernel writes `total` itself (last-CTA finalisation): no memset for it
+  const bool fused_total = pl->N == 2048 && !pl->force_generic;
+  const bool allreduce = (flags & CDB_FLAG_ALLREDUCE) != 0;
+  if (allreduce && (!fused_total || !h->comm || !d_chroma_total))
+    return cdb_fail(h, CDB_E_UNSUPPORTED,
+                    "CDB_FLAG_ALLREDUCE needs cdb_comm_init, a total output and frame_size 2048");
   if (!(flags & CDB_FLAG_ACCUMULATE)) {
-    if (d_chroma_total) CDB_CUDA(h, cudaMemsetAsync(d_chroma_total, 0, 12 * sizeof(double), st));
+    if (d_chroma_total && (!fused_total || n_clips == 0 || fpc == 0) && !allreduce)
+      CDB_CUDA(h, cudaMemsetAsync(d_chroma_total, 0, 12 * sizeof(double), st));
     if (d_chroma_clips && n_clips > 0)
       CDB_CUDA(h, cudaMemsetAsync(d_chroma_clips, 0, n_clips * 12 * sizeof(double), st));
   }
-  if (n_clips == 0 || fpc == 0) return 0;
+  if ((n_clips == 0 || fpc == 0) && !allreduce) return 0;
 
   HeArgs a;
   a.x = d_x;
@@ -1121,6 +1163,17 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
   a.clips = d_chroma_clips;
   a.frames = d_chroma_frames;
   a.pw_floats = a.pw_bytes = 0;
+  a.scratch = h->he_scratch;
+  a.accumulate = (flags & CDB_FLAG_ACCUMULATE) ? 1 : 0;
+  std::memset(&a.comm, 0, sizeof(a.comm));
+  if (allreduce) {
+    Comm* cm = h->comm;
+    a.comm.rank = cm->rank;
+    a.comm.world = cm->world;
+    a.comm.seq = ++cm->seq;  // every rank makes the same sequence of collective calls
+    for (int q = 0; q < cm->world; ++q) a.comm.mail[q] = cm->mail[q];
+    a.comm.status = cm->d_status;
+  }
 
   if ((flags & CDB_FLAG_PCM16) && (pl->N != 2048 || pl->force_generic))
     return cdb_fail(h, CDB_E_UNSUPPORTED,
@@ -1142,8 +1195,12 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
                         (size_t)pl->n_windows * sizeof(HeWin);
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t total_frames = n_clips * fpc;
-    int64_t grid = std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms);
+    // an empty shard still takes part in the all-reduce: one CTA that finalises zeros
+    int64_t grid = std::max<int64_t>(
+        1, std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms));
+    cdb_mark(h, st, "begin");
     kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
+    cdb_mark(h, st, pcm ? "he2048w_kernel<pcm16>" : "he2048w_kernel");
   } else if (pl->N == 8192 && !pl->force_generic) {
     // CDB_HE8192 = scalar (first generation: scalar butterflies, direct loads) | packed (packed
     // butterflies, direct loads) | staged (packed butterflies + bulk-async staging of the next frame)
@@ -1160,7 +1217,9 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, k8Threads, smem));
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
     int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
+    cdb_mark(h, st, "begin");
     kern<<<(unsigned)grid, k8Threads, smem, st>>>(a);
+    cdb_mark(h, st, "he8192_kernel");
   } else {
     const size_t smem = (size_t)pl->M * 8 + (size_t)(pl->M + 2) * 4 + HE_MAX_WINDOWS * 8;
     CDB_CUDA(h, cudaFuncSetAttribute(he_generic_kernel,
@@ -1170,7 +1229,9 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
                                                               kGenThreads, smem));
     if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
     int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
+    cdb_mark(h, st, "begin");
     he_generic_kernel<<<(unsigned)grid, kGenThreads, smem, st>>>(a);
+    cdb_mark(h, st, "he_generic_kernel");
   }
   h->launches += 1;
   CDB_CUDA(h, cudaGetLastError());

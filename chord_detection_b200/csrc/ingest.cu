@@ -31,13 +31,20 @@ __global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restr
                                                             int up, int down,
                                                             const float* __restrict__ taps, int n_taps,
                                                             int n_pre_pad, int n_pre_remove,
-                                                            float* __restrict__ y, int64_t n_out) {
+                                                            float* __restrict__ y, int64_t n_out,
+                                                            int use_smem) {
+  // taps staged in shared memory when they fit, read through L1 / L2 otherwise (very large rate
+  // ratios: more than ~58 K taps)
   extern __shared__ float s_taps[];
-  for (int i = threadIdx.x; i < n_taps; i += blockDim.x) s_taps[i] = taps[i];
-  __syncthreads();
+  const float* t = taps;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < n_taps; i += blockDim.x) s_taps[i] = taps[i];
+    __syncthreads();
+    t = s_taps;
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_out; m += stride)
-    y[m] = resample_poly_sample(x, n_in, up, down, s_taps, n_taps, n_pre_pad, n_pre_remove, m);
+    y[m] = resample_poly_sample(x, n_in, up, down, t, n_taps, n_pre_pad, n_pre_remove, m);
 }
 
 __global__ void __launch_bounds__(256) pcm16_to_mono_kernel(const int16_t* __restrict__ in,
@@ -104,7 +111,7 @@ extern "C" int cdb_resample_poly_f32(cdb_handle* h, const float* d_x, int64_t n_
                                      const float* d_taps, int n_taps, int n_pre_pad,
                                      int n_pre_remove, float* d_y, int64_t n_out, void* stream) {
   if (!h) return CDB_E_NULL;
-  if (n_in < 0 || n_out < 0 || up < 1 || down < 1 || n_taps < 1 || n_taps > 12288 || n_pre_pad < 0 ||
+  if (n_in < 0 || n_out < 0 || up < 1 || down < 1 || n_taps < 1 || n_pre_pad < 0 ||
       n_pre_remove < 0)
     return cdb_fail(h, CDB_E_INVALID, "invalid resampling plan (up %d, down %d, taps %d)", up, down,
                     n_taps);
@@ -112,9 +119,16 @@ extern "C" int cdb_resample_poly_f32(cdb_handle* h, const float* d_x, int64_t n_
   if (!d_x || !d_taps || !d_y) return cdb_fail(h, CDB_E_NULL, "null input / taps / output");
   CDB_CUDA(h, cudaSetDevice(h->device));
   const int64_t grid = std::min<int64_t>((n_out + 255) / 256, (int64_t)h->num_sms * 16);
-  resample_poly_kernel<<<(unsigned)std::max<int64_t>(grid, 1), 256, (size_t)n_taps * 4,
-                         (cudaStream_t)stream>>>(d_x, n_in, up, down, d_taps, n_taps, n_pre_pad,
-                                                 n_pre_remove, d_y, n_out);
+  // 20*max(up,down)+1 taps: 12 801 for 32 kHz or 96 kHz -> 22.05 kHz, i.e. more than the default
+  // 48 KB of dynamic shared memory: opt in up to the device limit, beyond that read from L2
+  size_t smem = (size_t)n_taps * sizeof(float);
+  const int use_smem = smem <= (size_t)h->smem_optin ? 1 : 0;
+  if (!use_smem) smem = 0;
+  if (smem > 48 * 1024)
+    CDB_CUDA(h, cudaFuncSetAttribute(resample_poly_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  resample_poly_kernel<<<(unsigned)std::max<int64_t>(grid, 1), 256, smem, (cudaStream_t)stream>>>(
+      d_x, n_in, up, down, d_taps, n_taps, n_pre_pad, n_pre_remove, d_y, n_out, use_smem);
   h->launches += 1;
   CDB_CUDA(h, cudaGetLastError());
   return 0;

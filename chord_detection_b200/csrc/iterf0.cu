@@ -398,7 +398,13 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
 }
 
 static int iterf0_get_plan(cdb_handle* h, const cdb_iterf0_params* p, IterF0Plan** out) {
-  std::string key = pod_key(*p);
+  if (p->channels < 1 || p->channels > CDB_ITERF0_MAX_CHANNELS)
+    return cdb_fail(h, CDB_E_INVALID, "channels %d", p->channels);
+  std::string key = cdb_key(p->fs, p->frame_size, p->power, p->channels, p->max_voices, p->tau_min,
+                            p->tau_max, p->tau_prec, p->Q, p->M, p->epsilon1, p->epsilon2, p->gamma,
+                            p->wfir_lambda, p->wfir_taps);
+  for (const auto* sos : {p->res1_b, p->res1_a, p->res2_b, p->res2_a, p->lp_b, p->lp_a})
+    key.append(reinterpret_cast<const char*>(sos), sizeof(double) * 3 * p->channels);
   auto it = h->iterf0_plans.find(key);
   if (it != h->iterf0_plans.end()) {
     *out = it->second;
@@ -621,14 +627,18 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     a.Ut = reinterpret_cast<double*>(wrest + (((size_t)nb * a.C * n_pad * 4 + 255) & ~(size_t)255));
     if (d_voices) a.voices = d_voices + c0 * fpc * 2 * p->max_voices;
     const int threads = nb * a.C;
+    cdb_mark(h, st, "begin");
     iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
+    cdb_mark(h, st, "iterf0_filter_kernel");
     const int64_t nframes = (int64_t)nb * fpc;
     if (use_s8k)
       iterf0_spectrum8k_kernel<<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
+    cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");
     const int pgrid = (int)std::min<int64_t>(nframes, pgrid_max);
     iterf0_periodicity_kernel<<<pgrid, 32 * p->M, per_smem, st>>>(a);
+    cdb_mark(h, st, "iterf0_periodicity_kernel");
     h->launches += 3;
     CDB_CUDA(h, cudaGetLastError());
   }

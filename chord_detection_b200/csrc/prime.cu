@@ -72,7 +72,8 @@ extern "C" int cdb_prime_window_sizes(const cdb_prime_params* p, int* sizes) {
 }
 
 static int prime_get_plan(cdb_handle* h, const cdb_prime_params* p, PrimePlan** out) {
-  std::string key = pod_key(*p);
+  std::string key = cdb_key(p->fs, p->num_harmonic, p->num_octave, p->harmonic_multiples_elim,
+                             p->harmonic_elim_runs);
   auto it = h->prime_plans.find(key);
   if (it != h->prime_plans.end()) {
     *out = it->second;
@@ -366,7 +367,9 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
                                                             smem));
   if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "window does not fit in shared memory");
   const int64_t grid = std::min<int64_t>(a.total_items, (int64_t)h->num_sms * per_sm);
+  cdb_mark(h, st, "begin");
   prime_kernel<<<(unsigned)grid, kPrimeThreads, smem, st>>>(a);
+  cdb_mark(h, st, "prime_kernel");
   h->launches += 1;
   CDB_CUDA(h, cudaGetLastError());
   return 0;

@@ -34,6 +34,45 @@ def init(backend=None):
     return rank, world, device
 
 
+def comm_init(device=None):
+    """Set up the fused all-reduce of the harmonic-energy kernel (include/chordb200.h cdb_comm_*):
+    every rank allocates its mailbox, the CUDA IPC handles travel through an all_gather_object on
+    the existing process group, and every rank maps its peers' mailboxes.  Returns True when the
+    in-kernel path is usable (ops.harmonic_energy(..., allreduce=True)); with one rank it is set up
+    as a world of one.  Raises nothing on failure (e.g. CUDA IPC unavailable in a sandbox): returns
+    False and callers keep using all_reduce_chroma (NCCL)."""
+    from . import _native as nat
+
+    if not torch.cuda.is_available():
+        return False
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h = nat.Handle.get(dev.index)
+    if getattr(h, "comm_world", 0):
+        return True
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+
+    def exchange(b):
+        if world == 1:
+            return [b]
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    ok = True
+    try:
+        h.comm_init(rank, world, exchange)
+    except (RuntimeError, ValueError):
+        ok = False
+    if world > 1:  # all ranks or none
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+        if not ok and getattr(h, "comm_world", 0):
+            h.comm_destroy()
+    return ok
+
+
 def shard_range(n_items, rank, world):
     """Contiguous, balanced [begin, end) of n_items for this rank (sizes differ by at most 1)."""
     return (n_items * rank) // world, (n_items * (rank + 1)) // world
@@ -60,12 +99,25 @@ def all_reduce_chroma(t):
     return t
 
 
-def harmonic_energy_sharded(x_local, fs, frames_local, frame_size, hop=None, **kw):
-    """HE over this rank's shard of a long signal (x_local = samples [s0, s1) of shard_frames),
-    then the all-reduce.  Returns the GLOBAL 12-bin sum on every rank (CUDA float64 tensor)."""
-    from . import ops
+def harmonic_energy_sharded(x_local, fs, frames_local, frame_size, hop=None, fused=None, **kw):
+    """HE over this rank's shard of a long signal (x_local = samples [s0, s1) of shard_frames) and
+    the sum over ranks.  Returns the GLOBAL 12-bin sum on every rank (CUDA float64 tensor).
+    fused=None: use the in-kernel all-reduce over peer memory when comm_init() succeeded and the
+    frame size is 2048, else NCCL; True / False force one or the other."""
+    from . import _native as nat, ops
 
-    total = torch.zeros(12, dtype=torch.float64, device=x_local.device)
+    dev = x_local.device
+    total = torch.zeros(12, dtype=torch.float64, device=dev)
+    if fused is None:
+        fused = (int(frame_size) == 2048 and x_local.is_cuda
+                 and bool(getattr(nat.Handle.get(dev.index), "comm_world", 0)))
+    if fused:
+        # a collective: a rank with an empty shard still launches (one CTA that contributes zeros)
+        xs = x_local if frames_local > 0 else x_local[:0]
+        ops.harmonic_energy(xs, fs, frame_size=frame_size, hop=hop,
+                            frames_per_clip=frames_local if frames_local > 0 else None,
+                            out_total=total, allreduce=True, **kw)
+        return total
     if frames_local > 0:
         ops.harmonic_energy(x_local, fs, frame_size=frame_size, hop=hop,
                             frames_per_clip=frames_local, out_total=total, **kw)

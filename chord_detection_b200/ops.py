@@ -86,13 +86,18 @@ def _ptr(t):
 
 def harmonic_energy(x, fs, frame_size=8192, num_harmonic=2, num_octave=2, num_bins=2, hop=None,
                     window="hamming", per_clip=False, per_frame=False, frames_per_clip=None,
-                    out_total=None, accumulate=False):
+                    out_total=None, accumulate=False, allreduce=False):
     """Harmonic-energy chromagram (reference harmonic_energy.py:31-73) -> ChromaResult.
 
     hop=None reproduces the reference's non-overlapping frames.  x may be int16
-    PCM (sample value s/32768): decoded inside the frame-2048 kernel, converted first otherwise."""
+    PCM (sample value s/32768): decoded inside the frame-2048 kernel, converted first otherwise.
+    allreduce=True (frame_size 2048, after distributed.comm_init()): `total` is the sum over ALL
+    ranks, exchanged inside the kernel over NVLink peer memory (CDB_FLAG_ALLREDUCE); a collective,
+    so every rank must call it, in the same order."""
     x, n_clips, clip_len, stride = _batch_view(x, allow_pcm16=True)
     flags = nat.CDB_FLAG_ACCUMULATE if accumulate else 0
+    if allreduce:
+        flags |= nat.CDB_FLAG_ALLREDUCE
     if x.dtype == torch.int16:
         if int(frame_size) == 2048:
             flags |= nat.CDB_FLAG_PCM16
@@ -149,8 +154,10 @@ class HostPipeline:
         self.host_out = torch.empty(12, dtype=torch.float64).pin_memory()
         self.h2d_bytes = 0
 
-    def run(self, x_host):
-        """x_host: 1-D CPU tensor of self.dtype (pinned for full PCIe speed) -> numpy [12] float64."""
+    def run(self, x_host, allreduce=False):
+        """x_host: 1-D CPU tensor of self.dtype (pinned for full PCIe speed) -> numpy [12] float64.
+        allreduce=True (after distributed.comm_init()): the result is the sum over all ranks; the
+        exchange rides in the LAST chunk's kernel (CDB_FLAG_ACCUMULATE | CDB_FLAG_ALLREDUCE)."""
         if x_host.dtype != self.dtype:
             raise ValueError("HostPipeline was built for %s input" % self.dtype)
         n = x_host.shape[0]
@@ -159,10 +166,11 @@ class HostPipeline:
         with torch.cuda.stream(self.compute_stream):
             self.total.zero_()
         i = 0
-        for f0 in range(0, n_frames, self.chunk_frames):
+        starts = list(range(0, n_frames, self.chunk_frames)) or [0]
+        for f0 in starts:
             nf = min(self.chunk_frames, n_frames - f0)
             s0 = f0 * self.hop
-            s1 = min(n, s0 + (nf - 1) * self.hop + self.frame_size)
+            s1 = min(n, s0 + (nf - 1) * self.hop + self.frame_size) if nf > 0 else s0
             b = i & 1
             buf = self.bufs[b]
             with torch.cuda.stream(self.copy_stream):
@@ -174,7 +182,8 @@ class HostPipeline:
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self.copied[b])
                 harmonic_energy(buf[: s1 - s0], self.fs, self.frame_size, hop=self.hop,
-                                frames_per_clip=nf, out_total=self.total, accumulate=True,
+                                frames_per_clip=nf if nf > 0 else None, out_total=self.total,
+                                accumulate=True, allreduce=allreduce and f0 == starts[-1],
                                 **self.kw)
                 self.consumed[b].record(self.compute_stream)
             i += 1
@@ -378,7 +387,13 @@ _workspaces = {}
 
 
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
+    """Grow-only IterF0 scratch per (host thread, device, CUDA stream): calls on different streams
+    or threads never share a buffer, and a buffer that is replaced goes back to PyTorch's caching
+    allocator, which only reuses it in stream order of the stream it was allocated on."""
+    import threading
+
+    key = (threading.get_ident(), device.type, device.index,
+           torch.cuda.current_stream(device).cuda_stream)
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
         _workspaces[key] = None

@@ -28,7 +28,9 @@
  *     constant tables for it (synchronous, cached in the handle).
  *   - Return value: 0 = OK; <0 = argument error (CDB_E_*); >0 = cudaError_t.
  *     cdb_last_error(h) returns a message for the last non-zero return on this handle.
- *   - One handle per (host thread, device).  No global mutable state.
+ *   - One handle per (host thread, device), used on ONE stream at a time: the handle's scratch
+ *     (ESACF workspace) is shared by consecutive calls and only stream order protects it.  Use a
+ *     second handle for a second concurrent stream.  No global mutable state.
  */
 #ifndef CHORDB200_H
 #define CHORDB200_H
@@ -47,6 +49,8 @@ extern "C" {
 #define CDB_E_NOGPU (-4)       /* no CUDA device / wrong architecture */
 
 #define CDB_FLAG_ACCUMULATE 1 /* do not zero the outputs first */
+#define CDB_FLAG_ALLREDUCE 4  /* cdb_he_chroma, frame_size 2048, after cdb_comm_connect: d_chroma_total receives the
+                                 sum over ALL ranks, exchanged inside the kernel over peer memory (see cdb_comm_*) */
 #define CDB_FLAG_PCM16 2      /* cdb_he_chroma, frame_size 2048: d_x is mono int16 PCM, sample value s/32768 */
 
 #define CDB_WINDOW_HAMMING 0 /* scipy.signal.hamming(N) symmetric (harmonic_energy.py:42) */
@@ -61,6 +65,14 @@ int cdb_destroy(cdb_handle* h);
 const char* cdb_last_error(cdb_handle* h);
 /* number of kernels launched through this handle since creation (bench `gpu_launches`) */
 int64_t cdb_launch_count(cdb_handle* h);
+
+/* Optional per-kernel timing of the calls made through this handle (bench.py's "dominant kernel's
+ * share"): cdb_profile_enable(h, 1) starts a recording (one CUDA event after every kernel launch on
+ * the caller's stream), cdb_profile_report waits for the recorded events and writes one
+ * "kernel_name milliseconds\n" line per distinct kernel (summed over the recording) into buf;
+ * returns the length written or <0.  cdb_profile_enable(h, 0) stops and clears. */
+int cdb_profile_enable(cdb_handle* h, int on);
+int64_t cdb_profile_report(cdb_handle* h, char* buf, int64_t buf_len);
 
 /* frame.py:9-14 generalised with a hop: frames start at g*hop for every
  * g*hop < clip_len; hop == frame_size reproduces the reference exactly. */
@@ -90,6 +102,24 @@ int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k1, double* 
 int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* d_x, int64_t n_clips,
                   int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
                   double* d_chroma_clips, float* d_chroma_frames, int flags, void* stream);
+
+/* ---------------- multi-GPU: the one exchange step of the path ----------------
+ * The reference has no parallelism; sharded runs need ONE sum of the per-GPU 12-bin vectors.  For
+ * the metric kernel this sum is fused into the kernel: the last CTA of every rank stores its 12
+ * doubles and a flag into every peer's mailbox over NVLink (P2P stores into cudaMalloc'ed memory
+ * mapped through CUDA IPC), waits for the peers' flags and adds the slots in rank order, so all
+ * ranks hold bit-identical totals when the kernel ends and no separate collective is launched.
+ *   1. every rank: cdb_comm_alloc(h, world, handle_out[CDB_IPC_HANDLE_BYTES])
+ *   2. exchange the handles (any transport; concatenated in rank order)
+ *   3. every rank: cdb_comm_connect(h, rank, world, all_handles[world * CDB_IPC_HANDLE_BYTES])
+ *   4. cdb_he_chroma(..., flags | CDB_FLAG_ALLREDUCE, ...) in lock-step on all ranks (a collective:
+ *      every rank must make the same sequence of such calls; an empty shard still calls).
+ * A peer that does not arrive within ~10 s makes the result NaN and cdb_comm_status() return 1. */
+#define CDB_IPC_HANDLE_BYTES 64
+int cdb_comm_alloc(cdb_handle* h, int world, unsigned char* ipc_handle_out);
+int cdb_comm_connect(cdb_handle* h, int rank, int world, const unsigned char* all_handles);
+int cdb_comm_status(cdb_handle* h);
+int cdb_comm_destroy(cdb_handle* h);
 
 /* ---------------- method 1: ESACF (esacf.py:41-134) ---------------- */
 #define CDB_STRETCH_TRUNCATE 0 /* librosa>=0.8 time_stretch on a <1024-sample SACF */

@@ -48,6 +48,7 @@ def _worker(rank, world, port, n, ret):
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     r, w, dev = D.init(backend="gloo")
     assert (r, w) == (rank, world) and dev.type == "cpu"
+    assert D.comm_init() is False  # the fused all-reduce needs CUDA peers; NCCL / gloo path stays
     x, fs = cases.make_input(dict(fn="s_poly_long", seed=3, fs=44100, n=n))
     N, hop = 2048, 512
     f0, f1, s0, s1 = D.shard_frames(n, N, hop, rank, world)

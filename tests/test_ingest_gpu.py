@@ -126,7 +126,9 @@ def test_device_load_matches_host_load(tmp_path):
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(8)
     for i, (fs, ch, n) in enumerate(((44100, 1, 30011), (48000, 2, 20000), (22050, 1, 5000),
-                                     (16000, 2, 7001), (8000, 1, 999))):
+                                     (16000, 2, 7001), (8000, 1, 999),
+                                     # 12 801 taps (> 48 KB of shared memory) and 882 021 taps (L2 path)
+                                     (32000, 1, 8000), (96000, 2, 9000), (44101, 1, 3000))):
         pcm = rng.integers(-20000, 20000, size=(n, ch) if ch > 1 else n).astype(np.int16)
         path = os.path.join(tmp_path, "c%d.wav" % i)
         wavfile.write(path, fs, pcm)
