@@ -274,6 +274,8 @@ def host_resample_poly(x, up, down, taps, n_pre_pad, n_pre_remove, n_out):
 
 def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
     """Host execution of the device auditory-channel filter (test hook, no GPU).
+    pipelined: 0 / 1 = reference-order chain (straight / software-pipelined), 2 / 3 = the hoisted
+    form the device runs by default (pipelined / straight).
     x float32 [n]; coef float64 [18] (res1 b,a | res2 b,a | lp b,a); taps float64 [13] -> float32 [n]"""
     import numpy as np
 
@@ -286,7 +288,7 @@ def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
     P = C.POINTER(C.c_double)
     F = C.POINTER(C.c_float)
     rc = lib().cdb_host_iterf0_filter(x.ctypes.data_as(F), x.shape[0], coef.ctypes.data_as(P),
-                                      float(lam), taps.ctypes.data_as(P), int(bool(pipelined)),
+                                      float(lam), taps.ctypes.data_as(P), int(pipelined),
                                       y.ctypes.data_as(F))
     if rc != 0:
         raise ValueError("cdb_host_iterf0_filter failed (%d)" % rc)

@@ -58,6 +58,8 @@ struct IterArgs {
   const float2* tw;
   const float2* wsplit;
   s8k::Tables s8;
+  double* w;    // [n_batch_clips][clip_len] whitened clips (hoisted filter form)
+  int structured;  // resonator numerators are [b0, 0, b2] / [b0, 0, 0] (always, for reference designs)
   float* yc;    // [n_batch_clips][C][n_pad]
   double* Ut;   // [n_batch_clips*fpc][M+1]
   double* Ud;   // [grid][2M] cancellation scratch
@@ -77,6 +79,28 @@ __global__ void __launch_bounds__(32) iterf0_filter_kernel(const IterArgs a) {
   const float* src = a.x + (a.clip0 + lc) * a.clip_stride;
   float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
   iff::filter_channel<true>(src, a.clip_len, a.n_pad, a.coef + ch * kCoefStride, a.lam, a.taps, dst);
+}
+
+// hoisted form (iterf0_filter.cuh): the whitener once per clip ...
+__global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
+  const int lc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= a.n_batch_clips) return;
+  const float* src = a.x + (a.clip0 + lc) * a.clip_stride;
+  iff::whiten_clip<true>(src, a.clip_len, a.lam, a.taps, a.w + (int64_t)lc * a.clip_len);
+}
+
+// ... then one thread per (clip, channel): resonators, |.|, (y + lowpass(y)) / 2
+__global__ void __launch_bounds__(32) iterf0_channel_kernel(const IterArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_batch_clips * a.C) return;
+  const int lc = t / a.C, ch = t - lc * a.C;
+  const double* src = a.w + (int64_t)lc * a.clip_len;
+  float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
+  const double* coef = a.coef + ch * kCoefStride;
+  if (a.structured)
+    iff::filter_channel_w<true, iff::SosR<2>, iff::SosR<1>>(src, a.clip_len, a.n_pad, coef, dst);
+  else
+    iff::filter_channel_w<true, iff::Sos, iff::Sos>(src, a.clip_len, a.n_pad, coef, dst);
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -472,7 +496,8 @@ static int iterf0_get_plan(cdb_handle* h, const cdb_iterf0_params* p, IterF0Plan
 static int64_t per_clip_bytes(const cdb_iterf0_params* p, int64_t clip_len) {
   const int64_t fpc = cdb_num_frames(clip_len, p->frame_size, p->frame_size);
   const int64_t n_pad = fpc * p->frame_size;
-  return (int64_t)p->channels * n_pad * 4 + fpc * (int64_t)(p->frame_size + 1) * 8;
+  return (int64_t)p->channels * n_pad * 4 + fpc * (int64_t)(p->frame_size + 1) * 8 +
+         ((clip_len * 8 + 255) & ~(int64_t)255);  // + the whitened clip (fp64)
 }
 
 static int64_t ud_bytes(const cdb_iterf0_params* p, int num_sms) {
@@ -487,6 +512,22 @@ extern "C" {
 int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double lam,
                            const double* taps, int pipelined, float* y) {
   if (!x || !coef || !taps || !y || n < 0) return -1;
+  if (pipelined == 2 || pipelined == 3) {
+    // the hoisted form the device runs by default: whiten the clip once, then the channel part
+    // (2: pipelined schedules, 3: straight loops -- bit-identical to each other)
+    std::vector<double> w((size_t)std::max<int64_t>(n, 1));
+    if (pipelined == 2) iff::whiten_clip<true>(x, n, lam, taps, w.data());
+    else iff::whiten_clip<false>(x, n, lam, taps, w.data());
+    const bool st = iff::resonators_structured(coef);
+    if (pipelined == 2) {
+      if (st) iff::filter_channel_w<true, iff::SosR<2>, iff::SosR<1>>(w.data(), n, n, coef, y);
+      else iff::filter_channel_w<true, iff::Sos, iff::Sos>(w.data(), n, n, coef, y);
+    } else {
+      if (st) iff::filter_channel_w<false, iff::SosR<2>, iff::SosR<1>>(w.data(), n, n, coef, y);
+      else iff::filter_channel_w<false, iff::Sos, iff::Sos>(w.data(), n, n, coef, y);
+    }
+    return 0;
+  }
   if (pipelined) iff::filter_channel<true>(x, n, n, coef, lam, taps, y);
   else iff::filter_channel<false>(x, n, n, coef, lam, taps, y);
   return 0;
@@ -589,6 +630,13 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   if (const char* sm = std::getenv("CDB_ITERF0_SPEC"))
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
+  // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
+  bool hoisted = true;
+  if (const char* fm = std::getenv("CDB_ITERF0_FILTER"))
+    if (fm[0] == 'c') hoisted = false;
+  a.structured = 1;
+  for (int c = 0; c < p->channels; ++c)
+    if (p->res1_b[c][1] != 0.0 || p->res2_b[c][1] != 0.0 || p->res2_b[c][2] != 0.0) a.structured = 0;
   a.fs = p->fs;
   a.K = (double)F / p->fs;  // periodicity.py:31
   a.tau_min = p->tau_min;
@@ -625,11 +673,21 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     a.n_batch_clips = nb;
     a.yc = reinterpret_cast<float*>(wrest);
     a.Ut = reinterpret_cast<double*>(wrest + (((size_t)nb * a.C * n_pad * 4 + 255) & ~(size_t)255));
+    a.w = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(a.Ut) +
+                                    (((size_t)nb * fpc * (F + 1) * 8 + 255) & ~(size_t)255));
     if (d_voices) a.voices = d_voices + c0 * fpc * 2 * p->max_voices;
     const int threads = nb * a.C;
     cdb_mark(h, st, "begin");
-    iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
-    cdb_mark(h, st, "iterf0_filter_kernel");
+    if (hoisted) {
+      iterf0_whiten_kernel<<<(nb + 31) / 32, 32, 0, st>>>(a);
+      cdb_mark(h, st, "iterf0_whiten_kernel");
+      iterf0_channel_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);
+      cdb_mark(h, st, "iterf0_channel_kernel");
+      h->launches += 1;
+    } else {
+      iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
+      cdb_mark(h, st, "iterf0_filter_kernel");
+    }
     const int64_t nframes = (int64_t)nb * fpc;
     if (use_s8k)
       iterf0_spectrum8k_kernel<<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);

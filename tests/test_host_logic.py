@@ -169,7 +169,25 @@ def test_host_iterf0_filter_pipelined_schedule_is_exact():
             assert np.array_equal(yp, ys)
             want = rn.auditory_channel(x.astype(np.float64), fs, fc)
             assert np.max(np.abs(yp - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
+            # the hoisted form the device runs by default (whitener once per clip, then the
+            # resonators: the two LTI blocks commute): pipelined == straight loop bit for bit, same
+            # bound against scipy, and the fp32 output equals the chain form's almost everywhere
+            yh = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=2)
+            assert np.array_equal(yh, nat.host_iterf0_filter(x, coef, lam, taps, pipelined=3))
+            assert np.max(np.abs(yh - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
+            assert np.mean(yh != yp) <= 1e-3
+    for n in (2, 3, 4, 5, 7, 8, 9, 12, 13, 14, 25, 26, 27):  # every pipeline-fill / tail alignment
+        x, _ = cases.make_input(dict(fn="s_poly", seed=40 + n, fs=fs, n=n))
+        yh = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=2)
+        assert np.array_equal(yh, nat.host_iterf0_filter(x, coef, lam, taps, pipelined=3))
+        want = rn.auditory_channel(x.astype(np.float64), fs, fcs[69])
+        assert np.max(np.abs(yh - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
+    gen = coef.copy()
+    gen[1], gen[7], gen[8] = 0.01, -0.02, 0.03  # unstructured numerators take the general biquads
+    assert np.array_equal(nat.host_iterf0_filter(x, gen, lam, taps, pipelined=2),
+                          nat.host_iterf0_filter(x, gen, lam, taps, pipelined=3))
     assert nat.host_iterf0_filter(np.zeros(0, dtype=np.float32), np.ones(18), lam, taps).shape == (0,)
+    assert nat.host_iterf0_filter(np.zeros(0, dtype=np.float32), np.ones(18), lam, taps, pipelined=2).shape == (0,)
 
 
 def test_host_iterf0_spectrum8k_matches_numpy_rfft():

@@ -122,3 +122,27 @@ def test_iterf0_c4_full_size_properties():
             warnings.simplefilter("ignore")
             want = rn.iterf0(base_np[c], fs)
         _close(clips[c], want)
+
+
+def test_iterf0_hoisted_filter_equals_reference_order_chain(monkeypatch):
+    """CDB_ITERF0_FILTER=chain runs the reference's order per channel (resonators, then the
+    whitener); the default computes the whitener once per clip and then the resonators (the two
+    linear blocks commute).  Voices must agree exactly (periods) / to rounding (saliences), the
+    chroma to 1e-9 -- on a batch with ragged length so every pipeline fill / tail path runs."""
+    from chord_detection_b200 import ops
+
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=230 + i, fs=22050, n=2 * 8192 + 1237))[0]
+                     for i in range(5)])
+    xd = torch.from_numpy(rows).to(_dev())
+    a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    monkeypatch.setenv("CDB_ITERF0_FILTER", "chain")
+    b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    torch.cuda.synchronize()
+    va, vb = a.extra.cpu().numpy(), b.extra.cpu().numpy()
+    assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0)
+    assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-6, atol=0)
+    _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.stack([rn.iterf0(r, 22050) for r in rows[:2]])
+    _close(a.clips[:2].cpu().numpy(), want)
