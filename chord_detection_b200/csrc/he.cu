@@ -48,6 +48,15 @@ struct HePlan {
   float2* d_wsplit = nullptr;  // [M+1]: (cos, sin)(2*pi*k/N)
   float2* d_twgen = nullptr;   // [M/2]: W_M^q = (cos, -sin)(2*pi*q/M)
   HeWin* d_wins = nullptr;
+  // "level" epilogue of the frame-2048 kernel (range maxima from a sparse table built with warp
+  // shuffles): per window the two table positions (slot*192 + bin) packed as lo | hi << 16, the
+  // levels (log2 of the span) that are needed, their slots, and which (level, row) pairs to store
+  bool levels_ok = false;
+  uint32_t* d_winpos = nullptr;  // [n_windows]
+  double* d_winwt = nullptr;     // [n_windows]
+  int n_level_slots = 0;
+  int level_slot[5] = {-1, -1, -1, -1, -1};
+  uint32_t level_rows[5] = {0, 0, 0, 0, 0};  // bit r: row r (bins 32r..32r+31) of this level is read
 };
 
 void cdb_free_he_plans(cdb_handle* h) {
@@ -224,6 +233,26 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
   if ((rc = cdb_upload(h, twgen, &pl->d_twgen))) return rc;
   if ((rc = cdb_upload(h, tw32, &pl->d_tw32))) return rc;
   if ((rc = cdb_upload(h, wins, &pl->d_wins))) return rc;
+  // sparse-table positions for the level epilogue: a window [k0, k0 + w) is max(T_l[k0], T_l[k0 + w - 2^l])
+  // with l = floor(log2 w), T_l[b] = max of the 2^l bins from b.  Usable when every window lies in
+  // bins 0..191 (the pruned spectrum), is at most 31 bins wide, and there are at most 64 windows.
+  if (N == 2048 && nw <= 64 && (kmax >> 5) <= 5 && max_width <= 31) {
+    std::vector<uint32_t> pos(nw);
+    std::vector<double> wt(nw);
+    for (int i = 0; i < nw; ++i) {
+      const int w = wins[i].k1 - wins[i].k0;
+      int l = 0;
+      while ((2 << l) <= w) ++l;
+      if (pl->level_slot[l] < 0) pl->level_slot[l] = pl->n_level_slots++;
+      const int a = wins[i].k0, b = wins[i].k0 + w - (1 << l);
+      pl->level_rows[l] |= (1u << (a >> 5)) | (1u << (b >> 5));
+      pos[i] = (uint32_t)(pl->level_slot[l] * 192 + a) | ((uint32_t)(pl->level_slot[l] * 192 + b) << 16);
+      wt[i] = wins[i].weight;
+    }
+    if ((rc = cdb_upload(h, pos, &pl->d_winpos))) return rc;
+    if ((rc = cdb_upload(h, wt, &pl->d_winwt))) return rc;
+    pl->levels_ok = true;
+  }
   h->he_plans[ks] = pl;
   *out = pl;
   return 0;
@@ -248,6 +277,11 @@ struct HeArgs {
   double* total;
   double* clips;
   float* frames;
+  // level epilogue (he2048w_kernel<.., LEVELS = true>)
+  const uint32_t* winpos;
+  const double* winwt;
+  int level_slot[5];
+  uint32_t level_rows[5];
   // frame-2048 kernel: grid-wide accumulators + CTA ticket (handle-owned, zero between launches),
   // whether `total` is overwritten or added to, and the optional fused all-reduce
   double* scratch;
@@ -420,8 +454,28 @@ struct TwStore {
   }
 };
 
-template <int NW, int KHI, bool PCM16>
+// rot(x, D)[lane] = x[(lane + D) & 31]
+template <int D>
+__device__ __forceinline__ float rot_lanes(float x, int lane) {
+  return __shfl_sync(0xffffffffu, x, (lane + D) & 31);
+}
+// next sparse-table level: T'[b] = max(T[b], T[b + D]) for the 6 rows b = lane + 32 r of the pruned
+// spectrum; the neighbour of the last D lanes of a row is the head of the next row, i.e. the SAME
+// rotation applied to the next row, so one shuffle per row serves both
+template <int D>
+__device__ __forceinline__ void level_up(float (&t)[6], int lane) {
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r[i] = rot_lanes<D>(t[i], lane);
+  r[6] = 0.0f;  // bins >= 192 are never part of a window
+  const bool same_row = lane + D < 32;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) t[i] = fmaxf(t[i], same_row ? r[i] : r[i + 1]);
+}
+
+template <int NW, int KHI, bool PCM16, bool LEVELS = false>
 __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
+  static_assert(!LEVELS || KHI == 5, "the level epilogue works on the pruned 192-bin spectrum");
   extern __shared__ __align__(128) unsigned char smem[];
   double* cta_acc = reinterpret_cast<double*>(smem);          // [12]
   uint64_t* mbar_all = reinterpret_cast<uint64_t*>(smem + 128);  // [NW] (NW <= 32)
@@ -451,6 +505,15 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
             win_sb = pk(wl.z * kIn, wl.w * kIn);
   double acc_total = 0.0, acc_clip = 0.0;
   int64_t my_clip = -1;
+  // level epilogue: this lane owns windows `lane` and `lane + 32` for every frame
+  uint32_t wpos0 = 0, wpos1 = 0;
+  if (LEVELS) {
+    if (lane < a.n_windows) wpos0 = a.winpos[lane];
+    if (lane + 32 < a.n_windows) wpos1 = a.winpos[lane + 32];
+    // the per-window weights sit behind the (padded) per-window values: wv[n_windows + 16 ..]
+    for (int i = lane; i < a.n_windows; i += 32) wv[a.n_windows + 16 + i] = a.winwt[i];
+    __syncwarp();
+  }
 
   const int64_t total_frames = a.n_clips * a.frames_per_clip;
   const int64_t stride_frames = (int64_t)gridDim.x * NW;
@@ -562,6 +625,7 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
       const int k2a = a.kmin >> 5, k2b = a.kmax >> 5;
       constexpr int K2END = (KHI < 0) ? 32 : KHI + 1;
       const float2* csp = a.wsplit + lane;
+      float pwr[LEVELS ? 6 : 1];
 #pragma unroll
       for (int k2 = 0; k2 < K2END; ++k2) {
         if (KHI >= 0 || (k2 >= k2a && k2 <= k2b)) {
@@ -577,7 +641,8 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
           const c64 x2 = fma2(bc(-cs.y), d, fma2(bc(cs.x), mul_mi(d), e));
           float xr, xi;
           upk(x2, xr, xi);
-          pw[lane + 32 * k2] = fmaf(xr, xr, xi * xi);
+          if constexpr (LEVELS) pwr[k2] = fmaf(xr, xr, xi * xi);
+          else pw[lane + 32 * k2] = fmaf(xr, xr, xi * xi);
         }
       }
       if (KHI < 0 && a.kmax == 1024 && lane == 0) {
@@ -586,22 +651,75 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
         const float xn = 2.0f * (zr - zi);
         pw[1024] = xn * xn;
       }
-      __syncwarp();
-      for (int wi = lane; wi < a.n_windows; wi += 32) {
-        const HeWin hw = swins[wi];
-        const float* p0 = pw + hw.k0;
-        const int last = hw.k1 - 1 - hw.k0;
-        float m = p0[0];
-        for (int j0 = 0; j0 < a.max_width; j0 += 8) {
+      if constexpr (LEVELS) {
+        // ---- window maxima from a sparse table of range maxima.  The power spectrum stays in
+        // registers (bin lane + 32 r in pwr[r]); level l holds max over 2^l bins starting at each
+        // bin and is built from level l - 1 with one lane rotation per row (level_up).  Only the
+        // (level, row) pairs some window reads are written to shared memory (conflict-free rows),
+        // and a window is then ONE or two loads instead of a per-lane gather over its bins.
+        // max is exact in any order: the maxima are bit-identical to the sequential scan.
+        float t[6];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) m = fmaxf(m, p0[min(j0 + j, last)]);
+        for (int r = 0; r < 6; ++r) t[r] = pwr[r];
+        auto put = [&](int l) {
+          const int slot = a.level_slot[l];
+          if (slot < 0) return;
+          const uint32_t rows = a.level_rows[l];
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (rows & (1u << r)) pw[slot * 192 + 32 * r + lane] = t[r];
+        };
+        put(0);
+        level_up<1>(t, lane);
+        put(1);
+        if (a.max_width >= 4) {
+          level_up<2>(t, lane);
+          put(2);
         }
-        wv[wi] = (double)sqrt_approx(sqrt_approx(0.25f * m)) * hw.weight;
+        if (a.max_width >= 8) {
+          level_up<4>(t, lane);
+          put(3);
+        }
+        if (a.max_width >= 16) {
+          level_up<8>(t, lane);
+          put(4);
+        }
+        __syncwarp();
+        auto window = [&](uint32_t wp, int wi) {
+          if (wi < a.n_windows) {
+            const int pa = wp & 0xffffu, pb = wp >> 16;
+            float m = pw[pa];
+            if (pb != pa) m = fmaxf(m, pw[pb]);
+            wv[wi + wi / a.wins_per_note] = (double)sqrt_approx(sqrt_approx(0.25f * m));
+          }
+        };
+        window(wpos0, lane);
+        window(wpos1, lane + 32);
+      } else {
+        __syncwarp();
+        for (int wi = lane; wi < a.n_windows; wi += 32) {
+          const HeWin hw = swins[wi];
+          const float* p0 = pw + hw.k0;
+          const int last = hw.k1 - 1 - hw.k0;
+          float m = p0[0];
+          for (int j0 = 0; j0 < a.max_width; j0 += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m = fmaxf(m, p0[min(j0 + j, last)]);
+          }
+          wv[wi] = (double)sqrt_approx(sqrt_approx(0.25f * m)) * hw.weight;
+        }
       }
       __syncwarp();
       if (lane < 12) {
         double sm = 0.0;
-        for (int j = 0; j < a.wins_per_note; ++j) sm += wv[lane * a.wins_per_note + j];
+        if constexpr (LEVELS) {
+          // (padded rows: a note's windows start every wins_per_note + 1 doubles -> conflict-free)
+          const double* wt = wv + a.n_windows + 16 + lane * a.wins_per_note;
+          const double* ws = wv + lane * (a.wins_per_note + 1);
+          for (int j = 0; j < a.wins_per_note; ++j) sm += __dmul_rn(ws[j], wt[j]);  // as the gather path: round, then add
+        } else {
+          for (int j = 0; j < a.wins_per_note; ++j) sm += wv[lane * a.wins_per_note + j];
+        }
         if (a.clips) {
           if (clip != my_clip) {
             if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + lane], acc_clip);
@@ -1185,12 +1303,24 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     // metric shape probes bins 22..186).
     const bool pruned = (pl->kmax >> 5) <= 5;
     const int nw = pruned ? 16 : 12;
-    a.pw_floats = pruned ? 192 : 1028;
-    a.pw_bytes = (a.pw_floats * 4 + pl->n_windows * 8 + 15) & ~15;
+    // CDB_HE_EPILOGUE = levels (default when the plan allows it: window maxima from a shuffle-built
+    // sparse table) | gather (every lane scans its windows in shared memory)
+    bool levels = pruned && pl->levels_ok;
+    if (const char* ep = std::getenv("CDB_HE_EPILOGUE"))
+      if (ep[0] == 'g') levels = false;
+    a.pw_floats = levels ? 192 * pl->n_level_slots : pruned ? 192 : 1028;
+    a.pw_bytes = (a.pw_floats * 4 + (levels ? 2 * pl->n_windows + 16 : pl->n_windows) * 8 + 15) & ~15;
+    a.winpos = pl->d_winpos;
+    a.winwt = pl->d_winwt;
+    for (int l = 0; l < 5; ++l) {
+      a.level_slot[l] = pl->level_slot[l];
+      a.level_rows[l] = pl->level_rows[l];
+    }
     const bool pcm = (flags & CDB_FLAG_PCM16) != 0;
     void (*kern)(const HeArgs) =
-        pruned ? (pcm ? he2048w_kernel<16, 5, true> : he2048w_kernel<16, 5, false>)
-               : (pcm ? he2048w_kernel<12, -1, true> : he2048w_kernel<12, -1, false>);
+        levels ? (pcm ? he2048w_kernel<16, 5, true, true> : he2048w_kernel<16, 5, false, true>)
+        : pruned ? (pcm ? he2048w_kernel<16, 5, true> : he2048w_kernel<16, 5, false>)
+                 : (pcm ? he2048w_kernel<12, -1, true> : he2048w_kernel<12, -1, false>);
     const size_t smem = 384 + 1024 * 8 + (size_t)nw * kScr * 8 + (size_t)nw * a.pw_bytes +
                         (size_t)pl->n_windows * sizeof(HeWin);
     CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1200,7 +1330,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
         1, std::min<int64_t>((total_frames + nw - 1) / nw, (int64_t)h->num_sms));
     cdb_mark(h, st, "begin");
     kern<<<(unsigned)grid, nw * 32, smem, st>>>(a);
-    cdb_mark(h, st, pcm ? "he2048w_kernel<pcm16>" : "he2048w_kernel");
+    cdb_mark(h, st, levels ? "he2048w_kernel<levels>" : "he2048w_kernel<gather>");
   } else if (pl->N == 8192 && !pl->force_generic) {
     // CDB_HE8192 = scalar (first generation: scalar butterflies, direct loads) | packed (packed
     // butterflies, direct loads) | staged (packed butterflies + bulk-async staging of the next frame)

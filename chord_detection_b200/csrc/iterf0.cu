@@ -240,15 +240,14 @@ constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 163
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* Ur = reinterpret_cast<double*>(smem);  // [nb]
-  __shared__ double lo[32], up[32], smax[32], part[2][32];
+  __shared__ double wlo[32 * 32], wup[32 * 32], wsmax[32 * 32];  // per-warp copies of the interval state
+  __shared__ double part[2][2][32];                              // [buffer][which][harmonic]
   __shared__ double sal[8], per[8], chroma[12];
   // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
   // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
   // thousands of bins per harmonic; with the table a range costs its two ragged ends plus one
   // entry per whole block (max is exact in any order: bit-identical to the plain scan)
   __shared__ double bmax[kPerBlocksMax];
-  __shared__ int s_q, s_qb;
-  __shared__ double s_tau, s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   const int M = a.M, nb = 2 * a.M;
   double* Ud = a.Ud + (int64_t)blockIdx.x * nb;
@@ -277,28 +276,30 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     int nv = 0;
     double prev = 0.0, mix = 0.0;
     for (;;) {
-      // ---- min_search (periodicity.py:114-142)
-      if (tid == 0) {
+      // ---- min_search (periodicity.py:114-142).  The interval bookkeeping (lo / up / smax and the
+      // split / best-interval logic) is replicated in EVERY warp on warp-private copies: all warps
+      // run the same scalar code on the same data, so they agree bit for bit and the search needs
+      // ONE block barrier per split (for the per-harmonic range maxima, double-buffered) instead of
+      // five around a single bookkeeping thread.
+      double* lo = wlo + warp * 32;
+      double* up = wup + warp * 32;
+      double* smax = wsmax + warp * 32;
+      if (lane == 0) {
         lo[0] = a.tau_min;
         up[0] = a.tau_max;
-        s_q = 0;
-        s_qb = 0;
       }
-      __syncthreads();
-      for (;;) {
-        const int qb = s_qb;
-        int q = s_q;
-        if (!((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1)) break;
-        __syncthreads();
-        if (tid == 0) {
-          q = q + 1;
-          lo[q] = (lo[qb] + up[qb]) * 0.5;
+      __syncwarp();
+      int q = 0, qb = 0, buf = 0;
+      while ((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1) {
+        q = q + 1;
+        __syncwarp();
+        if (lane == 0) {
+          const double mid = (lo[qb] + up[qb]) * 0.5;
+          lo[q] = mid;
           up[q] = up[qb];
-          up[qb] = lo[q];
-          s_q = q;
+          up[qb] = mid;
         }
-        __syncthreads();
-        q = s_q;
+        __syncwarp();
         if (warp >= 1 && warp < a.Mh) {  // smax_fn (:144-163), one warp per harmonic m
           const int m = warp;
 #pragma unroll
@@ -320,37 +321,40 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) part[which][m] = ((double)m * a.fs / up[qq] + a.e2) * mx;
+            if (lane == 0) part[buf][which][m] = ((double)m * a.fs / up[qq] + a.e2) * mx;
           }
         }
         __syncthreads();
-        if (tid == 0) {
-          for (int which = 0; which < 2; ++which) {
-            const int qq = which == 0 ? q : qb;
-            double sacc = 0.0;
-            for (int m = 1; m < a.Mh; ++m) sacc += part[which][m];
-            smax[qq] = sacc * (a.fs / lo[qq] + a.e1);
+        {
+          double s0 = 0.0, s1 = 0.0;  // sums over the harmonics in the reference's order
+          for (int m = 1; m < a.Mh; ++m) {
+            s0 += part[buf][0][m];
+            s1 += part[buf][1][m];
           }
+          if (lane == 0) {
+            smax[q] = s0 * (a.fs / lo[q] + a.e1);
+            smax[qb] = s1 * (a.fs / lo[qb] + a.e1);
+          }
+          __syncwarp();
           int best = 0;
           double bv = smax[0];
-          for (int j = 1; j <= q; ++j)
-            if (smax[j] > bv) {
-              bv = smax[j];
+          for (int j = 1; j <= q; ++j) {
+            const double v = smax[j];
+            if (v > bv) {
+              bv = v;
               best = j;
             }
-          s_qb = best;
+          }
+          qb = best;
         }
-        __syncthreads();
+        buf ^= 1;
       }
-      __syncthreads();
+      __syncwarp();
       if (tid == 0) {
-        const int qb = s_qb;
-        s_tau = (lo[qb] + up[qb]) * 0.5;
-        s_best = smax[qb];
-        sal[nv] = s_best;
-        per[nv] = s_tau;
+        sal[nv] = smax[qb];
+        per[nv] = (lo[qb] + up[qb]) * 0.5;
       }
-      __syncthreads();
+      const double s_tau = (lo[qb] + up[qb]) * 0.5, s_best = smax[qb];
       const double tau = s_tau, best = s_best;
       nv += 1;
       mix += best;
