@@ -1303,11 +1303,13 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     // metric shape probes bins 22..186).
     const bool pruned = (pl->kmax >> 5) <= 5;
     const int nw = pruned ? 16 : 12;
-    // CDB_HE_EPILOGUE = levels (default when the plan allows it: window maxima from a shuffle-built
-    // sparse table) | gather (every lane scans its windows in shared memory)
-    bool levels = pruned && pl->levels_ok;
+    // CDB_HE_EPILOGUE = gather (default: every lane scans its windows in shared memory) | levels
+    // (window maxima from a shuffle-built sparse table: 5 % fewer shared-memory wavefronts and 38 %
+    // fewer bank-conflict replays, but 7.7 % more instructions -- measured 6 % SLOWER, r02d: the
+    // kernel is issue / dependency-limited, not LSU-limited)
+    bool levels = false;
     if (const char* ep = std::getenv("CDB_HE_EPILOGUE"))
-      if (ep[0] == 'g') levels = false;
+      levels = ep[0] == 'l' && pruned && pl->levels_ok;
     a.pw_floats = levels ? 192 * pl->n_level_slots : pruned ? 192 : 1028;
     a.pw_bytes = (a.pw_floats * 4 + (levels ? 2 * pl->n_windows + 16 : pl->n_windows) * 8 + 15) & ~15;
     a.winpos = pl->d_winpos;

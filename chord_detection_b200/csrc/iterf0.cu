@@ -90,17 +90,17 @@ __global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
 }
 
 // ... then one thread per (clip, channel): resonators, |.|, (y + lowpass(y)) / 2
-__global__ void __launch_bounds__(32) iterf0_channel_kernel(const IterArgs a) {
+constexpr int kChanThreads = 64;
+template <bool STRUCTURED>
+__global__ void __launch_bounds__(kChanThreads, 12) iterf0_channel_kernel(const IterArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n_batch_clips * a.C) return;
   const int lc = t / a.C, ch = t - lc * a.C;
   const double* src = a.w + (int64_t)lc * a.clip_len;
   float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
   const double* coef = a.coef + ch * kCoefStride;
-  if (a.structured)
-    iff::filter_channel_w<true, iff::SosR<2>, iff::SosR<1>>(src, a.clip_len, a.n_pad, coef, dst);
-  else
-    iff::filter_channel_w<true, iff::Sos, iff::Sos>(src, a.clip_len, a.n_pad, coef, dst);
+  if (STRUCTURED) iff::filter_channel_w<true, 2, 1>(src, a.clip_len, a.n_pad, coef, dst);
+  else iff::filter_channel_w<true, 3, 3>(src, a.clip_len, a.n_pad, coef, dst);
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -240,8 +240,10 @@ constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 163
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* Ur = reinterpret_cast<double*>(smem);  // [nb]
-  __shared__ double wlo[32 * 32], wup[32 * 32], wsmax[32 * 32];  // per-warp copies of the interval state
-  __shared__ double part[2][2][32];                              // [buffer][which][harmonic]
+  __shared__ double lo[32], up[32], smax[32];      // the interval list of min_search
+  __shared__ double part[2][32], wgt[2][32];        // [which][harmonic]: weighted range maximum, weight
+  __shared__ int rlo[2][32], rhi[2][32];            // [which][harmonic]: bin range
+  __shared__ int s_q, s_qb, s_go;
   __shared__ double sal[8], per[8], chroma[12];
   // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
   // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
@@ -276,40 +278,62 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     int nv = 0;
     double prev = 0.0, mix = 0.0;
     for (;;) {
-      // ---- min_search (periodicity.py:114-142).  The interval bookkeeping (lo / up / smax and the
-      // split / best-interval logic) is replicated in EVERY warp on warp-private copies: all warps
-      // run the same scalar code on the same data, so they agree bit for bit and the search needs
-      // ONE block barrier per split (for the per-harmonic range maxima, double-buffered) instead of
-      // five around a single bookkeeping thread.
-      double* lo = wlo + warp * 32;
-      double* up = wup + warp * 32;
-      double* smax = wsmax + warp * 32;
-      if (lane == 0) {
+      // ---- min_search (periodicity.py:114-142).  Warp 0 keeps the interval list: it adds up the
+      // per-harmonic range maxima in the reference's order, picks the best interval, splits it and
+      // -- one harmonic per lane -- turns the two new intervals into bin ranges and weights
+      // (the FP64 divisions of smax_fn, :147-160, once per harmonic instead of once per lane of
+      // every warp).  The other warps only take range maxima.  Two block barriers per split.
+      auto prepare = [&]() {  // warp 0: split the best interval and publish the work of the next round
+        int go = 0;
+        if (lane == 0) {
+          int q = s_q;
+          const int qb = s_qb;
+          go = ((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1) ? 1 : 0;
+          if (go) {
+            q = q + 1;
+            const double mid = (lo[qb] + up[qb]) * 0.5;
+            lo[q] = mid;
+            up[q] = up[qb];
+            up[qb] = mid;
+            s_q = q;
+          }
+          s_go = go;
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        __syncwarp();
+        if (go && lane >= 1 && lane < a.Mh) {
+          const int m = lane;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            const int qq = which == 0 ? s_q : s_qb;
+            const double tau = 0.5 * (lo[qq] + up[qq]);
+            const double dt = up[qq] - lo[qq];
+            const int lowk = (int)((double)m * a.K / (tau + 0.5 * dt) + 0.5);
+            int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
+            if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
+            rlo[which][m] = lowk;
+            rhi[which][m] = highk;
+            wgt[which][m] = (double)m * a.fs / up[qq] + a.e2;
+          }
+        }
+      };
+      if (tid == 0) {
         lo[0] = a.tau_min;
         up[0] = a.tau_max;
+        s_q = 0;
+        s_qb = 0;
       }
-      __syncwarp();
-      int q = 0, qb = 0, buf = 0;
-      while ((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1) {
-        q = q + 1;
+      if (warp == 0) {
         __syncwarp();
-        if (lane == 0) {
-          const double mid = (lo[qb] + up[qb]) * 0.5;
-          lo[q] = mid;
-          up[q] = up[qb];
-          up[qb] = mid;
-        }
-        __syncwarp();
-        if (warp >= 1 && warp < a.Mh) {  // smax_fn (:144-163), one warp per harmonic m
+        prepare();
+      }
+      __syncthreads();
+      while (s_go) {
+        if (warp >= 1 && warp < a.Mh) {  // smax_fn (:144-163): one warp per harmonic m
           const int m = warp;
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
-            const int qq = which == 0 ? q : qb;
-            const double tau = 0.5 * (lo[qq] + up[qq]);
-            const double dt = up[qq] - lo[qq];
-            int lowk = (int)((double)m * a.K / (tau + 0.5 * dt) + 0.5);
-            int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
-            if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
+            const int lowk = rlo[which][m], highk = rhi[which][m];
             double mx = -INFINITY;
             const int b0 = (lowk + kPerBlock - 1) / kPerBlock, b1 = (highk + 1) / kPerBlock;  // whole blocks [b0, b1)
             if (lowk < 0 || b1 <= b0) {
@@ -321,40 +345,40 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) part[buf][which][m] = ((double)m * a.fs / up[qq] + a.e2) * mx;
+            if (lane == 0) part[which][m] = wgt[which][m] * mx;
           }
         }
         __syncthreads();
-        {
-          double s0 = 0.0, s1 = 0.0;  // sums over the harmonics in the reference's order
-          for (int m = 1; m < a.Mh; ++m) {
-            s0 += part[buf][0][m];
-            s1 += part[buf][1][m];
-          }
-          if (lane == 0) {
-            smax[q] = s0 * (a.fs / lo[q] + a.e1);
-            smax[qb] = s1 * (a.fs / lo[qb] + a.e1);
+        if (warp == 0) {
+          if (lane < 2) {  // lane 0: the new interval q, lane 1: the shrunk interval qb
+            const int qq = lane == 0 ? s_q : s_qb;
+            double sacc = 0.0;
+            for (int m = 1; m < a.Mh; ++m) sacc += part[lane][m];
+            smax[qq] = sacc * (a.fs / lo[qq] + a.e1);
           }
           __syncwarp();
-          int best = 0;
-          double bv = smax[0];
-          for (int j = 1; j <= q; ++j) {
-            const double v = smax[j];
-            if (v > bv) {
-              bv = v;
-              best = j;
-            }
+          if (lane == 0) {
+            const int q = s_q;
+            int best = 0;
+            double bv = smax[0];
+            for (int j = 1; j <= q; ++j)
+              if (smax[j] > bv) {
+                bv = smax[j];
+                best = j;
+              }
+            s_qb = best;
           }
-          qb = best;
+          __syncwarp();
+          prepare();
         }
-        buf ^= 1;
+        __syncthreads();
       }
-      __syncwarp();
       if (tid == 0) {
+        const int qb = s_qb;
         sal[nv] = smax[qb];
         per[nv] = (lo[qb] + up[qb]) * 0.5;
       }
-      const double s_tau = (lo[qb] + up[qb]) * 0.5, s_best = smax[qb];
+      const double s_tau = (lo[s_qb] + up[s_qb]) * 0.5, s_best = smax[s_qb];
       const double tau = s_tau, best = s_best;
       nv += 1;
       mix += best;
@@ -524,11 +548,11 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
     else iff::whiten_clip<false>(x, n, lam, taps, w.data());
     const bool st = iff::resonators_structured(coef);
     if (pipelined == 2) {
-      if (st) iff::filter_channel_w<true, iff::SosR<2>, iff::SosR<1>>(w.data(), n, n, coef, y);
-      else iff::filter_channel_w<true, iff::Sos, iff::Sos>(w.data(), n, n, coef, y);
+      if (st) iff::filter_channel_w<true, 2, 1>(w.data(), n, n, coef, y);
+      else iff::filter_channel_w<true, 3, 3>(w.data(), n, n, coef, y);
     } else {
-      if (st) iff::filter_channel_w<false, iff::SosR<2>, iff::SosR<1>>(w.data(), n, n, coef, y);
-      else iff::filter_channel_w<false, iff::Sos, iff::Sos>(w.data(), n, n, coef, y);
+      if (st) iff::filter_channel_w<false, 2, 1>(w.data(), n, n, coef, y);
+      else iff::filter_channel_w<false, 3, 3>(w.data(), n, n, coef, y);
     }
     return 0;
   }
@@ -685,7 +709,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     if (hoisted) {
       iterf0_whiten_kernel<<<(nb + 31) / 32, 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
-      iterf0_channel_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);
+      if (a.structured)
+        iterf0_channel_kernel<true><<<(threads + kChanThreads - 1) / kChanThreads, kChanThreads, 0, st>>>(a);
+      else
+        iterf0_channel_kernel<false><<<(threads + kChanThreads - 1) / kChanThreads, kChanThreads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
       h->launches += 1;
     } else {

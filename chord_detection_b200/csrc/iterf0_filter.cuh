@@ -205,22 +205,32 @@ IFF_HD void whiten_clip(const float* src, long long n, double lam, const double*
 }
 
 // resonator biquads with structurally zero numerator taps (iterative_f0.py:182-191):
-// res1 b = [rho1, 0, -rho1], res2 b = [rho2, 0, 0].  NB = 2: b1 == 0; NB = 1: b1 == b2 == 0.
-template <int NB>
-struct SosR {
-  double b0, b2, a1, a2, z0, z1;
+// res1 b = [rho1, 0, -rho1], res2 b = [rho2, 0, 0].  NB = 3: general, 2: b1 == 0, 1: b1 == b2 == 0.
+// Coefficients (shared by the two cascaded copies of a resonator) and state are separate so that a
+// cascade keeps ONE set of coefficients in registers.
+struct SosCoef {
+  double b0, b1, b2, a1, a2;
   IFF_HD void init(const double* c) {
     const double a0 = c[3];
     b0 = c[0] / a0;
+    b1 = c[1] / a0;
     b2 = c[2] / a0;
     a1 = c[4] / a0;
     a2 = c[5] / a0;
-    z0 = z1 = 0.0;
   }
-  IFF_HD double step(double x) {
-    const double y = fma(b0, x, z0);
-    z0 = fma(-a1, y, z1);
-    z1 = (NB == 2) ? fma(-a2, y, b2 * x) : -a2 * y;
+};
+template <int NB>
+struct SosState {
+  double z0 = 0.0, z1 = 0.0;
+  IFF_HD double step(const SosCoef& k, double x) {
+    const double y = fma(k.b0, x, z0);
+    if (NB == 3) {
+      z0 = fma(-k.a1, y, fma(k.b1, x, z1));
+      z1 = fma(-k.a2, y, k.b2 * x);
+    } else {
+      z0 = fma(-k.a1, y, z1);
+      z1 = (NB == 2) ? fma(-k.a2, y, k.b2 * x) : -k.a2 * y;
+    }
     return y;
   }
 };
@@ -233,30 +243,29 @@ IFF_HD bool resonators_structured(const double* coef) {
 // w: whitened clip (whiten_clip) -> dst: fp32 channel signal, dst[n .. n_pad) zero-filled.
 // PIPELINED: stage s (r1a, r1b, r2a, r2b, final) works on sample t - s; 8 samples per block, the
 // next block's inputs are loaded while this one computes, outputs leave as aligned float4 stores.
-template <bool PIPELINED, typename R1, typename R2>
+template <bool PIPELINED, int NB1, int NB2>
 IFF_HD void filter_channel_w(const double* w, long long n, long long n_pad, const double* coef,
                              float* dst) {
-  R1 r1a, r1b;
-  R2 r2a, r2b;
-  Sos lp;
-  r1a.init(coef);
-  r1b.init(coef);
-  r2a.init(coef + 6);
-  r2b.init(coef + 6);
-  lp.init(coef + 12);
+  SosCoef k1, k2, kl;
+  k1.init(coef);
+  k2.init(coef + 6);
+  kl.init(coef + 12);
+  SosState<NB1> r1a, r1b;
+  SosState<NB2> r2a, r2b;
+  SosState<3> lp;
   if (!PIPELINED) {
     for (long long t = 0; t < n; ++t) {
       double v = w[t];
-      v = r1a.step(v);
-      v = r1b.step(v);
-      v = r2a.step(v);
-      v = r2b.step(v);
-      double y = fabs(v);          // iterative_f0.py:60
-      y = (y + lp.step(y)) / 2.0;  // :61-63
+      v = r1a.step(k1, v);
+      v = r1b.step(k1, v);
+      v = r2a.step(k2, v);
+      v = r2b.step(k2, v);
+      double y = fabs(v);              // iterative_f0.py:60
+      y = (y + lp.step(kl, y)) / 2.0;  // :61-63
       dst[t] = (float)y;
     }
   } else {
-    constexpr int kBlk = 8, kLag = 4;
+    constexpr int kBlk = 4, kLag = 4;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
     double xcur[kBlk], xnext[kBlk];
 #pragma unroll
@@ -272,29 +281,26 @@ IFF_HD void filter_channel_w(const double* w, long long n, long long n_pad, cons
 #pragma unroll
       for (int j = 0; j < kBlk; ++j) {
         double y = fabs(v4);  // final stage: sample base + j - 4
-        y = (y + lp.step(y)) / 2.0;
+        y = (y + lp.step(kl, y)) / 2.0;
         out[j] = (float)y;
-        v4 = r2b.step(s3);
-        s3 = r2a.step(s2);
-        s2 = r1b.step(s1);
-        s1 = r1a.step(xcur[j]);
+        v4 = r2b.step(k2, s3);
+        s3 = r2a.step(k2, s2);
+        s2 = r1b.step(k1, s1);
+        s1 = r1a.step(k1, xcur[j]);
       }
-      // out[j] belongs to sample base - 4 + j: two groups of four, each 16-byte aligned
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const long long t0 = base - kLag + 4 * g;
-        if (t0 < 0 || t0 >= n) continue;
+      // out[j] belongs to sample base - 4 + j: one 16-byte aligned group of four
+      const long long t0 = base - kLag;
+      if (t0 >= 0 && t0 < n) {
         if (aligned && t0 + 4 <= n) {
 #if defined(__CUDA_ARCH__)
-          *reinterpret_cast<float4*>(dst + t0) =
-              make_float4(out[4 * g], out[4 * g + 1], out[4 * g + 2], out[4 * g + 3]);
+          *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
 #else
-          for (int q = 0; q < 4; ++q) dst[t0 + q] = out[4 * g + q];
+          for (int q = 0; q < 4; ++q) dst[t0 + q] = out[q];
 #endif
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (t0 + q < n) dst[t0 + q] = out[4 * g + q];
+            if (t0 + q < n) dst[t0 + q] = out[q];
         }
       }
 #pragma unroll
