@@ -240,10 +240,10 @@ constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 163
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* Ur = reinterpret_cast<double*>(smem);  // [nb]
-  __shared__ double lo[32], up[32], smax[32];      // the interval list of min_search
   __shared__ double part[2][32], wgt[2][32];        // [which][harmonic]: weighted range maximum, weight
   __shared__ int rlo[2][32], rhi[2][32];            // [which][harmonic]: bin range
-  __shared__ int s_q, s_qb, s_go;
+  __shared__ int s_go;
+  __shared__ double s_tau, s_best;
   __shared__ double sal[8], per[8], chroma[12];
   // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
   // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
 
   for (int64_t gf = blockIdx.x; gf < (int64_t)a.n_batch_clips * a.fpc; gf += gridDim.x) {
     const double* Uk = a.Ut + gf * (int64_t)(M + 1);
-    for (int i = tid; i < nb; i += nthr) {
+#pragma unroll 4
+    for (int i = tid; i < nb; i += nthr) {  // (unrolled: independent loads in flight)
       Ur[i] = Uk[i <= M ? i : nb - i];
       Ud[i] = 0.0;
     }
@@ -278,53 +279,60 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     int nv = 0;
     double prev = 0.0, mix = 0.0;
     for (;;) {
-      // ---- min_search (periodicity.py:114-142).  Warp 0 keeps the interval list: it adds up the
-      // per-harmonic range maxima in the reference's order, picks the best interval, splits it and
-      // -- one harmonic per lane -- turns the two new intervals into bin ranges and weights
-      // (the FP64 divisions of smax_fn, :147-160, once per harmonic instead of once per lane of
-      // every warp).  The other warps only take range maxima.  Two block barriers per split.
+      // ---- min_search (periodicity.py:114-142).  Warp 0 keeps the interval list IN REGISTERS, one
+      // interval per lane (lo, up, smax of interval j in lane j): it adds up the per-harmonic range
+      // maxima in the reference's order (lanes 0 / 1: the new / the shrunk interval), picks the best
+      // interval with three warp reductions on the order-preserving bit pattern of smax (first
+      // maximum wins, like the reference's strict `>` scan), splits it and -- one harmonic per lane --
+      // turns the two new intervals into bin ranges and weights (the FP64 divisions of smax_fn,
+      // :147-160, once per harmonic instead of once per lane of every warp).  The other warps only
+      // take range maxima.  Two block barriers per split.
+      double my_lo = 0.0, my_up = 0.0, my_smax = 0.0;  // warp 0: interval `lane`
+      int q = 0, qb = 0;                               // warp 0, uniform
+      double lo_q = 0.0, lo_qb = 0.0;                  // warp 0, uniform: lo of the two intervals in flight
       auto prepare = [&]() {  // warp 0: split the best interval and publish the work of the next round
-        int go = 0;
-        if (lane == 0) {
-          int q = s_q;
-          const int qb = s_qb;
-          go = ((up[qb] - lo[qb]) > a.tau_prec && q < a.Q - 1) ? 1 : 0;
-          if (go) {
-            q = q + 1;
-            const double mid = (lo[qb] + up[qb]) * 0.5;
-            lo[q] = mid;
-            up[q] = up[qb];
-            up[qb] = mid;
-            s_q = q;
+        const double lo_b = __shfl_sync(0xffffffffu, my_lo, qb), up_b = __shfl_sync(0xffffffffu, my_up, qb);
+        const int go = ((up_b - lo_b) > a.tau_prec && q < a.Q - 1) ? 1 : 0;
+        if (!go) {  // the search is over: publish the winning interval
+          const double best = __shfl_sync(0xffffffffu, my_smax, qb);
+          if (lane == 0) {
+            s_go = 0;
+            s_tau = (lo_b + up_b) * 0.5;
+            s_best = best;
           }
-          s_go = go;
+          return;
         }
-        go = __shfl_sync(0xffffffffu, go, 0);
-        __syncwarp();
-        if (go && lane >= 1 && lane < a.Mh) {
+        q = q + 1;
+        const double mid = (lo_b + up_b) * 0.5;
+        if (lane == q) {
+          my_lo = mid;
+          my_up = up_b;
+        }
+        if (lane == qb) my_up = mid;
+        lo_q = mid;
+        lo_qb = lo_b;
+        if (lane == 0) s_go = 1;
+        if (lane >= 1 && lane < a.Mh) {
           const int m = lane;
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
-            const int qq = which == 0 ? s_q : s_qb;
-            const double tau = 0.5 * (lo[qq] + up[qq]);
-            const double dt = up[qq] - lo[qq];
+            const double lo_i = which == 0 ? mid : lo_b, up_i = which == 0 ? up_b : mid;
+            const double tau = 0.5 * (lo_i + up_i);
+            const double dt = up_i - lo_i;
             const int lowk = (int)((double)m * a.K / (tau + 0.5 * dt) + 0.5);
             int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
             if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
             rlo[which][m] = lowk;
             rhi[which][m] = highk;
-            wgt[which][m] = (double)m * a.fs / up[qq] + a.e2;
+            wgt[which][m] = (double)m * a.fs / up_i + a.e2;
           }
         }
       };
-      if (tid == 0) {
-        lo[0] = a.tau_min;
-        up[0] = a.tau_max;
-        s_q = 0;
-        s_qb = 0;
-      }
       if (warp == 0) {
-        __syncwarp();
+        if (lane == 0) {
+          my_lo = a.tau_min;
+          my_up = a.tau_max;
+        }
         prepare();
       }
       __syncthreads();
@@ -350,35 +358,47 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
         }
         __syncthreads();
         if (warp == 0) {
-          if (lane < 2) {  // lane 0: the new interval q, lane 1: the shrunk interval qb
-            const int qq = lane == 0 ? s_q : s_qb;
-            double sacc = 0.0;
-            for (int m = 1; m < a.Mh; ++m) sacc += part[lane][m];
-            smax[qq] = sacc * (a.fs / lo[qq] + a.e1);
-          }
-          __syncwarp();
-          if (lane == 0) {
-            const int q = s_q;
-            int best = 0;
-            double bv = smax[0];
-            for (int j = 1; j <= q; ++j)
-              if (smax[j] > bv) {
-                bv = smax[j];
-                best = j;
+          // lanes 0 / 1: sum over the harmonics in the reference's order (loads first, then the
+          // dependent adds; harmonics >= Mh are predicated off)
+          double sacc = 0.0;
+          {
+            const int row = lane & 1;
+#pragma unroll
+            for (int m0 = 1; m0 < 32; m0 += 8) {  // 8 loads in flight, then their adds in order
+              if (m0 < a.Mh) {
+                double pv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pv[j] = (m0 + j < 32) ? part[row][m0 + j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (m0 + j < a.Mh) sacc += pv[j];
               }
-            s_qb = best;
+            }
           }
-          __syncwarp();
+          const double val = sacc * (a.fs / (lane == 0 ? lo_q : lo_qb) + a.e1);
+          const double v_q = __shfl_sync(0xffffffffu, val, 0), v_qb = __shfl_sync(0xffffffffu, val, 1);
+          if (lane == q) my_smax = v_q;
+          if (lane == qb) my_smax = v_qb;
+          // argmax over intervals 0..q, first maximum wins: order-preserving 64-bit key, high word,
+          // then low word among the ties, then the lowest lane
+          unsigned long long key = (unsigned long long)__double_as_longlong(my_smax);
+          key = (key >> 63) ? ~key : (key | 0x8000000000000000ull);
+          if (my_smax != my_smax) key = 0ull;  // NaN never wins a strict `>` (unless interval 0)
+          const bool in = lane <= q;
+          const unsigned hi = in ? (unsigned)(key >> 32) : 0u, lw = (unsigned)key;
+          const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+          const bool c1 = in && hi == mh;
+          const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lw : 0u);
+          const unsigned win = __ballot_sync(0xffffffffu, c1 && lw == ml);
+          qb = __ffs(win) - 1;
           prepare();
         }
         __syncthreads();
       }
       if (tid == 0) {
-        const int qb = s_qb;
-        sal[nv] = smax[qb];
-        per[nv] = (lo[qb] + up[qb]) * 0.5;
+        sal[nv] = s_best;
+        per[nv] = s_tau;
       }
-      const double s_tau = (lo[s_qb] + up[s_qb]) * 0.5, s_best = smax[s_qb];
       const double tau = s_tau, best = s_best;
       nv += 1;
       mix += best;
@@ -409,6 +429,7 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
       }
       __threadfence_block();
       __syncthreads();
+#pragma unroll 4
       for (int i = tid; i < nb; i += nthr) {
         const double d = Uk[i <= M ? i : nb - i] - __ldcg(&Ud[i]);
         Ur[i] = d > 0.0 ? d : 0.0;
