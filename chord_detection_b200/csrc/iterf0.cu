@@ -240,10 +240,9 @@ constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 163
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* Ur = reinterpret_cast<double*>(smem);  // [nb]
-  __shared__ double part[2][32], wgt[2][32];        // [which][harmonic]: weighted range maximum, weight
-  __shared__ int rlo[2][32], rhi[2][32];            // [which][harmonic]: bin range
+  __shared__ double part[2][32];  // [which][harmonic]: weighted range maximum
   __shared__ int s_go;
-  __shared__ double s_tau, s_best;
+  __shared__ double s_lo_b, s_up_b, s_tau, s_best;
   __shared__ double sal[8], per[8], chroma[12];
   // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
   // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
@@ -279,18 +278,22 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     int nv = 0;
     double prev = 0.0, mix = 0.0;
     for (;;) {
-      // ---- min_search (periodicity.py:114-142).  Warp 0 keeps the interval list IN REGISTERS, one
-      // interval per lane (lo, up, smax of interval j in lane j): it adds up the per-harmonic range
-      // maxima in the reference's order (lanes 0 / 1: the new / the shrunk interval), picks the best
-      // interval with three warp reductions on the order-preserving bit pattern of smax (first
-      // maximum wins, like the reference's strict `>` scan), splits it and -- one harmonic per lane --
-      // turns the two new intervals into bin ranges and weights (the FP64 divisions of smax_fn,
-      // :147-160, once per harmonic instead of once per lane of every warp).  The other warps only
-      // take range maxima.  Two block barriers per split.
+      // ---- min_search (periodicity.py:114-142): <= Q - 1 splits of the best interval; after every
+      // split the salience of the two new intervals is a sum over the harmonics of weighted RANGE
+      // maxima of the residual spectrum (smax_fn, :144-163).  The search is a latency chain, so:
+      //  * warp 0 keeps the interval list in REGISTERS, one interval per lane (lo, up, smax of
+      //    interval j in lane j); it adds up the per-harmonic terms in the reference's order (lanes
+      //    0 / 1: the new / the shrunk interval) and picks the best interval with three warp
+      //    reductions on the order-preserving bit pattern of smax (first maximum wins, like the
+      //    reference's strict `>` scan);
+      //  * warp m (harmonic m) derives its own bin ranges and weights: the six FP64 divisions run in
+      //    six LANES at once (one division latency, not six), then it takes both range maxima with
+      //    all loads issued up front (block maxima for whole 64-bin blocks, <= 14 loads per range);
+      //  * two block barriers per split.
       double my_lo = 0.0, my_up = 0.0, my_smax = 0.0;  // warp 0: interval `lane`
       int q = 0, qb = 0;                               // warp 0, uniform
       double lo_q = 0.0, lo_qb = 0.0;                  // warp 0, uniform: lo of the two intervals in flight
-      auto prepare = [&]() {  // warp 0: split the best interval and publish the work of the next round
+      auto prepare = [&]() {  // warp 0: split the best interval, or finish
         const double lo_b = __shfl_sync(0xffffffffu, my_lo, qb), up_b = __shfl_sync(0xffffffffu, my_up, qb);
         const int go = ((up_b - lo_b) > a.tau_prec && q < a.Q - 1) ? 1 : 0;
         if (!go) {  // the search is over: publish the winning interval
@@ -311,22 +314,39 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
         if (lane == qb) my_up = mid;
         lo_q = mid;
         lo_qb = lo_b;
-        if (lane == 0) s_go = 1;
-        if (lane >= 1 && lane < a.Mh) {
-          const int m = lane;
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-            const double lo_i = which == 0 ? mid : lo_b, up_i = which == 0 ? up_b : mid;
-            const double tau = 0.5 * (lo_i + up_i);
-            const double dt = up_i - lo_i;
-            const int lowk = (int)((double)m * a.K / (tau + 0.5 * dt) + 0.5);
-            int highk = (int)((double)m * a.K / (tau - 0.5 * dt) + 0.5);
-            if (highk > nb - 1) highk = nb - 1;  // numpy slice clamps
-            rlo[which][m] = lowk;
-            rhi[which][m] = highk;
-            wgt[which][m] = (double)m * a.fs / up_i + a.e2;
-          }
+        if (lane == 0) {
+          s_go = 1;
+          s_lo_b = lo_b;
+          s_up_b = up_b;
         }
+      };
+      // max of Ur over bins [lowk, highk] for the whole warp (every lane returns it)
+      auto range_max = [&](int lowk, int highk) -> double {
+        const int b0 = (lowk + kPerBlock - 1) / kPerBlock, b1 = (highk + 1) / kPerBlock;  // whole blocks [b0, b1)
+        const bool blocks = lowk >= 0 && b1 > b0;
+        const int head_end = blocks ? b0 * kPerBlock : highk + 1;   // head: [lowk, head_end), < 128 bins
+        const int tail_beg = blocks ? b1 * kPerBlock : highk + 1;   // tail: [tail_beg, highk], < 64 bins
+        double h[4], t[2], g[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = lowk + lane + 32 * j;
+          h[j] = (i >= 0 && i < head_end) ? Ur[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = tail_beg + lane + 32 * j;
+          t[j] = (i <= highk) ? Ur[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int bb = b0 + lane + 32 * j;
+          g[j] = (blocks && bb < b1) ? bmax[bb] : -INFINITY;
+        }
+        double mx = fmax(fmax(fmax(h[0], h[1]), fmax(h[2], h[3])), fmax(t[0], t[1]));
+        mx = fmax(mx, fmax(fmax(fmax(g[0], g[1]), fmax(g[2], g[3])), fmax(fmax(g[4], g[5]), fmax(g[6], g[7]))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        return mx;
       };
       if (warp == 0) {
         if (lane == 0) {
@@ -337,23 +357,30 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
       }
       __syncthreads();
       while (s_go) {
-        if (warp >= 1 && warp < a.Mh) {  // smax_fn (:144-163): one warp per harmonic m
+        if (warp >= 1 && warp < a.Mh) {
           const int m = warp;
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-            const int lowk = rlo[which][m], highk = rhi[which][m];
-            double mx = -INFINITY;
-            const int b0 = (lowk + kPerBlock - 1) / kPerBlock, b1 = (highk + 1) / kPerBlock;  // whole blocks [b0, b1)
-            if (lowk < 0 || b1 <= b0) {
-              for (int i = lowk + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
-            } else {
-              for (int i = lowk + lane; i < b0 * kPerBlock; i += 32) mx = fmax(mx, Ur[i]);
-              for (int b = b0 + lane; b < b1; b += 32) mx = fmax(mx, bmax[b]);
-              for (int i = b1 * kPerBlock + lane; i <= highk; i += 32) mx = fmax(mx, Ur[i]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) part[which][m] = wgt[which][m] * mx;
+          const double lo_b = s_lo_b, up_b = s_up_b;
+          const double mid = (lo_b + up_b) * 0.5;
+          // lane t < 6: which = t / 3 (0: the new interval [mid, up_b], 1: the shrunk one [lo_b, mid]),
+          // kind = t % 3 (0: low bin, 1: high bin, 2: weight)
+          const int t6 = lane < 6 ? lane : 0, which_l = t6 / 3, kind = t6 - 3 * which_l;
+          const double lo_i = which_l == 0 ? mid : lo_b, up_i = which_l == 0 ? up_b : mid;
+          const double tau = 0.5 * (lo_i + up_i);
+          const double dt = up_i - lo_i;
+          const double num = kind == 2 ? (double)m * a.fs : (double)m * a.K;
+          const double den = kind == 0 ? tau + 0.5 * dt : kind == 1 ? tau - 0.5 * dt : up_i;
+          const double qv = num / den;
+          int kk = (int)(qv + 0.5);
+          if (kind == 1 && kk > nb - 1) kk = nb - 1;  // numpy slice clamps
+          const double wv = qv + a.e2;
+          const int low0 = __shfl_sync(0xffffffffu, kk, 0), high0 = __shfl_sync(0xffffffffu, kk, 1);
+          const int low1 = __shfl_sync(0xffffffffu, kk, 3), high1 = __shfl_sync(0xffffffffu, kk, 4);
+          const double w0 = __shfl_sync(0xffffffffu, wv, 2), w1 = __shfl_sync(0xffffffffu, wv, 5);
+          const double mx0 = range_max(low0, high0);
+          const double mx1 = range_max(low1, high1);
+          if (lane == 0) {
+            part[0][m] = w0 * mx0;
+            part[1][m] = w1 * mx1;
           }
         }
         __syncthreads();
@@ -383,7 +410,7 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
           // then low word among the ties, then the lowest lane
           unsigned long long key = (unsigned long long)__double_as_longlong(my_smax);
           key = (key >> 63) ? ~key : (key | 0x8000000000000000ull);
-          if (my_smax != my_smax) key = 0ull;  // NaN never wins a strict `>` (unless interval 0)
+          if (my_smax != my_smax) key = 0ull;  // a NaN never wins a strict `>`
           const bool in = lane <= q;
           const unsigned hi = in ? (unsigned)(key >> 32) : 0u, lw = (unsigned)key;
           const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
