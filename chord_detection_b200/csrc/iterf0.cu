@@ -234,8 +234,27 @@ __constant__ double kHW9[9] = {0.0011244659258033, 0.11559343551383, 0.428173482
                                0.81822361914331,   1.0,              0.81822361914331,
                                0.42817348241183,   0.11559343551383, 0.0011244659258033};
 
-constexpr int kPerBlock = 64;                      // bins per block-maximum entry
-constexpr int kPerBlocksMax = 16384 / kPerBlock;   // nb = 2 * frame_size <= 16384
+// two-level table of maxima of the residual spectrum: B1 over aligned blocks of 32 bins, B2 over
+// aligned blocks of 32 B1 entries (1024 bins); nb = 2 * frame_size <= 16384
+constexpr int kB1Max = 16384 / 32, kB2Max = 16384 / 1024;
+
+// order-preserving map double -> uint64 (larger double <=> larger key; NaN is not expected)
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+// exact maximum over the warp with two REDUX operations (high word, then low word among the ties)
+__device__ __forceinline__ double warp_max_f64(double v) {
+  const unsigned long long k = dkey(v);
+  const unsigned hi = (unsigned)(k >> 32), lw = (unsigned)k;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lw : 0u);
+  return dkey_inv(((unsigned long long)mh << 32) | ml);
+}
 
 __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -244,11 +263,11 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
   __shared__ int s_go;
   __shared__ double s_lo_b, s_up_b, s_tau, s_best;
   __shared__ double sal[8], per[8], chroma[12];
-  // maxima of Ur over aligned blocks of 64 bins: the salience of a period interval is a sum of
-  // RANGE maxima of the residual spectrum (smax_fn), and the first intervals of every search span
-  // thousands of bins per harmonic; with the table a range costs its two ragged ends plus one
-  // entry per whole block (max is exact in any order: bit-identical to the plain scan)
-  __shared__ double bmax[kPerBlocksMax];
+  // the salience of a period interval is a sum of RANGE maxima of the residual spectrum (smax_fn),
+  // and the first intervals of every search span thousands of bins per harmonic: with the two-level
+  // table a range is at most five lane-parallel loads (ragged bins, ragged 32-bin blocks, whole
+  // 1024-bin blocks); max is exact in any order, so this is bit-identical to the plain scan
+  __shared__ double B1[kB1Max], B2[kB2Max];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   const int M = a.M, nb = 2 * a.M;
   double* Ud = a.Ud + (int64_t)blockIdx.x * nb;
@@ -263,17 +282,21 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
     if (tid < 8) sal[tid] = per[tid] = 0.0;
     if (tid < 12) chroma[tid] = 0.0;
     __syncthreads();
-    auto build_bmax = [&]() {  // one warp per block, two bins per lane
-      for (int b = warp; b * kPerBlock < nb; b += nthr >> 5) {
-        const int i0 = b * kPerBlock + lane;
-        double mx = i0 < nb ? Ur[i0] : -INFINITY;
-        if (i0 + 32 < nb) mx = fmax(mx, Ur[i0 + 32]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) bmax[b] = mx;
+    auto build_tables = [&]() {  // B1: one warp per 32-bin block; then B2 from B1 (after a barrier)
+      for (int b = warp; b * 32 < nb; b += nthr >> 5) {
+        const int i0 = b * 32 + lane;
+        const double mx = warp_max_f64(i0 < nb ? Ur[i0] : -INFINITY);
+        if (lane == 0) B1[b] = mx;
+      }
+      __syncthreads();
+      const int n1 = (nb + 31) / 32;
+      for (int c = warp; c * 32 < n1; c += nthr >> 5) {
+        const int j0 = c * 32 + lane;
+        const double mx = warp_max_f64(j0 < n1 ? B1[j0] : -INFINITY);
+        if (lane == 0) B2[c] = mx;
       }
     };
-    build_bmax();
+    build_tables();
     __syncthreads();
     int nv = 0;
     double prev = 0.0, mix = 0.0;
@@ -320,33 +343,25 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
           s_up_b = up_b;
         }
       };
-      // max of Ur over bins [lowk, highk] for the whole warp (every lane returns it)
+      // max of Ur over bins [lowk, highk] for the whole warp (every lane returns it): ragged bins,
+      // ragged 32-bin blocks (B1), whole 1024-bin blocks (B2) -- five predicated loads
       auto range_max = [&](int lowk, int highk) -> double {
-        const int b0 = (lowk + kPerBlock - 1) / kPerBlock, b1 = (highk + 1) / kPerBlock;  // whole blocks [b0, b1)
-        const bool blocks = lowk >= 0 && b1 > b0;
-        const int head_end = blocks ? b0 * kPerBlock : highk + 1;   // head: [lowk, head_end), < 128 bins
-        const int tail_beg = blocks ? b1 * kPerBlock : highk + 1;   // tail: [tail_beg, highk], < 64 bins
-        double h[4], t[2], g[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = lowk + lane + 32 * j;
-          h[j] = (i >= 0 && i < head_end) ? Ur[i] : -INFINITY;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = tail_beg + lane + 32 * j;
-          t[j] = (i <= highk) ? Ur[i] : -INFINITY;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int bb = b0 + lane + 32 * j;
-          g[j] = (blocks && bb < b1) ? bmax[bb] : -INFINITY;
-        }
-        double mx = fmax(fmax(fmax(h[0], h[1]), fmax(h[2], h[3])), fmax(t[0], t[1]));
-        mx = fmax(mx, fmax(fmax(fmax(g[0], g[1]), fmax(g[2], g[3])), fmax(fmax(g[4], g[5]), fmax(g[6], g[7]))));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        return mx;
+        if (lowk < 0) lowk = 0;  // (not reachable: periods and harmonics are positive)
+        const int a0 = (lowk + 31) >> 5, a1 = (highk + 1) >> 5;   // whole B1 blocks [a0, a1)
+        const bool wb = a1 > a0;
+        const int c0 = (a0 + 31) >> 5, c1 = a1 >> 5;              // whole B2 blocks [c0, c1)
+        const bool ws = wb && c1 > c0;
+        int i = lowk + lane;                                      // bins: head, or the first 32
+        double mx = (i < (wb ? a0 << 5 : highk + 1)) ? Ur[i] : -INFINITY;
+        i = (wb ? a1 << 5 : lowk + 32) + lane;                    // bins: tail, or the second 32
+        mx = fmax(mx, i <= highk ? Ur[i] : -INFINITY);
+        int j = a0 + lane;                                        // B1: head, or the first 32
+        mx = fmax(mx, (wb && j < (ws ? c0 << 5 : a1)) ? B1[j] : -INFINITY);
+        j = (ws ? c1 << 5 : a0 + 32) + lane;                      // B1: tail, or the second 32
+        mx = fmax(mx, (wb && j < a1) ? B1[j] : -INFINITY);
+        const int k = c0 + lane;
+        mx = fmax(mx, (ws && k < c1) ? B2[k] : -INFINITY);
+        return warp_max_f64(mx);
       };
       if (warp == 0) {
         if (lane == 0) {
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
         Ur[i] = d > 0.0 ? d : 0.0;
       }
       __syncthreads();
-      build_bmax();
+      build_tables();
       __syncthreads();
     }
     __syncthreads();
