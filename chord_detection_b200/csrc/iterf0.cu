@@ -90,17 +90,65 @@ __global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
 }
 
 // ... then one thread per (clip, channel): resonators, |.|, (y + lowpass(y)) / 2
-constexpr int kChanThreads = 64;
+// ... then the channels.  One CTA per clip, one thread per channel (ceil(C / 32) warps): resonators,
+// |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined loop with a different input path.
+// All channels of a clip read the SAME whitened samples, and a thread that fetches them one by one
+// has a single 8-byte load in flight (ncu r02e: 59 % of the stall samples were that load).  Here a
+// warp loads 32 consecutive samples at once (one coalesced 256-byte load, lane l keeps sample
+// T + l), the next 32 are fetched while these are consumed, and every iteration gets its sample by
+// a warp shuffle.
+constexpr int kChanLag = 4;
 template <bool STRUCTURED>
-__global__ void __launch_bounds__(kChanThreads, 12) iterf0_channel_kernel(const IterArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n_batch_clips * a.C) return;
-  const int lc = t / a.C, ch = t - lc * a.C;
-  const double* src = a.w + (int64_t)lc * a.clip_len;
-  float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
-  const double* coef = a.coef + ch * kCoefStride;
-  if (STRUCTURED) iff::filter_channel_w<true, 2, 1>(src, a.clip_len, a.n_pad, coef, dst);
-  else iff::filter_channel_w<true, 3, 3>(src, a.clip_len, a.n_pad, coef, dst);
+__global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
+  constexpr int NB1 = STRUCTURED ? 2 : 3, NB2 = STRUCTURED ? 1 : 3;
+  const int lc = blockIdx.x, lane = threadIdx.x & 31;
+  const int ch = threadIdx.x;
+  const bool active = ch < a.C;
+  const double* w = a.w + (int64_t)lc * a.clip_len;
+  float* dst = a.yc + ((int64_t)lc * a.C + (active ? ch : 0)) * a.n_pad;
+  const double* coef = a.coef + (active ? ch : 0) * kCoefStride;
+  iff::SosCoef k1, k2, kl;
+  k1.init(coef);
+  k2.init(coef + 6);
+  kl.init(coef + 12);
+  iff::SosState<NB1> r1a, r1b;
+  iff::SosState<NB2> r2a, r2b;
+  iff::SosState<3> lp;
+  const int64_t n = a.clip_len;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
+  double cur = lane < n ? w[lane] : 0.0;
+  for (int64_t T = 0; T < n + kChanLag; T += 32) {
+    const int64_t tn = T + 32 + lane;
+    const double nxt = tn < n ? w[tn] : 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double x = __shfl_sync(0xffffffffu, cur, 4 * g + j);
+        double y = fabs(v4);  // final stage: sample T + 4 g + j - 4   (iterative_f0.py:60)
+        y = (y + lp.step(kl, y)) / 2.0;  // :61-63
+        out[j] = (float)y;
+        v4 = r2b.step(k2, s3);
+        s3 = r2a.step(k2, s2);
+        s2 = r1b.step(k1, s1);
+        s1 = r1a.step(k1, x);
+      }
+      const int64_t t0 = T + 4 * g - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
+      if (active && t0 >= 0 && t0 < n) {
+        if (t0 + 4 <= n) {
+          *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (t0 + q < n) dst[t0 + q] = out[q];
+        }
+      }
+    }
+    cur = nxt;
+  }
+  if (active)
+    for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -315,7 +363,7 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
       //  * two block barriers per split.
       double my_lo = 0.0, my_up = 0.0, my_smax = 0.0;  // warp 0: interval `lane`
       int q = 0, qb = 0;                               // warp 0, uniform
-      double lo_q = 0.0, lo_qb = 0.0;                  // warp 0, uniform: lo of the two intervals in flight
+      double f_mine = 0.0;  // warp 0: fs / lo + e1 of the new (even lanes) / the shrunk (odd lanes) interval
       auto prepare = [&]() {  // warp 0: split the best interval, or finish
         const double lo_b = __shfl_sync(0xffffffffu, my_lo, qb), up_b = __shfl_sync(0xffffffffu, my_up, qb);
         const int go = ((up_b - lo_b) > a.tau_prec && q < a.Q - 1) ? 1 : 0;
@@ -335,13 +383,14 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
           my_up = up_b;
         }
         if (lane == qb) my_up = mid;
-        lo_q = mid;
-        lo_qb = lo_b;
         if (lane == 0) {
           s_go = 1;
           s_lo_b = lo_b;
           s_up_b = up_b;
         }
+        // the salience factors of the two intervals (fs / lo + e1, :162): computed here, while the
+        // harmonic warps work on the ranges, instead of after their barrier
+        f_mine = a.fs / ((lane & 1) == 0 ? mid : lo_b) + a.e1;
       };
       // max of Ur over bins [lowk, highk] for the whole warp (every lane returns it): ragged bins,
       // ragged 32-bin blocks (B1), whole 1024-bin blocks (B2) -- five predicated loads
@@ -417,7 +466,7 @@ __global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs
               }
             }
           }
-          const double val = sacc * (a.fs / (lane == 0 ? lo_q : lo_qb) + a.e1);
+          const double val = sacc * f_mine;
           const double v_q = __shfl_sync(0xffffffffu, val, 0), v_qb = __shfl_sync(0xffffffffu, val, 1);
           if (lane == q) my_smax = v_q;
           if (lane == qb) my_smax = v_qb;
@@ -772,10 +821,9 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     if (hoisted) {
       iterf0_whiten_kernel<<<(nb + 31) / 32, 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
-      if (a.structured)
-        iterf0_channel_kernel<true><<<(threads + kChanThreads - 1) / kChanThreads, kChanThreads, 0, st>>>(a);
-      else
-        iterf0_channel_kernel<false><<<(threads + kChanThreads - 1) / kChanThreads, kChanThreads, 0, st>>>(a);
+      const int chan_threads = 32 * ((a.C + 31) / 32);
+      if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
+      else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
       h->launches += 1;
     } else {
