@@ -275,7 +275,8 @@ def host_resample_poly(x, up, down, taps, n_pre_pad, n_pre_remove, n_out):
 def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
     """Host execution of the device auditory-channel filter (test hook, no GPU).
     pipelined: 0 / 1 = reference-order chain (straight / software-pipelined), 2 / 3 = the hoisted
-    form the device runs by default (pipelined / straight).
+    form the device runs by default (pipelined / straight), 4 = hoisted with the device's chunked
+    whitening schedule.
     x float32 [n]; coef float64 [18] (res1 b,a | res2 b,a | lp b,a); taps float64 [13] -> float32 [n]"""
     import numpy as np
 

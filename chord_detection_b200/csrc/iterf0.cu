@@ -59,6 +59,7 @@ struct IterArgs {
   const float2* wsplit;
   s8k::Tables s8;
   double* w;    // [n_batch_clips][clip_len] whitened clips (hoisted filter form)
+  int w_chunks;    // chunks per clip of the whitening kernel
   int structured;  // resonator numerators are [b0, 0, b2] / [b0, 0, 0] (always, for reference designs)
   float* yc;    // [n_batch_clips][C][n_pad]
   double* Ut;   // [n_batch_clips*fpc][M+1]
@@ -83,13 +84,17 @@ __global__ void __launch_bounds__(32) iterf0_filter_kernel(const IterArgs a) {
 
 // hoisted form (iterf0_filter.cuh): the whitener once per clip ...
 __global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
-  const int lc = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lc >= a.n_batch_clips) return;
+  // one thread per (clip, chunk of kWhitenChunk samples): see iff::whiten_clip
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)a.n_batch_clips * a.w_chunks) return;
+  const int64_t lc = t / a.w_chunks, c = t - lc * a.w_chunks;
   const float* src = a.x + (a.clip0 + lc) * a.clip_stride;
-  iff::whiten_clip<true>(src, a.clip_len, a.lam, a.taps, a.w + (int64_t)lc * a.clip_len);
+  const int64_t wb = c * iff::kWhitenChunk;
+  const int64_t b = wb > iff::kWhitenWarm ? wb - iff::kWhitenWarm : 0;
+  iff::whiten_clip<true>(src, a.clip_len, a.lam, a.taps, a.w + lc * a.clip_len, b, wb,
+                         wb + iff::kWhitenChunk);
 }
 
-// ... then one thread per (clip, channel): resonators, |.|, (y + lowpass(y)) / 2
 // ... then the channels.  One CTA per clip, one thread per channel (ceil(C / 32) warps): resonators,
 // |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined loop with a different input path.
 // All channels of a clip read the SAME whitened samples, and a thread that fetches them one by one
@@ -652,14 +657,22 @@ extern "C" {
 int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double lam,
                            const double* taps, int pipelined, float* y) {
   if (!x || !coef || !taps || !y || n < 0) return -1;
-  if (pipelined == 2 || pipelined == 3) {
+  if (pipelined == 2 || pipelined == 3 || pipelined == 4) {
     // the hoisted form the device runs by default: whiten the clip once, then the channel part
     // (2: pipelined schedules, 3: straight loops -- bit-identical to each other)
     std::vector<double> w((size_t)std::max<int64_t>(n, 1));
-    if (pipelined == 2) iff::whiten_clip<true>(x, n, lam, taps, w.data());
-    else iff::whiten_clip<false>(x, n, lam, taps, w.data());
-    const bool st = iff::resonators_structured(coef);
     if (pipelined == 2) {
+      iff::whiten_clip<true>(x, n, lam, taps, w.data());
+    } else if (pipelined == 3) {
+      iff::whiten_clip<false>(x, n, lam, taps, w.data());
+    } else {  // 4: the device's chunked schedule (iterf0_whiten_kernel)
+      for (int64_t wb = 0; wb < n; wb += iff::kWhitenChunk) {
+        const int64_t b = wb > iff::kWhitenWarm ? wb - iff::kWhitenWarm : 0;
+        iff::whiten_clip<true>(x, n, lam, taps, w.data(), b, wb, wb + iff::kWhitenChunk);
+      }
+    }
+    const bool st = iff::resonators_structured(coef);
+    if (pipelined != 3) {
       if (st) iff::filter_channel_w<true, 2, 1>(w.data(), n, n, coef, y);
       else iff::filter_channel_w<true, 3, 3>(w.data(), n, n, coef, y);
     } else {
@@ -819,7 +832,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     const int threads = nb * a.C;
     cdb_mark(h, st, "begin");
     if (hoisted) {
-      iterf0_whiten_kernel<<<(nb + 31) / 32, 32, 0, st>>>(a);
+      a.w_chunks = (int)((clip_len + iff::kWhitenChunk - 1) / iff::kWhitenChunk);
+      iterf0_whiten_kernel<<<(unsigned)(((int64_t)nb * a.w_chunks + 31) / 32), 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
       const int chan_threads = 32 * ((a.C + 31) / 32);
       if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);

@@ -143,14 +143,26 @@ IFF_HD void filter_channel(const float* src, long long n, long long n_pad, const
 // the straight chain by FP64 rounding (~1e-13 of the signal), far below the fp32 rounding of the
 // stored output; tests/test_host_logic.py holds it to the same 2e-7 bound against scipy.
 // ------------------------------------------------------------------------------------------------
+// Samples [begin, end) are filtered from ZERO state and written for t >= write_begin.  A clip is
+// either done in one piece (begin = write_begin = 0, end = n: the reference's arithmetic) or cut
+// into chunks that each start kWhitenWarm samples early: the 12 all-passes share one real pole
+// lambda (0.646 at 22.05 kHz, 0.756 at 44.1 kHz), so a state perturbation decays like
+// t^11 lambda^t -- below 1e-19 of its size after kWhitenWarm = 512 samples at either rate, i.e.
+// far below FP64 rounding -- and a chunk started from zero state 512 samples early produces the
+// same values as the sequential filter up to rounding (tests/test_host_logic.py: <= 1e-13).
+constexpr int kWhitenWarm = 512;
+constexpr int kWhitenChunk = 2048;
+
 template <bool PIPELINED>
-IFF_HD void whiten_clip(const float* src, long long n, double lam, const double* taps, double* w) {
+IFF_HD void whiten_clip(const float* src, long long n, double lam, const double* taps, double* w,
+                        long long begin = 0, long long write_begin = 0, long long end = -1) {
+  if (end < 0 || end > n) end = n;
   double z[kSections];
 #pragma unroll
   for (int i = 0; i < kSections; ++i) z[i] = 0.0;
   const double mlam = -lam;
   if (!PIPELINED) {
-    for (long long t = 0; t < n; ++t) {
+    for (long long t = begin; t < end; ++t) {
       const double v = (double)src[t];
       double u = v, xhat = taps[0] * v;  // wfir.py:28-43
 #pragma unroll
@@ -160,7 +172,7 @@ IFF_HD void whiten_clip(const float* src, long long n, double lam, const double*
         xhat = fma(taps[i + 1], y, xhat);
         u = y;
       }
-      w[t] = v - xhat;
+      if (t >= write_begin) w[t] = v - xhat;
     }
     return;
   }
@@ -173,19 +185,20 @@ IFF_HD void whiten_clip(const float* src, long long n, double lam, const double*
 #pragma unroll
   for (int i = 0; i <= kSections; ++i) u[i] = P[i] = vring[i] = 0.0;
 #pragma unroll
-  for (int j = 0; j < kRing; ++j) xcur[j] = j < n ? src[j] : 0.0f;
-  for (long long base = 0; base < n + kRing; base += kRing) {
+  for (int j = 0; j < kRing; ++j) xcur[j] = begin + j < end ? src[begin + j] : 0.0f;
+  for (long long base = begin; base < end + kRing; base += kRing) {
 #pragma unroll
     for (int j = 0; j < kRing; ++j) {
       const long long tn = base + kRing + j;
-      xnext[j] = tn < n ? src[tn] : 0.0f;
+      xnext[j] = tn < end ? src[tn] : 0.0f;
     }
 #pragma unroll
     for (int j = 0; j < kRing; ++j) {
       const long long t = base + j;
       {
         const double y = vring[j] - P[kSections];
-        if (t >= kRing && t - kRing < n) w[t - kRing] = y;
+        const long long ts = t - kRing;
+        if (ts >= write_begin && ts < end) w[ts] = y;
       }
 #pragma unroll
       for (int i = kSections - 1; i >= 0; --i) {

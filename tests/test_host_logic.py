@@ -158,7 +158,7 @@ def test_host_iterf0_filter_pipelined_schedule_is_exact():
     fs = 22050
     lam, taps = ops.wfir_design(fs)
     fcs = rn.iterf0_channels(70)
-    for seed, n in ((5, 20000), (6, 17), (7, 1), (8, 5000)):
+    for seed, n in ((5, 20000), (6, 17), (7, 1), (8, 5000), (9, 2049)):
         x, _ = cases.make_input(dict(fn="s_poly", seed=seed, fs=fs, n=n))
         for fc in (fcs[0], fcs[33], fcs[69]):
             r1, r2 = rn.auditory_filterbank_coefs(fs, fc)
@@ -176,6 +176,11 @@ def test_host_iterf0_filter_pipelined_schedule_is_exact():
             assert np.array_equal(yh, nat.host_iterf0_filter(x, coef, lam, taps, pipelined=3))
             assert np.max(np.abs(yh - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
             assert np.mean(yh != yp) <= 1e-3
+            # the device cuts the whitening into chunks of 2048 samples, each started from zero
+            # state 512 samples early (the whitener's memory is ~300 samples): same values
+            yc = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=4)
+            assert np.mean(yc != yh) <= 1e-3
+            assert np.max(np.abs(yc - want)) <= 2e-7 * max(np.max(np.abs(want)), 1e-30)
     for n in (2, 3, 4, 5, 7, 8, 9, 12, 13, 14, 25, 26, 27):  # every pipeline-fill / tail alignment
         x, _ = cases.make_input(dict(fn="s_poly", seed=40 + n, fs=fs, n=n))
         yh = nat.host_iterf0_filter(x, coef, lam, taps, pipelined=2)
