@@ -474,6 +474,11 @@ def main():
     prof = os.environ.get("CDB_PROFILE_RANGE") == "1"  # ncu --profile-from-start off
     if prof:
         torch.cuda.cudart().cudaProfilerStart()
+    if world > 1:
+        # one more untimed step after the host-side barrier: its in-kernel all-reduce ends on all
+        # GPUs within an NVLink round trip, so the device-timed region below starts aligned on every
+        # rank instead of charging the hosts' barrier-exit skew (tens of us) to the first timed step
+        step(args.warmup)
     e0.record()
     for i in range(args.steps):
         step(i)
@@ -482,7 +487,7 @@ def main():
     if prof:
         torch.cuda.cudart().cudaProfilerStop()
     ms_total = e0.elapsed_time(e1)
-    launches = ops.launch_count(local_rank) - launches0
+    launches = ops.launch_count(local_rank) - launches0 - (1 if world > 1 else 0)  # minus the aligning step
     if world > 1 and not fused:
         launches += args.steps  # the NCCL all-reduce kernel of every step
     clock_note = "sampled during the timed region"
