@@ -66,7 +66,7 @@ EXPORTS = [
     "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
     "cdb_host_pack_and_key", "cdb_host_py_round3",
     "cdb_profile_enable", "cdb_profile_report",
-    "cdb_comm_alloc", "cdb_comm_connect", "cdb_comm_status", "cdb_comm_destroy",
+    "cdb_comm_alloc", "cdb_comm_connect", "cdb_comm_status", "cdb_comm_destroy", "cdb_set_option",
 ]
 
 
@@ -109,6 +109,7 @@ def lib():
         L.cdb_profile_enable.argtypes = [vp, C.c_int]
         L.cdb_profile_report.argtypes = [vp, C.c_char_p, i64]
         L.cdb_profile_report.restype = i64
+        L.cdb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
         L.cdb_comm_alloc.argtypes = [vp, C.c_int, C.c_char_p]
         L.cdb_comm_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
         L.cdb_comm_status.argtypes = [vp]
@@ -157,13 +158,17 @@ class Handle:
         self.ptr = p
 
     @classmethod
-    def get(cls, device):
+    def get(cls, device, tag=None):
+        """The handle of this (thread, device); `tag` names additional handles for work that runs
+        CONCURRENTLY on other streams (a handle is used on one stream at a time: its scratch and
+        workspaces are shared by consecutive calls)."""
         cache = getattr(cls._tls, "cache", None)
         if cache is None:
             cache = cls._tls.cache = {}
-        h = cache.get(int(device))
+        key = int(device) if tag is None else (int(device), tag)
+        h = cache.get(key)
         if h is None:
-            h = cache[int(device)] = cls(device)
+            h = cache[key] = cls(device)
         return h
 
     def check(self, rc, what):
@@ -178,6 +183,9 @@ class Handle:
     @property
     def launches(self):
         return int(self.L.cdb_launch_count(self.ptr))
+
+    def set_option(self, name, value):
+        self.check(self.L.cdb_set_option(self.ptr, name.encode(), int(value)), "cdb_set_option")
 
     # -- per-kernel timing (cdb_profile_enable / cdb_profile_report) -----------
     def profile_start(self):

@@ -73,6 +73,16 @@ int64_t cdb_profile_report(cdb_handle* h, char* buf, int64_t buf_len) {
 
 int cdb_version(void) { return CDB_VERSION; }
 
+int cdb_set_option(cdb_handle* h, const char* name, int value) {
+  if (!h || !name) return CDB_E_NULL;
+  if (std::strcmp(name, "esacf_fit_warps") == 0) {
+    if (value < 0 || value > 8) return cdb_fail(h, CDB_E_INVALID, "esacf_fit_warps %d", value);
+    h->opt_esacf_fit_warps = value;
+    return 0;
+  }
+  return cdb_fail(h, CDB_E_INVALID, "unknown option %s", name);
+}
+
 int cdb_create(cdb_handle** out, int device) {
   if (!out) return CDB_E_NULL;
   *out = nullptr;

@@ -34,6 +34,7 @@ struct cdb_handle {
   double* he_scratch = nullptr;
   // one-shot all-reduce over peer (NVLink) memory, fused into the last CTA of a kernel (comm.cu)
   struct Comm* comm = nullptr;
+  int opt_esacf_fit_warps = 0;  // cdb_set_option("esacf_fit_warps"): 0 = the built-in default
   // optional per-kernel timing (cdb_profile_enable / cdb_profile_report): one CUDA event after
   // every launch on the caller's stream; off by default (no events, no cost)
   bool prof_on = false;

@@ -848,6 +848,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   // warps per CTA (one CTA per SM): fewer warps leave more of the 256 KB to L1, which holds the
   // fits' 3-vectors (local memory); CDB_ESACF_FIT_WARPS overrides
   int fit_warps = kFitWarpsDefault;  // measured (15 648 frames): 8 warps 35.7 ms, 7: 29.3, 6: 26.4, 5: 26.2, 4: 38.8
+  if (h->opt_esacf_fit_warps > 0) fit_warps = h->opt_esacf_fit_warps;  // cdb_set_option
   if (const char* fw = std::getenv("CDB_ESACF_FIT_WARPS")) fit_warps = std::atoi(fw);
   const size_t fit_warp_smem = (size_t)lmg::WORK_DOUBLES_Y * fit_lanes * sizeof(double);
   const int fit_warps_max = std::min<int>(kFitThreads / 32, (int)((size_t)h->smem_optin / fit_warp_smem));

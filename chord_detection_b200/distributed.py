@@ -124,29 +124,79 @@ def harmonic_energy_sharded(x_local, fs, frames_local, frame_size, hop=None, fus
     return all_reduce_chroma(total)
 
 
-def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4), reduce=True):
+_side = {}
+
+
+def _side_streams(dev):
+    """Streams (and their own library handles) for the methods that run next to each other."""
+    key = (dev.type, dev.index)
+    if key not in _side:
+        lo, hi = torch.cuda.Stream.priority_range()
+        # ESACF's fit kernel is one large persistent CTA per SM: give it priority so that its CTAs
+        # are placed as soon as an SM has room, the small CTAs of the other kernels fill the rest
+        _side[key] = {1: torch.cuda.Stream(dev, priority=hi), 3: torch.cuda.Stream(dev),
+                      4: torch.cuda.Stream(dev)}
+    return _side[key]
+
+
+def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4), reduce=True, concurrent=None):
     """Config C5: every rank runs the requested methods on its shard of clips ([n_local, clip_len]
     CUDA float32) and ONE all-reduce combines the [n_methods, 12] sums (reduce=False leaves the
     local sums for callers that loop over chunks and reduce once at the end).  Returns (global sums
-    [n_methods, 12], dict of per-clip results that stay sharded)."""
-    from . import ops
+    [n_methods, 12], dict of per-clip results that stay sharded).
+
+    concurrent (default: on CUDA, unless CDB_SEQUENTIAL_METHODS=1): the methods are independent, and
+    their kernels stress different resources -- ESACF's Levenberg-Marquardt fits are latency-bound
+    (FP64 pipe < 10 % busy), prime's Goertzel sums are FP64-throughput-bound, the iterative-F0
+    spectrum is shared-memory-bound -- so each method runs on its own stream (with its own library
+    handle: a handle serves one stream at a time) and the streams join before the results are used."""
+    from . import _native as nat, ops
 
     dev = clips_local.device
     sums = torch.zeros((len(methods), 12), dtype=torch.float64, device=dev)
     per_clip = {}
-    for i, m in enumerate(methods):
-        if clips_local.shape[0] == 0:
-            continue
-        if m == 1:
-            r = ops.esacf(clips_local, fs, per_clip=True)
-        elif m == 2:
-            r = ops.harmonic_energy(clips_local, fs, per_clip=True)
-        elif m == 3:
-            r = ops.iterative_f0(clips_local, fs, per_clip=True)
-        elif m == 4:
-            r = ops.prime_multif0(clips_local, fs, per_clip=True)
-        else:
+    if concurrent is None:
+        concurrent = clips_local.is_cuda and os.environ.get("CDB_SEQUENTIAL_METHODS") != "1"
+    fns = {1: ops.esacf, 2: ops.harmonic_energy, 3: ops.iterative_f0, 4: ops.prime_multif0}
+    for m in methods:
+        if m not in fns:
             raise ValueError("valid methods: 1, 2, 3, 4")
+    if clips_local.shape[0] == 0:
+        return (all_reduce_chroma(sums) if reduce else sums), per_clip
+    if not concurrent:
+        for i, m in enumerate(methods):
+            r = fns[m](clips_local, fs, per_clip=True)
+            sums[i] = r.total
+            per_clip[m] = r.clips
+        return (all_reduce_chroma(sums) if reduce else sums), per_clip
+    cur = torch.cuda.current_stream(dev)
+    side = _side_streams(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    results, done = {}, []
+    for m in methods:
+        if m == 2:
+            continue  # harmonic energy is ~0.1 % of the work: it stays on the caller's stream
+        s = side[m]
+        s.wait_event(ready)
+        clips_local.record_stream(s)
+        h = nat.Handle.get(dev.index, tag="method%d" % m)
+        if m == 1 and not getattr(h, "_co_run", False):
+            h.set_option("esacf_fit_warps", 5)  # leave shared memory for the co-running kernels
+            h._co_run = True
+        with torch.cuda.stream(s):
+            results[m] = fns[m](clips_local, fs, per_clip=True, handle=h)
+            e = torch.cuda.Event()
+            e.record(s)
+            done.append(e)
+    if 2 in methods:
+        results[2] = ops.harmonic_energy(clips_local, fs, per_clip=True)
+    for e in done:
+        cur.wait_event(e)
+    for i, m in enumerate(methods):
+        r = results[m]
+        r.total.record_stream(cur)
+        r.clips.record_stream(cur)
         sums[i] = r.total
         per_clip[m] = r.clips
     return (all_reduce_chroma(sums) if reduce else sums), per_clip

@@ -245,7 +245,7 @@ def esacf_params(fs, ham_samples, k=0.67, n_peaks_elim=6, peak_thresh=0.1, peak_
 
 
 def esacf(x, fs, ham_samples=None, ham_ms=46.4, n_peaks_elim=6, peak_thresh=0.1, peak_min_dist=10,
-          stretch_mode="truncate", per_clip=False, per_frame=False, debug=False):
+          stretch_mode="truncate", per_clip=False, per_frame=False, debug=False, handle=None):
     """ESACF chromagram (reference esacf.py:41-90) -> ChromaResult (float64 outputs).
 
     debug=True additionally returns, in ``extra``, a [n_frames, stride] float64 tensor of
@@ -253,7 +253,7 @@ def esacf(x, fs, ham_samples=None, ham_ms=46.4, n_peaks_elim=6, peak_thresh=0.1,
     x, n_clips, clip_len, stride = _batch_view(x)
     if ham_samples is None:
         ham_samples = int(fs * ham_ms / 1000.0)
-    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    h = handle or nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
     p = esacf_params(fs, ham_samples, 0.67, n_peaks_elim, peak_thresh, peak_min_dist, stretch_mode)
     fpc = nat.num_frames(clip_len, ham_samples, ham_samples)
     total = torch.empty(12, dtype=torch.float64, device=x.device)
@@ -271,11 +271,11 @@ def esacf(x, fs, ham_samples=None, ham_ms=46.4, n_peaks_elim=6, peak_thresh=0.1,
 
 
 def prime_multif0(x, fs, num_harmonic=1, num_octave=2, harmonic_multiples_elim=5,
-                  harmonic_elim_runs=2, per_clip=False, per_candidate=False):
+                  harmonic_elim_runs=2, per_clip=False, per_candidate=False, handle=None):
     """Prime-multiF0 chromagram (reference prime_multif0.py:41-91) -> ChromaResult (float64).
     per_candidate=True returns [n_clips, n_candidates, 12] in ``extra``."""
     x, n_clips, clip_len, stride = _batch_view(x)
-    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    h = handle or nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
     p = nat.PrimeParams(float(fs), int(num_harmonic), int(num_octave), int(harmonic_multiples_elim),
                         int(harmonic_elim_runs))
     n_cand = 12 * int(num_octave) * int(num_harmonic)
@@ -402,11 +402,11 @@ def _workspace(device, nbytes):
 
 
 def iterative_f0(x, fs, frame_size=8192, power=1.0, channel_freqs=None, per_clip=False,
-                 per_frame=False, voices=False, **periodicity_kwargs):
+                 per_frame=False, voices=False, handle=None, **periodicity_kwargs):
     """Iterative-F0 chromagram (reference iterative_f0.py:54-96 + periodicity.py) -> ChromaResult.
     voices=True returns [n_frames, 2*max_voices] (saliences | periods) in ``extra``."""
     x, n_clips, clip_len, stride = _batch_view(x)
-    h = nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    h = handle or nat.Handle.get(x.device.index if x.device.index is not None else torch.cuda.current_device())
     p = iterf0_params(fs, frame_size, power, channel_freqs, **periodicity_kwargs)
     fpc = nat.num_frames(clip_len, frame_size, frame_size)
     need = int(h.L.cdb_iterf0_workspace_bytes(C.byref(p), n_clips, clip_len))

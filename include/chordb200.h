@@ -66,6 +66,11 @@ const char* cdb_last_error(cdb_handle* h);
 /* number of kernels launched through this handle since creation (bench `gpu_launches`) */
 int64_t cdb_launch_count(cdb_handle* h);
 
+/* Per-handle tuning knobs.  "esacf_fit_warps" (1..7, 0 = default 6): warps of the persistent
+ * Levenberg-Marquardt CTA per SM; 5 leaves ~40 KB of shared memory per SM free so that kernels of
+ * OTHER handles / streams (prime, iterative F0) can run next to the fits (distributed.py). */
+int cdb_set_option(cdb_handle* h, const char* name, int value);
+
 /* Optional per-kernel timing of the calls made through this handle (bench.py's "dominant kernel's
  * share"): cdb_profile_enable(h, 1) starts a recording (one CUDA event after every kernel launch on
  * the caller's stream), cdb_profile_report waits for the recorded events and writes one

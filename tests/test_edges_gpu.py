@@ -221,3 +221,26 @@ def test_display_plot_frame_keeps_that_frames_intermediates():
     assert m4.frame_data["candidate"] == 0 and m4.frame_data["window_size"] == W
     _, wc4 = rn.prime(x[f * W:(f + 1) * W], fs, per_candidate=True)
     _close(m4.frame_data["chroma"], wc4[0])
+
+
+def test_all_methods_concurrent_streams_equal_sequential():
+    """distributed.all_methods_sharded runs the four methods on separate streams with separate
+    library handles (default on CUDA); the results must equal the one-after-the-other run
+    (sums of fp64 atomics: to rounding) and the oracle."""
+    from chord_detection_b200 import distributed as D
+
+    dev = _dev()
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=900 + i, fs=22050, n=20000))[0] for i in range(6)])
+    xd = torch.from_numpy(rows).to(dev)
+    for rep in range(2):  # second pass: handles, plans and workspaces already exist
+        s_seq, pc_seq = D.all_methods_sharded(xd, 22050, reduce=False, concurrent=False)
+        s_con, pc_con = D.all_methods_sharded(xd, 22050, reduce=False, concurrent=True)
+        torch.cuda.synchronize()
+        _close(s_con.cpu().numpy(), s_seq.cpu().numpy(), tol=1e-9)
+        for m in (1, 2, 3, 4):
+            _close(pc_con[m].cpu().numpy(), pc_seq[m].cpu().numpy(), tol=1e-9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _close(pc_con[2].cpu().numpy(), np.stack([rn.harmonic_energy_fast(r, 22050) for r in rows]))
+        _close(pc_con[4].cpu().numpy(), np.stack([rn.prime(r, 22050) for r in rows]))
+        _close(pc_con[3].cpu().numpy(), np.stack([rn.iterf0(r, 22050) for r in rows]))
