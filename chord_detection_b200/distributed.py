@@ -145,18 +145,21 @@ def all_methods_sharded(clips_local, fs, methods=(1, 2, 3, 4), reduce=True, conc
     local sums for callers that loop over chunks and reduce once at the end).  Returns (global sums
     [n_methods, 12], dict of per-clip results that stay sharded).
 
-    concurrent (default: on CUDA, unless CDB_SEQUENTIAL_METHODS=1): the methods are independent, and
-    their kernels stress different resources -- ESACF's Levenberg-Marquardt fits are latency-bound
-    (FP64 pipe < 10 % busy), prime's Goertzel sums are FP64-throughput-bound, the iterative-F0
-    spectrum is shared-memory-bound -- so each method runs on its own stream (with its own library
-    handle: a handle serves one stream at a time) and the streams join before the results are used."""
+    concurrent=True (or CDB_CONCURRENT_METHODS=1) runs every method on its own stream with its own
+    library handle (a handle serves one stream at a time) and joins the streams before the results
+    are used.  The kernels stress different resources (ESACF's fits are latency-bound with the FP64
+    pipe < 10 % busy, prime's Goertzel sums are FP64-throughput-bound, the iterative-F0 spectrum is
+    shared-memory-bound), but MEASURED on one B200 (8192 clips, scripts/time_c5.py, r02) the
+    concurrent run is within 1 % of the sequential one (1003 vs 1012 ms; 1041 ms without matching
+    shared-memory carve-outs, and forcing the maximal carve-out slows the sequential kernels by
+    10 %): the 188-226 KB persistent fit CTAs leave no room for co-resident CTAs.  Off by default."""
     from . import _native as nat, ops
 
     dev = clips_local.device
     sums = torch.zeros((len(methods), 12), dtype=torch.float64, device=dev)
     per_clip = {}
     if concurrent is None:
-        concurrent = clips_local.is_cuda and os.environ.get("CDB_SEQUENTIAL_METHODS") != "1"
+        concurrent = clips_local.is_cuda and os.environ.get("CDB_CONCURRENT_METHODS") == "1"
     fns = {1: ops.esacf, 2: ops.harmonic_energy, 3: ops.iterative_f0, 4: ops.prime_multif0}
     for m in methods:
         if m not in fns:

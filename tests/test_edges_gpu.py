@@ -224,8 +224,8 @@ def test_display_plot_frame_keeps_that_frames_intermediates():
 
 
 def test_all_methods_concurrent_streams_equal_sequential():
-    """distributed.all_methods_sharded runs the four methods on separate streams with separate
-    library handles (default on CUDA); the results must equal the one-after-the-other run
+    """distributed.all_methods_sharded(concurrent=True) runs the four methods on separate streams with
+    separate library handles; the results must equal the one-after-the-other run
     (sums of fp64 atomics: to rounding) and the oracle."""
     from chord_detection_b200 import distributed as D
 
