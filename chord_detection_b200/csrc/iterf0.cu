@@ -95,23 +95,47 @@ __global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
                          wb + iff::kWhitenChunk);
 }
 
-// ... then the channels.  One CTA per clip, one thread per channel (ceil(C / 32) warps): resonators,
-// |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined loop with a different input path.
-// All channels of a clip read the SAME whitened samples, and a thread that fetches them one by one
-// has a single 8-byte load in flight (ncu r02e: 59 % of the stall samples were that load).  Here a
-// warp loads 32 consecutive samples at once (one coalesced 256-byte load, lane l keeps sample
-// T + l), the next 32 are fetched while these are consumed, and every iteration gets its sample by
-// a warp shuffle.
+// ... then the channels: resonators, |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined
+// loop with a different input path.  All channels of a clip read the SAME whitened samples, and a
+// thread that fetches them one by one has a single 8-byte load in flight (ncu r02e: 59 % of the
+// stall samples were that load).  Here a warp loads 32 consecutive samples at once (one coalesced
+// 256-byte load, lane l keeps sample T + l), the next 32 are fetched while these are consumed, and
+// every iteration gets its sample by a warp shuffle.
+//   G == 1: a warp = 32 consecutive channels [ch0 + 32 b, +32) of ONE clip (C / 32 such blocks).
+//   G  > 1: the C % 32 = r leftover channels (70 = 2 x 32 + 6): a warp = r channels of each of G =
+//           32 / r clips (lane l: clip l / r, channel ch0 + l % r), so the leftovers fill a warp
+//           instead of wasting 26 of its 32 lanes per clip; it keeps G sample tiles and every lane
+//           picks its clip's sample out of G shuffles.
 constexpr int kChanLag = 4;
-template <bool STRUCTURED>
-__global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
+constexpr int kChanWarps = 4;  // warps per CTA (independent of each other)
+template <bool STRUCTURED, int G>
+__global__ void __launch_bounds__(32 * kChanWarps) iterf0_channel_kernel(const IterArgs a, int ch0,
+                                                                         int r, int n_units) {
   constexpr int NB1 = STRUCTURED ? 2 : 3, NB2 = STRUCTURED ? 1 : 3;
-  const int lc = blockIdx.x, lane = threadIdx.x & 31;
-  const int ch = threadIdx.x;
-  const bool active = ch < a.C;
-  const double* w = a.w + (int64_t)lc * a.clip_len;
-  float* dst = a.yc + ((int64_t)lc * a.C + (active ? ch : 0)) * a.n_pad;
-  const double* coef = a.coef + (active ? ch : 0) * kCoefStride;
+  const int lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kChanWarps + (threadIdx.x >> 5);  // warp-sized unit of work
+  if (unit >= n_units) return;
+  int lc0, ch, g = 0;
+  bool active = true;
+  if (G == 1) {
+    const int blocks = r;  // (G == 1: r = number of 32-channel blocks per clip)
+    lc0 = unit / blocks;
+    ch = ch0 + 32 * (unit - lc0 * blocks) + lane;
+    active = ch < a.C;  // (only a leftover block that could not be packed is partly filled)
+    if (!active) ch = ch0;
+  } else {
+    lc0 = unit * G;
+    g = lane / r;
+    ch = ch0 + (lane - g * r);
+    active = g < G && lc0 + g < a.n_batch_clips;
+    if (!active) {
+      g = 0;
+      ch = ch0;
+    }
+  }
+  const int lc = lc0 + g;
+  float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
+  const double* coef = a.coef + ch * kCoefStride;
   iff::SosCoef k1, k2, kl;
   k1.init(coef);
   k2.init(coef + 6);
@@ -120,18 +144,30 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
   iff::SosState<NB2> r2a, r2b;
   iff::SosState<3> lp;
   const int64_t n = a.clip_len;
+  const double* w[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q)
+    w[q] = a.w + (int64_t)(lc0 + q < a.n_batch_clips ? lc0 + q : lc0) * a.clip_len;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
-  double cur = lane < n ? w[lane] : 0.0;
+  double cur[G], nxt[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) cur[q] = lane < n ? w[q][lane] : 0.0;
   for (int64_t T = 0; T < n + kChanLag; T += 32) {
     const int64_t tn = T + 32 + lane;
-    const double nxt = tn < n ? w[tn] : 0.0;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int q = 0; q < G; ++q) nxt[q] = tn < n ? w[q][tn] : 0.0;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) {
       float out[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double x = __shfl_sync(0xffffffffu, cur, 4 * g + j);
-        double y = fabs(v4);  // final stage: sample T + 4 g + j - 4   (iterative_f0.py:60)
+        double x = __shfl_sync(0xffffffffu, cur[0], 4 * gi + j);
+#pragma unroll
+        for (int q = 1; q < G; ++q) {
+          const double xq = __shfl_sync(0xffffffffu, cur[q], 4 * gi + j);
+          x = g == q ? xq : x;
+        }
+        double y = fabs(v4);  // final stage: sample T + 4 gi + j - 4   (iterative_f0.py:60)
         y = (y + lp.step(kl, y)) / 2.0;  // :61-63
         out[j] = (float)y;
         v4 = r2b.step(k2, s3);
@@ -139,7 +175,7 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
         s2 = r1b.step(k1, s1);
         s1 = r1a.step(k1, x);
       }
-      const int64_t t0 = T + 4 * g - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
+      const int64_t t0 = T + 4 * gi - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
       if (active && t0 >= 0 && t0 < n) {
         if (t0 + 4 <= n) {
           *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
@@ -150,10 +186,32 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
         }
       }
     }
-    cur = nxt;
+#pragma unroll
+    for (int q = 0; q < G; ++q) cur[q] = nxt[q];
   }
   if (active)
     for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
+}
+
+// launches the channel kernels of one batch: full 32-channel blocks, then the leftover channels
+template <bool STRUCTURED>
+static void launch_channel_kernels(const IterArgs& a, cudaStream_t st) {
+  const int full = a.C / 32, r = a.C % 32;
+  if (full > 0) {
+    const int units = a.n_batch_clips * full;
+    iterf0_channel_kernel<STRUCTURED, 1><<<(units + kChanWarps - 1) / kChanWarps, 32 * kChanWarps, 0, st>>>(
+        a, 0, full, units);
+  }
+  if (r > 0) {
+    const int G = 32 / r >= 5 ? 5 : 32 / r >= 4 ? 4 : 32 / r >= 2 ? 2 : 1;
+    const int units = (a.n_batch_clips + G - 1) / G;
+    const int grid = (units + kChanWarps - 1) / kChanWarps;
+    if (G == 5) iterf0_channel_kernel<STRUCTURED, 5><<<grid, 32 * kChanWarps, 0, st>>>(a, 32 * full, r, units);
+    else if (G == 4) iterf0_channel_kernel<STRUCTURED, 4><<<grid, 32 * kChanWarps, 0, st>>>(a, 32 * full, r, units);
+    else if (G == 2) iterf0_channel_kernel<STRUCTURED, 2><<<grid, 32 * kChanWarps, 0, st>>>(a, 32 * full, r, units);
+    else iterf0_channel_kernel<STRUCTURED, 1><<<(a.n_batch_clips + kChanWarps - 1) / kChanWarps, 32 * kChanWarps, 0, st>>>(
+        a, 32 * full, 1, a.n_batch_clips);  // r > 16: one partly filled warp per clip
+  }
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -835,9 +893,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       a.w_chunks = (int)((clip_len + iff::kWhitenChunk - 1) / iff::kWhitenChunk);
       iterf0_whiten_kernel<<<(unsigned)(((int64_t)nb * a.w_chunks + 31) / 32), 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
-      const int chan_threads = 32 * ((a.C + 31) / 32);
-      if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
-      else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
+      if (a.structured) launch_channel_kernels<true>(a, st);
+      else launch_channel_kernels<false>(a, st);
       cdb_mark(h, st, "iterf0_channel_kernel");
       h->launches += 1;
     } else {
