@@ -15,14 +15,6 @@ int cdb_fail(cdb_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
-int cdb_aux_stream(cdb_handle* h) {
-  if (h->aux_stream) return 0;
-  CDB_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-  CDB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  CDB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  return 0;
-}
-
 void cdb_mark(cdb_handle* h, cudaStream_t st, const char* name) {
   if (!h || !h->prof_on) return;
   cudaEvent_t e = nullptr;
@@ -127,9 +119,6 @@ int cdb_destroy(cdb_handle* h) {
   if (h->he_scratch) cudaFree(h->he_scratch);
   for (void* p : h->owned) cudaFree(p);
   if (h->ws) cudaFree(h->ws);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
-  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   for (auto& m : h->prof_marks) cudaEventDestroy(m.second);
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   delete h;

@@ -34,10 +34,6 @@ struct cdb_handle {
   double* he_scratch = nullptr;
   // one-shot all-reduce over peer (NVLink) memory, fused into the last CTA of a kernel (comm.cu)
   struct Comm* comm = nullptr;
-  // auxiliary stream + events: a small kernel that would otherwise run alone at the tail of a big one
-  // (IterF0's leftover-channel kernel) is forked next to it and joined back into the caller's stream
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int opt_esacf_fit_warps = 0;  // cdb_set_option("esacf_fit_warps"): 0 = the built-in default
   // optional per-kernel timing (cdb_profile_enable / cdb_profile_report): one CUDA event after
   // every launch on the caller's stream; off by default (no events, no cost)
@@ -45,9 +41,6 @@ struct cdb_handle {
   std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
   std::vector<cudaEvent_t> prof_pool;
 };
-
-// creates the auxiliary stream / events on first use
-int cdb_aux_stream(cdb_handle* h);
 
 // marks the end of stage `name` (and the start of the next one) on stream st when profiling is on
 void cdb_mark(cdb_handle* h, cudaStream_t st, const char* name);
