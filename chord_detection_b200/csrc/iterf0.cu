@@ -60,9 +60,6 @@ struct IterArgs {
   s8k::Tables s8;
   double* w;    // [n_batch_clips][clip_len] whitened clips (hoisted filter form)
   int w_chunks;    // chunks per clip of the whitening kernel
-  double* chan_state;              // [rows][kChanState][32] filter state between segments
-  int* chan_flag;                  // [rows] segments finished
-  unsigned long long* chan_queue;  // unit counter of the channel kernel
   int structured;  // resonator numerators are [b0, 0, b2] / [b0, 0, 0] (always, for reference designs)
   float* yc;    // [n_batch_clips][C][n_pad]
   double* Ut;   // [n_batch_clips*fpc][M+1]
@@ -98,183 +95,65 @@ __global__ void __launch_bounds__(32) iterf0_whiten_kernel(const IterArgs a) {
                          wb + iff::kWhitenChunk);
 }
 
-// ... then the channels: resonators, |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined
-// loop with a different input path and a different schedule.
-//  * Input.  All channels of a clip read the SAME whitened samples, and a thread that fetches them
-//    one by one has a single 8-byte load in flight (ncu r02e: 59 % of the stall samples were that
-//    load).  A warp loads 32 consecutive samples at once (one coalesced 256-byte load, lane l keeps
-//    sample T + l), the next 32 are fetched while these are consumed, and every iteration gets its
-//    sample by a warp shuffle.
-//  * Work units.  A "row" is a warp's worth of channels: 32 consecutive channels of one clip, or --
-//    for the C % 32 = r leftover channels (70 = 2 x 32 + 6) -- r channels of each of G = 2 clips
-//    (lane l: clip l / r, channel 32 (C / 32) + l % r; a row keeps G sample tiles and a lane picks
-//    its clip's sample out of G shuffles).  The IIR state makes a row serial in time, and a warp
-//    that owned a whole row ran for milliseconds: with 1.2 - 1.7 "waves" of such warps per batch the
-//    kernel took two full waves (r02: 28 ms per 2048 clips where the arithmetic needs 15).  So a row
-//    is cut into SEGMENTS of kChanSeg samples; persistent warps take (segment, row) units from an
-//    atomic counter in segment-major order, load the row's filter state (14 doubles per lane:
-//    5 biquads + the 4 pipeline registers), run the segment, store the state and publish the row's
-//    segment count (release / acquire).  A unit only waits for the previous segment of its row,
-//    which was handed out a whole sweep of rows earlier: no deadlock (every unit that was handed out
-//    is running on a resident warp) and no idle tail.
+// ... then the channels.  One CTA per clip, one thread per channel (ceil(C / 32) warps): resonators,
+// |.|, (y + lowpass(y)) / 2 -- iff::filter_channel_w's pipelined loop with a different input path.
+// All channels of a clip read the SAME whitened samples, and a thread that fetches them one by one
+// has a single 8-byte load in flight (ncu r02e: 59 % of the stall samples were that load).  Here a
+// warp loads 32 consecutive samples at once (one coalesced 256-byte load, lane l keeps sample
+// T + l), the next 32 are fetched while these are consumed, and every iteration gets its sample by
+// a warp shuffle.
 constexpr int kChanLag = 4;
-constexpr int kChanWarps = 4;     // warps per CTA (independent of each other)
-constexpr int kChanSeg = 2048;    // samples per unit (a multiple of 32)
-constexpr int kChanState = 14;    // doubles of filter state per lane
-constexpr int kChanG = 2;         // clips sharing a leftover row
-
 template <bool STRUCTURED>
-__global__ void __launch_bounds__(32 * kChanWarps, 5) iterf0_channel_kernel(const IterArgs a) {
+__global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
   constexpr int NB1 = STRUCTURED ? 2 : 3, NB2 = STRUCTURED ? 1 : 3;
-  constexpr int G = kChanG;
-  const int lane = threadIdx.x & 31;
-  const int full = a.C >> 5, r = a.C & 31;
-  const int rows_full = a.n_batch_clips * full;
-  const int gl = r > 0 ? (32 / r >= G ? G : 1) : 1;  // clips per leftover row
-  const int rows_left = r > 0 ? (a.n_batch_clips + gl - 1) / gl : 0;
-  const int n_rows = rows_full + rows_left;
+  const int lc = blockIdx.x, lane = threadIdx.x & 31;
+  const int ch = threadIdx.x;
+  const bool active = ch < a.C;
+  const double* w = a.w + (int64_t)lc * a.clip_len;
+  float* dst = a.yc + ((int64_t)lc * a.C + (active ? ch : 0)) * a.n_pad;
+  const double* coef = a.coef + (active ? ch : 0) * kCoefStride;
+  iff::SosCoef k1, k2, kl;
+  k1.init(coef);
+  k2.init(coef + 6);
+  kl.init(coef + 12);
+  iff::SosState<NB1> r1a, r1b;
+  iff::SosState<NB2> r2a, r2b;
+  iff::SosState<3> lp;
   const int64_t n = a.clip_len;
-  const int n_seg = (int)((n + kChanSeg - 1) / kChanSeg);
-  const int64_t n_units = (int64_t)n_rows * n_seg;
-  for (;;) {
-    long long u = 0;
-    if (lane == 0) u = (long long)atomicAdd(a.chan_queue, 1ull);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if (u >= n_units) break;
-    const int seg = (int)(u / n_rows), row = (int)(u - (long long)seg * n_rows);
-    // ---- which clips / channel does this lane serve?
-    int lc0, ch, g = 0;
-    bool active = true;
-    const bool left = row >= rows_full;
-    if (!left) {
-      lc0 = row / full;
-      ch = 32 * (row - lc0 * full) + lane;
-    } else {
-      lc0 = (row - rows_full) * gl;
-      g = lane / r;
-      ch = 32 * full + (lane - g * r);
-      active = g < gl && lc0 + g < a.n_batch_clips;
-      if (!active) {
-        g = 0;
-        ch = 32 * full;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
+  double cur = lane < n ? w[lane] : 0.0;
+  for (int64_t T = 0; T < n + kChanLag; T += 32) {
+    const int64_t tn = T + 32 + lane;
+    const double nxt = tn < n ? w[tn] : 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double x = __shfl_sync(0xffffffffu, cur, 4 * g + j);
+        double y = fabs(v4);  // final stage: sample T + 4 g + j - 4   (iterative_f0.py:60)
+        y = (y + lp.step(kl, y)) / 2.0;  // :61-63
+        out[j] = (float)y;
+        v4 = r2b.step(k2, s3);
+        s3 = r2a.step(k2, s2);
+        s2 = r1b.step(k1, s1);
+        s1 = r1a.step(k1, x);
       }
-    }
-    const int lc = lc0 + g;
-    float* dst = a.yc + ((int64_t)lc * a.C + ch) * a.n_pad;
-    const double* coef = a.coef + ch * kCoefStride;
-    iff::SosCoef k1, k2, kl;
-    k1.init(coef);
-    k2.init(coef + 6);
-    kl.init(coef + 12);
-    iff::SosState<NB1> r1a, r1b;
-    iff::SosState<NB2> r2a, r2b;
-    iff::SosState<3> lp;
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
-    double* stp = a.chan_state + ((int64_t)row * kChanState) * 32 + lane;
-    if (seg > 0) {
-      // the previous segment of this row must be finished (it was handed out n_rows units ago)
-      if (lane == 0) {
-        int done;
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.chan_flag + row) : "memory");
-          if (done < seg) __nanosleep(200);
-        } while (done < seg);
-      }
-      __syncwarp();
-      r1a.z0 = __ldcg(stp + 0 * 32);
-      r1a.z1 = __ldcg(stp + 1 * 32);
-      r1b.z0 = __ldcg(stp + 2 * 32);
-      r1b.z1 = __ldcg(stp + 3 * 32);
-      r2a.z0 = __ldcg(stp + 4 * 32);
-      r2a.z1 = __ldcg(stp + 5 * 32);
-      r2b.z0 = __ldcg(stp + 6 * 32);
-      r2b.z1 = __ldcg(stp + 7 * 32);
-      lp.z0 = __ldcg(stp + 8 * 32);
-      lp.z1 = __ldcg(stp + 9 * 32);
-      s1 = __ldcg(stp + 10 * 32);
-      s2 = __ldcg(stp + 11 * 32);
-      s3 = __ldcg(stp + 12 * 32);
-      v4 = __ldcg(stp + 13 * 32);
-    }
-    const double* w[G];
+      const int64_t t0 = T + 4 * g - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
+      if (active && t0 >= 0 && t0 < n) {
+        if (t0 + 4 <= n) {
+          *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
 #pragma unroll
-    for (int q = 0; q < G; ++q)
-      w[q] = a.w + (int64_t)((left && lc0 + q < a.n_batch_clips) ? lc0 + q : lc0) * a.clip_len;
-    const int64_t S0 = (int64_t)seg * kChanSeg;
-    // the last segment also drains the pipeline (the output lags the input by kChanLag samples)
-    const int64_t S1 = seg == n_seg - 1 ? n + kChanLag : S0 + kChanSeg;
-    double cur[G], nxt[G];
-#pragma unroll
-    for (int q = 0; q < G; ++q) cur[q] = (S0 + lane < n) ? w[q][S0 + lane] : 0.0;
-    for (int64_t T = S0; T < S1; T += 32) {
-      const int64_t tn = T + 32 + lane;
-#pragma unroll
-      for (int q = 0; q < G; ++q) nxt[q] = tn < n ? w[q][tn] : 0.0;
-#pragma unroll
-      for (int gi = 0; gi < 8; ++gi) {
-        float out[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double x = __shfl_sync(0xffffffffu, cur[0], 4 * gi + j);
-#pragma unroll
-          for (int q = 1; q < G; ++q) {
-            const double xq = __shfl_sync(0xffffffffu, cur[q], 4 * gi + j);
-            x = g == q ? xq : x;
-          }
-          double y = fabs(v4);  // final stage: sample T + 4 gi + j - 4   (iterative_f0.py:60)
-          y = (y + lp.step(kl, y)) / 2.0;  // :61-63
-          out[j] = (float)y;
-          v4 = r2b.step(k2, s3);
-          s3 = r2a.step(k2, s2);
-          s2 = r1b.step(k1, s1);
-          s1 = r1a.step(k1, x);
-        }
-        const int64_t t0 = T + 4 * gi - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
-        if (active && t0 >= 0 && t0 < n) {
-          if (t0 + 4 <= n) {
-            *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (t0 + q < n) dst[t0 + q] = out[q];
-          }
+          for (int q = 0; q < 4; ++q)
+            if (t0 + q < n) dst[t0 + q] = out[q];
         }
       }
-#pragma unroll
-      for (int q = 0; q < G; ++q) cur[q] = nxt[q];
     }
-    if (seg < n_seg - 1) {
-      __stcg(stp + 0 * 32, r1a.z0);
-      __stcg(stp + 1 * 32, r1a.z1);
-      __stcg(stp + 2 * 32, r1b.z0);
-      __stcg(stp + 3 * 32, r1b.z1);
-      __stcg(stp + 4 * 32, r2a.z0);
-      __stcg(stp + 5 * 32, r2a.z1);
-      __stcg(stp + 6 * 32, r2b.z0);
-      __stcg(stp + 7 * 32, r2b.z1);
-      __stcg(stp + 8 * 32, lp.z0);
-      __stcg(stp + 9 * 32, lp.z1);
-      __stcg(stp + 10 * 32, s1);
-      __stcg(stp + 11 * 32, s2);
-      __stcg(stp + 12 * 32, s3);
-      __stcg(stp + 13 * 32, v4);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        const int v = seg + 1;
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.chan_flag + row), "r"(v) : "memory");
-      }
-    } else if (active) {
-      for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
-    }
+    cur = nxt;
   }
-}
-
-// rows (warp-sized groups of channels) of a batch of nb clips: see iterf0_channel_kernel
-static int64_t chan_rows(int C, int64_t nb) {
-  const int full = C >> 5, r = C & 31;
-  const int gl = r > 0 ? (32 / r >= kChanG ? kChanG : 1) : 1;
-  return nb * full + (r > 0 ? (nb + gl - 1) / gl : 0);
+  if (active)
+    for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -763,8 +642,7 @@ static int64_t per_clip_bytes(const cdb_iterf0_params* p, int64_t clip_len) {
   const int64_t fpc = cdb_num_frames(clip_len, p->frame_size, p->frame_size);
   const int64_t n_pad = fpc * p->frame_size;
   return (int64_t)p->channels * n_pad * 4 + fpc * (int64_t)(p->frame_size + 1) * 8 +
-         ((clip_len * 8 + 255) & ~(int64_t)255) +  // + the whitened clip (fp64)
-         (int64_t)((p->channels + 31) / 32) * (14 * 32 * 8 + 8);  // + channel-kernel state / flags per row
+         ((clip_len * 8 + 255) & ~(int64_t)255);  // + the whitened clip (fp64)
 }
 
 static int64_t ud_bytes(const cdb_iterf0_params* p, int num_sms) {
@@ -957,26 +835,11 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       a.w_chunks = (int)((clip_len + iff::kWhitenChunk - 1) / iff::kWhitenChunk);
       iterf0_whiten_kernel<<<(unsigned)(((int64_t)nb * a.w_chunks + 31) / 32), 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
-      {
-        // state | queue | flags behind the whitened clips; queue and flags start at zero
-        const int64_t rows = chan_rows(a.C, nb);
-        unsigned char* cs = reinterpret_cast<unsigned char*>(a.w) +
-                            (((size_t)nb * clip_len * 8 + 255) & ~(size_t)255);
-        a.chan_state = reinterpret_cast<double*>(cs);
-        a.chan_queue = reinterpret_cast<unsigned long long*>(cs + (size_t)rows * kChanState * 32 * 8);
-        a.chan_flag = reinterpret_cast<int*>(a.chan_queue + 1);
-        CDB_CUDA(h, cudaMemsetAsync(a.chan_queue, 0, 8 + (size_t)rows * 4, st));
-        void (*ck)(const IterArgs) = a.structured ? iterf0_channel_kernel<true> : iterf0_channel_kernel<false>;
-        int per_sm = 0;
-        CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ck, 32 * kChanWarps, 0));
-        if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "channel kernel does not fit");
-        const int64_t units = rows * ((clip_len + kChanSeg - 1) / kChanSeg);
-        const int64_t grid = std::min<int64_t>((units + kChanWarps - 1) / kChanWarps,
-                                               (int64_t)h->num_sms * per_sm);
-        ck<<<(unsigned)grid, 32 * kChanWarps, 0, st>>>(a);
-      }
+      const int chan_threads = 32 * ((a.C + 31) / 32);
+      if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
+      else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
-      h->launches += 1;  // whitening + channel kernel (the += 3 below counts filter + spectrum + periodicity)
+      h->launches += 1;
     } else {
       iterf0_filter_kernel<<<(threads + 31) / 32, 32, 0, st>>>(a);  // 32-thread CTAs: spread over all SMs
       cdb_mark(h, st, "iterf0_filter_kernel");
