@@ -172,7 +172,10 @@ __device__ __forceinline__ double comm_allreduce12(const CommArgs& c, double v, 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(c.mail[lane] + slot + 12), "l"(c.seq)
                  : "memory");
   bool ok = true;
-  if (lane < c.world) {
+  // after one time-out the communicator is dead: later collectives do not wait another 10 s each
+  const bool dead = c.status && *reinterpret_cast<volatile int*>(c.status) != 0;
+  if (dead) ok = false;
+  if (!dead && lane < c.world) {
     const double* flag = c.mail[c.rank] + ((size_t)par * c.world + lane) * CDB_MAIL_STRIDE + 12;
     unsigned long long got = 0, t0 = 0, t1 = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
