@@ -67,6 +67,7 @@ EXPORTS = [
     "cdb_host_pack_and_key", "cdb_host_py_round3",
     "cdb_profile_enable", "cdb_profile_report",
     "cdb_comm_alloc", "cdb_comm_connect", "cdb_comm_status", "cdb_comm_destroy", "cdb_set_option",
+    "cdb_host_he8192_fft",
 ]
 
 
@@ -110,6 +111,7 @@ def lib():
         L.cdb_profile_report.argtypes = [vp, C.c_char_p, i64]
         L.cdb_profile_report.restype = i64
         L.cdb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+        L.cdb_host_he8192_fft.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float)]
         L.cdb_comm_alloc.argtypes = [vp, C.c_int, C.c_char_p]
         L.cdb_comm_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
         L.cdb_comm_status.argtypes = [vp]
@@ -369,3 +371,19 @@ def host_pack_and_key(chroma):
     if rc != 0:
         raise ValueError("cdb_host_pack_and_key failed (%d)" % rc)
     return digits, keys
+
+
+def host_he8192_fft(frame, window="hamming"):
+    """Host execution of the frame-8192 team kernel's FFT (test hook, no GPU).
+    frame float32 [8192] -> complex64 [4096]: FFT of z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1]."""
+    import numpy as np
+
+    x = np.ascontiguousarray(frame, dtype=np.float32)
+    if x.shape != (8192,):
+        raise ValueError("expected 8192 samples")
+    z = np.zeros(8192, dtype=np.float32)
+    F = C.POINTER(C.c_float)
+    rc = lib().cdb_host_he8192_fft(x.ctypes.data_as(F), WINDOW_KINDS[window], z.ctypes.data_as(F))
+    if rc != 0:
+        raise ValueError("cdb_host_he8192_fft failed (%d)" % rc)
+    return z.view(np.complex64)

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "f32x2.cuh"
 #include "fft_packed.cuh"
+#include "he8192t.cuh"
 
 struct HeWin {
   int k0, k1, note, pad;
@@ -45,6 +46,7 @@ struct HePlan {
   float2* d_tw32 = nullptr;    // [32*32]: W_1024^(t*k1) at [k1*32+t]   (N == 2048)
   float2* d_tw8a = nullptr;    // [16*256]: W_4096^(t*k1) at [k1*256+t]  (N == 8192)
   float2* d_tw8b = nullptr;    // [16*16]:  W_256^(n3*k2) at [k2*16+n3]
+  float2* d_tw8t = nullptr;    // [64][16]: team kernel, thread t: W_4096^(8 a t) (a < 8) | W_4096^(b t) (b < 8)
   float2* d_wsplit = nullptr;  // [M+1]: (cos, sin)(2*pi*k/N)
   float2* d_twgen = nullptr;   // [M/2]: W_M^q = (cos, -sin)(2*pi*q/M)
   HeWin* d_wins = nullptr;
@@ -113,6 +115,16 @@ extern "C" int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// per-thread inter-pass twiddles of the frame-8192 team kernel (he8192t.cuh)
+static void he8192t_twiddles(float2* tw) {
+  for (int t = 0; t < 64; ++t)
+    for (int j = 0; j < 16; ++j) {
+      const int e = (j < 8 ? 8 * j : j - 8) * t;
+      const double ang = 2.0 * kPi * (double)e / 4096.0;
+      tw[t * 16 + j] = make_float2((float)std::cos(ang), (float)-std::sin(ang));
+    }
+}
 
 #define HE_MAX_WINDOWS 192
 
@@ -226,6 +238,11 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
     pl->win_a0 = (float)a0;
     if ((rc = cdb_upload(h, wl, &pl->d_winlane))) return rc;
   }
+  if (N == 8192) {
+    std::vector<float2> tw8t(64 * 16);
+    he8192t_twiddles(tw8t.data());
+    if ((rc = cdb_upload(h, tw8t, &pl->d_tw8t))) return rc;
+  }
   if ((rc = cdb_upload(h, tw8a, &pl->d_tw8a))) return rc;
   if ((rc = cdb_upload(h, tw8b, &pl->d_tw8b))) return rc;
   if ((rc = cdb_upload(h, win, &pl->d_win))) return rc;
@@ -271,6 +288,7 @@ struct HeArgs {
   const float2* tw32;
   const float2* tw8a;  // [16][256] W_4096^(t*k1)   (N == 8192)
   const float2* tw8b;  // [16][16]  W_256^(n3*k2)
+  const float2* tw8t;  // [64][16]  team kernel
   const float2* wsplit;
   const float2* twgen;
   const HeWin* wins;
@@ -1134,6 +1152,143 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
   }
 }
 
+// frame_size 8192, third generation (he8192t.cuh): a team of 64 threads per frame.
+__global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  c64* buf = reinterpret_cast<c64*>(smem);                           // [64][66] transpose; later Z[4096]
+  double* wv = reinterpret_cast<double*>(buf + h8t::kBuf);           // [n_windows]
+  const float2* zA = reinterpret_cast<const float2*>(buf);
+  const int tid = threadIdx.x;
+  const int M = 4096;
+  const int64_t total_frames = a.n_clips * a.frames_per_clip;
+  const int64_t f_begin = (total_frames * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t f_end = (total_frames * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+  double acc_total = 0.0, acc_clip = 0.0;
+  int64_t my_clip = -1;
+  int64_t clip = f_begin / a.frames_per_clip;
+  int64_t f = f_begin - clip * a.frames_per_clip;
+  const float4 wl = a.winlane[tid];
+  const c64 win_a0 = bc(a.win_a0), win_cb = pk(wl.x, wl.y), win_sb = pk(wl.z, wl.w);
+  const c64* tw = reinterpret_cast<const c64*>(a.tw8t) + tid * 16;
+
+  for (int64_t gf = f_begin; gf < f_end; ++gf) {
+    const int64_t s0 = f * a.hop;
+    const float* src = reinterpret_cast<const float*>(a.x) + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    {
+      const bool vec = (avail >= 8192) && ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+      auto ld = [&](int m) -> c64 {  // complex point m = (x[2m], x[2m+1])
+        if (vec) return ldg_c64(reinterpret_cast<const float2*>(src) + m);
+        const int64_t i = 2 * (int64_t)m;
+        return pk(i < avail ? __ldg(src + i) : 0.0f, i + 1 < avail ? __ldg(src + i + 1) : 0.0f);
+      };
+      h8t::pass1(tid, ld, win_a0, win_cb, win_sb, tw, buf);
+    }
+    __syncthreads();
+    {
+      c64 v[64];
+      h8t::pass2(tid, buf, v);
+      __syncthreads();  // every row is in registers: the buffer may take Z
+#pragma unroll
+      for (int k2 = 0; k2 < 64; ++k2) buf[tid + 64 * k2] = v[k2];
+    }
+    __syncthreads();
+    // ---- probe windows: 8 lanes per window; real-FFT split of the bins it covers, |X|^2, max
+    {
+      const int grp = tid >> 3, j = tid & 7;
+      for (int w0 = 0; w0 < a.n_windows; w0 += 8) {
+        const int wi = w0 + grp;
+        float m = -1.0f;
+        HeWin hw;
+        hw.k0 = hw.k1 = 0;
+        hw.weight = 0.0;
+        if (wi < a.n_windows) hw = a.wins[wi];
+        for (int k = hw.k0 + j; k < hw.k1; k += 8) {
+          float pwr;
+          if (k == M) {
+            const float xn = zA[0].x - zA[0].y;
+            pwr = xn * xn;
+          } else {
+            const float2 z = zA[k], pz = zA[(M - k) & (M - 1)];
+            const float2 cs = __ldg(&a.wsplit[k]);
+            const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+            const float xr = 0.5f * (er + (cs.x * di - cs.y * dr));
+            const float xi = 0.5f * (ei - (cs.x * dr + cs.y * di));
+            pwr = xr * xr + xi * xi;
+          }
+          m = fmaxf(m, pwr);
+        }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        if (j == 0 && wi < a.n_windows) wv[wi] = (double)sqrtf(sqrtf(m)) * hw.weight;
+      }
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double sum = 0.0;
+      for (int jj = 0; jj < a.wins_per_note; ++jj) sum += wv[tid * a.wins_per_note + jj];
+      if (a.clips) {
+        if (clip != my_clip) {
+          if (my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+          my_clip = clip;
+          acc_clip = 0.0;
+        }
+        acc_clip += sum;
+      }
+      acc_total += sum;
+      if (a.frames) a.frames[gf * 12 + tid] = (float)sum;
+    }
+    __syncthreads();  // wv and the Z buffer are free again
+    if (++f >= a.frames_per_clip) {
+      f = 0;
+      ++clip;
+    }
+  }
+  if (tid < 12) {
+    if (a.clips && my_clip >= 0) atomicAdd(&a.clips[my_clip * 12 + tid], acc_clip);
+    if (a.total) atomicAdd(&a.total[tid], acc_total);
+  }
+}
+
+struct HostFrameLoad {
+  const float* frame;
+  __host__ __device__ c64 operator()(int m) const { return pk(frame[2 * m], frame[2 * m + 1]); }
+};
+
+// Host execution (CPU tests, no GPU) of the team kernel's FFT: frame[8192] -> Z[4096] (the
+// 4096-point complex FFT of z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1]), thread by thread.
+extern "C" int cdb_host_he8192_fft(const float* frame, int window_kind, float* z_out) {
+  if (!frame || !z_out || window_kind < 0 || window_kind > 2) return -1;
+  double a0 = 1.0, a1 = 0.0;
+  if (window_kind == CDB_WINDOW_HAMMING) a0 = 0.54, a1 = 0.46;
+  if (window_kind == CDB_WINDOW_HANN) a0 = 0.5, a1 = 0.5;
+  std::vector<float2> tw(64 * 16);
+  he8192t_twiddles(tw.data());
+  std::vector<c64> buf(h8t::kBuf + 2, 0);
+  // 16-byte aligned view for the 128-bit row reads
+  c64* b = buf.data();
+  if (reinterpret_cast<uintptr_t>(b) & 15) ++b;
+  const HostFrameLoad ld{frame};
+  for (int t = 0; t < 64; ++t) {
+    const double b0 = 2.0 * kPi * (2 * t) / 8191.0, b1 = 2.0 * kPi * (2 * t + 1) / 8191.0;
+    const c64 cb = pk((float)(-a1 * std::cos(b0)), (float)(-a1 * std::cos(b1)));
+    const c64 sb = pk((float)(a1 * std::sin(b0)), (float)(a1 * std::sin(b1)));
+    h8t::pass1(t, ld, bc((float)a0), cb, sb, reinterpret_cast<const c64*>(tw.data()) + t * 16, b);
+  }
+  for (int t = 0; t < 64; ++t) {
+    c64 v[64];
+    h8t::pass2(t, b, v);
+    for (int k2 = 0; k2 < 64; ++k2) {
+      float re, im;
+      upk(v[k2], re, im);
+      z_out[2 * (t + 64 * k2)] = re;
+      z_out[2 * (t + 64 * k2) + 1] = im;
+    }
+  }
+  return 0;
+}
+
 // Generic power-of-two path: one CTA per frame at a time, in-place radix-2 DIT in shared memory.
 constexpr int kGenThreads = 256;
 
@@ -1274,6 +1429,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
   a.tw32 = pl->d_tw32;
   a.tw8a = pl->d_tw8a;
   a.tw8b = pl->d_tw8b;
+  a.tw8t = pl->d_tw8t;
   a.wsplit = pl->d_wsplit;
   a.twgen = pl->d_twgen;
   a.wins = pl->d_wins;
@@ -1338,6 +1494,22 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     // butterflies, direct loads) | staged (packed butterflies + bulk-async staging of the next frame)
     const char* k8 = std::getenv("CDB_HE8192");
     std::string mode = k8 ? k8 : kHe8192Default;
+    if (mode == "team") {
+      const size_t smem = (size_t)h8t::kBuf * 8 + HE_MAX_WINDOWS * 8;
+      CDB_CUDA(h, cudaFuncSetAttribute(he8192t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      int per_sm = 0;
+      CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, he8192t_kernel,
+                                                                h8t::kThreads, smem));
+      if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "frame does not fit in shared memory");
+      int64_t grid = std::min<int64_t>(n_clips * fpc, (int64_t)h->num_sms * per_sm);
+      cdb_mark(h, st, "begin");
+      he8192t_kernel<<<(unsigned)grid, h8t::kThreads, smem, st>>>(a);
+      cdb_mark(h, st, "he8192t_kernel");
+      h->launches += 1;
+      CDB_CUDA(h, cudaGetLastError());
+      return 0;
+    }
     void (*kern)(const HeArgs) = mode == "packed"   ? he8192p_kernel<false>
                                  : mode == "staged" ? he8192p_kernel<true>
                                                     : he8192_kernel;

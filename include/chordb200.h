@@ -102,6 +102,10 @@ typedef struct {
  * or <0.  Needs no GPU (used by CPU tests of the host logic). */
 int cdb_he_windows(const cdb_he_params* p, int* note, int* k0, int* k1, double* weight);
 
+/* host execution (CPU tests, no GPU) of the FFT of the frame-8192 "team" kernel: frame[8192] ->
+ * z_out[4096 complex, interleaved] = FFT_4096 of z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1] */
+int cdb_host_he8192_fft(const float* frame, int window_kind, float* z_out);
+
 /* d_x: float32 samples; with CDB_FLAG_PCM16 (frame_size 2048 only) int16 PCM, decoded in the kernel
  * exactly as s/32768.  d_chroma_frames: [n_clips*frames_per_clip, 12] float32 or NULL */
 int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* d_x, int64_t n_clips,

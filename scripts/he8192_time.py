@@ -17,7 +17,7 @@ g = torch.Generator(device=dev).manual_seed(1)
 x = x * (0.75 + 0.5 * torch.rand(x.numel(), device=dev, generator=g))
 nf = x.numel() // 8192
 out = {}
-for mode in ("scalar", "packed", "staged"):
+for mode in ("scalar", "packed", "staged", "team"):
     os.environ["CDB_HE8192"] = mode
     for _ in range(2):
         r = ops.harmonic_energy(x, 22050)

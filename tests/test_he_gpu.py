@@ -96,11 +96,11 @@ def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
     _assert_close(a.total.cpu().numpy(), b.total.cpu().numpy(), tol=1e-5)
     _assert_close(a.frames.cpu().numpy(), b.frames.cpu().numpy(), tol=1e-4)
     if frame_size == 8192:
-        # the three frame-8192 kernels: scalar butterflies / packed butterflies / packed + the next
-        # frame staged by bulk async copy (ragged and unaligned frames are read directly: hop 1001
-        # and the clip tail exercise that path)
+        # the frame-8192 kernels: scalar butterflies / packed butterflies / packed + the next frame
+        # staged by bulk async copy / 64-thread teams with radix-64 x 64 register FFTs (ragged and
+        # unaligned frames are read directly: hop 1001 and the clip tail exercise that path)
         monkeypatch.delenv("CDB_HE_FORCE_GENERIC")
-        for mode in ("scalar", "packed", "staged"):
+        for mode in ("scalar", "packed", "staged", "team"):
             monkeypatch.setenv("CDB_HE8192", mode)
             c = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
             _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(), tol=1e-5)

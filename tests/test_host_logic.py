@@ -302,3 +302,21 @@ def test_audio_load_host_path(tmp_path):
     assert fs2 == 22050 and x.dtype == np.float32 and np.array_equal(x, want)
     x0, fs0 = audio.load(path, sr=None)
     assert fs0 == 44100 and np.array_equal(x0, mono)
+
+
+def test_host_he8192_team_fft_matches_numpy():
+    """The 4096-point complex FFT of the frame-8192 "team" harmonic-energy kernel (radix 64 x 64,
+    window evaluated on the fly, packed FP32x2 butterflies), executed thread by thread on the host."""
+    import scipy.signal.windows as sw
+
+    rng = np.random.default_rng(21)
+    wins = {"hamming": sw.hamming(8192), "hann": sw.hann(8192), "rect": np.ones(8192)}
+    x, _ = cases.make_input(dict(fn="s_poly", seed=5, fs=22050, n=8192))
+    imp = np.zeros(8192, dtype=np.float32)
+    imp[4097] = 1.0
+    for kind, w in wins.items():
+        for sig in (rng.standard_normal(8192).astype(np.float32), x, imp, np.zeros(8192, dtype=np.float32)):
+            got = nat.host_he8192_fft(sig, kind)
+            xw = sig.astype(np.float64) * w
+            want = np.fft.fft(xw[0::2] + 1j * xw[1::2])
+            assert np.max(np.abs(got - want)) <= 5e-7 * max(np.max(np.abs(want)), 1e-30), kind
