@@ -103,7 +103,10 @@ def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
         for mode in ("scalar", "packed", "staged", "team"):
             monkeypatch.setenv("CDB_HE8192", mode)
             c = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
-            _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(), tol=1e-5)
+            # (the radix-16^3 kernels share one butterfly structure; the radix-64^2 team kernel
+            # rounds differently, like the generic kernel above)
+            _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(),
+                          tol=1e-4 if mode == "team" else 1e-5)
         monkeypatch.delenv("CDB_HE8192")
         xo = np.concatenate([np.zeros(1, dtype=np.float32), x])  # 4-byte-aligned view
         xd = torch.from_numpy(xo).to(_dev())[1:]
