@@ -40,6 +40,7 @@ struct HePlan {
   int kmin, kmax;  // probed bins, inclusive
   int max_width;   // widest probe window
   bool force_generic;
+  bool weights_fp32_exact = false;  // every 1 / harmonic weight survives a round trip through fp32
   float* d_win = nullptr;      // [N]
   float4* d_winlane = nullptr; // [32] per-lane window constants of the frame-2048 kernel
   float win_a0 = 1.0f;
@@ -47,6 +48,7 @@ struct HePlan {
   float2* d_tw8a = nullptr;    // [16*256]: W_4096^(t*k1) at [k1*256+t]  (N == 8192)
   float2* d_tw8b = nullptr;    // [16*16]:  W_256^(n3*k2) at [k2*16+n3]
   float2* d_tw8t = nullptr;    // [64][16]: team kernel, thread t: W_4096^(8 a t) (a < 8) | W_4096^(b t) (b < 8)
+  float4* d_tasks8t = nullptr; // [rounds][64]: team kernel epilogue tasks (bin | -1, cos, sin, weight)
   float2* d_wsplit = nullptr;  // [M+1]: (cos, sin)(2*pi*k/N)
   float2* d_twgen = nullptr;   // [M/2]: W_M^q = (cos, -sin)(2*pi*q/M)
   HeWin* d_wins = nullptr;
@@ -181,6 +183,9 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
   pl->kmax = kmax;
   pl->max_width = max_width;
   pl->force_generic = force_generic;
+  pl->weights_fp32_exact = true;
+  for (auto& w : wins)
+    if ((double)(float)w.weight != w.weight) pl->weights_fp32_exact = false;
 
   std::vector<float> win(N);
   for (int n = 0; n < N; ++n) {
@@ -242,6 +247,27 @@ static int he_get_plan(cdb_handle* h, const cdb_he_params* p, HePlan** out) {
     std::vector<float2> tw8t(64 * 16);
     he8192t_twiddles(tw8t.data());
     if ((rc = cdb_upload(h, tw8t, &pl->d_tw8t))) return rc;
+    // epilogue tasks: round r, thread t -> window 8 r + t / 8, bin k0 + t % 8
+    const int rounds = (nw + 7) / 8;
+    std::vector<float4> tasks((size_t)rounds * 64);
+    for (int r = 0; r < rounds; ++r)
+      for (int t = 0; t < 64; ++t) {
+        const int wi = 8 * r + (t >> 3);
+        int kk = -1;
+        float4 tk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wi < nw) {
+          tk.w = (float)wins[wi].weight;
+          const int k = wins[wi].k0 + (t & 7);
+          if (k < wins[wi].k1) {
+            kk = k;
+            tk.y = wsplit[k].x;
+            tk.z = wsplit[k].y;
+          }
+        }
+        std::memcpy(&tk.x, &kk, 4);
+        tasks[(size_t)r * 64 + t] = tk;
+      }
+    if ((rc = cdb_upload(h, tasks, &pl->d_tasks8t))) return rc;
   }
   if ((rc = cdb_upload(h, tw8a, &pl->d_tw8a))) return rc;
   if ((rc = cdb_upload(h, tw8b, &pl->d_tw8b))) return rc;
@@ -289,6 +315,8 @@ struct HeArgs {
   const float2* tw8a;  // [16][256] W_4096^(t*k1)   (N == 8192)
   const float2* tw8b;  // [16][16]  W_256^(n3*k2)
   const float2* tw8t;  // [64][16]  team kernel
+  int he8t_fast;       // team kernel: every window weight is exactly representable in fp32
+  const float4* tasks8t;  // team kernel epilogue tasks [rounds][64]
   const float2* wsplit;
   const float2* twgen;
   const HeWin* wins;
@@ -1170,6 +1198,17 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
   const float4 wl = a.winlane[tid];
   const c64 win_a0 = bc(a.win_a0), win_cb = pk(wl.x, wl.y), win_sb = pk(wl.z, wl.w);
   const c64* tw = reinterpret_cast<const c64*>(a.tw8t) + tid * 16;
+  // epilogue task table (probe windows of at most 8 bins whose weights are exact in fp32, i.e. the
+  // reference's 1 / harmonic for harmonic = 1, 2, 4, ...: round r, thread t -> window 8 r + t / 8,
+  // bin k0 + t % 8): (bin | -1, cos, sin of the split twiddle, weight)
+  // epilogue task table (probe windows of at most 8 bins whose weights are exact in fp32, i.e. the
+  // reference's 1 / harmonic for harmonic = 1, 2, 4, ...): round r, thread t -> window 8 r + t / 8,
+  // bin k0 + t % 8; (bin | -1, cos, sin of the split twiddle, weight) built on the host, read
+  // through L1 (the frame itself is loaded with the streaming hint so that it does not evict the
+  // tables from the small L1 that six 35 KB CTAs leave)
+  const float4* tasks = a.tasks8t + tid;
+  const int n_rounds = (a.n_windows + 7) >> 3;
+  const bool fast_epi = a.max_width <= 8 && a.he8t_fast;
 
   for (int64_t gf = f_begin; gf < f_end; ++gf) {
     const int64_t s0 = f * a.hop;
@@ -1184,7 +1223,8 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
       if (vec) {
         const float2* s2 = reinterpret_cast<const float2*>(src) + tid;
 #pragma unroll
-        for (int n1 = 0; n1 < 64; ++n1) xin[n1] = ldg_c64(s2 + 64 * n1);
+        for (int n1 = 0; n1 < 64; ++n1)
+          xin[n1] = __ldcs(reinterpret_cast<const unsigned long long*>(s2 + 64 * n1));
       } else {
 #pragma unroll
         for (int n1 = 0; n1 < 64; ++n1) {
@@ -1205,7 +1245,34 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
     }
     __syncthreads();
     // ---- probe windows: 8 lanes per window; real-FFT split of the bins it covers, |X|^2, max
-    {
+    if (fast_epi) {
+      // every (round, thread) task -- bin index, split twiddle, weight -- is frame-independent and
+      // sits in shared memory (built once per CTA): one 128-bit load instead of two global loads
+#pragma unroll 2
+      for (int r = 0; r < n_rounds; ++r) {
+        const float4 tk = __ldg(tasks + r * h8t::kThreads);
+        const int k = __float_as_int(tk.x);
+        float pwr = -1.0f;
+        if (k >= 0) {
+          if (k == M) {
+            const float xn = zA[0].x - zA[0].y;
+            pwr = xn * xn;
+          } else {
+            const float2 z = zA[k], pz = zA[(M - k) & (M - 1)];
+            const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
+            const float xr = 0.5f * (er + (tk.y * di - tk.z * dr));
+            const float xi = 0.5f * (ei - (tk.y * dr + tk.z * di));
+            pwr = xr * xr + xi * xi;
+          }
+        }
+        float m = pwr;
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        const int wi = 8 * r + (tid >> 3);
+        if ((tid & 7) == 0 && wi < a.n_windows) wv[wi] = (double)sqrtf(sqrtf(m)) * (double)tk.w;
+      }
+    } else {
       const int grp = tid >> 3, j = tid & 7;
       for (int w0 = 0; w0 < a.n_windows; w0 += 8) {
         const int wi = w0 + grp;
@@ -1448,6 +1515,7 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
   a.clips = d_chroma_clips;
   a.frames = d_chroma_frames;
   a.pw_floats = a.pw_bytes = 0;
+  a.he8t_fast = 0;
   a.scratch = h->he_scratch;
   a.accumulate = (flags & CDB_FLAG_ACCUMULATE) ? 1 : 0;
   std::memset(&a.comm, 0, sizeof(a.comm));
@@ -1506,7 +1574,9 @@ extern "C" int cdb_he_chroma(cdb_handle* h, const cdb_he_params* p, const void* 
     const char* k8 = std::getenv("CDB_HE8192");
     std::string mode = k8 ? k8 : kHe8192Default;
     if (mode == "team") {
-      const size_t smem = (size_t)h8t::kBuf * 8 + HE_MAX_WINDOWS * 8;
+      const size_t smem = (size_t)h8t::kBuf * 8 + (size_t)((pl->n_windows + 1) & ~1) * 8;
+      a.he8t_fast = pl->weights_fp32_exact ? 1 : 0;
+      a.tasks8t = pl->d_tasks8t;
       CDB_CUDA(h, cudaFuncSetAttribute(he8192t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
       int per_sm = 0;
