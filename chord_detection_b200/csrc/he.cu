@@ -15,7 +15,9 @@
 //                    evaluated on the fly; pass 2 output-pruned; split post-processing only for
 //                    the probed bins; window maxima and the 12 sums via a small per-warp buffer
 //                    + fp64 accumulators.
-//   he8192_kernel  — frame_size 8192 (the reference default): one CTA per frame, radix-16^3.
+//   he8192t_kernel — frame_size 8192 (the reference default): a team of 64 threads per frame,
+//                    radix-64 x radix-64 in registers, one transpose (he8192t.cuh); the older
+//                    256-thread radix-16^3 kernels (he8192_kernel, he8192p_kernel) remain selectable.
 //   he_generic_kernel — any power-of-two frame_size in [64, 16384]; one CTA per frame,
 //                    shared-memory radix-2 FFT.  Correctness path for the other shapes.
 // No tensor cores: there is no dense contraction here (BASELINE.json north_star).
@@ -828,10 +830,12 @@ __global__ void __launch_bounds__(NW * 32, 1) he2048w_kernel(const HeArgs a) {
 // overlap at this size); window and twiddle tables are read through L1.
 // ------------------------------------------------------------------------------------------
 constexpr int k8Threads = 256;
-// scalar | packed | staged (see the dispatch).  88 200 frames, hop = frame, 2.9 GB (r01H):
+// scalar | packed | staged | team (see the dispatch).  88 200 frames, hop = frame, 2.9 GB:
 // scalar 60.8 M frames/s (1.99 TB/s), packed 41.0 M (direct global loads end up exposed between the
-// window computations: long-scoreboard stalls x5), staged 63.7 M (2.09 TB/s, 23 % fewer instructions).
-static const char* const kHe8192Default = "staged";
+// window computations: long-scoreboard stalls x5), staged 63.7 M (2.09 TB/s, r01H); team (r02:
+// 64 threads per frame, radix-64 x 64, he8192t.cuh) 72.7 M (2.38 TB/s), and 73.5 M against 58.1 M
+// frames/s on 32 768 clips of 44 100 samples (6 frames per clip, the last one ragged).
+static const char* const kHe8192Default = "team";
 constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
 
 __global__ void __launch_bounds__(k8Threads, 2) he8192_kernel(const HeArgs a) {
