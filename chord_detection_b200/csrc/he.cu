@@ -1236,6 +1236,18 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
           xin[n1] = pk(i < avail ? __ldg(src + i) : 0.0f, i + 1 < avail ? __ldg(src + i + 1) : 0.0f);
         }
       }
+      // pull the NEXT frame of this CTA towards L2 while this one is processed (4 lines per thread)
+      if (gf + 1 < f_end) {
+        const int64_t nf = f + 1 < a.frames_per_clip ? f + 1 : 0;
+        const int64_t nclip = f + 1 < a.frames_per_clip ? clip : clip + 1;
+        const float* nsrc = reinterpret_cast<const float*>(a.x) + nclip * a.clip_stride + nf * a.hop;
+        const int64_t navail = a.clip_len - nf * a.hop;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t off = (int64_t)(tid + 64 * i) * 32;  // floats: one 128-byte line each
+          if (off < navail) asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + off));
+        }
+      }
       auto ld = [&](int m) -> c64 { return xin[m >> 6]; };  // m = 64 n1 + tid
       h8t::pass1(tid, ld, win_a0, win_cb, win_sb, tw, buf);
     }
