@@ -1185,6 +1185,7 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
 }
 
 // frame_size 8192, third generation (he8192t.cuh): a team of 64 threads per frame.
+constexpr int kTeamRounds = 6;  // epilogue rounds of the fast path (8 windows each: 48 windows)
 __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);                           // [64][66] transpose; later Z[4096]
@@ -1212,7 +1213,7 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
   // tables from the small L1 that six 35 KB CTAs leave)
   const float4* tasks = a.tasks8t + tid;
   const int n_rounds = (a.n_windows + 7) >> 3;
-  const bool fast_epi = a.max_width <= 8 && a.he8t_fast;
+  const bool fast_epi = a.max_width <= 8 && a.he8t_fast && n_rounds <= kTeamRounds;
 
   for (int64_t gf = f_begin; gf < f_end; ++gf) {
     const int64_t s0 = f * a.hop;
@@ -1259,15 +1260,21 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
 #pragma unroll
       for (int k2 = 0; k2 < 64; ++k2) buf[tid + 64 * k2] = v[k2];
     }
+    // the (frame-independent) tasks of all rounds are fetched before the barrier: their latency
+    // overlaps it, and the six rounds below are independent instruction streams
+    float4 tk[kTeamRounds];
+    if (fast_epi) {
+#pragma unroll
+      for (int r = 0; r < kTeamRounds; ++r)
+        tk[r] = r < n_rounds ? __ldg(tasks + r * h8t::kThreads) : make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+    }
     __syncthreads();
     // ---- probe windows: 8 lanes per window; real-FFT split of the bins it covers, |X|^2, max
     if (fast_epi) {
-      // every (round, thread) task -- bin index, split twiddle, weight -- is frame-independent and
-      // sits in shared memory (built once per CTA): one 128-bit load instead of two global loads
-#pragma unroll 2
-      for (int r = 0; r < n_rounds; ++r) {
-        const float4 tk = __ldg(tasks + r * h8t::kThreads);
-        const int k = __float_as_int(tk.x);
+      float m[kTeamRounds];
+#pragma unroll
+      for (int r = 0; r < kTeamRounds; ++r) {
+        const int k = __float_as_int(tk[r].x);
         float pwr = -1.0f;
         if (k >= 0) {
           if (k == M) {
@@ -1276,17 +1283,24 @@ __global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) 
           } else {
             const float2 z = zA[k], pz = zA[(M - k) & (M - 1)];
             const float er = z.x + pz.x, ei = z.y - pz.y, dr = z.x - pz.x, di = z.y + pz.y;
-            const float xr = 0.5f * (er + (tk.y * di - tk.z * dr));
-            const float xi = 0.5f * (ei - (tk.y * dr + tk.z * di));
+            const float xr = 0.5f * (er + (tk[r].y * di - tk[r].z * dr));
+            const float xi = 0.5f * (ei - (tk[r].y * dr + tk[r].z * di));
             pwr = xr * xr + xi * xi;
           }
         }
-        float m = pwr;
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        const int wi = 8 * r + (tid >> 3);
-        if ((tid & 7) == 0 && wi < a.n_windows) wv[wi] = (double)sqrtf(sqrtf(m)) * (double)tk.w;
+        m[r] = pwr;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int r = 0; r < kTeamRounds; ++r) m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], o));
+      }
+      if ((tid & 7) == 0) {
+#pragma unroll
+        for (int r = 0; r < kTeamRounds; ++r) {
+          const int wi = 8 * r + (tid >> 3);
+          if (wi < a.n_windows) wv[wi] = (double)sqrtf(sqrtf(m[r])) * (double)tk[r].w;
+        }
       }
     } else {
       const int grp = tid >> 3, j = tid & 7;
