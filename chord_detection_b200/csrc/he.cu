@@ -833,7 +833,7 @@ constexpr int k8Threads = 256;
 // scalar | packed | staged | team (see the dispatch).  88 200 frames, hop = frame, 2.9 GB:
 // scalar 60.8 M frames/s (1.99 TB/s), packed 41.0 M (direct global loads end up exposed between the
 // window computations: long-scoreboard stalls x5), staged 63.7 M (2.09 TB/s, r01H); team (r02:
-// 64 threads per frame, radix-64 x 64, he8192t.cuh) 72.7 M (2.38 TB/s), and 73.5 M against 58.1 M
+// 64 threads per frame, radix-64 x 64, he8192t.cuh) 83.8 M (2.75 TB/s), and 81 M against 58 M
 // frames/s on 32 768 clips of 44 100 samples (6 frames per clip, the last one ragged).
 static const char* const kHe8192Default = "team";
 constexpr int k8RowB = 18;  // padded row (float2) of the second exchange: aligned 128-bit reads
@@ -1186,7 +1186,7 @@ __global__ void __launch_bounds__(k8Threads, 2) he8192p_kernel(const HeArgs a) {
 
 // frame_size 8192, third generation (he8192t.cuh): a team of 64 threads per frame.
 constexpr int kTeamRounds = 6;  // epilogue rounds of the fast path (8 windows each: 48 windows)
-__global__ void __launch_bounds__(h8t::kThreads) he8192t_kernel(const HeArgs a) {
+__global__ void __launch_bounds__(h8t::kThreads, 6) he8192t_kernel(const HeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);                           // [64][66] transpose; later Z[4096]
   double* wv = reinterpret_cast<double*>(buf + h8t::kBuf);           // [n_windows]
