@@ -93,20 +93,25 @@ def test_he_fast_and_generic_kernels_agree(monkeypatch, frame_size, hop, fs):
     a = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
     monkeypatch.setenv("CDB_HE_FORCE_GENERIC", "1")
     b = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
-    _assert_close(a.total.cpu().numpy(), b.total.cpu().numpy(), tol=1e-5)
+    # (two fp32 FFTs of different structure: radix-2 in shared memory vs radix-32 / radix-64 in
+    # registers; the parity bar against the oracle is 1e-4 and is tested separately)
+    _assert_close(a.total.cpu().numpy(), b.total.cpu().numpy(), tol=1e-5 if frame_size == 2048 else 5e-5)
     _assert_close(a.frames.cpu().numpy(), b.frames.cpu().numpy(), tol=1e-4)
     if frame_size == 8192:
         # the frame-8192 kernels: scalar butterflies / packed butterflies / packed + the next frame
         # staged by bulk async copy / 64-thread teams with radix-64 x 64 register FFTs (ragged and
         # unaligned frames are read directly: hop 1001 and the clip tail exercise that path)
         monkeypatch.delenv("CDB_HE_FORCE_GENERIC")
+        res = {}
         for mode in ("scalar", "packed", "staged", "team"):
             monkeypatch.setenv("CDB_HE8192", mode)
-            c = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True)
-            # (the radix-16^3 kernels share one butterfly structure; the radix-64^2 team kernel
-            # rounds differently, like the generic kernel above)
-            _assert_close(a.frames.cpu().numpy(), c.frames.cpu().numpy(),
-                          tol=1e-4 if mode == "team" else 1e-5)
+            res[mode] = _he(x, fs, frame_size=frame_size, hop=hop, per_frame=True).frames.cpu().numpy()
+        # the radix-16^3 kernels share one butterfly structure; the radix-64^2 team kernel (the
+        # default) rounds differently, like the generic kernel above
+        for mode in ("scalar", "packed"):
+            _assert_close(res[mode], res["staged"], tol=1e-5)
+        _assert_close(res["team"], res["staged"], tol=1e-4)
+        assert np.array_equal(res["team"], a.frames.cpu().numpy())  # team is the default
         monkeypatch.delenv("CDB_HE8192")
         xo = np.concatenate([np.zeros(1, dtype=np.float32), x])  # 4-byte-aligned view
         xd = torch.from_numpy(xo).to(_dev())[1:]
