@@ -51,6 +51,18 @@ def _worker(rank, world, port, n, ret):
         solo = D.harmonic_energy_sharded(xl, fs, 0 if empty else f1 - f0, 2048, hop=512, fused=False)
         assert torch.allclose(t3, solo, rtol=1e-12, atol=0)
         assert nat.Handle.get(dev.index).comm_status() == 0
+        # the end-to-end pipeline (pinned host buffer -> chunked H2D -> kernel) rides the exchange in
+        # its LAST chunk (ACCUMULATE | ALLREDUCE): every rank gets the sum over the ranks' signals
+        from chord_detection_b200 import ops
+
+        xr, _ = cases.make_input(dict(fn="s_poly_long", seed=30 + rank, fs=44100, n=1500 * 512 + 11))
+        host = torch.from_numpy(xr).pin_memory()
+        pipe = ops.HostPipeline(dev, fs, 2048, hop=512, chunk_frames=400)
+        local = torch.from_numpy(pipe.run(host)).to(dev)
+        if world > 1:
+            dist.all_reduce(local)
+        fused = pipe.run(host, allreduce=True)
+        assert np.allclose(fused, local.cpu().numpy(), rtol=1e-12, atol=0)
     clips = np.stack([cases.make_input(dict(fn="s_poly", seed=60 + i, fs=22050, n=9000))[0] for i in range(6)])
     c0, c1 = D.shard_range(6, rank, world)
     sums, _ = D.all_methods_sharded(torch.from_numpy(clips[c0:c1]).to(dev), 22050, methods=(2, 4))
