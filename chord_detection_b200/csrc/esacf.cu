@@ -33,6 +33,7 @@
 #include "acf_fft.cuh"
 #include "common.cuh"
 #include "lm_gauss.cuh"
+#include "lm_normal.cuh"
 #include "peaks.cuh"
 
 struct EsacfPlan {
@@ -547,6 +548,81 @@ __global__ void __launch_bounds__(kStreamThreads) esacf_fit_stream_kernel(const 
   }
 }
 
+// Fit kernel, third design (lm_normal.cuh): every fit lives in registers, the Jacobian is folded
+// into the 3 x 3 normal equations as its rows are produced, and the only shared memory is the
+// lane-interleaved copy of the <= 21 samples (168 B per fit instead of 1 176 B), so an SM holds
+// kNormalThreads fits instead of 192.  Same task queue and lock-step rounds as esacf_fit_kernel.
+constexpr int kNormalThreads = 512;
+template <bool XI>
+__global__ void __launch_bounds__(kNormalThreads, 1) esacf_fit_normal_kernel(const EsacfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* ysm = reinterpret_cast<double*>(smem) + (size_t)warp * (lmg::MMAX * 32) + lane;  // [sample][lane]
+  const int L = a.L;
+  const int half = L / 2 + 2;
+  const size_t pad_l = ((size_t)L + 7) & ~(size_t)7, pad_h = ((size_t)half * 2 + 7) & ~(size_t)7;
+  const size_t per_frame = pad_l + 2 * pad_h;
+  const int n_suspect = a.ws_counters[0];
+  const int total = n_suspect + a.ws_counters[4];
+  using Lm = lmg::LmNormal<32, false, XI>;
+  lmg::Problem pr;
+  pr.y = ysm;
+  pr.m = 0;
+  pr.x0 = 0.0;
+  Lm sm;
+  int task = atomicAdd(&a.ws_counters[1], 1);
+  int64_t res_at = 0;
+  bool need_init = true;
+  while (__any_sync(0xffffffffu, task < total)) {
+    if (task < total) {
+      bool fitting = true;
+      if (need_init) {
+        need_init = false;
+        const int tcode = task < n_suspect ? a.ws_tasks[task]
+                                           : a.ws_tasks[a.task_cap - 1 - (task - n_suspect)];
+        const int fb = tcode >> 11, pi = tcode & 2047;
+        res_at = (int64_t)fb * half + pi;
+        const int16_t* cand = reinterpret_cast<const int16_t*>(a.ws_scratch + per_frame * (size_t)fb + pad_l);
+        const int idx = cand[pi];
+        const int lo = idx - 10, hi = min(idx + 11, L);  // slice(i-10, i+11), peakutils width 10
+        if (a.skip_fit || lo < 0 || hi - lo < 3) {
+          fitting = false;  // empty slice -> RuntimeError in peakutils -> peak dropped
+          a.ws_res[res_at] = NAN;
+        } else {
+          const double* yg = a.ws_y + (int64_t)fb * L + lo;
+          pr.m = hi - lo;
+          pr.x0 = (double)lo;
+          double ymax = __ldg(yg);
+          for (int i = 0; i < pr.m; ++i) {
+            const double v = __ldg(yg + i);
+            ysm[i * 32] = v;
+            ymax = fmax(ymax, v);
+          }
+          const double p0[3] = {ymax, (double)lo, 5.0};  // peakutils gaussian_fit start
+          sm.init(p0);
+          sm.begin(pr);
+        }
+      }
+      if (fitting && sm.phase == Lm::JAC) sm.jac_block(pr);
+      if (fitting && sm.phase == Lm::STEP) {
+        sm.step_block();
+        sm.trial_block(pr);
+      }
+      if (fitting && sm.phase == Lm::DONE) {
+        const bool ok = (sm.info >= 1 && sm.info <= 4) && isfinite(sm.p[0]) && isfinite(sm.p[1]) &&
+                        isfinite(sm.p[2]);
+        a.ws_res[res_at] = ok ? sm.p[1] : NAN;
+        fitting = false;
+      }
+      if (!fitting) {
+        task = atomicAdd(&a.ws_counters[1], 1);
+        need_init = true;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(64) esacf_bin_kernel(const EsacfArgs a) {
   __shared__ double cta_total[12];
   if (threadIdx.x < 12) cta_total[threadIdx.x] = 0.0;
@@ -652,6 +728,10 @@ int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* n
   const int info = suspend_after == -1   ? lmg::lmdif_stream<0>(pr, p, &nf)
                    : suspend_after == -4 ? lmg::lmdif_stream<4>(pr, p, &nf)
                    : suspend_after == -7 ? lmg::lmdif_stream<7>(pr, p, &nf)
+                   // -10 / -11: LmNormal (normal equations, lm_normal.cuh) with the generic
+                   // lmpar / qrsolv and with their register forms (bit-identical to each other)
+                   : suspend_after == -10 ? lmg::lmdif_normal<true>(pr, p, &nf)
+                   : suspend_after == -11 ? lmg::lmdif_normal<false>(pr, p, &nf)
                                          : lmg::lmdif(pr, p, &nf, suspend_after);
   p_out[0] = p[0];
   p_out[1] = p[1];
@@ -776,7 +856,15 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
 
   // large batches: the fit kernel ends with a latency-bound tail (one 800-evaluation fit takes
   // ~40 ms on its own), which is amortised over the batch
-  const int64_t Bmax = std::min<int64_t>(n_frames, 65536);
+  // (up to 262 144 frames = 14 GB of workspace at 44.1 kHz, never more than a third of the free memory)
+  int64_t Bmax = std::min<int64_t>(n_frames, 262144);
+  if (Bmax > 65536) {
+    size_t mem_free = 0, mem_total = 0;
+    CDB_CUDA(h, cudaMemGetInfo(&mem_free, &mem_total));
+    const size_t per_frame = (2 * (size_t)N + 2 * (size_t)L + (size_t)L / 2 + 2) * sizeof(double) + 4 * (size_t)L;
+    const int64_t fit = (int64_t)((mem_free + h->ws_bytes) / 3 / per_frame);
+    Bmax = std::max<int64_t>(65536, std::min<int64_t>(Bmax, fit / 4096 * 4096));
+  }
   const size_t half = (size_t)L / 2 + 2;
   const size_t scratch_pf = (peaks_scratch_bytes(L) + 15) & ~(size_t)15;
   const size_t long_cap = (size_t)Bmax * 4 + 4096;  // ~0.1 long fits per frame measured
@@ -870,19 +958,37 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     const char* pr = std::getenv("CDB_ESACF_PRIO");
     a.prioritise = (pr && pr[0] == '0') ? 0 : 1;
   }
-  // experimental register-resident fit kernel (see esacf_fit_stream_kernel)
-  void (*stream_kernel)(const EsacfArgs) = nullptr;
-  int stream_per_sm = 0;
-  if (const char* lm = std::getenv("CDB_ESACF_LM")) {
-    const std::string m = lm;
-    stream_kernel = m == "stream"    ? esacf_fit_stream_kernel<7>
-                    : m == "stream4" ? esacf_fit_stream_kernel<4>
-                    : m == "givens"  ? esacf_fit_stream_kernel<0>
-                                     : nullptr;
+  // fit kernel: the register-resident normal-equations kernel (esacf_fit_normal_kernel) unless
+  // CDB_ESACF_LM selects the stored-Jacobian kernel ("lmsm": esacf_fit_kernel, round 1 / 2 default)
+  // or one of the LmStream experiments
+  void (*stream_kernel)(const EsacfArgs) = esacf_fit_normal_kernel<true>;
+  std::string lm_mode = "normal";
+  if (const char* lm = std::getenv("CDB_ESACF_LM")) lm_mode = lm;
+  int stream_per_sm = 0, stream_threads = kStreamThreads;
+  size_t stream_smem = 0;
+  {
+    const std::string& m = lm_mode;
+    stream_kernel = m == "normal"     ? esacf_fit_normal_kernel<true>
+                    : m == "normal_x" ? esacf_fit_normal_kernel<false>
+                    : m == "stream"   ? esacf_fit_stream_kernel<7>
+                    : m == "stream4"  ? esacf_fit_stream_kernel<4>
+                    : m == "givens"   ? esacf_fit_stream_kernel<0>
+                                      : nullptr;
     if (stream_kernel) {
+      if (m == "normal" || m == "normal_x") {
+        stream_threads = kNormalThreads;
+        if (const char* fw = std::getenv("CDB_ESACF_FIT_WARPS"))
+          stream_threads = 32 * std::max(1, std::min(kNormalThreads / 32, std::atoi(fw)));
+        else if (h->opt_esacf_fit_warps > 0)  // cdb_set_option
+          stream_threads = 32 * std::min(kNormalThreads / 32, h->opt_esacf_fit_warps);
+        stream_smem = (size_t)(stream_threads / 32) * lmg::MMAX * 32 * sizeof(double);
+        CDB_CUDA(h, cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)stream_smem));
+      }
       CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&stream_per_sm, stream_kernel,
-                                                                kStreamThreads, 0));
-      if (stream_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "stream fit kernel does not fit");
+                                                                stream_threads, stream_smem));
+      if (stream_smem) stream_per_sm = std::min(stream_per_sm, 1);  // one persistent CTA per SM
+      if (stream_per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "fit kernel does not fit");
       a.evict_rounds = 0;
     }
   }
@@ -919,7 +1025,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
     esacf_pick_kernel<<<(B + 31) / 32, 32, 0, st>>>(a);
     cdb_mark(h, st, "esacf_pick_kernel");
     if (stream_kernel) {
-      stream_kernel<<<h->num_sms * stream_per_sm, kStreamThreads, 0, st>>>(a);
+      stream_kernel<<<h->num_sms * stream_per_sm, stream_threads, stream_smem, st>>>(a);
     } else {
       fit_kernel<<<h->num_sms * fit_per_sm, fit_threads, fit_smem, st>>>(a, 0);
       if (a.evict_rounds > 0)

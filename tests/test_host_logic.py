@@ -282,6 +282,39 @@ def test_host_streaming_lm_matches_scipy_curve_fit(variant):
     assert same_nfev >= 0.98 * n
 
 
+def test_host_normal_lm_matches_scipy_curve_fit():
+    """lmg::LmNormal (csrc/lm_normal.cuh, the device default since round 2: Jacobian rows folded into
+    the 3 x 3 normal equations, pivoted Cholesky instead of qrfac, no per-fit arrays) has SciPy's
+    success / failure pattern, centres and evaluation counts; its register-form lmpar / qrsolv (-11)
+    are bit-identical to the generic ones of lm_gauss.cuh (-10)."""
+    n, worst, same_nfev = 0, 0.0, 0
+    for d in _esacf_frames():
+        y = d["esacf"]
+        for i in d["peaks"]:
+            i = int(i)
+            lo, hi = i - 10, min(i + 11, len(y))
+            if lo < 0:
+                continue
+            info, p, nfev = nat.host_gauss_fit(lo, y[lo:hi], suspend_after=-11)
+            assert (info, p, nfev) == nat.host_gauss_fit(lo, y[lo:hi], suspend_after=-10)
+            log = []
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ref = tp.gaussian_fit(np.arange(lo, hi), y[lo:hi], _log=log)
+                ok_ref = True
+            except Exception:
+                ok_ref = False
+            assert (1 <= info <= 4) == ok_ref
+            if ok_ref:
+                worst = max(worst, abs(p[1] - ref) / abs(ref))
+                same_nfev += int(log[0] == nfev)
+                n += 1
+    assert n > 200
+    assert worst < 5e-5
+    assert same_nfev >= 0.98 * n
+
+
 def test_audio_load_host_path(tmp_path):
     """audio.load (the host twin of audio.load_device): decode, float32 mean over channels,
     resample_poly to 22 050 Hz; read_wav keeps 16-bit PCM as stored."""
