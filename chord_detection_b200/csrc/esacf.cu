@@ -553,7 +553,6 @@ __global__ void __launch_bounds__(kStreamThreads) esacf_fit_stream_kernel(const 
 // lane-interleaved copy of the <= 21 samples (168 B per fit instead of 1 176 B), so an SM holds
 // kNormalThreads fits instead of 192.  Same task queue and lock-step rounds as esacf_fit_kernel.
 constexpr int kNormalThreads = 512;
-template <bool XI>
 __global__ void __launch_bounds__(kNormalThreads, 1) esacf_fit_normal_kernel(const EsacfArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -564,7 +563,7 @@ __global__ void __launch_bounds__(kNormalThreads, 1) esacf_fit_normal_kernel(con
   const size_t per_frame = pad_l + 2 * pad_h;
   const int n_suspect = a.ws_counters[0];
   const int total = n_suspect + a.ws_counters[4];
-  using Lm = lmg::LmNormal<32, false, XI>;
+  using Lm = lmg::LmNormal<32, 0>;
   lmg::Problem pr;
   pr.y = ysm;
   pr.m = 0;
@@ -728,10 +727,10 @@ int cdb_host_gauss_fit2(int m, double x0, const double* y, double* p_out, int* n
   const int info = suspend_after == -1   ? lmg::lmdif_stream<0>(pr, p, &nf)
                    : suspend_after == -4 ? lmg::lmdif_stream<4>(pr, p, &nf)
                    : suspend_after == -7 ? lmg::lmdif_stream<7>(pr, p, &nf)
-                   // -10 / -11: LmNormal (normal equations, lm_normal.cuh) with the generic
-                   // lmpar / qrsolv and with their register forms (bit-identical to each other)
-                   : suspend_after == -10 ? lmg::lmdif_normal<true>(pr, p, &nf)
-                   : suspend_after == -11 ? lmg::lmdif_normal<false>(pr, p, &nf)
+                   // -10 / -11: LmNormal (normal equations, lm_normal.cuh) with MINPACK's lmpar /
+                   // qrsolv and with the Cholesky form of the trust-region search (the device kernel)
+                   : suspend_after == -10 ? lmg::lmdif_normal<1>(pr, p, &nf)
+                   : suspend_after == -11 ? lmg::lmdif_normal<0>(pr, p, &nf)
                                          : lmg::lmdif(pr, p, &nf, suspend_after);
   p_out[0] = p[0];
   p_out[1] = p[1];
@@ -961,21 +960,20 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
   // fit kernel: the register-resident normal-equations kernel (esacf_fit_normal_kernel) unless
   // CDB_ESACF_LM selects the stored-Jacobian kernel ("lmsm": esacf_fit_kernel, round 1 / 2 default)
   // or one of the LmStream experiments
-  void (*stream_kernel)(const EsacfArgs) = esacf_fit_normal_kernel<true>;
+  void (*stream_kernel)(const EsacfArgs) = esacf_fit_normal_kernel;
   std::string lm_mode = "normal";
   if (const char* lm = std::getenv("CDB_ESACF_LM")) lm_mode = lm;
   int stream_per_sm = 0, stream_threads = kStreamThreads;
   size_t stream_smem = 0;
   {
     const std::string& m = lm_mode;
-    stream_kernel = m == "normal"     ? esacf_fit_normal_kernel<true>
-                    : m == "normal_x" ? esacf_fit_normal_kernel<false>
+    stream_kernel = m == "normal"     ? esacf_fit_normal_kernel
                     : m == "stream"   ? esacf_fit_stream_kernel<7>
                     : m == "stream4"  ? esacf_fit_stream_kernel<4>
                     : m == "givens"   ? esacf_fit_stream_kernel<0>
                                       : nullptr;
     if (stream_kernel) {
-      if (m == "normal" || m == "normal_x") {
+      if (m == "normal") {
         stream_threads = kNormalThreads;
         if (const char* fw = std::getenv("CDB_ESACF_FIT_WARPS"))
           stream_threads = 32 * std::max(1, std::min(kNormalThreads / 32, std::atoi(fw)));

@@ -17,6 +17,11 @@
 //   no residual vector, no work area; the samples y are the only array that is read.
 //   Cost per Jacobian: 12 exp + 21 x ~30 FP64 instructions (LmSM: 12 exp + ~3 500 with their
 //   shared-memory loads and stores).
+// The trust-region parameter search (MINPACK lmpar) is restated on the same 3 x 3 matrices: instead
+// of qrsolv's Givens elimination of sqrt(par) D below R, each iterate factors A = R^T R + par D^2
+// by an (unpivoted) Cholesky with reciprocal square roots and solves with its factor S -- the same S
+// (S^T S = A), the same Newton iteration on ||D x(par)|| - delta, ~100 instructions per iterate
+// instead of ~500.  MODE 1 keeps MINPACK's own lmpar / qrsolv (lm_gauss.cuh) for comparison.
 // Rounding: forming G squares the condition number of J.  For fits that converge inside their data
 // window cond(J D^-1) is 10..1e3 and R is accurate to 1e-10 or better, far inside what xtol =
 // 1.49e-8 leaves undetermined anyway; for runaway fits (centre tens of samples outside the window:
@@ -29,16 +34,19 @@
 
 namespace lmg {
 
+struct Exp4 {
+  double a, b, c, d;
+};
+
 #ifdef __CUDA_ARCH__
 #define LMN_UNROLL _Pragma("unroll")
 #define LMN_ROWLOOP _Pragma("unroll 2")
 // Division and square root as straight-line code (ncu r02x: with the out-of-line IEEE helpers of
-// lm_gauss.cuh half of all stall samples of this kernel sat in their call / range-check branches,
-// and independent quotients could not overlap).  MUFU seed, two Newton steps, one residual
-// correction: correctly rounded for operands in the normal range except for rare 1-ulp cases;
-// zero / infinite operands give the IEEE result through selects; subnormal divisors behave like
-// zero and results that would be subnormal flush to zero (only fits that have long left their data
-// window ever see such values).
+// lm_gauss.cuh half of all stall samples sat in their call / range-check branches and independent
+// quotients could not overlap).  MUFU seed, two Newton steps, one residual correction: correctly
+// rounded for operands in the normal range except for rare 1-ulp cases; zero / infinite operands
+// give the IEEE result through selects; subnormal divisors behave like zero and results that
+// would be subnormal flush to zero (only fits that have long left their data window see those).
 __device__ __forceinline__ double ndiv(double a, double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
@@ -51,7 +59,8 @@ __device__ __forceinline__ double ndiv(double a, double b) {
   const double q1 = fma(fma(-b, q0, a), r, q0);
   return (fabs(q1) <= 1.7976931348623157e308) ? q1 : q0s;  // (NaN -> q0s)
 }
-__device__ __forceinline__ double nsqrt(double x) {
+// root = sqrt(x), half_inv = 0.5 / sqrt(x) (Goldschmidt: both come out of the same iteration)
+__device__ __forceinline__ void sqrt_pair(double x, double& root, double& half_inv) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y, hh = 0.5 * y;
@@ -62,23 +71,44 @@ __device__ __forceinline__ double nsqrt(double x) {
   g = fma(g, r, g);
   hh = fma(hh, r, hh);
   g = fma(fma(-g, g, x), hh, g);
-  return (x == 0.0 || x == 1.0 / 0.0) ? x : g;  // (negative / NaN: the seed is NaN already)
+  const bool edge = x == 0.0 || x == 1.0 / 0.0;  // (negative / NaN: the seed is NaN already)
+  root = edge ? x : g;
+  half_inv = edge ? 0.5 * y : hh;  // inf for 0, 0 for inf
 }
-template <bool XI>
-__device__ __forceinline__ double dexp(double a);
-template <>
-__device__ __forceinline__ double dexp<true>(double a) { return exp(a); }
-__device__ __noinline__ double dexp_call(double a) { return exp(a); }
-template <>
-__device__ __forceinline__ double dexp<false>(double a) { return dexp_call(a); }
+// four independent exponentials in one out-of-line body (exp() is ~45 FP64 instructions inline and
+// the fit needs 16 per round: inlined at every site they made the kernel 69 KB, twice the 32 KB
+// mid-level instruction cache, and 37 % of all stall samples were instruction fetches, ncu r02y)
+__device__ __noinline__ Exp4 exp4(double a, double b, double c, double d) {
+  Exp4 r;
+  r.a = exp(a);
+  r.b = exp(b);
+  r.c = exp(c);
+  r.d = exp(d);
+  return r;
+}
 #else
 #define LMN_UNROLL
 #define LMN_ROWLOOP
 inline double ndiv(double a, double b) { return a / b; }
-inline double nsqrt(double a) { return sqrt(a); }
-template <bool XI>
-inline double dexp(double a) { return exp(a); }
+inline void sqrt_pair(double x, double& root, double& half_inv) {
+  root = sqrt(x);
+  half_inv = 0.5 / root;
+}
+inline Exp4 exp4(double a, double b, double c, double d) {
+  Exp4 r;
+  r.a = exp(a);
+  r.b = exp(b);
+  r.c = exp(c);
+  r.d = exp(d);
+  return r;
+}
 #endif
+LMG_HD inline double nsqrt(double x) {
+  double g, hh;
+  sqrt_pair(x, g, hh);
+  return g;
+}
+LMG_HD inline double norm3(double a, double b, double c) { return nsqrt(a * a + b * b + c * c); }
 
 // v[idx] for idx in 0..2 with compile-time register indices (a dynamically indexed array would be
 // placed in local memory)
@@ -99,100 +129,38 @@ LMG_HD inline void put3(double* v, int idx, double x) {
 #endif
 }
 
-// qrsolv for n = 3, r column-major with leading dimension 3, every index a compile-time constant.
-// Same operations in the same order as lmg::qrsolv<1, 3>.
-#define LMN_R(i, j) r[(i) + 3 * (j)]
-LMG_HD inline void qrsolv3(double* r, const int* ipvt, const double* diag, const double* qtb,
-                           double* x, double* sdiag, double* wa) {
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) {
-    LMN_UNROLL
-    for (int i = j; i < NP; ++i) LMN_R(i, j) = LMN_R(j, i);
-    x[j] = LMN_R(j, j);
-    wa[j] = qtb[j];
-  }
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) {
-    const double dl = get3(diag, ipvt[j]);
-    if (dl != 0.0) {
-      LMN_UNROLL
-      for (int k = j; k < NP; ++k) sdiag[k] = 0.0;
-      sdiag[j] = dl;
-      double qtbpj = 0.0;
-      LMN_UNROLL
-      for (int k = j; k < NP; ++k) {
-        if (sdiag[k] == 0.0) continue;
-        double c, s;
-        if (fabs(LMN_R(k, k)) < fabs(sdiag[k])) {
-          const double cotan = ndiv(LMN_R(k, k), sdiag[k]);
-          s = ndiv(0.5, nsqrt(0.25 + 0.25 * (cotan * cotan)));
-          c = s * cotan;
-        } else {
-          const double tn = ndiv(sdiag[k], LMN_R(k, k));
-          c = ndiv(0.5, nsqrt(0.25 + 0.25 * (tn * tn)));
-          s = c * tn;
-        }
-        LMN_R(k, k) = c * LMN_R(k, k) + s * sdiag[k];
-        const double temp = c * wa[k] + s * qtbpj;
-        qtbpj = -s * wa[k] + c * qtbpj;
-        wa[k] = temp;
-        LMN_UNROLL
-        for (int i = k + 1; i < NP; ++i) {
-          const double t = c * LMN_R(i, k) + s * sdiag[i];
-          sdiag[i] = -s * LMN_R(i, k) + c * sdiag[i];
-          LMN_R(i, k) = t;
-        }
-      }
-    }
-    sdiag[j] = LMN_R(j, j);
-    LMN_R(j, j) = x[j];
-  }
-  int nsing = NP;
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) {
-    if (sdiag[j] == 0.0 && nsing == NP) nsing = j;
-    if (nsing < NP) wa[j] = 0.0;
-  }
-  LMN_UNROLL
-  for (int j = NP - 1; j >= 0; --j) {  // j = nsing-1 .. 0
-    if (j < nsing) {
-      double sum = 0.0;
-      LMN_UNROLL
-      for (int i = j + 1; i < NP; ++i)
-        if (i < nsing) sum += LMN_R(i, j) * wa[i];
-      wa[j] = ndiv(wa[j] - sum, sdiag[j]);
-    }
-  }
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) put3(x, ipvt[j], wa[j]);
-}
+// The 3 x 3 upper triangle R of the pivoted factorisation (J P = Q R)
+struct Tri3 {
+  double r00, r01, r02, r11, r12, r22;
+};
 
-// lmpar for n = 3 (same operations in the same order as lmg::lmpar<1, 3>)
-LMG_HD inline void lmpar3(double* r, const int* ipvt, const double* diag, const double* qtb,
-                          double delta, double* par, double* x, double* sdiag, double* wa1,
-                          double* wa2) {
-  int nsing = NP;
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) {
-    wa1[j] = qtb[j];
-    if (LMN_R(j, j) == 0.0 && nsing == NP) nsing = j;
-    if (nsing < NP) wa1[j] = 0.0;
+// MINPACK lmpar for n = 3, working in the PIVOTED coordinates throughout:
+//   R, qtb as lmdif has them; dp[j] = diag[ipvt[j]]; z = P^T x (the caller scatters it).
+// Same sequence of decisions as lmpar (Gauss-Newton step first; bounds parl / paru; at most 10
+// Newton iterates on phi(par) = ||D x(par)|| - delta, accepted within 10 %); x(par) and the Newton
+// correction come from the Cholesky factor S of A = R^T R + par D^2, which is the matrix qrsolv
+// produces by rotations (S^T S = A; its diagonal is bounded below by sqrt(par) dp[j], which is used
+// as a floor against cancellation).  Norms are summed in pivoted order.
+LMG_HD inline void lmpar_chol(const Tri3& R, const double* dp, const double* qtb, double delta,
+                              double* par, double* z) {
+  const int nsing = R.r00 == 0.0 ? 0 : (R.r11 == 0.0 ? 1 : (R.r22 == 0.0 ? 2 : 3));
+  // Gauss-Newton direction (column-oriented back substitution, components >= nsing are zero)
+  double w0 = nsing > 0 ? qtb[0] : 0.0, w1 = nsing > 1 ? qtb[1] : 0.0, w2 = nsing > 2 ? qtb[2] : 0.0;
+  if (nsing > 2) {
+    w2 = ndiv(w2, R.r22);
+    w0 -= R.r02 * w2;
+    w1 -= R.r12 * w2;
   }
-  LMN_UNROLL
-  for (int j = NP - 1; j >= 0; --j) {
-    if (j < nsing) {
-      wa1[j] = ndiv(wa1[j], LMN_R(j, j));
-      const double temp = wa1[j];
-      LMN_UNROLL
-      for (int i = 0; i < j; ++i) wa1[i] -= LMN_R(i, j) * temp;
-    }
+  if (nsing > 1) {
+    w1 = ndiv(w1, R.r11);
+    w0 -= R.r01 * w1;
   }
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) put3(x, ipvt[j], wa1[j]);
-  int iter = 0;
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
-  double dxnorm = nsqrt(wa2[0] * wa2[0] + wa2[1] * wa2[1] + wa2[2] * wa2[2]);
+  if (nsing > 0) w0 = ndiv(w0, R.r00);
+  z[0] = w0;
+  z[1] = w1;
+  z[2] = w2;
+  double d0 = dp[0] * z[0], d1 = dp[1] * z[1], d2 = dp[2] * z[2];
+  double dxnorm = norm3(d0, d1, d2);
   double fp = dxnorm - delta;
   if (fp <= 0.1 * delta) {
     *par = 0.0;
@@ -200,67 +168,71 @@ LMG_HD inline void lmpar3(double* r, const int* ipvt, const double* diag, const 
   }
   double parl = 0.0;
   if (nsing >= NP) {
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) {
-      const int l = ipvt[j];
-      wa1[j] = get3(diag, l) * ndiv(get3(wa2, l), dxnorm);
-    }
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) {
-      double sum = 0.0;
-      LMN_UNROLL
-      for (int i = 0; i < j; ++i) sum += LMN_R(i, j) * wa1[i];
-      wa1[j] = ndiv(wa1[j] - sum, LMN_R(j, j));
-    }
-    const double temp = nsqrt(wa1[0] * wa1[0] + wa1[1] * wa1[1] + wa1[2] * wa1[2]);
-    parl = ndiv(ndiv(ndiv(fp, delta), temp), temp);
+    const double rdx = ndiv(1.0, dxnorm);
+    double v0 = dp[0] * (d0 * rdx), v1 = dp[1] * (d1 * rdx), v2 = dp[2] * (d2 * rdx);
+    v0 = ndiv(v0, R.r00);
+    v1 = ndiv(v1 - R.r01 * v0, R.r11);
+    v2 = ndiv(v2 - (R.r02 * v0 + R.r12 * v1), R.r22);
+    const double t2 = v0 * v0 + v1 * v1 + v2 * v2;
+    parl = ndiv(ndiv(fp, delta), t2);
   }
-  LMN_UNROLL
-  for (int j = 0; j < NP; ++j) {
-    double sum = 0.0;
-    LMN_UNROLL
-    for (int i = 0; i <= j; ++i) sum += LMN_R(i, j) * qtb[i];
-    wa1[j] = ndiv(sum, get3(diag, ipvt[j]));
-  }
-  const double gnorm = nsqrt(wa1[0] * wa1[0] + wa1[1] * wa1[1] + wa1[2] * wa1[2]);
+  // b = R^T qtb = P^T J^T f; scaled gradient norm -> upper bound
+  const double b0 = R.r00 * qtb[0];
+  const double b1 = R.r01 * qtb[0] + R.r11 * qtb[1];
+  const double b2 = R.r02 * qtb[0] + R.r12 * qtb[1] + R.r22 * qtb[2];
+  const double gnorm = norm3(ndiv(b0, dp[0]), ndiv(b1, dp[1]), ndiv(b2, dp[2]));
   double paru = ndiv(gnorm, delta);
   if (paru == 0.0) paru = ndiv(DWARF, fmin(delta, 0.1));
   *par = fmax(*par, parl);
   *par = fmin(*par, paru);
   if (*par == 0.0) *par = ndiv(gnorm, dxnorm);
+  // R^T R
+  const double g00 = R.r00 * R.r00, g01 = R.r00 * R.r01, g02 = R.r00 * R.r02;
+  const double g11 = fma(R.r01, R.r01, R.r11 * R.r11), g12 = fma(R.r01, R.r02, R.r11 * R.r12);
+  const double g22 = fma(R.r02, R.r02, fma(R.r12, R.r12, R.r22 * R.r22));
+  const double e0 = dp[0] * dp[0], e1 = dp[1] * dp[1], e2 = dp[2] * dp[2];
+  const double rdelta = ndiv(1.0, delta);
+  int iter = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
   for (;;) {
     ++iter;
     if (*par == 0.0) *par = fmax(DWARF, 0.001 * paru);
-    double temp = nsqrt(*par);
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) wa1[j] = temp * diag[j];
-    qrsolv3(r, ipvt, wa1, qtb, x, sdiag, wa2);
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) wa2[j] = diag[j] * x[j];
-    dxnorm = nsqrt(wa2[0] * wa2[0] + wa2[1] * wa2[1] + wa2[2] * wa2[2]);
-    temp = fp;
+    const double pr = *par;
+    // S^T S = R^T R + par D^2
+    double s00, i0, s11, i1, s22, i2;
+    sqrt_pair(fma(pr, e0, g00), s00, i0);
+    i0 += i0;
+    const double s01 = g01 * i0, s02 = g02 * i0;
+    sqrt_pair(fmax(fma(-s01, s01, fma(pr, e1, g11)), pr * e1), s11, i1);
+    i1 += i1;
+    const double s12 = fma(-s01, s02, g12) * i1;
+    sqrt_pair(fmax(fma(-s12, s12, fma(-s02, s02, fma(pr, e2, g22))), pr * e2), s22, i2);
+    i2 += i2;
+    // S^T t = b, S z = t
+    const double t0 = b0 * i0;
+    const double t1 = fma(-s01, t0, b1) * i1;
+    const double t2 = fma(-s12, t1, fma(-s02, t0, b2)) * i2;
+    z[2] = t2 * i2;
+    z[1] = fma(-s12, z[2], t1) * i1;
+    z[0] = fma(-s02, z[2], fma(-s01, z[1], t0)) * i0;
+    d0 = dp[0] * z[0];
+    d1 = dp[1] * z[1];
+    d2 = dp[2] * z[2];
+    dxnorm = norm3(d0, d1, d2);
+    const double temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) {
-      const int l = ipvt[j];
-      wa1[j] = get3(diag, l) * ndiv(get3(wa2, l), dxnorm);
-    }
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) {
-      wa1[j] = ndiv(wa1[j], sdiag[j]);
-      const double t = wa1[j];
-      LMN_UNROLL
-      for (int i = j + 1; i < NP; ++i) wa1[i] -= LMN_R(i, j) * t;
-    }
-    temp = nsqrt(wa1[0] * wa1[0] + wa1[1] * wa1[1] + wa1[2] * wa1[2]);
-    const double parc = ndiv(ndiv(ndiv(fp, delta), temp), temp);
-    if (fp > 0.0) parl = fmax(parl, *par);
-    if (fp < 0.0) paru = fmin(paru, *par);
-    *par = fmax(parl, *par + parc);
+    // Newton correction: || S^-T D^2 z / ||D z|| ||^2
+    const double rdx = ndiv(1.0, dxnorm);
+    const double v0 = (dp[0] * (d0 * rdx)) * i0;
+    const double v1 = fma(-s01, v0, dp[1] * (d1 * rdx)) * i1;
+    const double v2 = fma(-s12, v1, fma(-s02, v0, dp[2] * (d2 * rdx))) * i2;
+    const double parc = ndiv(fp * rdelta, v0 * v0 + v1 * v1 + v2 * v2);
+    if (fp > 0.0) parl = fmax(parl, pr);
+    if (fp < 0.0) paru = fmin(paru, pr);
+    *par = fmax(parl, pr + parc);
   }
 }
 
@@ -268,19 +240,19 @@ LMG_HD inline void lmpar3(double* r, const int* ipvt, const double* diag, const 
 // (lmg::residuals' recurrence): e = value at the current sample
 struct GaussWalk {
   double e = 0.0, r = 0.0, q = 0.0, e0 = 0.0, rdn = 0.0;
-  // ninv = -1 / (2 dev^2 + eps), q2 = exp(2 ninv) (shared by the walks that have the same dev).
-  // Returns the unit-amplitude value at i0 (so that a second amplitude can share the exponentials)
   LMG_HD static double neg_inv(double dev) { return ndiv(-1.0, 2.0 * dev * dev + EPSMCH); }
-  template <bool XI>
-  LMG_HD double init(double ampl, double d0c, double ic, double ninv, double q2) {
+  // ninv = -1 / (2 dev^2 + eps); extra: one more exponent evaluated in the same exp4 call.
+  // Returns (unit-amplitude value at i0, exp(extra)).
+  LMG_HD void init(double ampl, double d0c, double ic, double ninv, double extra, double* u_out,
+                   double* extra_out) {
     const double dc = d0c + ic;
-    const double u = dexp<XI>((dc * dc) * ninv);
-    e0 = ampl * u;
-    q = q2;
-    r = dexp<XI>(ninv * (2.0 * dc + 1.0));
-    rdn = dexp<XI>(ninv * (1.0 - 2.0 * dc));
+    const Exp4 x = exp4((dc * dc) * ninv, ninv * (2.0 * dc + 1.0), ninv * (1.0 - 2.0 * dc), extra);
+    e0 = ampl * x.a;
+    r = x.b;
+    rdn = x.c;
     e = e0;
-    return u;
+    *u_out = x.a;
+    *extra_out = x.d;
   }
   LMG_HD void turn_down() {
     e = e0;
@@ -292,14 +264,16 @@ struct GaussWalk {
   }
 };
 
-// GENERIC = true: lmpar / qrsolv of lm_gauss.cuh (dynamically indexed 3-vectors; the host
-// cross-check of the register forms above); false: lmpar3 / qrsolv3.  ST: element stride of pr.y.
-// XI: exp() expanded in line (its independent calls overlap) or called out of line (smaller code).
-template <int ST = 1, bool GENERIC = false, bool XI = true>
+// MODE 0: lmpar_chol; MODE 1: MINPACK's lmpar / qrsolv (lm_gauss.cuh) on the same R (host
+// comparison).  ST: element stride of pr.y.
+template <int ST = 1, int MODE = 0>
 struct LmNormal {
   enum { JAC = 1, STEP = 2, DONE = 5 };
-  double p[NP], diag[NP], qtf[NP], wa1[NP], wa2[NP], wa3[NP], wq[NP];
-  double a[NP * NP];  // R factor, element (i, j) at a[i + 3 j]
+  double p[NP], diag[NP], qtf[NP];
+  double wa1[NP];  // the step (negated solution of the trust-region problem)
+  double wa2[NP];  // trial point
+  double zp[NP];   // the step in pivoted order
+  Tri3 R;
   int ipvt[NP];
   double par, delta, xnorm, fnorm, gnorm, pnorm;
   int iter, nfev, info, phase;
@@ -319,7 +293,8 @@ struct LmNormal {
     GaussWalk g;
     {
       const double ninv = GaussWalk::neg_inv(q[2]);
-      g.template init<XI>(q[0], pr.x0 - q[1], ic, ninv, dexp<XI>(2.0 * ninv));
+      double u;
+      g.init(q[0], pr.x0 - q[1], ic, ninv, 2.0 * ninv, &u, &g.q);
     }
     double f = g.e - pr.y[i0 * ST];
     double ss = f * f;
@@ -369,12 +344,15 @@ struct LmNormal {
     GaussWalk g0, gc, gs;
     double ea;  // the model with amplitude p[0] + h[0]: same exponentials as g0
     {
-      const double ninv = GaussWalk::neg_inv(p[2]), q2 = dexp<XI>(2.0 * ninv);
-      const double u = g0.template init<XI>(p[0], pr.x0 - p[1], ic, ninv, q2);
-      ea = (p[0] + h[0]) * u;
-      gc.template init<XI>(p[0], pr.x0 - (p[1] + h[1]), ic, ninv, q2);  // (same dev: same ninv, q2)
+      const double ninv = GaussWalk::neg_inv(p[2]);
       const double ninvs = GaussWalk::neg_inv(p[2] + h[2]);
-      gs.template init<XI>(p[0], pr.x0 - p[1], ic, ninvs, dexp<XI>(2.0 * ninvs));
+      double u, uc, us, q2, q2s, dummy;
+      g0.init(p[0], pr.x0 - p[1], ic, ninv, 2.0 * ninv, &u, &q2);
+      gc.init(p[0], pr.x0 - (p[1] + h[1]), ic, ninv, 2.0 * ninvs, &uc, &q2s);  // (same dev as g0)
+      gs.init(p[0], pr.x0 - p[1], ic, ninvs, 0.0, &us, &dummy);
+      g0.q = gc.q = q2;
+      gs.q = q2s;
+      ea = (p[0] + h[0]) * u;
     }
     const double ea0 = ea;
     double G00 = 0.0, G01 = 0.0, G02 = 0.0, G11 = 0.0, G12 = 0.0, G22 = 0.0;
@@ -415,9 +393,10 @@ struct LmNormal {
     nfev += NP;
 
     // column norms of J (qrfac's acnorm) and the pivoted Cholesky factor of G
-    wa2[0] = nsqrt(G00);
-    wa2[1] = nsqrt(G11);
-    wa2[2] = nsqrt(G22);
+    double acn[NP];
+    acn[0] = nsqrt(G00);
+    acn[1] = nsqrt(G11);
+    acn[2] = nsqrt(G22);
     int i0p = 0, i1p = 1, i2p = 2;
     double s00 = G00, s01 = G01, s02 = G02, s11 = G11, s12 = G12, s22 = G22;
     double b0 = g[0], b1 = g[1], b2 = g[2];
@@ -438,10 +417,11 @@ struct LmNormal {
         int ti = i0p; i0p = i2p; i2p = ti;
       }
     }
-    double r00 = nsqrt(s00), r01 = 0.0, r02 = 0.0, r11 = 0.0, r12 = 0.0, r22 = 0.0;
+    double r00, r01 = 0.0, r02 = 0.0, r11, r12 = 0.0, r22, inv;
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    sqrt_pair(s00, r00, inv);
     if (r00 != 0.0) {
-      const double inv = ndiv(1.0, r00);
+      inv += inv;
       r01 = s01 * inv;
       r02 = s02 * inv;
       q0 = b0 * inv;
@@ -459,27 +439,26 @@ struct LmNormal {
       t = b1; b1 = b2; b2 = t;
       int ti = i1p; i1p = i2p; i2p = ti;
     }
-    r11 = nsqrt(s11);
+    sqrt_pair(s11, r11, inv);
     if (r11 != 0.0) {
-      const double inv = ndiv(1.0, r11);
+      inv += inv;
       r12 = s12 * inv;
       q1 = b1 * inv;
       s22 = fma(-r12, r12, s22);
       b2 = fma(-r12, q1, b2);
     }
     s22 = s22 > 0.0 ? s22 : 0.0;
-    r22 = nsqrt(s22);
-    if (r22 != 0.0) q2 = ndiv(b2, r22);
+    sqrt_pair(s22, r22, inv);
+    if (r22 != 0.0) q2 = b2 * (inv + inv);
     ipvt[0] = i0p;
     ipvt[1] = i1p;
     ipvt[2] = i2p;
-    a[0] = r00;
-    a[3] = r01;
-    a[6] = r02;
-    a[4] = r11;
-    a[7] = r12;
-    a[8] = r22;
-    a[1] = a[2] = a[5] = 0.0;
+    R.r00 = r00;
+    R.r01 = r01;
+    R.r02 = r02;
+    R.r11 = r11;
+    R.r12 = r12;
+    R.r22 = r22;
     qtf[0] = q0;
     qtf[1] = q1;
     qtf[2] = q2;
@@ -487,50 +466,54 @@ struct LmNormal {
     if (iter == 1) {
       LMN_UNROLL
       for (int j = 0; j < NP; ++j) {
-        diag[j] = wa2[j];
-        if (wa2[j] == 0.0) diag[j] = 1.0;
+        diag[j] = acn[j];
+        if (acn[j] == 0.0) diag[j] = 1.0;
       }
-      LMN_UNROLL
-      for (int j = 0; j < NP; ++j) wa3[j] = diag[j] * p[j];
-      xnorm = nsqrt(wa3[0] * wa3[0] + wa3[1] * wa3[1] + wa3[2] * wa3[2]);
+      xnorm = norm3(diag[0] * p[0], diag[1] * p[1], diag[2] * p[2]);
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
     gnorm = 0.0;
     if (fnorm != 0.0) {
       const double rf = ndiv(1.0, fnorm);  // (MINPACK divides each qtf[i]: <= 1 ulp apart)
-      LMN_UNROLL
-      for (int j = 0; j < NP; ++j) {
-        const double an = get3(wa2, ipvt[j]);
-        if (an != 0.0) {
-          double sum = 0.0;
-          LMN_UNROLL
-          for (int i = 0; i <= j; ++i) sum += a[i + 3 * j] * (qtf[i] * rf);
-          gnorm = fmax(gnorm, fabs(ndiv(sum, an)));
-        }
-      }
+      const double t0 = q0 * rf, t1 = q1 * rf, t2 = q2 * rf;
+      const double an0 = get3(acn, i0p), an1 = get3(acn, i1p), an2 = get3(acn, i2p);
+      if (an0 != 0.0) gnorm = fmax(gnorm, fabs(ndiv(r00 * t0, an0)));
+      if (an1 != 0.0) gnorm = fmax(gnorm, fabs(ndiv(r01 * t0 + r11 * t1, an1)));
+      if (an2 != 0.0) gnorm = fmax(gnorm, fabs(ndiv(r02 * t0 + r12 * t1 + r22 * t2, an2)));
     }
     if (gnorm <= gtol) {
       info = 4;
       phase = DONE;
     } else {
       LMN_UNROLL
-      for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], wa2[j]);
+      for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], acn[j]);
       phase = STEP;
     }
   }
 
   // trust-region step: leaves the trial point in wa2
   LMG_HD void step_block() {
-    if (GENERIC) lmpar<1, NP>(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
-    else lmpar3(a, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wq);
+    if (MODE == 1) {
+      double a[NP * NP], x[NP], s3[NP], s4[NP], s5[NP];
+      a[0] = R.r00; a[3] = R.r01; a[6] = R.r02; a[4] = R.r11; a[7] = R.r12; a[8] = R.r22;
+      a[1] = a[2] = a[5] = 0.0;
+      lmpar<1, NP>(a, ipvt, diag, qtf, delta, &par, x, s3, s4, s5);
+      for (int j = 0; j < NP; ++j) zp[j] = x[ipvt[j]];
+    } else {
+      double dp[NP];
+      LMN_UNROLL
+      for (int j = 0; j < NP; ++j) dp[j] = get3(diag, ipvt[j]);
+      lmpar_chol(R, dp, qtf, delta, &par, zp);
+    }
     LMN_UNROLL
     for (int j = 0; j < NP; ++j) {
-      wa1[j] = -wa1[j];
-      wa2[j] = p[j] + wa1[j];
-      wa3[j] = diag[j] * wa1[j];
+      zp[j] = -zp[j];
+      put3(wa1, ipvt[j], zp[j]);
     }
-    pnorm = nsqrt(wa3[0] * wa3[0] + wa3[1] * wa3[1] + wa3[2] * wa3[2]);
+    LMN_UNROLL
+    for (int j = 0; j < NP; ++j) wa2[j] = p[j] + wa1[j];
+    pnorm = norm3(diag[0] * wa1[0], diag[1] * wa1[1], diag[2] * wa1[2]);
     if (iter == 1) delta = fmin(delta, pnorm);
   }
 
@@ -540,21 +523,17 @@ struct LmNormal {
     const int maxfev = 200 * (NP + 1);
     ++nfev;
     const double fnorm1 = resid_norm(pr, wa2);
+    const double rfn = ndiv(1.0, fnorm);
     double actred = -1.0;
     if (0.1 * fnorm1 < fnorm) {
-      const double q = ndiv(fnorm1, fnorm);
+      const double q = fnorm1 * rfn;
       actred = 1.0 - q * q;
     }
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) wa3[j] = 0.0;
-    LMN_UNROLL
-    for (int j = 0; j < NP; ++j) {
-      const double temp = get3(wa1, ipvt[j]);
-      LMN_UNROLL
-      for (int i = 0; i <= j; ++i) wa3[i] += a[i + 3 * j] * temp;
-    }
-    const double rfn = ndiv(1.0, fnorm);
-    const double temp1 = nsqrt(wa3[0] * wa3[0] + wa3[1] * wa3[1] + wa3[2] * wa3[2]) * rfn;
+    // || J step || = || R P^T step ||
+    const double j0 = R.r00 * zp[0] + R.r01 * zp[1] + R.r02 * zp[2];
+    const double j1 = R.r11 * zp[1] + R.r12 * zp[2];
+    const double j2 = R.r22 * zp[2];
+    const double temp1 = norm3(j0, j1, j2) * rfn;
     const double temp2 = (nsqrt(par) * pnorm) * rfn;
     const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
     const double dirder = -(temp1 * temp1 + temp2 * temp2);
@@ -573,11 +552,8 @@ struct LmNormal {
     }
     if (ratio >= 1e-4) {
       LMN_UNROLL
-      for (int j = 0; j < NP; ++j) {
-        p[j] = wa2[j];
-        wa2[j] = diag[j] * p[j];
-      }
-      xnorm = nsqrt(wa2[0] * wa2[0] + wa2[1] * wa2[1] + wa2[2] * wa2[2]);
+      for (int j = 0; j < NP; ++j) p[j] = wa2[j];
+      xnorm = norm3(diag[0] * p[0], diag[1] * p[1], diag[2] * p[2]);
       fnorm = fnorm1;
       ++iter;
     }
@@ -597,18 +573,19 @@ struct LmNormal {
 };
 
 // lmdif through LmNormal (single-fit driver: host tests)
-template <bool GENERIC>
+template <int MODE>
 LMG_HD inline int lmdif_normal(const Problem& pr, double* p, int* nfev_out) {
   if (pr.m < NP) {
     *nfev_out = 0;
     return 0;
   }
-  LmNormal<1, GENERIC> sm;
+  using Lm = LmNormal<1, MODE>;
+  Lm sm;
   sm.init(p);
   sm.begin(pr);
-  while (sm.phase != LmNormal<1, GENERIC>::DONE) {
-    if (sm.phase == LmNormal<1, GENERIC>::JAC) sm.jac_block(pr);
-    if (sm.phase == LmNormal<1, GENERIC>::STEP) {
+  while (sm.phase != Lm::DONE) {
+    if (sm.phase == Lm::JAC) sm.jac_block(pr);
+    if (sm.phase == Lm::STEP) {
       sm.step_block();
       sm.trial_block(pr);
     }

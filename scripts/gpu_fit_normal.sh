@@ -7,7 +7,7 @@ export CDB_PARITY_REPORT_DIR=gpurun_out/${TAG}_parity
 timeout 900 python -m pytest tests/test_esacf_gpu.py -m gpu -q > gpurun_out/${TAG}_pytest_esacf.log 2>&1; tail -5 gpurun_out/${TAG}_pytest_esacf.log
 unset CDB_PARITY_REPORT_DIR
 for nc in 64 256; do
-for cfg in "lmsm:" "normal:16" "normal:12" "normal_x:16" "normal:16:skip"; do
+for cfg in "lmsm:" "normal:16" "normal:12" "normal:16:skip"; do
   IFS=: read lm w skip <<< "$cfg"
   export CDB_ESACF_LM=$lm
   if [ -n "$w" ]; then export CDB_ESACF_FIT_WARPS=$w; else unset CDB_ESACF_FIT_WARPS; fi
