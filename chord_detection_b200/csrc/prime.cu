@@ -15,8 +15,11 @@
 // the bin -> pitch-class map depend only on (fs, W, bin): they are tabulated on the host in
 // float64 with the reference's own arithmetic (np.fft.fftfreq: k * (1.0 / (W * (1 / fs)))).
 #include <cmath>
+#include <complex>
+#include <cstdlib>
 #include <cstring>
 
+#include "cfft32.cuh"
 #include "common.cuh"
 
 constexpr int kPrimeThreads = 128;
@@ -39,6 +42,17 @@ struct PrimePlan {
   int* d_offh = nullptr;
   int maxW = 0, maxH = 0;
   std::map<int64_t, int*> start_cache;  // clip_len -> device prefix of windows per candidate
+  // FP32 screen (prime_screen_kernel): candidates grouped by FFT size M = 256 * R1, R1 = 2, 4, 8, 16
+  bool screen_ok = false;
+  std::vector<int> cls_cands[4];            // candidates of class q (R1 = 2 << q), loop order
+  int* d_cls_cands[4] = {nullptr, nullptr, nullptr, nullptr};
+  cf32::cplx* d_chirp = nullptr;            // concatenated exp(-i pi n^2 / W_c), offsets = off_w
+  cf32::cplx* d_bhat = nullptr;             // concatenated chirp-filter spectra / M, digit-reversed
+  cf32::cplx* d_tw32 = nullptr;             // W_M^t for the four sizes: offsets 0, 512, 1536, 3584
+  double2* d_tw64 = nullptr;                // concatenated (cos, sin)(2 pi j / W_c), offsets = off_w
+  float* d_kappa = nullptr;                 // [n_cand] screen error bound / ||x w||_2
+  int* d_offb = nullptr;                    // [n_cand] offset of candidate c in d_bhat
+  std::map<int64_t, int*> cls_start_cache[4];  // clip_len -> prefix of windows per class candidate
 };
 
 void cdb_free_prime_plans(cdb_handle* h) {
@@ -69,6 +83,123 @@ extern "C" int cdb_prime_window_sizes(const cdb_prime_params* p, int* sizes) {
   if (sizes)
     for (int i = 0; i < n; ++i) sizes[i] = W[i];
   return n;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// FP32 screen tables.  For candidate c with window W and H kept bins the W-point DFT is evaluated
+// at bins 0..H-1 by Bluestein's identity on an FFT of M >= W + H - 1 points:
+//   X[k] = w[k] sum_n (x[n] w[n]) conj(w[k - n]),  w[n] = exp(-i pi n^2 / W)      (|X[k]| = |sum|)
+// Error bound of the screen (why a candidate set built from it cannot miss the true maximum).
+// With u = 2^-24, L = log2 M, FFT twiddles and filter spectrum rounded from long double:
+//   * a radix-2-equivalent FFT computes y^ with ||fl(y^) - y^||_2 <= L eta ||y^||_2,
+//     eta = mu + gamma_4 (sqrt 2 + mu) <= 6.7 u          (Higham, ASNA 2nd ed., Thm 24.2);
+//   * input products x w and the pointwise filter product add <= 3 u and <= 3.3 u relative;
+//   * the inverse transform adds another L eta relative to its own output;
+//   * ||z||_2 <= max|B^| ||x w||_2 for the convolution z (B^ = FFT_M(filter), 1/M folded in);
+// so max_k | |z32[k]| - |X[k]| | <= ||z32 - z||_2 <= (2 L * 6.7 + 6.3) u max|B^| ||x w||_2 =: kappa_c
+// ||x w||_2.  kappa_c is tabulated per candidate from the actual max|B^| (x 1.05 for the FP32
+// norm and magnitude roundings); the CPU suite measures the real error at < 1/10 of it.
+static int prime_screen_r1(int W, int H) {
+  const int need = W + H - 1;
+  for (int r1 = 2; r1 <= 16; r1 *= 2)
+    if (need <= 256 * r1) return r1;
+  return 0;
+}
+
+static void prime_screen_tables(int W, int H, int R1, std::vector<cf32::cplx>& chirp,
+                                std::vector<cf32::cplx>& bhat, std::vector<double2>& tw64,
+                                float* kappa) {
+  typedef std::complex<long double> lc;
+  const int M = R1 * 256;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<lc> b((size_t)M, lc(0.0L, 0.0L));
+  for (int n = 0; n < W; ++n) {
+    const long long e = ((long long)n * n) % (2LL * W);  // n^2 mod 2W keeps the angle exact
+    const long double ang = -pi * (long double)e / (long double)W;
+    chirp.push_back(cf32::mk((float)cosl(ang), (float)sinl(ang)));
+    const lc cw(cosl(ang), -sinl(ang));  // conj chirp = the filter, lags -(W-1) .. H-1
+    if (n < H) b[n] = cw;
+    if (n) b[M - n] = cw;
+    const long double a2 = 2.0L * pi * (long double)n / (long double)W;
+    double2 t;
+    t.x = (double)cosl(a2);
+    t.y = (double)sinl(a2);
+    tw64.push_back(t);
+  }
+  for (int i = 1, j = 0; i < M; ++i) {  // iterative radix-2 FFT of the filter
+    int bit = M >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(b[i], b[j]);
+  }
+  for (int len = 2; len <= M; len <<= 1)
+    for (int i = 0; i < M; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const long double ang = -2.0L * pi * (long double)k / (long double)len;
+        const lc w(cosl(ang), sinl(ang));
+        const lc u = b[i + k], v = b[i + k + len / 2] * w;
+        b[i + k] = u + v;
+        b[i + k + len / 2] = u - v;
+      }
+  const size_t o = bhat.size();
+  bhat.resize(o + (size_t)M);
+  long double bmax = 0.0L;
+  for (int k = 0; k < M; ++k) {
+    bmax = std::max(bmax, std::abs(b[k]));
+    const lc v = b[k] / (long double)M;
+    bhat[o + cf32::digit_pos(k, R1)] = cf32::mk((float)v.real(), (float)v.imag());
+  }
+  int L = 0;
+  while ((1 << L) < M) ++L;
+  const double u = 5.9604644775390625e-8;  // 2^-24
+  *kappa = (float)(1.05 * (2.0 * L * 6.7 + 6.3) * u * (double)bmax);
+}
+
+static void prime_tw32(std::vector<cf32::cplx>& tw) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int r1 = 2; r1 <= 16; r1 *= 2) {
+    const int M = r1 * 256;
+    for (int k = 0; k < M; ++k) {
+      const long double ang = -2.0L * pi * (long double)k / (long double)M;
+      tw.push_back(cf32::mk((float)cosl(ang), (float)sinl(ang)));
+    }
+  }
+}
+static int prime_tw32_offset(int R1) { return 256 * (R1 - 2); }  // 0, 512, 1536, 3584
+static int prime_class_of(int R1) { return R1 == 2 ? 0 : R1 == 4 ? 1 : R1 == 8 ? 2 : 3; }
+
+static int prime_build_screen(cdb_handle* h, PrimePlan* pl) {
+  std::vector<cf32::cplx> chirp, bhat, tw;
+  std::vector<double2> tw64;
+  std::vector<float> kappa;
+  std::vector<int> offb;
+  pl->screen_ok = true;
+  for (int c = 0; c < pl->n_cand; ++c) {
+    const int R1 = prime_screen_r1(pl->W[c], pl->H[c]);
+    if (!R1 || pl->H[c] < 1) {
+      pl->screen_ok = false;  // (the Goertzel kernel serves the whole call)
+      return 0;
+    }
+  }
+  for (int c = 0; c < pl->n_cand; ++c) {
+    const int R1 = prime_screen_r1(pl->W[c], pl->H[c]);
+    pl->cls_cands[prime_class_of(R1)].push_back(c);
+    offb.push_back((int)bhat.size());
+    float kp = 0.f;
+    prime_screen_tables(pl->W[c], pl->H[c], R1, chirp, bhat, tw64, &kp);
+    kappa.push_back(kp);
+  }
+  prime_tw32(tw);
+  int rc;
+  if ((rc = cdb_upload(h, chirp, &pl->d_chirp)) || (rc = cdb_upload(h, bhat, &pl->d_bhat)) ||
+      (rc = cdb_upload(h, tw, &pl->d_tw32)) || (rc = cdb_upload(h, tw64, &pl->d_tw64)) ||
+      (rc = cdb_upload(h, kappa, &pl->d_kappa)) || (rc = cdb_upload(h, offb, &pl->d_offb)))
+    return rc;
+  for (int q = 0; q < 4; ++q)
+    if (!pl->cls_cands[q].empty() && (rc = cdb_upload(h, pl->cls_cands[q], &pl->d_cls_cands[q])))
+      return rc;
+  return 0;
 }
 
 static int prime_get_plan(cdb_handle* h, const cdb_prime_params* p, PrimePlan** out) {
@@ -138,6 +269,10 @@ static int prime_get_plan(cdb_handle* h, const cdb_prime_params* p, PrimePlan** 
     }
   }
   int rc;
+  if ((rc = prime_build_screen(h, pl))) {
+    delete pl;
+    return rc;
+  }
   if ((rc = cdb_upload(h, win, &pl->d_win)) || (rc = cdb_upload(h, invsum, &pl->d_invsum)) ||
       (rc = cdb_upload(h, note, &pl->d_note)) || (rc = cdb_upload(h, elim, &pl->d_elim)) ||
       (rc = cdb_upload(h, pl->W, &pl->d_W)) || (rc = cdb_upload(h, pl->H, &pl->d_H)) ||
@@ -297,6 +432,377 @@ __global__ void __launch_bounds__(kPrimeThreads) prime_kernel(const PrimeArgs a)
   if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// prime_screen_kernel<R1, T>: FP32 screen + FP64 decision (default).
+// The Goertzel kernel above spends W * H FP64 recurrence steps per window to produce H magnitudes
+// of which the method uses TWO (the maxima of two elimination rounds).  Here the H magnitudes come
+// from an FP32 Bluestein transform (two FFT_M in shared memory, cfft32.cuh) with a proven error bound
+// delta = kappa_c ||x w||_2 (prime_screen_tables); every bin whose FP32 magnitude lies within
+// 2 delta of the FP32 maximum is then evaluated EXACTLY (FP64 direct DFT from an exact-angle
+// table, one warp per bin) and the maximum -- first index on exact ties, numpy.argmax -- is taken
+// among those: the true FP64 maximum is always in that set, and the value added to the chroma is
+// the FP64 one.  Almost always one or two bins; a flat spectrum degrades to evaluating every bin.
+// The window is pre-scaled by an exact power of two so that FP32 range is never an issue; windows
+// with NaN / Inf samples take the evaluate-every-bin path.
+struct PrimeScreenArgs {
+  PrimeArgs a;
+  const int* cls_cands;   // candidates of this class
+  const int* cls_start;   // [n_cls + 1] prefix of windows per class candidate within a clip
+  int n_cls;
+  const cf32::cplx* chirp;
+  const cf32::cplx* bhat;
+  const cf32::cplx* tw;   // W_M^t of this class
+  const double2* tw64;
+  const float* kappa;
+  const int* offb;
+};
+
+template <int T>
+__device__ __forceinline__ void block_argmax(double& bv, int& bi, double* red_v, int* red_i) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  __syncthreads();  // (red_* may still be read from the previous use)
+  if (lane == 0) {
+    red_v[warp] = bv;
+    red_i[warp] = bi;
+  }
+  __syncthreads();
+  bv = red_v[0];
+  bi = red_i[0];
+#pragma unroll
+  for (int w = 1; w < T / 32; ++w)
+    if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) {
+      bv = red_v[w];
+      bi = red_i[w];
+    }
+}
+
+template <int R1, int T>
+__global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs sa) {
+  constexpr int M = R1 * 256;
+  constexpr int NV = (M * 4 / 5 + T - 1) / T + 1;  // samples per thread (W + H - 1 <= M, H ~ W/4)
+  extern __shared__ __align__(16) unsigned char smem[];
+  const PrimeArgs& a = sa.a;
+  cf32::cplx* buf = reinterpret_cast<cf32::cplx*>(smem);                       // [padded(M)]
+  float* s32 = reinterpret_cast<float*>(smem + sizeof(cf32::cplx) * cf32::padded_size(M));  // [maxH]
+  // xs (the scaled FP32 window, dead after the first pass) shares its space with s64 | list
+  unsigned char* region = reinterpret_cast<unsigned char*>(s32) + sizeof(float) * ((M / 4 + 3) & ~3);
+  float* xs = reinterpret_cast<float*>(region);                                // [W]
+  double* s64 = reinterpret_cast<double*>(region);                             // [H] NaN = not evaluated
+  short* list = reinterpret_cast<short*>(region + sizeof(double) * (M / 4));   // [H]
+  __shared__ double red_v[T / 32];
+  __shared__ int red_i[T / 32];
+  __shared__ double cta_total[12];
+  __shared__ int n_list;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 12) cta_total[tid] = 0.0;
+  __syncthreads();
+  const int64_t items_per_clip = sa.cls_start[sa.n_cls];
+  const int64_t total_items = items_per_clip * a.n_clips;
+
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int64_t clip = item / items_per_clip;
+    const int r = (int)(item - clip * items_per_clip);
+    int q = 0;
+    while (q + 1 < sa.n_cls && sa.cls_start[q + 1] <= r) ++q;
+    const int c = sa.cls_cands[q];
+    const int frame = r - sa.cls_start[q];
+    const int W = a.W[c], H = a.H[c];
+    const int64_t s0 = (int64_t)frame * W;
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    const double* win = a.win + a.offw[c];
+    const double invsum = a.invsum[c];
+
+    // windowed samples in FP64 (the very products the FP64 evaluation uses), largest magnitude
+    double v[NV];
+    double amax = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int n = tid + j * T;
+      v[j] = (n < W && n < avail) ? (double)__ldg(src + n) * win[n] : 0.0;
+      bad |= !(fabs(v[j]) <= 1.7976931348623157e308);
+      amax = fmax(amax, fabs(v[j]));
+    }
+    {
+      int bi = bad ? 1 : 0;  // any NaN / Inf: carried in the index slot (max over the block)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        bi |= __shfl_xor_sync(0xffffffffu, bi, o);
+      }
+      __syncthreads();
+      if (lane == 0) {
+        red_v[warp] = amax;
+        red_i[warp] = bi;
+      }
+      __syncthreads();
+      amax = red_v[0];
+      bi = red_i[0];
+#pragma unroll
+      for (int w = 1; w < T / 32; ++w) {
+        amax = fmax(amax, red_v[w]);
+        bi |= red_i[w];
+      }
+      bad = bi != 0;
+    }
+    if (!bad && amax == 0.0) continue;  // silence: every bin is 0, argmax = bin 0, f = 0 -> no note (:73)
+    bool full = bad;                    // evaluate every bin in FP64
+    float delta = 0.f;
+    if (!full) {
+      // exact power-of-two scale: largest sample in [1, 2)
+      const double sc = scalbn(1.0, -ilogb(amax));
+      float nrm = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int n = tid + j * T;
+        const float f = (float)(v[j] * sc);
+        if (n < W) xs[n] = f;
+        nrm = fmaf(f, f, nrm);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+      __syncthreads();
+      if (lane == 0) red_v[warp] = (double)nrm;
+      __syncthreads();
+      double n2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < T / 32; ++w) n2 += red_v[w];
+      delta = sa.kappa[c] * (float)sqrt(n2) * 1.01f;
+      // Bluestein: FFT_M(x w chirp) . filter spectrum -> inverse FFT_M, |.| of the first H outputs
+      const cf32::cplx* chirp = sa.chirp + a.offw[c];
+      const cf32::cplx* bhat = sa.bhat + sa.offb[c];
+      auto in = [&](int n) {
+        if (n >= W) return cf32::mk(0.f, 0.f);
+        const cf32::cplx ch = chirp[n];
+        const float f = xs[n];
+        return cf32::mk(f * ch.x, f * ch.y);
+      };
+      auto out = [&](int n, cf32::cplx z) {
+        if (n < H) s32[n] = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+      };
+      for (int u = tid; u < 256; u += T) cf32::fwd_p1<R1>(buf, sa.tw, u, in);
+      __syncthreads();
+      for (int u = tid; u < R1 * 16; u += T) cf32::fwd_p2<R1>(buf, sa.tw, u);
+      __syncthreads();
+      for (int u = tid; u < R1 * 16; u += T) cf32::mid_p3(buf, bhat, u);
+      __syncthreads();
+      for (int u = tid; u < R1 * 16; u += T) cf32::bwd_p2<R1>(buf, sa.tw, u);
+      __syncthreads();
+      for (int u = tid; u < 256; u += T) cf32::bwd_p1<R1>(buf, sa.tw, u, out);
+      __syncthreads();
+    }
+    for (int k = tid; k < H; k += T) s64[k] = __longlong_as_double(0x7ff8000000000000LL);
+    const int8_t* note = a.note + a.offh[c];
+    const uint8_t* elim = a.elim + a.offh[c];
+    const double2* tw64 = sa.tw64 + a.offw[c];
+    for (int run = 0; run < a.runs; ++run) {
+      if (tid == 0) n_list = 0;
+      float thr = -1.f;
+      if (!full) {
+        double bv = -1.0;
+        int bi = 0;
+        for (int k = tid; k < H; k += T) bv = fmax(bv, (double)s32[k]);
+        block_argmax<T>(bv, bi, red_v, red_i);  // (syncs: also orders n_list = 0 and the s64 stores)
+        thr = (float)bv - 2.f * delta;
+        if (!((float)bv <= 3.0e38f)) {  // overflow / NaN in the screen: evaluate everything
+          full = true;
+          thr = -1.f;
+        }
+      } else {
+        __syncthreads();
+      }
+      for (int k = tid; k < H; k += T)
+        if (full || s32[k] >= thr) list[atomicAdd(&n_list, 1)] = (short)k;
+      __syncthreads();
+      const int nl = n_list;
+      // FP64 evaluation of the listed bins that have none yet: X[k] = sum_n xw[n] exp(-2 pi i nk/W)
+      for (int i = warp; i < nl; i += T / 32) {
+        const int k = list[i];
+        if (!isnan(s64[k])) continue;
+        double re = 0.0, im = 0.0;
+        int j = (int)(((long long)lane * k) % W);
+        const int step = (int)((32LL * k) % W);
+        for (int n = lane; n < W; n += 32) {
+          const double xv = (n < avail) ? (double)__ldg(src + n) * win[n] : 0.0;
+          const double2 t = tw64[j];
+          re = fma(xv, t.x, re);
+          im = fma(xv, t.y, im);
+          j += step;
+          j -= j >= W ? W : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          re += __shfl_xor_sync(0xffffffffu, re, o);
+          im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        if (lane == 0) s64[k] = sqrt(re * re + im * im) * invsum;
+      }
+      __syncthreads();
+      double bv = -1.0;
+      int bi = 0x7fffffff;
+      for (int i = tid; i < nl; i += T) {
+        const int k = list[i];
+        const double val = s64[k];
+        if (val > bv || (val == bv && k < bi)) {
+          bv = val;
+          bi = k;
+        }
+      }
+      block_argmax<T>(bv, bi, red_v, red_i);
+      if (tid == 0 && bi < H) {
+        const int nt = note[bi];
+        if (nt >= 0) {  // hz_to_note raised otherwise: `continue` skips the elimination too (:73-74)
+          cta_total[nt] += bv;
+          if (a.clips) atomicAdd(&a.clips[clip * 12 + nt], bv);
+          if (a.cands) atomicAdd(&a.cands[(clip * a.n_cand + c) * 12 + nt], bv);
+          const uint8_t mask = elim[bi];
+          for (int m = 1; m < a.nmult; ++m)
+            if (mask & (1u << (m - 1))) {
+              s32[m * bi] = 0.f;
+              s64[m * bi] = 0.0;
+            }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
+}
+
+template <int R1, int T>
+static int prime_launch_screen(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a, int64_t clip_len,
+                               cudaStream_t st) {
+  const int q = prime_class_of(R1);
+  const std::vector<int>& cc = pl->cls_cands[q];
+  if (cc.empty()) return 0;
+  std::vector<int> start(cc.size() + 1, 0);
+  for (size_t i = 0; i < cc.size(); ++i)
+    start[i + 1] = start[i] + (int)cdb_num_frames(clip_len, pl->W[cc[i]], pl->W[cc[i]]);
+  if (start.back() == 0) return 0;
+  int* d_start = nullptr;
+  auto it = pl->cls_start_cache[q].find(clip_len);
+  if (it == pl->cls_start_cache[q].end()) {
+    int rc = cdb_upload(h, start, &d_start);
+    if (rc) return rc;
+    pl->cls_start_cache[q][clip_len] = d_start;
+  } else {
+    d_start = it->second;
+  }
+  PrimeScreenArgs sa;
+  sa.a = a;
+  sa.cls_cands = pl->d_cls_cands[q];
+  sa.cls_start = d_start;
+  sa.n_cls = (int)cc.size();
+  sa.chirp = pl->d_chirp;
+  sa.bhat = pl->d_bhat;
+  sa.tw = pl->d_tw32 + prime_tw32_offset(R1);
+  sa.tw64 = pl->d_tw64;
+  sa.kappa = pl->d_kappa;
+  sa.offb = pl->d_offb;
+  constexpr int M = R1 * 256;
+  const size_t smem = sizeof(cf32::cplx) * cf32::padded_size(M) + sizeof(float) * ((M / 4 + 3) & ~3) +
+                      std::max<size_t>(sizeof(float) * M, (sizeof(double) + sizeof(short)) * (M / 4)) + 16;
+  auto kernel = prime_screen_kernel<R1, T>;
+  CDB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+  if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "screen kernel does not fit");
+  const int64_t items = (int64_t)start.back() * a.n_clips;
+  const int64_t grid = std::min<int64_t>(items, (int64_t)h->num_sms * per_sm);
+  kernel<<<(unsigned)grid, T, smem, st>>>(sa);
+  h->launches += 1;
+  return 0;
+}
+
+// Host execution (CPU tests, no GPU) of the screen of ONE window of W samples: the same tables and
+// the same cfft32.cuh passes as prime_screen_kernel, units executed sequentially.  s_screen[H]: FP32
+// Bluestein magnitudes (in the units of the reference's spectrum), s_exact[H]: the FP64 direct DFT
+// the kernel uses for its decisions, *delta: the screen's error bound in the same units.
+template <int R1>
+static void prime_host_fft(int W, int H, const std::vector<float>& xs, const std::vector<cf32::cplx>& chirp,
+                           const std::vector<cf32::cplx>& bhat, std::vector<float>& mag) {
+  constexpr int M = R1 * 256;
+  std::vector<cf32::cplx> tw_all;
+  prime_tw32(tw_all);
+  const cf32::cplx* tw = tw_all.data() + prime_tw32_offset(R1);
+  std::vector<cf32::cplx> buf((size_t)cf32::padded_size(M), cf32::mk(0.f, 0.f));
+  auto in = [&](int n) {
+    if (n >= W) return cf32::mk(0.f, 0.f);
+    return cf32::mk(xs[n] * chirp[n].x, xs[n] * chirp[n].y);
+  };
+  auto out = [&](int n, cf32::cplx z) {
+    if (n < H) mag[n] = std::sqrt(std::fmaf(z.x, z.x, z.y * z.y));
+  };
+  for (int u = 0; u < 256; ++u) cf32::fwd_p1<R1>(buf.data(), tw, u, in);
+  for (int u = 0; u < R1 * 16; ++u) cf32::fwd_p2<R1>(buf.data(), tw, u);
+  for (int u = 0; u < R1 * 16; ++u) cf32::mid_p3(buf.data(), bhat.data(), u);
+  for (int u = 0; u < R1 * 16; ++u) cf32::bwd_p2<R1>(buf.data(), tw, u);
+  for (int u = 0; u < 256; ++u) cf32::bwd_p1<R1>(buf.data(), tw, u, out);
+}
+
+extern "C" int cdb_host_prime_screen(int W, const float* x, double* s_screen, double* s_exact,
+                                     double* delta) {
+  if (W < 4 || !x || !s_screen || !s_exact || !delta) return -1;
+  const int num_freqs = (W % 2) ? (W + 1) / 2 : W / 2 + 1;
+  const int H = num_freqs / 2;
+  const int R1 = prime_screen_r1(W, H);
+  if (!R1 || H < 1) return -2;
+  const double pi = 3.14159265358979323846;
+  std::vector<double> xw((size_t)W);
+  double sum = 0.0, amax = 0.0;
+  for (int i = 0; i < W; ++i) {
+    const double wv = 0.5 + 0.5 * std::cos(pi * (double)(2 * i + 1 - W) / (double)(W - 1));
+    sum += std::fabs(wv);
+    xw[i] = (double)x[i] * wv;
+    amax = std::fmax(amax, std::fabs(xw[i]));
+  }
+  const double invsum = 1.0 / sum;
+  std::vector<cf32::cplx> chirp, bhat;
+  std::vector<double2> tw64;
+  float kappa = 0.f;
+  prime_screen_tables(W, H, R1, chirp, bhat, tw64, &kappa);
+  for (int k = 0; k < H; ++k) {
+    double re = 0.0, im = 0.0;
+    for (int n = 0; n < W; ++n) {
+      const double2 t = tw64[(size_t)(((long long)n * k) % W)];
+      re = std::fma(xw[n], t.x, re);
+      im = std::fma(xw[n], t.y, im);
+    }
+    s_exact[k] = std::sqrt(re * re + im * im) * invsum;
+    s_screen[k] = 0.0;
+  }
+  *delta = 0.0;
+  if (amax == 0.0 || !std::isfinite(amax)) return H;
+  const double sc = std::scalbn(1.0, -std::ilogb(amax));
+  std::vector<float> xs((size_t)W), mag((size_t)H, 0.f);
+  float nrm = 0.f;
+  for (int i = 0; i < W; ++i) {
+    xs[i] = (float)(xw[i] * sc);
+    nrm = std::fmaf(xs[i], xs[i], nrm);
+  }
+  switch (R1) {
+    case 2: prime_host_fft<2>(W, H, xs, chirp, bhat, mag); break;
+    case 4: prime_host_fft<4>(W, H, xs, chirp, bhat, mag); break;
+    case 8: prime_host_fft<8>(W, H, xs, chirp, bhat, mag); break;
+    default: prime_host_fft<16>(W, H, xs, chirp, bhat, mag); break;
+  }
+  for (int k = 0; k < H; ++k) s_screen[k] = (double)mag[k] / sc * invsum;
+  *delta = (double)(kappa * (float)std::sqrt((double)nrm) * 1.01f) / sc * invsum;
+  return H;
+}
+
 extern "C" {
 
 int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x, int64_t n_clips,
@@ -359,6 +865,19 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   a.total = d_chroma_total;
   a.clips = d_chroma_clips;
   a.cands = d_chroma_cands;
+  bool screen = pl->screen_ok;
+  if (const char* pm = std::getenv("CDB_PRIME")) screen = screen && std::string(pm) != "goertzel";
+  if (screen) {
+    cdb_mark(h, st, "begin");
+    if ((rc = prime_launch_screen<2, 128>(h, pl, a, clip_len, st)) ||
+        (rc = prime_launch_screen<4, 128>(h, pl, a, clip_len, st)) ||
+        (rc = prime_launch_screen<8, 128>(h, pl, a, clip_len, st)) ||
+        (rc = prime_launch_screen<16, 256>(h, pl, a, clip_len, st)))
+      return rc;
+    cdb_mark(h, st, "prime_screen_kernel");
+    CDB_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (size_t)(pl->maxW + pl->maxH + 2) * sizeof(double);
   CDB_CUDA(h, cudaFuncSetAttribute(prime_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));

@@ -238,6 +238,13 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
                      int64_t clip_len, int64_t clip_stride, double* d_chroma_total,
                      double* d_chroma_clips, double* d_chroma_cands, int flags, void* stream);
 
+/* cdb_host_prime_screen: host execution (CPU tests, no GPU) of the FP32 screen that
+ * cdb_prime_chroma runs per analysis window (csrc/prime.cu, prime_screen_kernel): window of W
+ * samples (np.hanning applied inside) -> s_screen[H] FP32 Bluestein magnitudes, s_exact[H] the FP64
+ * direct DFT the kernel decides with (both in the units of mlab.magnitude_spectrum,
+ * prime_multif0.py:59), *delta the screen's error bound.  Returns H = kept bins, < 0 on error. */
+int cdb_host_prime_screen(int W, const float* x, double* s_screen, double* s_exact, double* delta);
+
 /* ---------------- ingestion: the decode step of librosa.load (multipitch.py:25), SURVEY 8f-2 ---------------- */
 /* d_pcm: interleaved int16 [n_frames, channels] -> d_out[n_frames] float32 = mean over channels of
  * s/32768 (soundfile PCM_16 -> float32, then librosa.to_mono); exact.  Halves the host->device

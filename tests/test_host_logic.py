@@ -315,6 +315,44 @@ def test_host_normal_lm_matches_scipy_curve_fit(variant):
     assert same_nfev >= 0.98 * n
 
 
+def test_host_prime_screen_error_bound_and_exact_dft():
+    """Prime-multiF0 (csrc/prime.cu, prime_screen_kernel): the FP64 direct DFT the kernel decides
+    with equals mlab.magnitude_spectrum's |FFT(x * hanning)| / sum|w| (prime_multif0.py:59), and the
+    FP32 Bluestein screen stays far inside its proven error bound delta on tones, noise, impulses,
+    tiny and huge amplitudes, for window sizes of every FFT class (incl. the class boundaries) --
+    so the set {k : s32[k] >= max s32 - 2 delta} always contains the true maximum."""
+    rng = np.random.default_rng(5)
+    for W in (357, 409, 410, 674, 819, 820, 1348, 1639, 1640, 2696):
+        n = np.arange(W)
+        signals = [
+            rng.standard_normal(W),
+            np.sin(2 * np.pi * n * (7.5 / W)) + 0.5 * np.sin(2 * np.pi * n * (31.25 / W)),
+            np.sin(2 * np.pi * n * 0.4),
+            1e-20 * rng.standard_normal(W),
+            3e4 * np.sin(2 * np.pi * n * (12.5 / W)),
+        ]
+        for x in signals:
+            x = x.astype(np.float32)
+            s32, s64, delta = nat.host_prime_screen(x)
+            H = len(s64)
+            num_freqs = (W + 1) // 2 if W % 2 else W // 2 + 1
+            assert H == num_freqs // 2
+            w = np.hanning(W)
+            want = np.abs(np.fft.fft(x.astype(np.float64) * w))[:H] / np.abs(w).sum()
+            scale = np.abs(np.fft.fft(x.astype(np.float64) * w)).max() / np.abs(w).sum()
+            assert np.max(np.abs(s64 - want)) <= 1e-12 * scale
+            assert delta > 0
+            assert np.max(np.abs(s32 - s64)) <= 0.1 * delta
+            cands = np.nonzero(s32 >= s32.max() - 2 * delta)[0]
+            assert int(np.argmax(s64)) in cands
+    # tonal windows: the bound is tight enough for the candidate set to be one or two bins
+    x = np.sin(2 * np.pi * np.arange(1348) * (40.3 / 1348)).astype(np.float32)
+    s32, s64, delta = nat.host_prime_screen(x)
+    assert delta < 1e-4 * s64.max()
+    assert (s32 >= s32.max() - 2 * delta).sum() == 1
+    assert nat.host_prime_screen(np.zeros(500, dtype=np.float32))[2] == 0.0  # silence
+
+
 def test_audio_load_host_path(tmp_path):
     """audio.load (the host twin of audio.load_device): decode, float32 mean over channels,
     resample_poly to 22 050 Hz; read_wav keeps 16-bit PCM as stored."""

@@ -76,6 +76,42 @@ def test_prime_per_candidate_and_params():
     _close(got, rn.prime(x44, 44100))
 
 
+def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
+    """The default kernel (FP32 Bluestein screen + FP64 evaluation of the bins that can be the
+    maximum, prime_screen_kernel) against the all-FP64 Goertzel kernel (CDB_PRIME=goertzel) and the
+    oracle, per clip and per candidate: polyphonic clips, white noise, a tone above the kept quarter
+    of the spectrum (flat screen -> every bin is evaluated), silence, tiny and huge amplitudes,
+    ragged last windows, 44.1 kHz (the 4096-point class)."""
+    from chord_detection_b200 import ops
+
+    rng = np.random.default_rng(11)
+    n = 30011
+    t = np.arange(n)
+    rows = [
+        cases.make_input(dict(fn="s_poly", seed=601, fs=22050, n=n))[0],
+        cases.make_input(dict(fn="s_poly", seed=602, fs=22050, n=n))[0],
+        rng.standard_normal(n).astype(np.float32) * 0.1,
+        np.sin(2 * np.pi * 0.4 * t).astype(np.float32),
+        np.zeros(n, dtype=np.float32),
+        (1e-18 * cases.make_input(dict(fn="s_poly", seed=603, fs=22050, n=n))[0]).astype(np.float32),
+        (3e4 * cases.make_input(dict(fn="s_poly", seed=604, fs=22050, n=n))[0]).astype(np.float32),
+    ]
+    xd = torch.from_numpy(np.stack(rows)).to(_dev())
+    for fs in (22050, 44100):
+        res = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
+        monkeypatch.setenv("CDB_PRIME", "goertzel")
+        ref = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
+        monkeypatch.delenv("CDB_PRIME")
+        got_c, ref_c = res.extra.cpu().numpy(), ref.extra.cpu().numpy()
+        for i in range(len(rows)):
+            scale = max(np.abs(ref_c[i]).max(), 1e-300)
+            assert np.max(np.abs(got_c[i] - ref_c[i])) <= 1e-9 * scale, (fs, i)
+        _close(res.clips.cpu().numpy()[0], rn.prime(rows[0], fs))
+        _close(res.clips.cpu().numpy()[2], rn.prime(rows[2], fs))
+        assert np.all(res.clips.cpu().numpy()[4] == 0.0)
+        _close(res.total.cpu().numpy(), res.clips.cpu().numpy().sum(axis=0), 1e-12)
+
+
 def test_prime_window_sizes_host_table():
     from chord_detection_b200 import ops
 
