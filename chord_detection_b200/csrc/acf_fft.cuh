@@ -110,8 +110,13 @@ AFFT_HD void dft_regs(cplx (&v)[R]) {
 }
 
 // ---- forward, natural -> digit-reversed ------------------------------------------------------
+// Twiddle tables are laid out so that the lanes of a warp (consecutive units) read consecutive
+// entries (round 2; with one natural-order table W_M^t a warp load touched up to 32 cache lines and
+// the kernel sat at 76 % L1 throughput):
+//   tw[k1*256 + n'] = W_M^(n' k1), k1 < R1 (M entries) | tw[M + k2*16 + n''] = W_256^(n'' k2) (256),
+//   bhat transposed: bhat[i*(16 R1) + u] = element i of unit u.
 // P1 unit n' in [0, 256): v[n1] = in(n1*256 + n'), DFT over n1 -> k1, times W_M^(n' k1),
-// stored at k1*256 + n'.   tw[t] = W_M^t, t in [0, M).
+// stored at k1*256 + n'.
 template <int R1, class In>
 AFFT_HD void fwd_p1(cplx* buf, const cplx* tw, int np, In in) {
   cplx v[R1];
@@ -120,7 +125,7 @@ AFFT_HD void fwd_p1(cplx* buf, const cplx* tw, int np, In in) {
   dft_regs<R1>(v);
   buf[pad(np)] = v[0];
 #pragma unroll
-  for (int k1 = 1; k1 < R1; ++k1) buf[pad(k1 * 256 + np)] = cmul(v[k1], tw[np * k1]);
+  for (int k1 = 1; k1 < R1; ++k1) buf[pad(k1 * 256 + np)] = cmul(v[k1], tw[k1 * 256 + np]);
 }
 // P2 unit u = k1*16 + n'': DFT over n2 (stride 16) -> k2, times W_256^(n'' k2)
 template <int R1>
@@ -132,17 +137,17 @@ AFFT_HD void fwd_p2(cplx* buf, const cplx* tw, int u) {
   dft_regs<16>(v);
   buf[pad(base)] = v[0];
 #pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) buf[pad(base + k2 * 16)] = cmul(v[k2], tw[R1 * npp * k2]);
+  for (int k2 = 1; k2 < 16; ++k2) buf[pad(base + k2 * 16)] = cmul(v[k2], tw[R1 * 256 + k2 * 16 + npp]);
 }
 // P3 . (x chirp spectrum, conj) . P3 of unit u = k1*16 + k2 on its 16 contiguous elements.
-// bhat is the chirp spectrum / M in digit-reversed order (same indexing as buf, unpadded).
-AFFT_HD void mid_p3(cplx* buf, const cplx* bhat, int u) {
+// bhat is the chirp spectrum / M in digit-reversed order, transposed (see above); nu = 16 R1.
+AFFT_HD void mid_p3(cplx* buf, const cplx* bhat, int nu, int u) {
   cplx v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = buf[pad(u * 16 + i)];
   dft_regs<16>(v);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = cconj(cmul(v[i], bhat[u * 16 + i]));
+  for (int i = 0; i < 16; ++i) v[i] = cconj(cmul(v[i], bhat[i * nu + u]));
   dft_regs<16>(v);
 #pragma unroll
   for (int i = 0; i < 16; ++i) buf[pad(u * 16 + i)] = v[i];
@@ -154,7 +159,7 @@ AFFT_HD void bwd_p2(cplx* buf, const cplx* tw, int u) {
   cplx v[16];
   v[0] = buf[pad(base)];
 #pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(buf[pad(base + k2 * 16)], tw[R1 * npp * k2]);
+  for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(buf[pad(base + k2 * 16)], tw[R1 * 256 + k2 * 16 + npp]);
   dft_regs<16>(v);
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) buf[pad(base + n2 * 16)] = v[n2];
@@ -165,7 +170,7 @@ AFFT_HD void bwd_p1(const cplx* buf, const cplx* tw, int np, Out out) {
   cplx v[R1];
   v[0] = buf[pad(np)];
 #pragma unroll
-  for (int k1 = 1; k1 < R1; ++k1) v[k1] = cmul(buf[pad(k1 * 256 + np)], tw[np * k1]);
+  for (int k1 = 1; k1 < R1; ++k1) v[k1] = cmul(buf[pad(k1 * 256 + np)], tw[k1 * 256 + np]);
   dft_regs<R1>(v);
 #pragma unroll
   for (int n1 = 0; n1 < R1; ++n1) out(n1 * 256 + np, cconj(v[n1]));
@@ -191,8 +196,8 @@ struct AcfCtx {
   const double* lo;        // [N][B]
   const double* hi;        // [N][B]
   const cplx* chirp;       // [N]  w[n] = exp(-i pi n^2 / N)
-  const cplx* bhat;        // [M]  FFT_M(conj chirp) / M, digit-reversed
-  const cplx* tw;          // [M]  W_M^t
+  const cplx* bhat;        // [M]  FFT_M(conj chirp) / M, digit-reversed, transposed
+  const cplx* tw;          // [M + 256]  pass-1 | pass-2 twiddles
   cplx* buf;               // [padded_size(M)]
   double* Sa;              // [K]
   double* Sb;              // [K]
@@ -250,7 +255,7 @@ struct AcfUnit {
     switch (pass) {
       case 0: fwd_p1<R1>(c.buf, c.tw, u, AcfIn{c, d}); break;
       case 1: fwd_p2<R1>(c.buf, c.tw, u); break;
-      case 2: mid_p3(c.buf, c.bhat, u); break;
+      case 2: mid_p3(c.buf, c.bhat, R1 * 16, u); break;
       case 3: bwd_p2<R1>(c.buf, c.tw, u); break;
       case 4: bwd_p1<R1>(c.buf, c.tw, u, AcfOut{c, d}); break;
       default: {  // power-compressed spectra of frame d from Z (in buf): bin k = u

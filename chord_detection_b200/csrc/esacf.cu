@@ -51,12 +51,13 @@ void cdb_free_esacf_plans(cdb_handle* h) {
   h->esacf_plans.clear();
 }
 
-// chirp [N] | chirp spectrum / M, digit-reversed [M] | FFT twiddles [M]; long double on the host
+// chirp [N] | chirp spectrum / M, digit-reversed and transposed [M] | FFT twiddles [M + 256] in the
+// coalesced layouts of acf_fft.cuh; long double on the host
 static void build_acf_tables(int N, int R1, std::vector<afft::cplx>& out) {
   typedef std::complex<long double> lc;
   const int M = R1 * 256;
   const long double pi = 3.14159265358979323846264338327950288L;
-  out.assign((size_t)N + 2 * (size_t)M, afft::mk(0.0, 0.0));
+  out.assign((size_t)N + 2 * (size_t)M + 256, afft::mk(0.0, 0.0));
   std::vector<lc> b((size_t)M, lc(0.0L, 0.0L));
   for (int n = 0; n < N; ++n) {
     const long long e = ((long long)n * n) % (2LL * N);  // n^2 mod 2N keeps the angle exact
@@ -85,10 +86,19 @@ static void build_acf_tables(int N, int R1, std::vector<afft::cplx>& out) {
   }
   for (int k = 0; k < M; ++k) {
     const lc v = b[k] / (long double)M;
-    out[(size_t)N + afft::digit_pos(k, R1)] = afft::mk((double)v.real(), (double)v.imag());
-    const long double ang = -2.0L * pi * (long double)k / (long double)M;
-    out[(size_t)N + M + k] = afft::mk((double)cosl(ang), (double)sinl(ang));
+    const int dp = afft::digit_pos(k, R1);  // element dp % 16 of unit dp / 16, stored transposed
+    out[(size_t)N + (size_t)(dp % 16) * (16 * R1) + dp / 16] = afft::mk((double)v.real(), (double)v.imag());
   }
+  for (int k1 = 0; k1 < R1; ++k1)
+    for (int np = 0; np < 256; ++np) {
+      const long double ang = -2.0L * pi * (long double)((np * k1) % M) / (long double)M;
+      out[(size_t)N + M + k1 * 256 + np] = afft::mk((double)cosl(ang), (double)sinl(ang));
+    }
+  for (int k2 = 0; k2 < 16; ++k2)
+    for (int npp = 0; npp < 16; ++npp) {
+      const long double ang = -2.0L * pi * (long double)((npp * k2) % 256) / 256.0L;
+      out[(size_t)N + 2 * (size_t)M + k2 * 16 + npp] = afft::mk((double)cosl(ang), (double)sinl(ang));
+    }
 }
 
 // smallest supported FFT size for the Bluestein convolution of an N-point DFT (0: none)

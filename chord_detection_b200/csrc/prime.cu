@@ -148,7 +148,8 @@ static void prime_screen_tables(int W, int H, int R1, std::vector<cf32::cplx>& c
   for (int k = 0; k < M; ++k) {
     bmax = std::max(bmax, std::abs(b[k]));
     const lc v = b[k] / (long double)M;
-    bhat[o + cf32::digit_pos(k, R1)] = cf32::mk((float)v.real(), (float)v.imag());
+    const int dp = cf32::digit_pos(k, R1);  // element dp % 16 of unit dp / 16, stored transposed
+    bhat[o + (size_t)(dp % 16) * (16 * R1) + dp / 16] = cf32::mk((float)v.real(), (float)v.imag());
   }
   int L = 0;
   while ((1 << L) < M) ++L;
@@ -156,17 +157,27 @@ static void prime_screen_tables(int W, int H, int R1, std::vector<cf32::cplx>& c
   *kappa = (float)(1.05 * (2.0 * L * 6.7 + 6.3) * u * (double)bmax);
 }
 
+// FFT twiddles in the layouts of cfft32.cuh: for each size M = 256 R1 the pass-1 table
+// tw1[k1*256 + n'] = W_M^(n' k1) (M entries); then once the pass-2 table tw2[k2*16 + n''] =
+// W_256^(n'' k2) (256 entries, the same for every size).
 static void prime_tw32(std::vector<cf32::cplx>& tw) {
   const long double pi = 3.14159265358979323846264338327950288L;
   for (int r1 = 2; r1 <= 16; r1 *= 2) {
     const int M = r1 * 256;
-    for (int k = 0; k < M; ++k) {
-      const long double ang = -2.0L * pi * (long double)k / (long double)M;
+    for (int k1 = 0; k1 < r1; ++k1)
+      for (int np = 0; np < 256; ++np) {
+        const long double ang = -2.0L * pi * (long double)((np * k1) % M) / (long double)M;
+        tw.push_back(cf32::mk((float)cosl(ang), (float)sinl(ang)));
+      }
+  }
+  for (int k2 = 0; k2 < 16; ++k2)
+    for (int npp = 0; npp < 16; ++npp) {
+      const long double ang = -2.0L * pi * (long double)((npp * k2) % 256) / 256.0L;
       tw.push_back(cf32::mk((float)cosl(ang), (float)sinl(ang)));
     }
-  }
 }
 static int prime_tw32_offset(int R1) { return 256 * (R1 - 2); }  // 0, 512, 1536, 3584
+constexpr int kPrimeTw2Offset = 256 * (2 + 4 + 8 + 16);
 static int prime_class_of(int R1) { return R1 == 2 ? 0 : R1 == 4 ? 1 : R1 == 8 ? 2 : 3; }
 
 static int prime_build_screen(cdb_handle* h, PrimePlan* pl) {
@@ -452,11 +463,14 @@ struct PrimeScreenArgs {
   int n_cls;
   const cf32::cplx* chirp;
   const cf32::cplx* bhat;
-  const cf32::cplx* tw;   // W_M^t of this class
+  const cf32::cplx* tw;   // pass-1 twiddles of this class
+  const cf32::cplx* tw2;  // pass-2 twiddles
   const double2* tw64;
   const float* kappa;
   const int* offb;
 };
+
+constexpr int kPrimeDirectMax = 4;  // listed bins evaluated by the whole CTA, one after the other
 
 template <int T>
 __device__ __forceinline__ void block_argmax(double& bv, int& bi, double* red_v, int* red_i) {
@@ -500,6 +514,7 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
   double* s64 = reinterpret_cast<double*>(region);                             // [H] NaN = not evaluated
   short* list = reinterpret_cast<short*>(region + sizeof(double) * (M / 4));   // [H]
   __shared__ double red_v[T / 32];
+  __shared__ double red_w[T / 32];
   __shared__ int red_i[T / 32];
   __shared__ double cta_total[12];
   __shared__ int n_list;
@@ -593,16 +608,17 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
       };
       for (int u = tid; u < 256; u += T) cf32::fwd_p1<R1>(buf, sa.tw, u, in);
       __syncthreads();
-      for (int u = tid; u < R1 * 16; u += T) cf32::fwd_p2<R1>(buf, sa.tw, u);
+      for (int u = tid; u < R1 * 16; u += T) cf32::fwd_p2<R1>(buf, sa.tw2, u);
       __syncthreads();
-      for (int u = tid; u < R1 * 16; u += T) cf32::mid_p3(buf, bhat, u);
+      for (int u = tid; u < R1 * 16; u += T) cf32::mid_p3(buf, bhat, R1 * 16, u);
       __syncthreads();
-      for (int u = tid; u < R1 * 16; u += T) cf32::bwd_p2<R1>(buf, sa.tw, u);
+      for (int u = tid; u < R1 * 16; u += T) cf32::bwd_p2<R1>(buf, sa.tw2, u);
       __syncthreads();
       for (int u = tid; u < 256; u += T) cf32::bwd_p1<R1>(buf, sa.tw, u, out);
       __syncthreads();
     }
     for (int k = tid; k < H; k += T) s64[k] = __longlong_as_double(0x7ff8000000000000LL);
+    bool parked = false;
     const int8_t* note = a.note + a.offh[c];
     const uint8_t* elim = a.elim + a.offh[c];
     const double2* tw64 = sa.tw64 + a.offw[c];
@@ -626,29 +642,93 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
         if (full || s32[k] >= thr) list[atomicAdd(&n_list, 1)] = (short)k;
       __syncthreads();
       const int nl = n_list;
-      // FP64 evaluation of the listed bins that have none yet: X[k] = sum_n xw[n] exp(-2 pi i nk/W)
-      for (int i = warp; i < nl; i += T / 32) {
-        const int k = list[i];
-        if (!isnan(s64[k])) continue;
-        double re = 0.0, im = 0.0;
-        int j = (int)(((long long)lane * k) % W);
-        const int step = (int)((32LL * k) % W);
-        for (int n = lane; n < W; n += 32) {
-          const double xv = (n < avail) ? (double)__ldg(src + n) * win[n] : 0.0;
-          const double2 t = tw64[j];
-          re = fma(xv, t.x, re);
-          im = fma(xv, t.y, im);
-          j += step;
-          j -= j >= W ? W : 0;
-        }
+      // FP64 evaluation of the listed bins that have none yet: X[k] = sum_n xw[n] exp(-2 pi i nk/W).
+      // Usually one or two bins: the whole CTA evaluates each from the windowed samples it still
+      // holds in registers (all table loads of a thread are independent and issued together).
+      // Long lists (flat screens): the samples are parked in the FFT buffer, one warp per bin.
+      if (nl <= kPrimeDirectMax) {
+        for (int i = 0; i < nl; ++i) {
+          const int k = list[i];
+          if (!isnan(s64[k])) continue;  // (uniform: every thread reads the same entry)
+          // thread t holds samples t + j T: exp(-2 pi i k (t + j T) / W) = p0 r^j with p0 and r from
+          // the exact-angle table (two loads; per-sample table reads would touch 32 cache lines
+          // per warp instruction); the phasor is re-read from the table every 4 steps
+          double re = 0.0, im = 0.0;
+          int j = (int)(((long long)tid * k) % W);
+          const int step = (int)(((long long)T * k) % W);
+          const int step4 = (int)((4LL * step) % W);
+          const double2 r = tw64[step];
+          double2 ph = tw64[j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          re += __shfl_xor_sync(0xffffffffu, re, o);
-          im += __shfl_xor_sync(0xffffffffu, im, o);
+          for (int jj = 0; jj < NV; ++jj) {
+            if ((jj & 3) == 0 && jj) {
+              j += step4;
+              j -= j >= W ? W : 0;
+              ph = tw64[j];
+            }
+            re = fma(v[jj], ph.x, re);
+            im = fma(v[jj], ph.y, im);
+            const double px = fma(ph.x, r.x, -(ph.y * r.y));
+            ph.y = fma(ph.x, r.y, ph.y * r.x);
+            ph.x = px;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+          }
+          if (lane == 0) {
+            red_v[warp] = re;
+            red_w[warp] = im;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            re = red_v[0];
+            im = red_w[0];
+#pragma unroll
+            for (int w = 1; w < T / 32; ++w) {
+              re += red_v[w];
+              im += red_w[w];
+            }
+            s64[k] = sqrt(re * re + im * im) * invsum;
+          }
+          __syncthreads();
         }
-        if (lane == 0) s64[k] = sqrt(re * re + im * im) * invsum;
+      } else {
+        double* xw = reinterpret_cast<double*>(buf);  // [W] (the FFT buffer is free now)
+        if (!parked) {
+#pragma unroll
+          for (int jj = 0; jj < NV; ++jj) {
+            const int n = tid + jj * T;
+            if (n < W) xw[n] = v[jj];
+          }
+          parked = true;
+          __syncthreads();
+        }
+        for (int i = warp; i < nl; i += T / 32) {
+          const int k = list[i];
+          if (!isnan(s64[k])) continue;
+          double re = 0.0, im = 0.0;
+          int j = (int)(((long long)lane * k) % W);
+          const int step = (int)((32LL * k) % W);
+#pragma unroll 4
+          for (int n = lane; n < W; n += 32) {
+            const double xv = xw[n];
+            const double2 t = tw64[j];
+            re = fma(xv, t.x, re);
+            im = fma(xv, t.y, im);
+            j += step;
+            j -= j >= W ? W : 0;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+          }
+          if (lane == 0) s64[k] = sqrt(re * re + im * im) * invsum;
+        }
+        __syncthreads();
       }
-      __syncthreads();
       double bv = -1.0;
       int bi = 0x7fffffff;
       for (int i = tid; i < nl; i += T) {
@@ -708,6 +788,7 @@ static int prime_launch_screen(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a,
   sa.chirp = pl->d_chirp;
   sa.bhat = pl->d_bhat;
   sa.tw = pl->d_tw32 + prime_tw32_offset(R1);
+  sa.tw2 = pl->d_tw32 + kPrimeTw2Offset;
   sa.tw64 = pl->d_tw64;
   sa.kappa = pl->d_kappa;
   sa.offb = pl->d_offb;
@@ -737,6 +818,7 @@ static void prime_host_fft(int W, int H, const std::vector<float>& xs, const std
   std::vector<cf32::cplx> tw_all;
   prime_tw32(tw_all);
   const cf32::cplx* tw = tw_all.data() + prime_tw32_offset(R1);
+  const cf32::cplx* tw2 = tw_all.data() + kPrimeTw2Offset;
   std::vector<cf32::cplx> buf((size_t)cf32::padded_size(M), cf32::mk(0.f, 0.f));
   auto in = [&](int n) {
     if (n >= W) return cf32::mk(0.f, 0.f);
@@ -746,9 +828,9 @@ static void prime_host_fft(int W, int H, const std::vector<float>& xs, const std
     if (n < H) mag[n] = std::sqrt(std::fmaf(z.x, z.x, z.y * z.y));
   };
   for (int u = 0; u < 256; ++u) cf32::fwd_p1<R1>(buf.data(), tw, u, in);
-  for (int u = 0; u < R1 * 16; ++u) cf32::fwd_p2<R1>(buf.data(), tw, u);
-  for (int u = 0; u < R1 * 16; ++u) cf32::mid_p3(buf.data(), bhat.data(), u);
-  for (int u = 0; u < R1 * 16; ++u) cf32::bwd_p2<R1>(buf.data(), tw, u);
+  for (int u = 0; u < R1 * 16; ++u) cf32::fwd_p2<R1>(buf.data(), tw2, u);
+  for (int u = 0; u < R1 * 16; ++u) cf32::mid_p3(buf.data(), bhat.data(), R1 * 16, u);
+  for (int u = 0; u < R1 * 16; ++u) cf32::bwd_p2<R1>(buf.data(), tw2, u);
   for (int u = 0; u < 256; ++u) cf32::bwd_p1<R1>(buf.data(), tw, u, out);
 }
 
