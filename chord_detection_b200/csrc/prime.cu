@@ -654,9 +654,10 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
           // the exact-angle table (two loads; per-sample table reads would touch 32 cache lines
           // per warp instruction); the phasor is re-read from the table every 4 steps
           double re = 0.0, im = 0.0;
-          int j = (int)(((long long)tid * k) % W);
-          const int step = (int)(((long long)T * k) % W);
-          const int step4 = (int)((4LL * step) % W);
+          // (32-bit: tid k < 2^20; a 64-bit remainder is a ~150-instruction subroutine)
+          int j = (int)(((unsigned)tid * (unsigned)k) % (unsigned)W);
+          const int step = (int)(((unsigned)T * (unsigned)k) % (unsigned)W);
+          const int step4 = (int)((4u * (unsigned)step) % (unsigned)W);
           const double2 r = tw64[step];
           double2 ph = tw64[j];
 #pragma unroll
@@ -709,8 +710,8 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
           const int k = list[i];
           if (!isnan(s64[k])) continue;
           double re = 0.0, im = 0.0;
-          int j = (int)(((long long)lane * k) % W);
-          const int step = (int)((32LL * k) % W);
+          int j = (int)(((unsigned)lane * (unsigned)k) % (unsigned)W);
+          const int step = (int)((32u * (unsigned)k) % (unsigned)W);
 #pragma unroll 4
           for (int n = lane; n < W; n += 32) {
             const double xv = xw[n];
@@ -951,8 +952,9 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   if (const char* pm = std::getenv("CDB_PRIME")) screen = screen && std::string(pm) != "goertzel";
   if (screen) {
     cdb_mark(h, st, "begin");
-    if ((rc = prime_launch_screen<2, 128>(h, pl, a, clip_len, st)) ||
-        (rc = prime_launch_screen<4, 128>(h, pl, a, clip_len, st)) ||
+    // T = 16 R1 threads: every FFT pass keeps every thread busy (the inner passes have 16 R1 units)
+    if ((rc = prime_launch_screen<2, 32>(h, pl, a, clip_len, st)) ||
+        (rc = prime_launch_screen<4, 64>(h, pl, a, clip_len, st)) ||
         (rc = prime_launch_screen<8, 128>(h, pl, a, clip_len, st)) ||
         (rc = prime_launch_screen<16, 256>(h, pl, a, clip_len, st)))
       return rc;
