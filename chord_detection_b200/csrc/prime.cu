@@ -500,8 +500,8 @@ __device__ __forceinline__ void block_argmax(double& bv, int& bi, double* red_v,
     }
 }
 
-template <int R1, int T>
-__global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs sa) {
+template <int R1, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) prime_screen_kernel(const PrimeScreenArgs sa) {
   constexpr int M = R1 * 256;
   constexpr int NV = (M * 4 / 5 + T - 1) / T + 1;  // samples per thread (W + H - 1 <= M, H ~ W/4)
   extern __shared__ __align__(16) unsigned char smem[];
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(T) prime_screen_kernel(const PrimeScreenArgs s
   if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
 }
 
-template <int R1, int T>
+template <int R1, int T, int MINB>
 static int prime_launch_screen(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a, int64_t clip_len,
                                cudaStream_t st) {
   const int q = prime_class_of(R1);
@@ -796,7 +796,7 @@ static int prime_launch_screen(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a,
   constexpr int M = R1 * 256;
   const size_t smem = sizeof(cf32::cplx) * cf32::padded_size(M) + sizeof(float) * ((M / 4 + 3) & ~3) +
                       std::max<size_t>(sizeof(float) * M, (sizeof(double) + sizeof(short)) * (M / 4)) + 16;
-  auto kernel = prime_screen_kernel<R1, T>;
+  auto kernel = prime_screen_kernel<R1, T, MINB>;
   CDB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
@@ -952,12 +952,20 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   if (const char* pm = std::getenv("CDB_PRIME")) screen = screen && std::string(pm) != "goertzel";
   if (screen) {
     cdb_mark(h, st, "begin");
-    // T = 16 R1 threads: every FFT pass keeps every thread busy (the inner passes have 16 R1 units)
-    if ((rc = prime_launch_screen<2, 32>(h, pl, a, clip_len, st)) ||
-        (rc = prime_launch_screen<4, 64>(h, pl, a, clip_len, st)) ||
-        (rc = prime_launch_screen<8, 128>(h, pl, a, clip_len, st)) ||
-        (rc = prime_launch_screen<16, 256>(h, pl, a, clip_len, st)))
+    // T = 16 R1 threads: every FFT pass keeps every thread busy (the inner passes have 16 R1 units).
+    // Warps per SM: the kernel compiles to 128 registers (16 warps); capped at 96 it keeps all but
+    // 8 bytes in registers (20 warps), at 80 it spills ~110 bytes (24 warps).  CDB_PRIME_WARPS=16 / 20 / 24.
+    int warps = 20;
+    if (const char* pw = std::getenv("CDB_PRIME_WARPS")) warps = std::atoi(pw);
+#define PRIME_SCREEN_ALL(B2, B4, B8, B16)                                       \
+  ((rc = prime_launch_screen<2, 32, B2>(h, pl, a, clip_len, st)) ||           \
+   (rc = prime_launch_screen<4, 64, B4>(h, pl, a, clip_len, st)) ||           \
+   (rc = prime_launch_screen<8, 128, B8>(h, pl, a, clip_len, st)) ||          \
+   (rc = prime_launch_screen<16, 256, B16>(h, pl, a, clip_len, st)))
+    if (warps >= 24 ? PRIME_SCREEN_ALL(24, 12, 6, 3)
+                    : warps >= 20 ? PRIME_SCREEN_ALL(20, 10, 5, 2) : PRIME_SCREEN_ALL(16, 8, 4, 2))
       return rc;
+#undef PRIME_SCREEN_ALL
     cdb_mark(h, st, "prime_screen_kernel");
     CDB_CUDA(h, cudaGetLastError());
     return 0;
