@@ -726,6 +726,7 @@ __global__ void __launch_bounds__(T, MINB) prime_screen_kernel(const PrimeScreen
             re += __shfl_xor_sync(0xffffffffu, re, o);
             im += __shfl_xor_sync(0xffffffffu, im, o);
           }
+          __syncwarp();  // (every lane has read s64[k] above before lane 0 overwrites it)
           if (lane == 0) s64[k] = sqrt(re * re + im * im) * invsum;
         }
         __syncthreads();
