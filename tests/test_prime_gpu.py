@@ -112,6 +112,22 @@ def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
         _close(res.total.cpu().numpy(), res.clips.cpu().numpy().sum(axis=0), 1e-12)
 
 
+def test_prime_screen_occupancy_variants_agree(monkeypatch):
+    """CDB_PRIME_WARPS = 16 / 20 / 24 (register caps of the screen kernel) only change how many
+    windows are resident per SM: per-candidate results agree to the last bits of the atomics' sum."""
+    from chord_detection_b200 import ops
+
+    x, fs = cases.make_input(dict(fn="s_poly", seed=611, fs=22050, n=44100))
+    xd = torch.from_numpy(x).to(_dev())
+    base = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
+    assert base.sum() > 0
+    for w in ("16", "24"):
+        monkeypatch.setenv("CDB_PRIME_WARPS", w)
+        got = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
+        monkeypatch.delenv("CDB_PRIME_WARPS")
+        assert np.allclose(got, base, rtol=1e-12, atol=0), w
+
+
 def test_prime_window_sizes_host_table():
     from chord_detection_b200 import ops
 
