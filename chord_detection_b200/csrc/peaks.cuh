@@ -18,46 +18,56 @@ namespace pk {
 PK_HD inline int find_peaks(const double* y, int L, double thres_rel, int min_dist, int8_t* sgn,
                             int16_t* cand, int16_t* order) {
   if (L < 2) return 0;
-  double ymax = y[0], ymin = y[0];
-  for (int i = 1; i < L; ++i) {
-    ymax = fmax(ymax, y[i]);
-    ymin = fmin(ymin, y[i]);
-  }
-  const double thres = thres_rel * (ymax - ymin) + ymin;
+  // ONE pass over y: extrema, and every index where the plateau-filled first difference changes
+  // from + to -.  (peakutils fills a run of zero differences [a, b] with the slope on its left
+  // for 2k < a + b and the slope on its right otherwise -- the leftmost / rightmost runs take their
+  // only neighbour -- so a run with a rising left and a falling right neighbour yields exactly one
+  // candidate, at ceil((a + b) / 2); the threshold is applied afterwards.  The first version
+  // materialised the sign array in global scratch and walked y three times.)
+  (void)sgn;
   const int nd = L - 1;
-  int zeros = 0;
-  for (int i = 0; i < nd; ++i) {
-    const double d = y[i + 1] - y[i];
-    sgn[i] = d > 0.0 ? 1 : (d < 0.0 ? -1 : 0);
-    zeros += (d == 0.0);
-  }
-  if (zeros == nd) return 0;  // totally flat
-  // propagate neighbouring slopes into plateaus (runs of dy == 0)
+  double ymax = y[0], ymin = y[0];
+  int nc = 0;
+  int prev = 0;      // filled sign at i - 1 (0: nothing yet / inside the leftmost plateau)
+  bool any = false;  // a non-zero difference seen
+  double cur_y = y[0];
   int i = 0;
   while (i < nd) {
-    if (sgn[i] != 0) {
+    const double nxt = y[i + 1];
+    ymax = fmax(ymax, nxt);
+    ymin = fmin(ymin, nxt);
+    const double d = nxt - cur_y;
+    cur_y = nxt;
+    if (d != 0.0) {
+      const int cur = d > 0.0 ? 1 : -1;
+      if (prev > 0 && cur < 0) cand[nc++] = (int16_t)i;
+      prev = cur;
+      any = true;
       ++i;
       continue;
     }
-    int a = i, b = i;
-    while (b + 1 < nd && sgn[b + 1] == 0) ++b;
-    if (a == 0) {  // leftmost plateau takes the slope to its right
-      const int8_t v = sgn[b + 1];
-      for (int k = a; k <= b; ++k) sgn[k] = v;
-    } else if (b == nd - 1) {  // rightmost plateau takes the slope to its left
-      const int8_t v = sgn[a - 1];
-      for (int k = a; k <= b; ++k) sgn[k] = v;
-    } else {  // left half <- left slope; middle (>= median) and right half <- right slope
-      const int8_t lv = sgn[a - 1], rv = sgn[b + 1];
-      for (int k = a; k <= b; ++k) sgn[k] = (2 * k < a + b) ? lv : rv;
-    }
-    i = b + 1;
+    // run of zero differences [a, b]
+    const int a = i;
+    int b = i;
+    while (b + 1 < nd && y[b + 2] == cur_y) ++b;  // (y[b + 2] - y[b + 1] == 0 <=> equal: finite data)
+    if (b == nd - 1) break;                        // rightmost run takes the slope on its left: no change
+    const double yn = y[b + 2];
+    ymax = fmax(ymax, yn);
+    ymin = fmin(ymin, yn);
+    const int rv = yn > cur_y ? 1 : -1;
+    if (a > 0 && prev > 0 && rv < 0) cand[nc++] = (int16_t)((a + b + 1) >> 1);
+    prev = rv;  // position b + 1 carries rv itself
+    any = true;
+    cur_y = yn;
+    i = b + 2;
   }
-  int nc = 0;
-  for (int k = 0; k < L; ++k) {
-    const int r = (k < nd) ? sgn[k] : 0;
-    const int l = (k > 0) ? sgn[k - 1] : 0;
-    if (r < 0 && l > 0 && y[k] > thres) cand[nc++] = (int16_t)k;
+  if (!any) return 0;  // totally flat
+  const double thres = thres_rel * (ymax - ymin) + ymin;
+  {
+    int out = 0;
+    for (int c = 0; c < nc; ++c)
+      if (y[cand[c]] > thres) cand[out++] = cand[c];
+    nc = out;
   }
   if (nc > 1 && min_dist > 1) {
     // order = candidates by height, highest first (ties: larger index first)
