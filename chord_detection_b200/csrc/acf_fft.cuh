@@ -129,7 +129,7 @@ AFFT_HD void fwd_p1(cplx* buf, const cplx* tw, int np, In in) {
 }
 // P2 unit u = k1*16 + n'': DFT over n2 (stride 16) -> k2, times W_256^(n'' k2)
 template <int R1>
-AFFT_HD void fwd_p2(cplx* buf, const cplx* tw, int u) {
+AFFT_HD void fwd_p2(cplx* buf, const cplx* tw2, int u) {
   const int base = (u >> 4) * 256 + (u & 15), npp = u & 15;
   cplx v[16];
 #pragma unroll
@@ -137,7 +137,7 @@ AFFT_HD void fwd_p2(cplx* buf, const cplx* tw, int u) {
   dft_regs<16>(v);
   buf[pad(base)] = v[0];
 #pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) buf[pad(base + k2 * 16)] = cmul(v[k2], tw[R1 * 256 + k2 * 16 + npp]);
+  for (int k2 = 1; k2 < 16; ++k2) buf[pad(base + k2 * 16)] = cmul(v[k2], tw2[k2 * 16 + npp]);
 }
 // P3 . (x chirp spectrum, conj) . P3 of unit u = k1*16 + k2 on its 16 contiguous elements.
 // bhat is the chirp spectrum / M in digit-reversed order, transposed (see above); nu = 16 R1.
@@ -154,12 +154,12 @@ AFFT_HD void mid_p3(cplx* buf, const cplx* bhat, int nu, int u) {
 }
 // ---- backward, digit-reversed -> natural -----------------------------------------------------
 template <int R1>
-AFFT_HD void bwd_p2(cplx* buf, const cplx* tw, int u) {
+AFFT_HD void bwd_p2(cplx* buf, const cplx* tw2, int u) {
   const int base = (u >> 4) * 256 + (u & 15), npp = u & 15;
   cplx v[16];
   v[0] = buf[pad(base)];
 #pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(buf[pad(base + k2 * 16)], tw[R1 * 256 + k2 * 16 + npp]);
+  for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(buf[pad(base + k2 * 16)], tw2[k2 * 16 + npp]);
   dft_regs<16>(v);
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) buf[pad(base + n2 * 16)] = v[n2];
@@ -197,7 +197,8 @@ struct AcfCtx {
   const double* hi;        // [N][B]
   const cplx* chirp;       // [N]  w[n] = exp(-i pi n^2 / N)
   const cplx* bhat;        // [M]  FFT_M(conj chirp) / M, digit-reversed, transposed
-  const cplx* tw;          // [M + 256]  pass-1 | pass-2 twiddles
+  const cplx* tw;          // [M]  pass-1 twiddles
+  const cplx* tw2;         // [256]  pass-2 twiddles (the kernel keeps them in shared memory)
   cplx* buf;               // [padded_size(M)]
   double* Sa;              // [K]
   double* Sb;              // [K]
@@ -254,9 +255,9 @@ struct AcfUnit {
   AFFT_HD void operator()(int u) const {
     switch (pass) {
       case 0: fwd_p1<R1>(c.buf, c.tw, u, AcfIn{c, d}); break;
-      case 1: fwd_p2<R1>(c.buf, c.tw, u); break;
+      case 1: fwd_p2<R1>(c.buf, c.tw2, u); break;
       case 2: mid_p3(c.buf, c.bhat, R1 * 16, u); break;
-      case 3: bwd_p2<R1>(c.buf, c.tw, u); break;
+      case 3: bwd_p2<R1>(c.buf, c.tw2, u); break;
       case 4: bwd_p1<R1>(c.buf, c.tw, u, AcfOut{c, d}); break;
       default: {  // power-compressed spectra of frame d from Z (in buf): bin k = u
         double* S = d ? c.Sb : c.Sa;

@@ -305,6 +305,9 @@ struct AcfExecDev {
 #endif
   }
 };
+__host__ __device__ constexpr size_t acf_tw2_offset(int M, int K) {
+  return (size_t)afft::padded_size(M) * sizeof(afft::cplx) + 2 * (size_t)K * sizeof(double) + 16;
+}
 template <int R1>
 __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kernel(const EsacfArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -326,6 +329,14 @@ __global__ void __launch_bounds__(R1 * 16, R1 == 16 ? 2 : 4) esacf_acf_fft_kerne
   c.Sb = c.Sa + a.K;
   c.live = reinterpret_cast<int*>(c.Sb + a.K);
   if (threadIdx.x < 2) c.live[threadIdx.x] = 0;  // (published by the barriers of the first DFT)
+  // pass-2 twiddles (4 KB) in shared memory: a third of the stall samples of this kernel waited on
+  // table loads from L1 / L2 (ncu r02D); the first barrier of the first DFT publishes them
+  {
+    afft::cplx* tw2s = reinterpret_cast<afft::cplx*>(smem + ((acf_tw2_offset(M, a.K) + 15) & ~(size_t)15));
+    const afft::cplx* tw2g = a.acf_tables + a.N + 2 * M;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tw2s[i] = tw2g[i];
+    c.tw2 = tw2s;
+  }
   c.half_kexp = 0.5 * a.kexp;
   c.clip_pos = a.clip_pos;
   c.prefix = a.prefix;
@@ -784,6 +795,7 @@ int cdb_host_esacf_acf(int N, double kexp, int clip_pos, int prefix, int n_frame
   c.chirp = tables.data();
   c.bhat = tables.data() + N;
   c.tw = tables.data() + N + M;
+  c.tw2 = tables.data() + N + 2 * M;
   c.buf = buf.data();
   c.Sa = S.data();
   c.Sb = S.data() + K;
@@ -927,8 +939,7 @@ int cdb_esacf_chroma(cdb_handle* h, const cdb_esacf_params* p, const float* d_x,
       : bins == 3 ? esacf_acf_kernel<3> : esacf_acf_kernel<4>;
   CDB_CUDA(h, cudaFuncSetAttribute(acf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)acf_smem));
-  const size_t acf_fft_smem =
-      (size_t)afft::padded_size(fft_r1 * 256) * sizeof(afft::cplx) + 2 * (size_t)a.K * sizeof(double) + 16;
+  const size_t acf_fft_smem = ((acf_tw2_offset(fft_r1 * 256, a.K) + 15) & ~(size_t)15) + 256 * sizeof(afft::cplx);
   void (*acf_fft_kernel)(const EsacfArgs) =
       fft_r1 == 8 ? esacf_acf_fft_kernel<8> : esacf_acf_fft_kernel<16>;
   if (fft_r1)
