@@ -60,7 +60,7 @@ EXPORTS = [
     "cdb_version", "cdb_create", "cdb_destroy", "cdb_last_error", "cdb_launch_count",
     "cdb_num_frames", "cdb_he_windows", "cdb_he_chroma", "cdb_esacf_chroma",
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
-    "cdb_prime_chroma", "cdb_host_prime_screen", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
+    "cdb_prime_chroma", "cdb_host_prime_screen", "cdb_host_prime_screen2", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
     "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
     "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
     "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
@@ -266,8 +266,9 @@ def host_gauss_fit(x0, y, suspend_after=0):
     return info, [p[0], p[1], p[2]], nfev.value
 
 
-def host_prime_screen(x):
+def host_prime_screen(x, variant=0):
     """Host execution of the prime-multiF0 FP32 screen of one window (test hook, no GPU).
+    variant 0: the CTA kernel's transforms, 1: the warp-per-window kernel's.
     x: float32 [W] -> (s_screen [H], s_exact [H], delta)"""
     import numpy as np
 
@@ -278,10 +279,10 @@ def host_prime_screen(x):
     delta = C.c_double(0.0)
     D = C.POINTER(C.c_double)
     L = lib()
-    L.cdb_host_prime_screen.argtypes = [C.c_int, C.POINTER(C.c_float), D, D, D]
-    L.cdb_host_prime_screen.restype = C.c_int
-    H = L.cdb_host_prime_screen(W, x.ctypes.data_as(C.POINTER(C.c_float)), s32.ctypes.data_as(D),
-                                s64.ctypes.data_as(D), C.byref(delta))
+    L.cdb_host_prime_screen2.argtypes = [C.c_int, C.POINTER(C.c_float), D, D, D, C.c_int]
+    L.cdb_host_prime_screen2.restype = C.c_int
+    H = L.cdb_host_prime_screen2(W, x.ctypes.data_as(C.POINTER(C.c_float)), s32.ctypes.data_as(D),
+                                 s64.ctypes.data_as(D), C.byref(delta), int(variant))
     if H < 0:
         raise ValueError("cdb_host_prime_screen failed: %d" % H)
     return s32[:H], s64[:H], delta.value

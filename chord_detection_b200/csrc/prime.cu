@@ -21,6 +21,7 @@
 
 #include "cfft32.cuh"
 #include "common.cuh"
+#include "prime_warp.cuh"
 
 constexpr int kPrimeThreads = 128;
 constexpr int kPrimeMaxCand = 96;
@@ -53,6 +54,17 @@ struct PrimePlan {
   float* d_kappa = nullptr;                 // [n_cand] screen error bound / ||x w||_2
   int* d_offb = nullptr;                    // [n_cand] offset of candidate c in d_bhat
   std::map<int64_t, int*> cls_start_cache[4];  // clip_len -> prefix of windows per class candidate
+  // warp-per-window screen (prime_screen_warp_kernel, prime_warp.cuh): class 0 = one 1024-point
+  // transform pair, class 1 = 2048 points as two; larger windows stay with the CTA kernel
+  std::vector<int> wcls_cands[2];
+  int* d_wcls_cands[2] = {nullptr, nullptr};
+  c64* d_bhatw = nullptr;     // per candidate [k2][k1] filter spectrum / M (class 1: even bins | odd bins)
+  int* d_offbw = nullptr;     // [n_cand]
+  float* d_kappaw = nullptr;  // [n_cand]
+  c64* d_tw1024 = nullptr;    // [k1][l] W_1024^(l k1)
+  c64* d_w2048 = nullptr;     // [n] W_2048^n, n < 1024
+  std::map<int64_t, int*> wcls_start_cache[2];
+  bool warp_ok = false;
 };
 
 void cdb_free_prime_plans(cdb_handle* h) {
@@ -105,6 +117,63 @@ static int prime_screen_r1(int W, int H) {
   for (int r1 = 2; r1 <= 16; r1 *= 2)
     if (need <= 256 * r1) return r1;
   return 0;
+}
+
+// filter spectrum FFT_M(b) (natural order, long double) of the chirp filter of a W-point window
+static void prime_filter_spectrum(int W, int H, int M, std::vector<std::complex<long double>>& b) {
+  typedef std::complex<long double> lc;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  b.assign((size_t)M, lc(0.0L, 0.0L));
+  for (int n = 0; n < W; ++n) {
+    const long long e = ((long long)n * n) % (2LL * W);
+    const long double ang = -pi * (long double)e / (long double)W;
+    const lc cw(cosl(ang), -sinl(ang));
+    if (n < H) b[n] = cw;
+    if (n) b[M - n] = cw;
+  }
+  for (int i = 1, j = 0; i < M; ++i) {
+    int bit = M >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(b[i], b[j]);
+  }
+  for (int len = 2; len <= M; len <<= 1)
+    for (int i = 0; i < M; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const long double ang = -2.0L * pi * (long double)k / (long double)len;
+        const lc w(cosl(ang), sinl(ang));
+        const lc u = b[i + k], v = b[i + k + len / 2] * w;
+        b[i + k] = u + v;
+        b[i + k + len / 2] = u - v;
+      }
+}
+
+// tables of the warp kernel for one candidate: class 0 (M = 1024) [k2][k1] of B^[k1 + 32 k2] / M;
+// class 1 (M = 2048) the even bins B^[2k] / M in that layout, then the odd bins B^[2k + 1] / M
+static void prime_warp_tables(int W, int H, int cls, std::vector<c64>& bhatw, float* kappa) {
+  typedef std::complex<long double> lc;
+  const int M = cls ? 2048 : 1024;
+  std::vector<lc> b;
+  prime_filter_spectrum(W, H, M, b);
+  long double bmax = 0.0L;
+  for (int k = 0; k < M; ++k) bmax = std::max(bmax, std::abs(b[k]));
+  const size_t o = bhatw.size();
+  bhatw.resize(o + (size_t)M);
+  for (int half = 0; half < (cls ? 2 : 1); ++half)
+    for (int k2 = 0; k2 < 32; ++k2)
+      for (int k1 = 0; k1 < 32; ++k1) {
+        const int k = k1 + 32 * k2;
+        const lc v = b[cls ? 2 * k + half : k] / (long double)M;
+        bhatw[o + (size_t)half * 1024 + k2 * 32 + k1] = pk((float)v.real(), (float)v.imag());
+      }
+  int L = 0;
+  while ((1 << L) < M) ++L;
+  const double u = 5.9604644775390625e-8;  // 2^-24
+  *kappa = (float)(1.05 * (2.0 * L * 6.7 + 6.3) * u * (double)bmax);
+}
+static int prime_warp_class(int W, int H) {
+  const int need = W + H - 1;
+  return need <= 1024 ? 0 : need <= 2048 ? 1 : -1;
 }
 
 static void prime_screen_tables(int W, int H, int R1, std::vector<cf32::cplx>& chirp,
@@ -210,6 +279,40 @@ static int prime_build_screen(cdb_handle* h, PrimePlan* pl) {
   for (int q = 0; q < 4; ++q)
     if (!pl->cls_cands[q].empty() && (rc = cdb_upload(h, pl->cls_cands[q], &pl->d_cls_cands[q])))
       return rc;
+  // warp-per-window kernel: candidates that fit 1024 / 2048 points; the rest keep the CTA kernel
+  {
+    std::vector<c64> bhatw, tw1024, w2048;
+    std::vector<int> offbw;
+    std::vector<float> kappaw;
+    for (int c = 0; c < pl->n_cand; ++c) {
+      const int cls = prime_warp_class(pl->W[c], pl->H[c]);
+      offbw.push_back((int)bhatw.size());
+      float kp = 0.f;
+      if (cls >= 0) {
+        pl->wcls_cands[cls].push_back(c);
+        prime_warp_tables(pl->W[c], pl->H[c], cls, bhatw, &kp);
+      }
+      kappaw.push_back(kp);
+    }
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int l = 0; l < 32; ++l) {
+        const long double ang = -2.0L * pi * (long double)(l * k1) / 1024.0L;
+        tw1024.push_back(pk((float)cosl(ang), (float)sinl(ang)));
+      }
+    for (int n = 0; n < 1024; ++n) {
+      const long double ang = -2.0L * pi * (long double)n / 2048.0L;
+      w2048.push_back(pk((float)cosl(ang), (float)sinl(ang)));
+    }
+    if ((rc = cdb_upload(h, bhatw, &pl->d_bhatw)) || (rc = cdb_upload(h, offbw, &pl->d_offbw)) ||
+        (rc = cdb_upload(h, kappaw, &pl->d_kappaw)) || (rc = cdb_upload(h, tw1024, &pl->d_tw1024)) ||
+        (rc = cdb_upload(h, w2048, &pl->d_w2048)))
+      return rc;
+    for (int q = 0; q < 2; ++q)
+      if (!pl->wcls_cands[q].empty() && (rc = cdb_upload(h, pl->wcls_cands[q], &pl->d_wcls_cands[q])))
+        return rc;
+    pl->warp_ok = true;
+  }
   return 0;
 }
 
@@ -809,6 +912,322 @@ static int prime_launch_screen(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// prime_screen_warp_kernel<CLS>: the same screen + FP64 decision as prime_screen_kernel, ONE WARP per
+// window (prime_warp.cuh): 1024-point transforms with 32 points per lane in packed FP32x2
+// arithmetic and one shared-memory transpose each, no block barrier anywhere in the window loop,
+// every reduction a warp shuffle.  CLS 0: W + H - 1 <= 1024 (one transform pair); CLS 1: <= 2048
+// (radix-2 split around two pairs).  ~2 500 / ~5 000 warp-instructions per window against ~6 000 /
+// ~12 000 of the CTA kernel (three-pass scalar transforms, five block barriers).
+struct PrimeWarpArgs {
+  PrimeArgs a;
+  const int* cls_cands;
+  const int* cls_start;  // [n_cls + 1]
+  int n_cls;
+  const c64* chirp;      // (cf32::cplx table: same bits)
+  const c64* bhatw;
+  const int* offbw;
+  const float* kappa;
+  const c64* tw1024;
+  const c64* w2048;
+  const double2* tw64;
+};
+
+constexpr int kPwWarps = 4;
+template <int CLS>
+struct PwSmem {
+  static constexpr int M = CLS ? 2048 : 1024;
+  static constexpr int HMAX = CLS ? 416 : 224;  // H <= (M + 1) / 5 + 1
+  static constexpr size_t kWarpBytes =
+      sizeof(c64) * pw::kScr + sizeof(float) * M + sizeof(double) * HMAX + sizeof(float) * HMAX;
+  static constexpr size_t kSharedTables = sizeof(c64) * 1024 * (CLS ? 2 : 1);
+  static constexpr size_t kBytes = kSharedTables + kPwWarps * kWarpBytes;
+};
+
+__device__ __forceinline__ double pw_warp_sum(double v) {  // every lane gets the sum
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(kPwWarps * 32, CLS ? 2 : 3) prime_screen_warp_kernel(const PrimeWarpArgs sa) {
+  using S = PwSmem<CLS>;
+  constexpr int M = S::M;
+  constexpr int NJ = M / 32;  // samples per lane
+  extern __shared__ __align__(16) unsigned char smem[];
+  const PrimeArgs& a = sa.a;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  c64* tw = reinterpret_cast<c64*>(smem);  // [k1][l]
+  c64* w2k = tw + 1024;                    // (CLS 1) W_2048^n
+  unsigned char* wb = smem + S::kSharedTables + (size_t)warp * S::kWarpBytes;
+  c64* scr = reinterpret_cast<c64*>(wb);
+  double* s64 = reinterpret_cast<double*>(scr + pw::kScr);
+  float* xs = reinterpret_cast<float*>(s64 + S::HMAX);
+  float* s32 = xs + M;
+  __shared__ double cta_total[12];
+  for (int i = tid; i < 1024; i += kPwWarps * 32) {
+    tw[i] = sa.tw1024[i];
+    if (CLS) w2k[i] = sa.w2048[i];
+  }
+  if (tid < 12) cta_total[tid] = 0.0;
+  __syncthreads();
+
+  const int64_t items_per_clip = sa.cls_start[sa.n_cls];
+  const int64_t total_items = items_per_clip * a.n_clips;
+  for (int64_t item = (int64_t)blockIdx.x * kPwWarps + warp; item < total_items;
+       item += (int64_t)gridDim.x * kPwWarps) {
+    const int64_t clip = item / items_per_clip;
+    const int r = (int)(item - clip * items_per_clip);
+    int q = 0;
+    while (q + 1 < sa.n_cls && sa.cls_start[q + 1] <= r) ++q;
+    const int c = sa.cls_cands[q];
+    const int frame = r - sa.cls_start[q];
+    const int W = a.W[c], H = a.H[c];
+    const int64_t s0 = (int64_t)frame * W;
+    const float* src = a.x + clip * a.clip_stride + s0;
+    const int64_t avail = a.clip_len - s0;
+    const int lim = (int)(avail < (int64_t)W ? (avail > 0 ? avail : 0) : (int64_t)W);  // samples present
+    const double* win = a.win + a.offw[c];
+    const double invsum = a.invsum[c];
+    const int nj = (W + 31) >> 5;
+
+    // largest windowed sample (FP64 products, the ones the FP64 evaluation uses)
+    double amax = 0.0;
+    int badi = 0;
+    for (int j = 0; j < nj; ++j) {
+      const int n = lane + 32 * j;
+      const double v = n < lim ? (double)__ldg(src + n) * win[n] : 0.0;
+      badi |= !(fabs(v) <= 1.7976931348623157e308);
+      amax = fmax(amax, fabs(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      badi |= __shfl_xor_sync(0xffffffffu, badi, o);
+    }
+    if (!badi && amax == 0.0) continue;  // silence (see prime_screen_kernel)
+    bool full = badi != 0;
+    float delta = 0.f;
+    __syncwarp();
+    if (!full) {
+      const double sc = scalbn(1.0, -ilogb(amax));
+      float nrm = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < NJ; ++j) {
+        const int n = lane + 32 * j;
+        const float f = n < lim ? (float)(((double)__ldg(src + n) * win[n]) * sc) : 0.f;
+        xs[n] = f;
+        nrm = fmaf(f, f, nrm);
+      }
+      delta = sa.kappa[c] * (float)sqrt(pw_warp_sum((double)nrm)) * 1.01f;
+      __syncwarp();
+      const c64* chirp = sa.chirp + a.offw[c];
+      const c64* bh = sa.bhatw + sa.offbw[c];
+      c64 v[32];
+      if (CLS == 0) {
+        {
+          c64 in[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = 32 * j + lane;
+            in[j] = n < W ? mul2(bc(xs[n]), chirp[n]) : 0ull;
+          }
+          pw::p1(lane, in, tw, scr);
+        }
+        __syncwarp();
+        pw::p2(lane, scr, v);
+        __syncwarp();
+        {
+          c64 u[32];
+#pragma unroll
+          for (int k2 = 0; k2 < 32; ++k2) u[k2] = conj2(cmul2(v[k2], bh[k2 * 32 + lane]));
+          pw::p1(lane, u, tw, scr);
+        }
+        __syncwarp();
+        pw::p2(lane, scr, v);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < (S::HMAX + 31) / 32; ++m) {
+          const int n = lane + 32 * m;
+          float zr, zi;
+          upk(v[m], zr, zi);
+          if (n < H) s32[n] = sqrtf(fmaf(zr, zr, zi * zi));
+        }
+      } else {
+        constexpr int NM = (S::HMAX + 31) / 32;
+        c64 fe[NM];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          {
+            c64 in[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = 32 * j + lane;
+              const c64 ya = n < W ? mul2(bc(xs[n]), chirp[n]) : 0ull;
+              const c64 yb = n + 1024 < W ? mul2(bc(xs[n + 1024]), chirp[n + 1024]) : 0ull;
+              in[j] = half ? cmul2(sub2(ya, yb), w2k[n]) : add2(ya, yb);
+            }
+            pw::p1(lane, in, tw, scr);
+          }
+          __syncwarp();
+          pw::p2(lane, scr, v);
+          __syncwarp();
+          {
+            c64 u[32];
+            const c64* bq = bh + half * 1024;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) u[k2] = conj2(cmul2(v[k2], bq[k2 * 32 + lane]));
+            pw::p1(lane, u, tw, scr);
+          }
+          __syncwarp();
+          pw::p2(lane, scr, v);
+          __syncwarp();
+          if (half == 0) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) fe[m] = v[m];
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          const int n = lane + 32 * m;
+          // conj z[n] = Fe[n] + W_2048^n Fo[n]   (conj of z = IFe + W_2048^-n IFo)
+          const c64 zc = add2(fe[m], cmul2(v[m], w2k[n]));
+          float zr, zi;
+          upk(zc, zr, zi);
+          if (n < H) s32[n] = sqrtf(fmaf(zr, zr, zi * zi));
+        }
+      }
+    }
+    for (int k = lane; k < H; k += 32) s64[k] = __longlong_as_double(0x7ff8000000000000LL);
+    __syncwarp();
+    const int8_t* note = a.note + a.offh[c];
+    const uint8_t* elim = a.elim + a.offh[c];
+    const double2* tw64 = sa.tw64 + a.offw[c];
+    for (int run = 0; run < a.runs; ++run) {
+      float thr = -1.f;
+      if (!full) {
+        float vm = -1.f;
+        for (int k = lane; k < H; k += 32) vm = fmaxf(vm, s32[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vm = fmaxf(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+        thr = vm - 2.f * delta;
+        if (!(vm <= 3.0e38f)) {
+          full = true;
+          thr = -1.f;
+        }
+      }
+      double bv = -1.0;
+      int bi = 0x7fffffff;
+      for (int base = 0; base < H; base += 32) {
+        const int k = base + lane;
+        unsigned mask = __ballot_sync(0xffffffffu, k < H && (full || s32[k] >= thr));
+        while (mask) {
+          const int kk = base + __ffs(mask) - 1;
+          mask &= mask - 1;
+          double val = s64[kk];
+          if (isnan(val)) {
+            // FP64 direct DFT of bin kk: lanes over n = lane + 32 j, phasor by recurrence from the
+            // exact-angle table (re-read every 4 steps)
+            double re = 0.0, im = 0.0;
+            int jx = (int)(((unsigned)lane * (unsigned)kk) % (unsigned)W);
+            const int step = (int)((32u * (unsigned)kk) % (unsigned)W);
+            const int step4 = (int)((4u * (unsigned)step) % (unsigned)W);
+            const double2 rr = tw64[step];
+            double2 ph = tw64[jx];
+#pragma unroll 4
+            for (int j = 0; j < nj; ++j) {
+              if ((j & 3) == 0 && j) {
+                jx += step4;
+                jx -= jx >= W ? W : 0;
+                ph = tw64[jx];
+              }
+              const int n = lane + 32 * j;
+              const double xv = n < lim ? (double)__ldg(src + n) * win[n] : 0.0;
+              re = fma(xv, ph.x, re);
+              im = fma(xv, ph.y, im);
+              const double px = fma(ph.x, rr.x, -(ph.y * rr.y));
+              ph.y = fma(ph.x, rr.y, ph.y * rr.x);
+              ph.x = px;
+            }
+            re = pw_warp_sum(re);
+            im = pw_warp_sum(im);
+            val = sqrt(re * re + im * im) * invsum;
+            __syncwarp();
+            if (lane == 0) s64[kk] = val;
+          }
+          if (val > bv) {  // (ascending kk: the first maximum wins, numpy.argmax)
+            bv = val;
+            bi = kk;
+          }
+        }
+      }
+      __syncwarp();
+      if (bi < H) {
+        const int nt = note[bi];
+        if (nt >= 0) {
+          if (lane == 0) {
+            atomicAdd(&cta_total[nt], bv);
+            if (a.clips) atomicAdd(&a.clips[clip * 12 + nt], bv);
+            if (a.cands) atomicAdd(&a.cands[(clip * a.n_cand + c) * 12 + nt], bv);
+          }
+          const uint8_t mask = elim[bi];
+          if (lane >= 1 && lane < a.nmult && (mask & (1u << (lane - 1)))) {
+            s32[lane * bi] = 0.f;
+            s64[lane * bi] = 0.0;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (a.total && tid < 12 && cta_total[tid] != 0.0) atomicAdd(&a.total[tid], cta_total[tid]);
+}
+
+template <int CLS>
+static int prime_launch_warp(cdb_handle* h, PrimePlan* pl, const PrimeArgs& a, int64_t clip_len,
+                             cudaStream_t st) {
+  const std::vector<int>& cc = pl->wcls_cands[CLS];
+  if (cc.empty()) return 0;
+  std::vector<int> start(cc.size() + 1, 0);
+  for (size_t i = 0; i < cc.size(); ++i)
+    start[i + 1] = start[i] + (int)cdb_num_frames(clip_len, pl->W[cc[i]], pl->W[cc[i]]);
+  if (start.back() == 0) return 0;
+  int* d_start = nullptr;
+  auto it = pl->wcls_start_cache[CLS].find(clip_len);
+  if (it == pl->wcls_start_cache[CLS].end()) {
+    int rc = cdb_upload(h, start, &d_start);
+    if (rc) return rc;
+    pl->wcls_start_cache[CLS][clip_len] = d_start;
+  } else {
+    d_start = it->second;
+  }
+  PrimeWarpArgs sa;
+  sa.a = a;
+  sa.cls_cands = pl->d_wcls_cands[CLS];
+  sa.cls_start = d_start;
+  sa.n_cls = (int)cc.size();
+  sa.chirp = reinterpret_cast<const c64*>(pl->d_chirp);
+  sa.bhatw = pl->d_bhatw;
+  sa.offbw = pl->d_offbw;
+  sa.kappa = pl->d_kappaw;
+  sa.tw1024 = pl->d_tw1024;
+  sa.w2048 = pl->d_w2048;
+  sa.tw64 = pl->d_tw64;
+  const size_t smem = PwSmem<CLS>::kBytes;
+  auto kernel = prime_screen_warp_kernel<CLS>;
+  CDB_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CDB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPwWarps * 32, smem));
+  if (per_sm < 1) return cdb_fail(h, CDB_E_UNSUPPORTED, "warp screen kernel does not fit");
+  const int64_t items = (int64_t)start.back() * a.n_clips;
+  const int64_t grid = std::min<int64_t>((items + kPwWarps - 1) / kPwWarps, (int64_t)h->num_sms * per_sm);
+  kernel<<<(unsigned)grid, kPwWarps * 32, smem, st>>>(sa);
+  h->launches += 1;
+  return 0;
+}
+
 // Host execution (CPU tests, no GPU) of the screen of ONE window of W samples: the same tables and
 // the same cfft32.cuh passes as prime_screen_kernel, units executed sequentially.  s_screen[H]: FP32
 // Bluestein magnitudes (in the units of the reference's spectrum), s_exact[H]: the FP64 direct DFT
@@ -836,13 +1255,77 @@ static void prime_host_fft(int W, int H, const std::vector<float>& xs, const std
   for (int u = 0; u < 256; ++u) cf32::bwd_p1<R1>(buf.data(), tw, u, out);
 }
 
-extern "C" int cdb_host_prime_screen(int W, const float* x, double* s_screen, double* s_exact,
-                                     double* delta) {
+// the warp kernel's transforms, lane by lane on the host (class 0 / 1 of prime_warp.cuh)
+static void prime_host_warp_fft(int W, int H, int cls, const std::vector<float>& xs_in,
+                                const std::vector<cf32::cplx>& chirp_f, std::vector<float>& mag) {
+  const int M = cls ? 2048 : 1024;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<c64> tw(1024), w2k(1024), bh, chirp((size_t)W), scr((size_t)pw::kScr, 0ull);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const long double ang = -2.0L * pi * (long double)(l * k1) / 1024.0L;
+      tw[k1 * 32 + l] = pk((float)cosl(ang), (float)sinl(ang));
+    }
+  for (int n = 0; n < 1024; ++n) {
+    const long double ang = -2.0L * pi * (long double)n / 2048.0L;
+    w2k[n] = pk((float)cosl(ang), (float)sinl(ang));
+  }
+  for (int n = 0; n < W; ++n) chirp[n] = pk(chirp_f[n].x, chirp_f[n].y);
+  float kp;
+  prime_warp_tables(W, H, cls, bh, &kp);
+  std::vector<float> xs((size_t)M, 0.f);
+  for (int n = 0; n < W; ++n) xs[n] = xs_in[n];
+  std::vector<c64> V(32 * 32), FE(32 * 32);
+  auto y = [&](int n) { return n < W ? mul2(bc(xs[n]), chirp[n]) : 0ull; };
+  for (int half = 0; half < (cls ? 2 : 1); ++half) {
+    for (int lane = 0; lane < 32; ++lane) {
+      c64 in[32];
+      for (int j = 0; j < 32; ++j) {
+        const int n = 32 * j + lane;
+        if (!cls) in[j] = y(n);
+        else in[j] = half ? cmul2(sub2(y(n), y(n + 1024)), w2k[n]) : add2(y(n), y(n + 1024));
+      }
+      pw::p1(lane, in, tw.data(), scr.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      c64 v[32];
+      pw::p2(lane, scr.data(), v);
+      for (int k2 = 0; k2 < 32; ++k2) V[lane * 32 + k2] = v[k2];
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      c64 u[32];
+      for (int k2 = 0; k2 < 32; ++k2)
+        u[k2] = conj2(cmul2(V[lane * 32 + k2], bh[(size_t)half * 1024 + k2 * 32 + lane]));
+      pw::p1(lane, u, tw.data(), scr.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      c64 v[32];
+      pw::p2(lane, scr.data(), v);
+      for (int m = 0; m < 32; ++m) {
+        const int n = lane + 32 * m;
+        c64 zc = v[m];
+        if (cls && half == 0) {
+          FE[lane * 32 + m] = v[m];
+          continue;
+        }
+        if (cls) zc = add2(FE[lane * 32 + m], cmul2(v[m], w2k[n]));
+        float zr, zi;
+        upk(zc, zr, zi);
+        if (n < H) mag[n] = std::sqrt(std::fmaf(zr, zr, zi * zi));
+      }
+    }
+  }
+}
+
+// variant 0: the CTA kernel's three-pass transforms (cfft32.cuh); 1: the warp kernel's (prime_warp.cuh)
+extern "C" int cdb_host_prime_screen2(int W, const float* x, double* s_screen, double* s_exact,
+                                      double* delta, int variant) {
   if (W < 4 || !x || !s_screen || !s_exact || !delta) return -1;
   const int num_freqs = (W % 2) ? (W + 1) / 2 : W / 2 + 1;
   const int H = num_freqs / 2;
   const int R1 = prime_screen_r1(W, H);
-  if (!R1 || H < 1) return -2;
+  const int cls = prime_warp_class(W, H);
+  if (!R1 || H < 1 || (variant == 1 && cls < 0)) return -2;
   const double pi = 3.14159265358979323846;
   std::vector<double> xw((size_t)W);
   double sum = 0.0, amax = 0.0;
@@ -857,6 +1340,10 @@ extern "C" int cdb_host_prime_screen(int W, const float* x, double* s_screen, do
   std::vector<double2> tw64;
   float kappa = 0.f;
   prime_screen_tables(W, H, R1, chirp, bhat, tw64, &kappa);
+  if (variant == 1) {
+    std::vector<c64> tmp;
+    prime_warp_tables(W, H, cls, tmp, &kappa);
+  }
   for (int k = 0; k < H; ++k) {
     double re = 0.0, im = 0.0;
     for (int n = 0; n < W; ++n) {
@@ -876,15 +1363,23 @@ extern "C" int cdb_host_prime_screen(int W, const float* x, double* s_screen, do
     xs[i] = (float)(xw[i] * sc);
     nrm = std::fmaf(xs[i], xs[i], nrm);
   }
-  switch (R1) {
-    case 2: prime_host_fft<2>(W, H, xs, chirp, bhat, mag); break;
-    case 4: prime_host_fft<4>(W, H, xs, chirp, bhat, mag); break;
-    case 8: prime_host_fft<8>(W, H, xs, chirp, bhat, mag); break;
-    default: prime_host_fft<16>(W, H, xs, chirp, bhat, mag); break;
+  if (variant == 1) {
+    prime_host_warp_fft(W, H, cls, xs, chirp, mag);
+  } else {
+    switch (R1) {
+      case 2: prime_host_fft<2>(W, H, xs, chirp, bhat, mag); break;
+      case 4: prime_host_fft<4>(W, H, xs, chirp, bhat, mag); break;
+      case 8: prime_host_fft<8>(W, H, xs, chirp, bhat, mag); break;
+      default: prime_host_fft<16>(W, H, xs, chirp, bhat, mag); break;
+    }
   }
   for (int k = 0; k < H; ++k) s_screen[k] = (double)mag[k] / sc * invsum;
   *delta = (double)(kappa * (float)std::sqrt((double)nrm) * 1.01f) / sc * invsum;
   return H;
+}
+extern "C" int cdb_host_prime_screen(int W, const float* x, double* s_screen, double* s_exact,
+                                     double* delta) {
+  return cdb_host_prime_screen2(W, x, s_screen, s_exact, delta, 0);
 }
 
 extern "C" {
@@ -950,7 +1445,24 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   a.clips = d_chroma_clips;
   a.cands = d_chroma_cands;
   bool screen = pl->screen_ok;
-  if (const char* pm = std::getenv("CDB_PRIME")) screen = screen && std::string(pm) != "goertzel";
+  bool warp_kernel = pl->warp_ok;
+  if (const char* pm = std::getenv("CDB_PRIME")) {
+    const std::string m = pm;
+    screen = screen && m != "goertzel";
+    warp_kernel = warp_kernel && m != "cta";  // "cta": the CTA-per-window screen for every class
+  }
+  if (screen && warp_kernel) {
+    cdb_mark(h, st, "begin");
+    if ((rc = prime_launch_warp<0>(h, pl, a, clip_len, st)) || (rc = prime_launch_warp<1>(h, pl, a, clip_len, st)))
+      return rc;
+    // windows beyond 2048 points (44.1 kHz): the CTA kernel's 4096-point class
+    bool big = false;
+    for (int c : pl->cls_cands[3]) big = big || prime_warp_class(pl->W[c], pl->H[c]) < 0;
+    if (big && (rc = prime_launch_screen<16, 256, 2>(h, pl, a, clip_len, st))) return rc;
+    cdb_mark(h, st, "prime_screen_kernel");
+    CDB_CUDA(h, cudaGetLastError());
+    return 0;
+  }
   if (screen) {
     cdb_mark(h, st, "begin");
     // T = 16 R1 threads: every FFT pass keeps every thread busy (the inner passes have 16 R1 units).

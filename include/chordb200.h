@@ -244,6 +244,10 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
  * direct DFT the kernel decides with (both in the units of mlab.magnitude_spectrum,
  * prime_multif0.py:59), *delta the screen's error bound.  Returns H = kept bins, < 0 on error. */
 int cdb_host_prime_screen(int W, const float* x, double* s_screen, double* s_exact, double* delta);
+/* variant 0: the CTA-per-window kernel's three-pass transforms (cfft32.cuh); 1: the warp-per-window
+ * kernel's radix-32 x 32 packed transforms (prime_warp.cuh; windows with W + H - 1 <= 2048). */
+int cdb_host_prime_screen2(int W, const float* x, double* s_screen, double* s_exact, double* delta,
+                           int variant);
 
 /* ---------------- ingestion: the decode step of librosa.load (multipitch.py:25), SURVEY 8f-2 ---------------- */
 /* d_pcm: interleaved int16 [n_frames, channels] -> d_out[n_frames] float32 = mean over channels of

@@ -315,14 +315,19 @@ def test_host_normal_lm_matches_scipy_curve_fit(variant):
     assert same_nfev >= 0.98 * n
 
 
-def test_host_prime_screen_error_bound_and_exact_dft():
+@pytest.mark.parametrize("variant", [1, 0])
+def test_host_prime_screen_error_bound_and_exact_dft(variant):
     """Prime-multiF0 (csrc/prime.cu, prime_screen_kernel): the FP64 direct DFT the kernel decides
     with equals mlab.magnitude_spectrum's |FFT(x * hanning)| / sum|w| (prime_multif0.py:59), and the
     FP32 Bluestein screen stays far inside its proven error bound delta on tones, noise, impulses,
     tiny and huge amplitudes, for window sizes of every FFT class (incl. the class boundaries) --
-    so the set {k : s32[k] >= max s32 - 2 delta} always contains the true maximum."""
+    so the set {k : s32[k] >= max s32 - 2 delta} always contains the true maximum.  variant 1: the
+    warp-per-window kernel's radix-32 x 32 packed transforms (prime_warp.cuh: one 1024-point pair, or
+    a radix-2 split around two), executed lane by lane; variant 0: the CTA kernel's three-pass
+    transforms (cfft32.cuh)."""
     rng = np.random.default_rng(5)
-    for W in (357, 409, 410, 674, 819, 820, 1348, 1639, 1640, 2696):
+    sizes = (357, 409, 410, 674, 819, 820, 821, 1348, 1639) + ((1640, 2696) if variant == 0 else ())
+    for W in sizes:
         n = np.arange(W)
         signals = [
             rng.standard_normal(W),
@@ -333,7 +338,7 @@ def test_host_prime_screen_error_bound_and_exact_dft():
         ]
         for x in signals:
             x = x.astype(np.float32)
-            s32, s64, delta = nat.host_prime_screen(x)
+            s32, s64, delta = nat.host_prime_screen(x, variant)
             H = len(s64)
             num_freqs = (W + 1) // 2 if W % 2 else W // 2 + 1
             assert H == num_freqs // 2
@@ -347,10 +352,10 @@ def test_host_prime_screen_error_bound_and_exact_dft():
             assert int(np.argmax(s64)) in cands
     # tonal windows: the bound is tight enough for the candidate set to be one or two bins
     x = np.sin(2 * np.pi * np.arange(1348) * (40.3 / 1348)).astype(np.float32)
-    s32, s64, delta = nat.host_prime_screen(x)
+    s32, s64, delta = nat.host_prime_screen(x, variant)
     assert delta < 1e-4 * s64.max()
     assert (s32 >= s32.max() - 2 * delta).sum() == 1
-    assert nat.host_prime_screen(np.zeros(500, dtype=np.float32))[2] == 0.0  # silence
+    assert nat.host_prime_screen(np.zeros(500, dtype=np.float32), variant)[2] == 0.0  # silence
 
 
 def test_audio_load_host_path(tmp_path):

@@ -77,9 +77,10 @@ def test_prime_per_candidate_and_params():
 
 
 def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
-    """The default kernel (FP32 Bluestein screen + FP64 evaluation of the bins that can be the
-    maximum, prime_screen_kernel) against the all-FP64 Goertzel kernel (CDB_PRIME=goertzel) and the
-    oracle, per clip and per candidate: polyphonic clips, white noise, a tone above the kept quarter
+    """The default kernels (FP32 Bluestein screen + FP64 evaluation of the bins that can be the
+    maximum: the warp-per-window prime_screen_warp_kernel, and the CTA-per-window
+    prime_screen_kernel, CDB_PRIME=cta) against the all-FP64 Goertzel kernel (CDB_PRIME=goertzel)
+    and the oracle, per clip and per candidate: polyphonic clips, white noise, a tone above the kept quarter
     of the spectrum (flat screen -> every bin is evaluated), silence, tiny and huge amplitudes,
     ragged last windows, 44.1 kHz (the 4096-point class)."""
     from chord_detection_b200 import ops
@@ -102,10 +103,14 @@ def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
         monkeypatch.setenv("CDB_PRIME", "goertzel")
         ref = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
         monkeypatch.delenv("CDB_PRIME")
-        got_c, ref_c = res.extra.cpu().numpy(), ref.extra.cpu().numpy()
+        monkeypatch.setenv("CDB_PRIME", "cta")
+        cta = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
+        monkeypatch.delenv("CDB_PRIME")
+        got_c, ref_c, cta_c = res.extra.cpu().numpy(), ref.extra.cpu().numpy(), cta.extra.cpu().numpy()
         for i in range(len(rows)):
             scale = max(np.abs(ref_c[i]).max(), 1e-300)
             assert np.max(np.abs(got_c[i] - ref_c[i])) <= 1e-9 * scale, (fs, i)
+            assert np.max(np.abs(cta_c[i] - ref_c[i])) <= 1e-9 * scale, (fs, i)
         _close(res.clips.cpu().numpy()[0], rn.prime(rows[0], fs))
         _close(res.clips.cpu().numpy()[2], rn.prime(rows[2], fs))
         assert np.all(res.clips.cpu().numpy()[4] == 0.0)
@@ -121,6 +126,9 @@ def test_prime_screen_occupancy_variants_agree(monkeypatch):
     xd = torch.from_numpy(x).to(_dev())
     base = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
     assert base.sum() > 0
+    monkeypatch.setenv("CDB_PRIME", "cta")
+    base_cta = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
+    assert np.allclose(base_cta, base, rtol=1e-12, atol=0)
     for w in ("16", "24"):
         monkeypatch.setenv("CDB_PRIME_WARPS", w)
         got = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
