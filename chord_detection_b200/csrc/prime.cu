@@ -1445,11 +1445,14 @@ int cdb_prime_chroma(cdb_handle* h, const cdb_prime_params* p, const float* d_x,
   a.clips = d_chroma_clips;
   a.cands = d_chroma_cands;
   bool screen = pl->screen_ok;
-  bool warp_kernel = pl->warp_ok;
+  // "warp": the warp-per-window screen (prime_screen_warp_kernel) where it applies.  Correct and
+  // tested, but measured slower than the CTA-per-window kernel so far (r02M: 52.2 vs 43.2 ms per
+  // 2 048 clips), so the CTA kernel stays the default.
+  bool warp_kernel = false;
   if (const char* pm = std::getenv("CDB_PRIME")) {
     const std::string m = pm;
     screen = screen && m != "goertzel";
-    warp_kernel = warp_kernel && m != "cta";  // "cta": the CTA-per-window screen for every class
+    warp_kernel = pl->warp_ok && m == "warp";
   }
   if (screen && warp_kernel) {
     cdb_mark(h, st, "begin");

@@ -18,7 +18,7 @@ def t(fn, reps=3):
     return sorted(ts)[len(ts) // 2]
 out = {}
 res = {}
-for mode in ("screen", "cta", "goertzel"):
+for mode in ("screen", "warp", "goertzel"):
     os.environ["CDB_PRIME"] = mode
     ms = t(lambda: ops.prime_multif0(x, 22050))
     res[mode] = ops.prime_multif0(x, 22050, per_clip=True).clips.cpu().numpy()

@@ -77,10 +77,10 @@ def test_prime_per_candidate_and_params():
 
 
 def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
-    """The default kernels (FP32 Bluestein screen + FP64 evaluation of the bins that can be the
-    maximum: the warp-per-window prime_screen_warp_kernel, and the CTA-per-window
-    prime_screen_kernel, CDB_PRIME=cta) against the all-FP64 Goertzel kernel (CDB_PRIME=goertzel)
-    and the oracle, per clip and per candidate: polyphonic clips, white noise, a tone above the kept quarter
+    """The screen kernels (FP32 Bluestein screen + FP64 evaluation of the bins that can be the
+    maximum: the default CTA-per-window prime_screen_kernel and the warp-per-window
+    prime_screen_warp_kernel, CDB_PRIME=warp) against the all-FP64 Goertzel kernel
+    (CDB_PRIME=goertzel) and the oracle, per clip and per candidate: polyphonic clips, white noise, a tone above the kept quarter
     of the spectrum (flat screen -> every bin is evaluated), silence, tiny and huge amplitudes,
     ragged last windows, 44.1 kHz (the 4096-point class)."""
     from chord_detection_b200 import ops
@@ -103,7 +103,7 @@ def test_prime_screen_kernel_equals_goertzel_kernel(monkeypatch):
         monkeypatch.setenv("CDB_PRIME", "goertzel")
         ref = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
         monkeypatch.delenv("CDB_PRIME")
-        monkeypatch.setenv("CDB_PRIME", "cta")
+        monkeypatch.setenv("CDB_PRIME", "warp")
         cta = ops.prime_multif0(xd, fs, per_clip=True, per_candidate=True)
         monkeypatch.delenv("CDB_PRIME")
         got_c, ref_c, cta_c = res.extra.cpu().numpy(), ref.extra.cpu().numpy(), cta.extra.cpu().numpy()
@@ -126,7 +126,7 @@ def test_prime_screen_occupancy_variants_agree(monkeypatch):
     xd = torch.from_numpy(x).to(_dev())
     base = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
     assert base.sum() > 0
-    monkeypatch.setenv("CDB_PRIME", "cta")
+    monkeypatch.setenv("CDB_PRIME", "warp")
     base_cta = ops.prime_multif0(xd, fs, per_candidate=True).extra.cpu().numpy()
     assert np.allclose(base_cta, base, rtol=1e-12, atol=0)
     for w in ("16", "24"):
