@@ -1,0 +1,14 @@
+#!/bin/bash
+# Short GPU visit: full parity suite, smoke(), the bench line.  Usage: bash scripts/gpu_check.sh TAG
+TAG=${1:-r02x}
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
+timeout 900 python bench.py --steps 100 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 300 gpurun_out/${TAG}_bench.err
+python - <<PY
+import json
+r = json.loads([l for l in open("gpurun_out/${TAG}_bench.json") if l.startswith("{")][-1])
+print("bench M frames/s %.1f" % (r["value"] / 1e6), "ms/step %.4f" % r["ms_per_step"], "frac %.3f" % r["roofline"]["frac"], "e2e %.1f" % (r["e2e"]["value"] / 1e6))
+for k, v in r.get("secondary", {}).items():
+    print(" ", k, "%.4g %s" % (v["value"], v["unit"]), "%.1f ms" % v["ms"], v["kernel_ms"])
+PY
