@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(32) esacf_filter_kernel(const EsacfArgs a) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const double y = __dadd_rn(z[i], __dmul_rn(mlam, u));
-      z[i] = __dsub_rn(__dmul_rn(u, 1.0), __dmul_rn(y, mlam));
+      z[i] = __dsub_rn(u, __dmul_rn(y, mlam));  // (b[1] = 1: u * 1.0 is u exactly)
       xhat = __dadd_rn(xhat, __dmul_rn(a.taps[i + 1], y));
       u = y;
     }
