@@ -62,7 +62,7 @@ EXPORTS = [
     "cdb_iterf0_workspace_bytes", "cdb_iterf0_chroma", "cdb_prime_window_sizes",
     "cdb_prime_chroma", "cdb_host_prime_screen", "cdb_host_prime_screen2", "cdb_pack_and_key", "cdb_esacf_debug_stride", "cdb_host_gauss_fit",
     "cdb_host_find_peaks", "cdb_pcm16_to_mono_f32", "cdb_host_esacf_acf", "cdb_host_gauss_fit2",
-    "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_filter",
+    "cdb_host_iterf0_spectrum8k", "cdb_host_iterf0_spectrum8k_v", "cdb_host_iterf0_filter",
     "cdb_resample_poly_f32", "cdb_host_resample_poly_f32",
     "cdb_host_pack_and_key", "cdb_host_py_round3",
     "cdb_profile_enable", "cdb_profile_report",
@@ -137,6 +137,7 @@ def lib():
         L.cdb_host_iterf0_filter.argtypes = [C.POINTER(C.c_float), C.c_int64, C.POINTER(dbl), dbl,
                                              C.POINTER(dbl), C.c_int, C.POINTER(C.c_float)]
         L.cdb_host_iterf0_spectrum8k.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(dbl)]
+        L.cdb_host_iterf0_spectrum8k_v.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(dbl)]
         L.cdb_host_esacf_acf.argtypes = [C.c_int, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(dbl),
                                          C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]
         _lib = L
@@ -328,17 +329,18 @@ def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
     return y
 
 
-def host_iterf0_spectrum8k(yc):
+def host_iterf0_spectrum8k(yc, variant=0):
     """Host execution of the frame-8192 summary-spectrum kernel (test hook, no GPU).
-    yc: [C, 8192] float32 filtered channels -> U[8193] float64."""
+    yc: [C, 8192] float32 filtered channels -> U[8193] float64.  variant 0: P3 + MAG phases,
+    1: the pair phase (CDB_ITERF0_SPEC=pair)."""
     import numpy as np
 
     yc = np.ascontiguousarray(np.atleast_2d(yc), dtype=np.float32)
     if yc.shape[1] != 8192:
         raise ValueError("frame size must be 8192")
     U = np.zeros(8193)
-    rc = lib().cdb_host_iterf0_spectrum8k(yc.ctypes.data_as(C.POINTER(C.c_float)), yc.shape[0],
-                                          U.ctypes.data_as(C.POINTER(C.c_double)))
+    rc = lib().cdb_host_iterf0_spectrum8k_v(yc.ctypes.data_as(C.POINTER(C.c_float)), yc.shape[0],
+                                            int(variant), U.ctypes.data_as(C.POINTER(C.c_double)))
     if rc != 0:
         raise ValueError("cdb_host_iterf0_spectrum8k failed (%d)" % rc)
     return U

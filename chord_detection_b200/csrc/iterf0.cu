@@ -253,6 +253,9 @@ static s8k::Tables s8k_tables(const float* win, const float2* t) {
   return T;
 }
 
+// PAIR: P3 and MAG as one phase on row pairs (s8k::p3mag; three barriers per channel, results
+// identical to the four-phase form, which stays selectable as CDB_ITERF0_SPEC=s8k)
+template <bool PAIR>
 __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);
@@ -270,16 +273,21 @@ __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(con
     __syncthreads();
     s8k::p2(t, a.s8, buf);
     __syncthreads();
-    s8k::p3(t, buf);
-    __syncthreads();
-    s8k::mag(t, buf, a.s8, U, Unyq);
+    if (PAIR) {
+      s8k::p3mag(t, buf, a.s8, U, Unyq);
+    } else {
+      s8k::p3(t, buf);
+      __syncthreads();
+      s8k::mag(t, buf, a.s8, U, Unyq);
+    }
     __syncthreads();
   }
   double* out = a.Ut + gf * (int64_t)(s8k::kM + 1);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) out[s8k::bin_of(t, h, j)] = (double)U[h][j];
+    for (int j = 0; j < 16; ++j)
+      out[PAIR ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)U[h][j];
   if (t == 0) out[s8k::kM] = (double)Unyq;
 }
 
@@ -688,8 +696,9 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
 
 // Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
 // channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.
-int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U) {
-  if (!yc || !U || C < 1) return -1;
+// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<false>), 1: the pair phase (<true>).
+int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U) {
+  if (!yc || !U || C < 1 || variant < 0 || variant > 1) return -1;
   const int F = s8k::kM;
   const double pi = 3.14159265358979323846;
   std::vector<float> win(F);
@@ -708,14 +717,22 @@ int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U) {
     const float* src = yc + (size_t)ch * F;
     for (int t = 0; t < s8k::kThreads; ++t) s8k::p1(t, src, T, buf.data());
     for (int t = 0; t < s8k::kThreads; ++t) s8k::p2(t, T, buf.data());
-    for (int t = 0; t < s8k::kThreads; ++t) s8k::p3(t, buf.data());
-    for (int t = 0; t < s8k::kThreads; ++t) s8k::mag(t, buf.data(), T, acc[t].U, acc[t].nyq);
+    if (variant == 1) {
+      for (int t = 0; t < s8k::kThreads; ++t) s8k::p3mag(t, buf.data(), T, acc[t].U, acc[t].nyq);
+    } else {
+      for (int t = 0; t < s8k::kThreads; ++t) s8k::p3(t, buf.data());
+      for (int t = 0; t < s8k::kThreads; ++t) s8k::mag(t, buf.data(), T, acc[t].U, acc[t].nyq);
+    }
   }
   for (int t = 0; t < s8k::kThreads; ++t)
     for (int h = 0; h < 2; ++h)
-      for (int j = 0; j < 16; ++j) U[s8k::bin_of(t, h, j)] = (double)acc[t].U[h][j];
+      for (int j = 0; j < 16; ++j)
+        U[variant == 1 ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)acc[t].U[h][j];
   U[F] = (double)acc[0].nyq;
   return 0;
+}
+int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U) {
+  return cdb_host_iterf0_spectrum8k_v(yc, C, 0, U);
 }
 
 int64_t cdb_iterf0_workspace_bytes(const cdb_iterf0_params* p, int64_t n_clips, int64_t clip_len) {
@@ -780,8 +797,11 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   a.tw = pl->d_tw;
   a.wsplit = pl->d_wsplit;
   bool use_s8k = pl->d_s8k != nullptr && p->power == 1.0;
-  if (const char* sm = std::getenv("CDB_ITERF0_SPEC"))
+  bool s8k_pair = false;  // CDB_ITERF0_SPEC = s8k (default) | pair (P3 + MAG as one phase) | generic
+  if (const char* sm = std::getenv("CDB_ITERF0_SPEC")) {
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
+    if (sm[0] == 'p') s8k_pair = true;
+  }
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
   bool hoisted = true;
@@ -814,9 +834,12 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
   const size_t s8k_smem = (size_t)s8k::kBufLen * sizeof(c64);
-  if (use_s8k)
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel,
+  if (use_s8k) {
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
+  }
   const size_t per_smem = (size_t)2 * pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_smem));
@@ -845,8 +868,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       cdb_mark(h, st, "iterf0_filter_kernel");
     }
     const int64_t nframes = (int64_t)nb * fpc;
-    if (use_s8k)
-      iterf0_spectrum8k_kernel<<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    if (use_s8k && s8k_pair)
+      iterf0_spectrum8k_kernel<true><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    else if (use_s8k)
+      iterf0_spectrum8k_kernel<false><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");

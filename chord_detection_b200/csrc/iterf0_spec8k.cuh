@@ -165,4 +165,101 @@ F32X2_HD int bin_of(int t, int h, int k3) {
   return (u >> 4) + 32 * (u & 15) + 512 * k3;
 }
 
+// ---- P3 and MAG in one phase ("pair" variant) ------------------------------------------------------
+// The Hermitian partner of row u is one other row pu (mag() above), and pu(pu(u)) = u: the 512 rows
+// are 255 pairs + the two self-paired rows 0 and 8.  Thread t takes one pair (thread 0: rows 0 and
+// 8), runs BOTH 16-point DFTs in registers and forms the magnitudes from them: the P3 stores and
+// the MAG row loads (192 of the 448 KB of shared-memory traffic per transform) and one block
+// barrier per channel disappear.  For a bin k of row u and its partner M - k of row pu,
+//   2 X[k] = s + d w,   2 X[M-k] = conj(s - d w),   s = Z[k] + conj Z[M-k], d = Z[k] - conj Z[M-k],
+// because csd[M-k] = conj csd[k] holds exactly in the table (every k but the self-paired 4096), so
+// one complex product serves two bins and only the table rows of the first row of a pair are read.
+// |s - d w|^2 is bit for bit what mag() computes for the partner bin (negation and conjugation are
+// exact, the products and sums are the same ones), and every bin is still accumulated over the
+// channels in channel order by one thread: results identical to p3() + mag().
+F32X2_HD void pair_rows(int t, int& ua, int& ub) {
+  if (t >= 16) {  // k1 = 1..15 with 32 - k1
+    ua = t;
+    ub = ((32 - (t >> 4)) << 4) + (15 - (t & 15));
+  } else if (t >= 8) {  // k1 = 16 with itself, k2 with 15 - k2
+    ua = 256 + (t - 8);
+    ub = 256 + 15 - (t - 8);
+  } else if (t >= 1) {  // k1 = 0: k2 with 16 - k2
+    ua = t;
+    ub = 16 - t;
+  } else {  // the two self-paired rows
+    ua = 0;
+    ub = 8;
+  }
+}
+F32X2_HD int pair_bin_of(int t, int h, int k3) {
+  int ua, ub;
+  pair_rows(t, ua, ub);
+  const int u = h ? ub : ua;
+  return (u >> 4) + 32 * (u & 15) + 512 * k3;
+}
+
+F32X2_HD void row_dft16(const c64* row, c64 (&v)[16]) {
+  c64 in[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const Pair q = ld_pair(row + 2 * i);
+    in[2 * i] = q.a;
+    in[2 * i + 1] = q.b;
+  }
+  dft16(in, v);
+}
+F32X2_HD float half_abs(c64 x2) {  // |x2| / 2
+  float xr, xi;
+  upk(mul2(x2, x2), xr, xi);
+  return 0.5f * sqrt_approx(xr + xi);
+}
+
+// U[0][k3]: row ua, U[1][k3]: row ub of pair_rows(t)
+F32X2_HD void p3mag(int t, const c64* buf, const Tables& T, float (&U)[2][16], float& Unyq) {
+  int ua, ub;
+  pair_rows(t, ua, ub);
+  c64 va[16], vb[16];
+  row_dft16(buf + ua * 18, va);
+  row_dft16(buf + ub * 18, vb);
+  if (t != 0) {
+    const c64* cs = T.csd + ua * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const Pair c = ld_pair(cs + 2 * i);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k3 = 2 * i + e;
+        const c64 pc = conj2(vb[15 - k3]);
+        const c64 s = add2(va[k3], pc), d = sub2(va[k3], pc);
+        const c64 dw = cmul2(d, e ? c.b : c.a);
+        U[0][k3] += half_abs(add2(s, dw));
+        U[1][15 - k3] += half_abs(sub2(s, dw));
+      }
+    }
+  } else {
+    const c64* cs0 = T.csd;           // row 0: bin 512 k3 pairs with 512 (16 - k3); 0 and 4096 with themselves
+    const c64* cs8 = T.csd + 8 * 16;  // row 8: bin 256 + 512 k3 pairs with k3' = 15 - k3
+#pragma unroll
+    for (int k3 = 0; k3 <= 8; ++k3) {
+      const c64 pc = conj2(va[(16 - k3) & 15]);
+      const c64 s = add2(va[k3], pc), d = sub2(va[k3], pc);
+      const c64 dw = cmul2(d, cs0[k3]);
+      U[0][k3] += half_abs(add2(s, dw));
+      if (k3 != 0 && k3 != 8) U[0][16 - k3] += half_abs(sub2(s, dw));
+    }
+#pragma unroll
+    for (int k3 = 0; k3 < 8; ++k3) {
+      const c64 pc = conj2(vb[15 - k3]);
+      const c64 s = add2(vb[k3], pc), d = sub2(vb[k3], pc);
+      const c64 dw = cmul2(d, cs8[k3]);
+      U[1][k3] += half_abs(add2(s, dw));
+      U[1][15 - k3] += half_abs(sub2(s, dw));
+    }
+    float zr, zi;  // X[8192] = Re Z[0] - Im Z[0]
+    upk(va[0], zr, zi);
+    Unyq += fabsf(zr - zi);
+  }
+}
+
 }  // namespace s8k

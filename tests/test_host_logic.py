@@ -215,8 +215,35 @@ def test_host_iterf0_spectrum8k_matches_numpy_rfft():
         want = np.abs(np.fft.rfft(yc32.astype(np.float64) * win, 16384, axis=1)).sum(axis=0)
         assert got.shape == want.shape == (8193,)
         assert np.max(np.abs(got - want)) <= 2e-6 * max(np.max(want), 1e-30)
+        # the pair phase (CDB_ITERF0_SPEC=pair: both rows of a Hermitian pair in one thread's
+        # registers, one complex product per two bins) must give the same bits
+        assert np.array_equal(nat.host_iterf0_spectrum8k(yc32, variant=1), got)
     with pytest.raises(ValueError):
         nat.host_iterf0_spectrum8k(np.zeros((1, 4096), dtype=np.float32))
+
+
+def test_host_iterf0_spectrum8k_pair_rows_cover_every_bin_once():
+    """Index algebra of the pair phase, restated here: thread t owns rows (ua, ub); every one of the
+    512 rows of 16 bins is owned exactly once and ub is the Hermitian partner row of ua."""
+    def rows(t):
+        if t >= 16:
+            return t, ((32 - (t >> 4)) << 4) + (15 - (t & 15))
+        if t >= 8:
+            return 256 + (t - 8), 256 + 15 - (t - 8)
+        if t >= 1:
+            return t, 16 - t
+        return 0, 8
+
+    seen = []
+    for t in range(256):
+        ua, ub = rows(t)
+        seen += [ua, ub]
+        if t:
+            for k3 in range(16):
+                ka = (ua >> 4) + 32 * (ua & 15) + 512 * k3
+                kb = (ub >> 4) + 32 * (ub & 15) + 512 * (15 - k3)
+                assert ka + kb == 8192
+    assert sorted(seen) == list(range(512))
 
 
 def test_host_gaussian_fit_matches_scipy_curve_fit():

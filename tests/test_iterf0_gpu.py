@@ -46,10 +46,11 @@ def test_iterf0_matches_reference_golden(golden, cid):
     assert rn.pack_chroma(got) == g["digits"]
 
 
-@pytest.mark.parametrize("spec", ["s8k", "generic"])
+@pytest.mark.parametrize("spec", ["s8k", "pair", "generic"])
 def test_iterf0_voices_match_oracle(spec, monkeypatch):
     """Per frame: the (salience, period) of every voice slot, i.e. the whole tau search; with the
-    frame-8192 register-FFT summary-spectrum kernel (default) and the generic radix-2 one."""
+    frame-8192 register-FFT summary-spectrum kernel (default), its pair-phase form and the generic
+    radix-2 one."""
     from chord_detection_b200 import ops
 
     monkeypatch.setenv("CDB_ITERF0_SPEC", spec)
@@ -146,3 +147,28 @@ def test_iterf0_hoisted_filter_equals_reference_order_chain(monkeypatch):
         warnings.simplefilter("ignore")
         want = np.stack([rn.iterf0(r, 22050) for r in rows[:2]])
     _close(a.clips[:2].cpu().numpy(), want)
+
+
+def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
+    """CDB_ITERF0_SPEC=pair (P3 + MAG as one phase on Hermitian row pairs) against the four-phase
+    kernel on a ragged batch: same arithmetic per bin, so voices and chroma must agree (the host
+    execution of the two forms is bit-identical, tests/test_host_logic.py)."""
+    from chord_detection_b200 import ops
+
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=260 + i, fs=22050, n=3 * 8192 + 517))[0]
+                     for i in range(6)])
+    xd = torch.from_numpy(rows).to(_dev())
+    monkeypatch.setenv("CDB_ITERF0_SPEC", "s8k")
+    a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    monkeypatch.setenv("CDB_ITERF0_SPEC", "pair")
+    b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    torch.cuda.synchronize()
+    va, vb = a.extra.cpu().numpy(), b.extra.cpu().numpy()
+    assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0)
+    assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-6, atol=0)
+    _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
+    exact = bool(np.array_equal(va, vb) and torch.equal(a.frames, b.frames))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "iterf0_pair_exact.txt"), "w") as f:
+            f.write("pair == s8k bit for bit: %s\n" % exact)
