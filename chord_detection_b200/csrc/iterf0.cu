@@ -253,9 +253,14 @@ static s8k::Tables s8k_tables(const float* win, const float2* t) {
   return T;
 }
 
-// PAIR: P3 and MAG as one phase on row pairs (s8k::p3mag; three barriers per channel, results
-// identical to the four-phase form, which stays selectable as CDB_ITERF0_SPEC=s8k)
-template <bool PAIR>
+// V = 0: four phases P1 | P2 | P3 | MAG.  V = 1 ("pair"): P3 and MAG as one phase on row pairs
+// (s8k::p3mag; three barriers per channel).  V = 2 ("early"): pair, and the register part of the
+// NEXT channel's P1 (loads, window, 32-point DFT, twiddles) runs before the barrier that frees the
+// buffer, so warps that finish a channel early do not idle there and the global loads of P1 are
+// not all issued right behind a barrier.  V = 3 ("fetch"): pair, and only the loads and the window
+// of the next channel run before that barrier (16 packed values instead of 32 across it).
+// Same arithmetic per bin in all of them: identical results.
+template <int V>
 __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);
@@ -268,26 +273,58 @@ __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(con
 #pragma unroll
     for (int j = 0; j < 16; ++j) U[h][j] = 0.f;
   const float* src = a.yc + (int64_t)lc * a.C * a.n_pad + f * s8k::kM;
-  for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
-    s8k::p1(t, src, a.s8, buf);
-    __syncthreads();
-    s8k::p2(t, a.s8, buf);
-    __syncthreads();
-    if (PAIR) {
-      s8k::p3mag(t, buf, a.s8, U, Unyq);
-    } else {
-      s8k::p3(t, buf);
+  if (V == 2) {
+    c64 v[32];
+    s8k::p1_compute(t, src, a.s8, v);
+    for (int ch = 0; ch < a.C; ++ch) {
+      s8k::p1_store(t, v, buf);
       __syncthreads();
-      s8k::mag(t, buf, a.s8, U, Unyq);
+      s8k::p2(t, a.s8, buf);
+      __syncthreads();
+      s8k::p3mag(t, buf, a.s8, U, Unyq);
+      src += a.n_pad;
+      if (ch + 1 < a.C) s8k::p1_compute(t, src, a.s8, v);
+      __syncthreads();
     }
-    __syncthreads();
+  } else if (V == 3) {
+    c64 x[16];
+    s8k::p1_load(t, src, a.s8, x);
+    for (int ch = 0; ch < a.C; ++ch) {
+      {
+        c64 v[32];
+        s8k::p1_dft(t, x, a.s8, v);
+        s8k::p1_store(t, v, buf);
+      }
+      __syncthreads();
+      s8k::p2(t, a.s8, buf);
+      __syncthreads();
+      s8k::p3mag(t, buf, a.s8, U, Unyq);
+      src += a.n_pad;
+      if (ch + 1 < a.C) s8k::p1_load(t, src, a.s8, x);
+      __syncthreads();
+    }
+  } else {
+    for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
+      s8k::p1(t, src, a.s8, buf);
+      __syncthreads();
+      s8k::p2(t, a.s8, buf);
+      __syncthreads();
+      if (V == 1) {
+        s8k::p3mag(t, buf, a.s8, U, Unyq);
+      } else {
+        s8k::p3(t, buf);
+        __syncthreads();
+        s8k::mag(t, buf, a.s8, U, Unyq);
+      }
+      __syncthreads();
+    }
   }
   double* out = a.Ut + gf * (int64_t)(s8k::kM + 1);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      out[PAIR ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)U[h][j];
+      out[V ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)U[h][j];
   if (t == 0) out[s8k::kM] = (double)Unyq;
 }
 
@@ -696,7 +733,7 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
 
 // Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
 // channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.
-// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<false>), 1: the pair phase (<true>).
+// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<0>), 1: the pair phase (<1>, <2>).
 int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U) {
   if (!yc || !U || C < 1 || variant < 0 || variant > 1) return -1;
   const int F = s8k::kM;
@@ -797,10 +834,15 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   a.tw = pl->d_tw;
   a.wsplit = pl->d_wsplit;
   bool use_s8k = pl->d_s8k != nullptr && p->power == 1.0;
-  bool s8k_pair = false;  // CDB_ITERF0_SPEC = s8k (default) | pair (P3 + MAG as one phase) | generic
+  // CDB_ITERF0_SPEC = s8k (default) | pair (P3 + MAG as one phase) | early (pair + the next
+  // channel's P1 registers before the barrier) | fetch (pair + the next channel's loads before
+  // the barrier) | generic
+  int s8k_v = 0;
   if (const char* sm = std::getenv("CDB_ITERF0_SPEC")) {
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
-    if (sm[0] == 'p') s8k_pair = true;
+    if (sm[0] == 'p') s8k_v = 1;
+    if (sm[0] == 'e') s8k_v = 2;
+    if (sm[0] == 'f') s8k_v = 3;
   }
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
@@ -835,9 +877,13 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
   const size_t s8k_smem = (size_t)s8k::kBufLen * sizeof(c64);
   if (use_s8k) {
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<false>,
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<0>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<true>,
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<3>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   }
   const size_t per_smem = (size_t)2 * pl->M * 8;
@@ -868,10 +914,14 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       cdb_mark(h, st, "iterf0_filter_kernel");
     }
     const int64_t nframes = (int64_t)nb * fpc;
-    if (use_s8k && s8k_pair)
-      iterf0_spectrum8k_kernel<true><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    if (use_s8k && s8k_v == 3)
+      iterf0_spectrum8k_kernel<3><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    else if (use_s8k && s8k_v == 2)
+      iterf0_spectrum8k_kernel<2><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    else if (use_s8k && s8k_v == 1)
+      iterf0_spectrum8k_kernel<1><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else if (use_s8k)
-      iterf0_spectrum8k_kernel<false><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+      iterf0_spectrum8k_kernel<0><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");

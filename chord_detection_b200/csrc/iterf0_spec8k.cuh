@@ -68,22 +68,41 @@ F32X2_HD void dft16(const c64 (&in)[16], c64 (&v)[16]) {
   fft16p_dit_tail(v);
 }
 
-// src: the 8192 filtered samples of this (frame, channel)
-F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
+// src: the 8192 filtered samples of this (frame, channel).  p1_compute: loads, window, 32-point DFT
+// and the inter-pass twiddles, all in registers (it touches no shared memory, so it may run before
+// the barrier that frees the buffer); p1_store: the 32 strided stores.
+F32X2_HD void p1_load(int t, const float* src, const Tables& T, c64 (&x)[16]) {  // windowed z[256 n1 + t]
   const c64* s2 = reinterpret_cast<const c64*>(src);  // (x[2m], x[2m+1]) pairs, 8-byte aligned
-  c64 v[32];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int m = 256 * n1 + t;
+    x[n1] = mul2(s2[m], T.win2[m]);
+  }
+}
+F32X2_HD void p1_dft(int t, const c64 (&x)[16], const Tables& T, c64 (&v)[32]) {
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const int n1 = br5(2 * p);  // < 16; its butterfly partner n1 + 16 is zero padding
-    const int m = 256 * n1 + t;
-    const c64 x = mul2(s2[m], T.win2[m]);
-    v[2 * p] = x;
-    v[2 * p + 1] = x;
+    v[2 * p] = x[n1];
+    v[2 * p + 1] = x[n1];
   }
   fft32p_dit_tail<-1>(v);
-  buf[pad(t)] = v[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
+  for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
+}
+F32X2_HD void p1_compute(int t, const float* src, const Tables& T, c64 (&v)[32]) {
+  c64 x[16];
+  p1_load(t, src, T, x);
+  p1_dft(t, x, T, v);
+}
+F32X2_HD void p1_store(int t, const c64 (&v)[32], c64* buf) {
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = v[k1];
+}
+F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
+  c64 v[32];
+  p1_compute(t, src, T, v);
+  p1_store(t, v, buf);
 }
 
 F32X2_HD void p2(int t, const Tables& T, c64* buf) {

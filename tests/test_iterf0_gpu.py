@@ -46,7 +46,7 @@ def test_iterf0_matches_reference_golden(golden, cid):
     assert rn.pack_chroma(got) == g["digits"]
 
 
-@pytest.mark.parametrize("spec", ["s8k", "pair", "generic"])
+@pytest.mark.parametrize("spec", ["s8k", "pair", "early", "fetch", "generic"])
 def test_iterf0_voices_match_oracle(spec, monkeypatch):
     """Per frame: the (salience, period) of every voice slot, i.e. the whole tau search; with the
     frame-8192 register-FFT summary-spectrum kernel (default), its pair-phase form and the generic
@@ -150,9 +150,10 @@ def test_iterf0_hoisted_filter_equals_reference_order_chain(monkeypatch):
 
 
 def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
-    """CDB_ITERF0_SPEC=pair (P3 + MAG as one phase on Hermitian row pairs) against the four-phase
-    kernel on a ragged batch: same arithmetic per bin, so voices and chroma must agree (the host
-    execution of the two forms is bit-identical, tests/test_host_logic.py)."""
+    """CDB_ITERF0_SPEC=pair / early / fetch (P3 + MAG as one phase on Hermitian row pairs; with the
+    next channel's P1, or only its loads, ahead of the barrier) against the four-phase kernel on a
+    ragged batch: same arithmetic per bin, so voices and chroma must agree (the host execution of
+    the two forms is bit-identical, tests/test_host_logic.py)."""
     from chord_detection_b200 import ops
 
     rows = np.stack([cases.make_input(dict(fn="s_poly", seed=260 + i, fs=22050, n=3 * 8192 + 517))[0]
@@ -160,15 +161,20 @@ def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
     xd = torch.from_numpy(rows).to(_dev())
     monkeypatch.setenv("CDB_ITERF0_SPEC", "s8k")
     a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
-    monkeypatch.setenv("CDB_ITERF0_SPEC", "pair")
-    b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
     torch.cuda.synchronize()
-    va, vb = a.extra.cpu().numpy(), b.extra.cpu().numpy()
-    assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0)
-    assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-6, atol=0)
-    _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
-    exact = bool(np.array_equal(va, vb) and torch.equal(a.frames, b.frames))
+    va = a.extra.cpu().numpy()
+    notes = []
+    for spec in ("pair", "early", "fetch"):
+        monkeypatch.setenv("CDB_ITERF0_SPEC", spec)
+        b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+        torch.cuda.synchronize()
+        vb = b.extra.cpu().numpy()
+        assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0), spec
+        assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-6, atol=0), spec
+        _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
+        notes.append("%s == s8k bit for bit: %s" % (
+            spec, bool(np.array_equal(va, vb) and torch.equal(a.frames, b.frames))))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         with open(os.path.join(out, "iterf0_pair_exact.txt"), "w") as f:
-            f.write("pair == s8k bit for bit: %s\n" % exact)
+            f.write("\n".join(notes) + "\n")
