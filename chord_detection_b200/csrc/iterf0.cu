@@ -156,6 +156,141 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
     for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
 }
 
+// ---- the same filter chain, one WARP per unit of work ("units" form, CDB_ITERF0_CHAN=units) -------
+// With C = 70 channels a clip is two full warps and one warp with 6 busy lanes: the kernel above
+// issues three warps of FP64 work per clip for 2.19 warps' worth of channels, and it is bound by the
+// FP64 pipe.  Here the left-over channels (C mod 32 per clip) of G = floor(32 / (C mod 32)) clips
+// share ONE warp (C = 70: 5 clips x 6 channels = 30 lanes), so a clip costs 2.2 warps.  A unit is a
+// warp: units [0, clips * fw) are (clip, 32 channels) as before (samples broadcast by shuffles),
+// the rest are left-over groups.  A left-over warp needs the samples of G clips: they are staged
+// per warp in shared memory (cp.async, 8 bytes per lane and clip, double-buffered: the next 32
+// samples of every clip land while these are consumed), rows 33 doubles apart so that the lanes of
+// different clips read different banks; one LDS.64 replaces the two SHFL of the broadcast.
+// Every (clip, channel) runs exactly the instruction sequence of iterf0_channel_kernel: identical
+// output.  Units of the two kinds take the same time and are dealt to the SMs by the same grid, so
+// there is no serial tail (the two-kernel form of this idea had one).
+constexpr int kChanMaxGroup = 8;
+constexpr int kChanUnitsPerCta = 1;  // 32-thread CTAs: ptxas fits both paths in 80 registers (24 warps per SM)
+
+template <bool STRUCTURED>
+struct ChanLane {
+  static constexpr int NB1 = STRUCTURED ? 2 : 3, NB2 = STRUCTURED ? 1 : 3;
+  iff::SosCoef k1, k2, kl;
+  iff::SosState<NB1> r1a, r1b;
+  iff::SosState<NB2> r2a, r2b;
+  iff::SosState<3> lp;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
+  float* dst;
+  // 32 samples T .. T + 31 (getx(i) = whitened sample T + i of this lane's clip)
+  template <class GetX>
+  __device__ __forceinline__ void chunk(int64_t T, int64_t n, bool active, GetX getx) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double x = getx(4 * g + j);
+        double y = fabs(v4);             // final stage: sample T + 4 g + j - 4   (iterative_f0.py:60)
+        y = (y + lp.step(kl, y)) / 2.0;  // :61-63
+        out[j] = (float)y;
+        v4 = r2b.step(k2, s3);
+        s3 = r2a.step(k2, s2);
+        s2 = r1b.step(k1, s1);
+        s1 = r1a.step(k1, x);
+      }
+      const int64_t t0 = T + 4 * g - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
+      if (active && t0 >= 0 && t0 < n) {
+        if (t0 + 4 <= n) {
+          *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (t0 + q < n) dst[t0 + q] = out[q];
+        }
+      }
+    }
+  }
+};
+
+template <bool STRUCTURED>
+__global__ void __launch_bounds__(32 * kChanUnitsPerCta, 24)
+    iterf0_channel_units_kernel(const IterArgs a, const int fw, const int lo, const int G) {
+  __shared__ __align__(16) double stage[kChanUnitsPerCta][2][kChanMaxGroup][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * kChanUnitsPerCta + warp;
+  const int64_t n_full = (int64_t)a.n_batch_clips * fw;
+  const int64_t n_left = lo ? ((int64_t)a.n_batch_clips + G - 1) / G : 0;
+  if (u >= n_full + n_left) return;  // (warp-uniform; no block barrier in this kernel)
+  const bool left = u >= n_full;
+  const int64_t n = a.clip_len;
+  int64_t lc;       // clip of this lane (within the batch)
+  int ch, ci = 0;   // channel; row of the lane's clip in the stage
+  bool active = true;
+  if (!left) {
+    lc = u / fw;
+    ch = (int)(u - lc * fw) * 32 + lane;
+  } else {
+    ci = lane / lo;
+    lc = (u - n_full) * G + ci;
+    ch = fw * 32 + (lane - ci * lo);
+    active = ci < G && lc < a.n_batch_clips;
+    if (!active) {  // idle lanes run the arithmetic on the group's first clip and store nothing
+      ci = 0;
+      lc = (u - n_full) * G;
+      ch = fw * 32;
+    }
+  }
+  ChanLane<STRUCTURED> L;
+  {
+    const double* coef = a.coef + ch * kCoefStride;
+    L.k1.init(coef);
+    L.k2.init(coef + 6);
+    L.kl.init(coef + 12);
+    L.dst = a.yc + (lc * a.C + ch) * a.n_pad;
+  }
+  if (!left) {
+    const double* w = a.w + lc * n;
+    double cur = lane < n ? w[lane] : 0.0;
+    for (int64_t T = 0; T < n + kChanLag; T += 32) {
+      const int64_t tn = T + 32 + lane;
+      const double nxt = tn < n ? w[tn] : 0.0;
+      L.chunk(T, n, true, [&](int i) { return __shfl_sync(0xffffffffu, cur, i); });
+      cur = nxt;
+    }
+  } else {
+    double (*st)[kChanMaxGroup][33] = stage[warp];
+    const int64_t g0 = (u - n_full) * G;  // first clip of the group
+    const double* wg = a.w + g0 * n;
+    auto fetch = [&](int buf, int64_t T0) {  // samples T0 .. T0 + 31 of the group's clips -> st[buf]
+      const int64_t tn = T0 + lane;
+      for (int r = 0; r < G; ++r) {
+        double* d = &st[buf][r][lane];
+        if (g0 + r < a.n_batch_clips && tn < n) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(wg + (int64_t)r * n + tn)
+                       : "memory");
+        } else {
+          *d = 0.0;
+        }
+      }
+    };
+    fetch(0, 0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    int b = 0;
+    for (int64_t T = 0; T < n + kChanLag; T += 32) {
+      fetch(b ^ 1, T + 32);
+      const double* row = st[b][ci];
+      L.chunk(T, n, active, [&](int i) { return row[i]; });
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      b ^= 1;
+    }
+  }
+  if (active)
+    for (int64_t t = n; t < a.n_pad; ++t) L.dst[t] = 0.0f;
+}
+
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
 
 __global__ void __launch_bounds__(kSpecThreads) iterf0_spectrum_kernel(const IterArgs a) {
@@ -849,6 +984,11 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   bool hoisted = true;
   if (const char* fm = std::getenv("CDB_ITERF0_FILTER"))
     if (fm[0] == 'c') hoisted = false;
+  // CDB_ITERF0_CHAN = clip (default: a CTA per clip, a thread per channel) | units (a warp per 32
+  // channels of a clip or per group of left-over channels of several clips)
+  bool chan_units = false;
+  if (const char* cm = std::getenv("CDB_ITERF0_CHAN"))
+    if (cm[0] == 'u') chan_units = true;
   a.structured = 1;
   for (int c = 0; c < p->channels; ++c)
     if (p->res1_b[c][1] != 0.0 || p->res2_b[c][1] != 0.0 || p->res2_b[c][2] != 0.0) a.structured = 0;
@@ -905,7 +1045,16 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       iterf0_whiten_kernel<<<(unsigned)(((int64_t)nb * a.w_chunks + 31) / 32), 32, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_whiten_kernel");
       const int chan_threads = 32 * ((a.C + 31) / 32);
-      if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
+      const int fw = a.C / 32, lo = a.C % 32;
+      if (chan_units && lo > 0) {  // one warp per unit, left-over channels of G clips in one warp
+        const int G = std::min(32 / lo, kChanMaxGroup);
+        const int64_t units = (int64_t)nb * fw + ((int64_t)nb + G - 1) / G;
+        const unsigned grid = (unsigned)((units + kChanUnitsPerCta - 1) / kChanUnitsPerCta);
+        if (a.structured)
+          iterf0_channel_units_kernel<true><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G);
+        else
+          iterf0_channel_units_kernel<false><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G);
+      } else if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
       else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
       h->launches += 1;

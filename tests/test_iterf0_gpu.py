@@ -178,3 +178,31 @@ def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
     if os.path.isdir(out):
         with open(os.path.join(out, "iterf0_pair_exact.txt"), "w") as f:
             f.write("\n".join(notes) + "\n")
+
+
+@pytest.mark.parametrize("n_clips,channels", [(1, 70), (5, 70), (7, 70), (11, 70), (6, 40), (10, 33), (3, 64)])
+def test_iterf0_channel_units_kernel_equals_clip_kernel(n_clips, channels, monkeypatch):
+    """CDB_ITERF0_CHAN=units (a warp per 32 channels of a clip, the left-over channels of G clips
+    packed into one warp and fed from a shared-memory stage) against the CTA-per-clip kernel: whole
+    and ragged groups, a clip length that ends inside a 32-sample chunk, channel counts with
+    G = 5 (70), 4 (40), the cap of 8 (33) and no left-over warp at all (64: falls back)."""
+    from chord_detection_b200 import ops
+
+    freqs = None if channels == 70 else rn.iterf0_channels(channels)
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=300 + i, fs=22050, n=2 * 8192 + 1237))[0]
+                     for i in range(n_clips)])
+    xd = torch.from_numpy(rows).to(_dev())
+    monkeypatch.setenv("CDB_ITERF0_CHAN", "clip")
+    a = ops.iterative_f0(xd, 22050, channel_freqs=freqs, per_clip=True, per_frame=True, voices=True)
+    monkeypatch.setenv("CDB_ITERF0_CHAN", "units")
+    b = ops.iterative_f0(xd, 22050, channel_freqs=freqs, per_clip=True, per_frame=True, voices=True)
+    torch.cuda.synchronize()
+    va, vb = a.extra.cpu().numpy(), b.extra.cpu().numpy()
+    assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0)
+    assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-6, atol=0)
+    _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "iterf0_units_exact.txt"), "a") as f:
+            f.write("units == clip bit for bit (%d clips, %d channels): %s\n" % (
+                n_clips, channels, bool(np.array_equal(va, vb) and torch.equal(a.frames, b.frames))))
