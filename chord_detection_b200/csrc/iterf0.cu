@@ -214,29 +214,36 @@ struct ChanLane {
 
 template <bool STRUCTURED>
 __global__ void __launch_bounds__(32 * kChanUnitsPerCta, 24)
-    iterf0_channel_units_kernel(const IterArgs a, const int fw, const int lo, const int G) {
+    iterf0_channel_units_kernel(const IterArgs a, const int fw, const int lo, const int G, const int dbg) {
   __shared__ __align__(16) double stage[kChanUnitsPerCta][2][kChanMaxGroup][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * kChanUnitsPerCta + warp;
   const int64_t n_full = (int64_t)a.n_batch_clips * fw;
   const int64_t n_left = lo ? ((int64_t)a.n_batch_clips + G - 1) / G : 0;
   if (u >= n_full + n_left) return;  // (warp-uniform; no block barrier in this kernel)
-  const bool left = u >= n_full;
+  // the left-over groups come FIRST in the grid (dbg bit 0: last): they are the slower kind of unit
+  // and would otherwise form the tail of the launch
+  const bool left_last = dbg & 1;
+  const bool left = left_last ? u >= n_full : u < n_left;
+  const int64_t uf = left_last ? u : u - n_left;        // full unit index
+  const int64_t ul = left_last ? u - n_full : u;        // left-over group index
+  if ((dbg & 2) && left) return;   // timing aids: full units only / left-over units only
+  if ((dbg & 4) && !left) return;
   const int64_t n = a.clip_len;
   int64_t lc;       // clip of this lane (within the batch)
   int ch, ci = 0;   // channel; row of the lane's clip in the stage
   bool active = true;
   if (!left) {
-    lc = u / fw;
-    ch = (int)(u - lc * fw) * 32 + lane;
+    lc = uf / fw;
+    ch = (int)(uf - lc * fw) * 32 + lane;
   } else {
     ci = lane / lo;
-    lc = (u - n_full) * G + ci;
+    lc = ul * G + ci;
     ch = fw * 32 + (lane - ci * lo);
     active = ci < G && lc < a.n_batch_clips;
     if (!active) {  // idle lanes run the arithmetic on the group's first clip and store nothing
       ci = 0;
-      lc = (u - n_full) * G;
+      lc = ul * G;
       ch = fw * 32;
     }
   }
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(32 * kChanUnitsPerCta, 24)
     }
   } else {
     double (*st)[kChanMaxGroup][33] = stage[warp];
-    const int64_t g0 = (u - n_full) * G;  // first clip of the group
+    const int64_t g0 = ul * G;  // first clip of the group
     const double* wg = a.w + g0 * n;
     auto fetch = [&](int buf, int64_t T0) {  // samples T0 .. T0 + 31 of the group's clips -> st[buf]
       const int64_t tn = T0 + lane;
@@ -388,14 +395,10 @@ static s8k::Tables s8k_tables(const float* win, const float2* t) {
   return T;
 }
 
-// V = 0: four phases P1 | P2 | P3 | MAG.  V = 1 ("pair"): P3 and MAG as one phase on row pairs
-// (s8k::p3mag; three barriers per channel).  V = 2 ("early"): pair, and the register part of the
-// NEXT channel's P1 (loads, window, 32-point DFT, twiddles) runs before the barrier that frees the
-// buffer, so warps that finish a channel early do not idle there and the global loads of P1 are
-// not all issued right behind a barrier.  V = 3 ("fetch"): pair, and only the loads and the window
-// of the next channel run before that barrier (16 packed values instead of 32 across it).
-// Same arithmetic per bin in all of them: identical results.
-template <int V>
+// PAIR (default): P3 and MAG as one phase on Hermitian row pairs (s8k::p3mag: no P3 stores, no MAG
+// row loads, one complex product per two bins, three barriers per channel); !PAIR: the four phases
+// P1 | P2 | P3 | MAG (CDB_ITERF0_SPEC=s8k).  Same arithmetic per bin: identical results.
+template <bool PAIR>
 __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);
@@ -408,58 +411,26 @@ __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(con
 #pragma unroll
     for (int j = 0; j < 16; ++j) U[h][j] = 0.f;
   const float* src = a.yc + (int64_t)lc * a.C * a.n_pad + f * s8k::kM;
-  if (V == 2) {
-    c64 v[32];
-    s8k::p1_compute(t, src, a.s8, v);
-    for (int ch = 0; ch < a.C; ++ch) {
-      s8k::p1_store(t, v, buf);
-      __syncthreads();
-      s8k::p2(t, a.s8, buf);
-      __syncthreads();
+  for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
+    s8k::p1(t, src, a.s8, buf);
+    __syncthreads();
+    s8k::p2(t, a.s8, buf);
+    __syncthreads();
+    if (PAIR) {
       s8k::p3mag(t, buf, a.s8, U, Unyq);
-      src += a.n_pad;
-      if (ch + 1 < a.C) s8k::p1_compute(t, src, a.s8, v);
+    } else {
+      s8k::p3(t, buf);
       __syncthreads();
+      s8k::mag(t, buf, a.s8, U, Unyq);
     }
-  } else if (V == 3) {
-    c64 x[16];
-    s8k::p1_load(t, src, a.s8, x);
-    for (int ch = 0; ch < a.C; ++ch) {
-      {
-        c64 v[32];
-        s8k::p1_dft(t, x, a.s8, v);
-        s8k::p1_store(t, v, buf);
-      }
-      __syncthreads();
-      s8k::p2(t, a.s8, buf);
-      __syncthreads();
-      s8k::p3mag(t, buf, a.s8, U, Unyq);
-      src += a.n_pad;
-      if (ch + 1 < a.C) s8k::p1_load(t, src, a.s8, x);
-      __syncthreads();
-    }
-  } else {
-    for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
-      s8k::p1(t, src, a.s8, buf);
-      __syncthreads();
-      s8k::p2(t, a.s8, buf);
-      __syncthreads();
-      if (V == 1) {
-        s8k::p3mag(t, buf, a.s8, U, Unyq);
-      } else {
-        s8k::p3(t, buf);
-        __syncthreads();
-        s8k::mag(t, buf, a.s8, U, Unyq);
-      }
-      __syncthreads();
-    }
+    __syncthreads();
   }
   double* out = a.Ut + gf * (int64_t)(s8k::kM + 1);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      out[V ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)U[h][j];
+      out[PAIR ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)U[h][j];
   if (t == 0) out[s8k::kM] = (double)Unyq;
 }
 
@@ -868,7 +839,7 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
 
 // Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
 // channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.
-// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<0>), 1: the pair phase (<1>, <2>).
+// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<false>), 1: the pair phase (<true>, default).
 int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U) {
   if (!yc || !U || C < 1 || variant < 0 || variant > 1) return -1;
   const int F = s8k::kM;
@@ -969,15 +940,11 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   a.tw = pl->d_tw;
   a.wsplit = pl->d_wsplit;
   bool use_s8k = pl->d_s8k != nullptr && p->power == 1.0;
-  // CDB_ITERF0_SPEC = s8k (default) | pair (P3 + MAG as one phase) | early (pair + the next
-  // channel's P1 registers before the barrier) | fetch (pair + the next channel's loads before
-  // the barrier) | generic
-  int s8k_v = 0;
+  // CDB_ITERF0_SPEC = pair (default: P3 + MAG as one phase) | s8k (four phases) | generic
+  bool s8k_pair = true;
   if (const char* sm = std::getenv("CDB_ITERF0_SPEC")) {
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
-    if (sm[0] == 'p') s8k_v = 1;
-    if (sm[0] == 'e') s8k_v = 2;
-    if (sm[0] == 'f') s8k_v = 3;
+    if (sm[0] == 's') s8k_pair = false;
   }
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
@@ -989,6 +956,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   bool chan_units = false;
   if (const char* cm = std::getenv("CDB_ITERF0_CHAN"))
     if (cm[0] == 'u') chan_units = true;
+  int chan_dbg = 0;  // CDB_ITERF0_CHAN_DBG: 1 = left-over groups last, 2 / 4 = timing aids (wrong results)
+  if (const char* dm = std::getenv("CDB_ITERF0_CHAN_DBG")) chan_dbg = std::atoi(dm);
   a.structured = 1;
   for (int c = 0; c < p->channels; ++c)
     if (p->res1_b[c][1] != 0.0 || p->res2_b[c][1] != 0.0 || p->res2_b[c][2] != 0.0) a.structured = 0;
@@ -1017,13 +986,9 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
   const size_t s8k_smem = (size_t)s8k::kBufLen * sizeof(c64);
   if (use_s8k) {
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<0>,
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<3>,
+    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   }
   const size_t per_smem = (size_t)2 * pl->M * 8;
@@ -1051,9 +1016,9 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
         const int64_t units = (int64_t)nb * fw + ((int64_t)nb + G - 1) / G;
         const unsigned grid = (unsigned)((units + kChanUnitsPerCta - 1) / kChanUnitsPerCta);
         if (a.structured)
-          iterf0_channel_units_kernel<true><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G);
+          iterf0_channel_units_kernel<true><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G, chan_dbg);
         else
-          iterf0_channel_units_kernel<false><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G);
+          iterf0_channel_units_kernel<false><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G, chan_dbg);
       } else if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
       else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
@@ -1063,14 +1028,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       cdb_mark(h, st, "iterf0_filter_kernel");
     }
     const int64_t nframes = (int64_t)nb * fpc;
-    if (use_s8k && s8k_v == 3)
-      iterf0_spectrum8k_kernel<3><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
-    else if (use_s8k && s8k_v == 2)
-      iterf0_spectrum8k_kernel<2><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
-    else if (use_s8k && s8k_v == 1)
-      iterf0_spectrum8k_kernel<1><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    if (use_s8k && s8k_pair)
+      iterf0_spectrum8k_kernel<true><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else if (use_s8k)
-      iterf0_spectrum8k_kernel<0><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+      iterf0_spectrum8k_kernel<false><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");

@@ -12,6 +12,8 @@
 //   P3  2 units/thread (k1, k2): 16-point DFT of 16 CONTIGUOUS elements -> Z[k1 + 32 k2 + 512 k3]
 //   MAG the Hermitian partner Z[8192 - k] of a unit's 16 outputs is one other contiguous row (in
 //       reverse order): |X[k]| accumulates in 32 + 1 per-thread registers over the channels.
+//   P3 + MAG run as ONE phase on row pairs by default (p3mag below); the separate phases are kept
+//   as CDB_ITERF0_SPEC=s8k.
 // Index i of the buffer lives at i + 2*(i >> 4): rows of 16 elements start 144 bytes apart, so the
 // 128-bit row reads of P3 / MAG and the strided 64-bit accesses of P1 / P2 are all conflict-free.
 // (The radix-2 kernel this replaces ran 13 barrier-separated passes with 44 % bank conflicts.)
@@ -68,41 +70,22 @@ F32X2_HD void dft16(const c64 (&in)[16], c64 (&v)[16]) {
   fft16p_dit_tail(v);
 }
 
-// src: the 8192 filtered samples of this (frame, channel).  p1_compute: loads, window, 32-point DFT
-// and the inter-pass twiddles, all in registers (it touches no shared memory, so it may run before
-// the barrier that frees the buffer); p1_store: the 32 strided stores.
-F32X2_HD void p1_load(int t, const float* src, const Tables& T, c64 (&x)[16]) {  // windowed z[256 n1 + t]
+// src: the 8192 filtered samples of this (frame, channel)
+F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
   const c64* s2 = reinterpret_cast<const c64*>(src);  // (x[2m], x[2m+1]) pairs, 8-byte aligned
-#pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) {
-    const int m = 256 * n1 + t;
-    x[n1] = mul2(s2[m], T.win2[m]);
-  }
-}
-F32X2_HD void p1_dft(int t, const c64 (&x)[16], const Tables& T, c64 (&v)[32]) {
+  c64 v[32];
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const int n1 = br5(2 * p);  // < 16; its butterfly partner n1 + 16 is zero padding
-    v[2 * p] = x[n1];
-    v[2 * p + 1] = x[n1];
+    const int m = 256 * n1 + t;
+    const c64 x = mul2(s2[m], T.win2[m]);
+    v[2 * p] = x;
+    v[2 * p + 1] = x;
   }
   fft32p_dit_tail<-1>(v);
+  buf[pad(t)] = v[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
-}
-F32X2_HD void p1_compute(int t, const float* src, const Tables& T, c64 (&v)[32]) {
-  c64 x[16];
-  p1_load(t, src, T, x);
-  p1_dft(t, x, T, v);
-}
-F32X2_HD void p1_store(int t, const c64 (&v)[32], c64* buf) {
-#pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = v[k1];
-}
-F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
-  c64 v[32];
-  p1_compute(t, src, T, v);
-  p1_store(t, v, buf);
+  for (int k1 = 1; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
 }
 
 F32X2_HD void p2(int t, const Tables& T, c64* buf) {
