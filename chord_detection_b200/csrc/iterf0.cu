@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
 // output.  Units of the two kinds take the same time and are dealt to the SMs by the same grid, so
 // there is no serial tail (the two-kernel form of this idea had one).
 constexpr int kChanMaxGroup = 8;
-constexpr int kChanUnitsPerCta = 1;  // 32-thread CTAs: ptxas fits both paths in 80 registers (24 warps per SM)
+// UPC = units (warps) per CTA: 1 -> 24 CTAs per SM, 3 -> 8 CTAs of 96 threads per SM
 
 template <bool STRUCTURED>
 struct ChanLane {
@@ -212,12 +212,12 @@ struct ChanLane {
   }
 };
 
-template <bool STRUCTURED>
-__global__ void __launch_bounds__(32 * kChanUnitsPerCta, 24)
+template <bool STRUCTURED, int UPC>
+__global__ void __launch_bounds__(32 * UPC, 24 / UPC)
     iterf0_channel_units_kernel(const IterArgs a, const int fw, const int lo, const int G, const int dbg) {
-  __shared__ __align__(16) double stage[kChanUnitsPerCta][2][kChanMaxGroup][33];
+  __shared__ __align__(16) double stage[UPC][2][kChanMaxGroup][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t u = (int64_t)blockIdx.x * kChanUnitsPerCta + warp;
+  const int64_t u = (int64_t)blockIdx.x * UPC + warp;
   const int64_t n_full = (int64_t)a.n_batch_clips * fw;
   const int64_t n_left = lo ? ((int64_t)a.n_batch_clips + G - 1) / G : 0;
   if (u >= n_full + n_left) return;  // (warp-uniform; no block barrier in this kernel)
@@ -956,6 +956,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   bool chan_units = false;
   if (const char* cm = std::getenv("CDB_ITERF0_CHAN"))
     if (cm[0] == 'u') chan_units = true;
+  int chan_upc = 1;  // CDB_ITERF0_CHAN_UPC: units per CTA of the units kernel (1 or 3)
+  if (const char* um = std::getenv("CDB_ITERF0_CHAN_UPC")) chan_upc = std::atoi(um) == 3 ? 3 : 1;
   int chan_dbg = 0;  // CDB_ITERF0_CHAN_DBG: 1 = left-over groups last, 2 / 4 = timing aids (wrong results)
   if (const char* dm = std::getenv("CDB_ITERF0_CHAN_DBG")) chan_dbg = std::atoi(dm);
   a.structured = 1;
@@ -1014,11 +1016,22 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       if (chan_units && lo > 0) {  // one warp per unit, left-over channels of G clips in one warp
         const int G = std::min(32 / lo, kChanMaxGroup);
         const int64_t units = (int64_t)nb * fw + ((int64_t)nb + G - 1) / G;
-        const unsigned grid = (unsigned)((units + kChanUnitsPerCta - 1) / kChanUnitsPerCta);
-        if (a.structured)
-          iterf0_channel_units_kernel<true><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G, chan_dbg);
-        else
-          iterf0_channel_units_kernel<false><<<grid, 32 * kChanUnitsPerCta, 0, st>>>(a, fw, lo, G, chan_dbg);
+        auto launch = [&](auto kern, int upc) -> cudaError_t {
+          if (chan_dbg & 8) {  // ask for the largest shared-memory carve-out (24 CTAs x 4 KB per SM)
+            const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                       cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+          }
+          kern<<<(unsigned)((units + upc - 1) / upc), 32 * upc, 0, st>>>(a, fw, lo, G, chan_dbg);
+          return cudaSuccess;
+        };
+        if (chan_upc == 3) {
+          if (a.structured) CDB_CUDA(h, launch(iterf0_channel_units_kernel<true, 3>, 3));
+          else CDB_CUDA(h, launch(iterf0_channel_units_kernel<false, 3>, 3));
+        } else {
+          if (a.structured) CDB_CUDA(h, launch(iterf0_channel_units_kernel<true, 1>, 1));
+          else CDB_CUDA(h, launch(iterf0_channel_units_kernel<false, 1>, 1));
+        }
       } else if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
       else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);
       cdb_mark(h, st, "iterf0_channel_kernel");
