@@ -156,21 +156,28 @@ __global__ void __launch_bounds__(128) iterf0_channel_kernel(const IterArgs a) {
     for (int64_t t = n; t < a.n_pad; ++t) dst[t] = 0.0f;
 }
 
-// ---- the same filter chain, one WARP per unit of work ("units" form, CDB_ITERF0_CHAN=units) -------
-// With C = 70 channels a clip is two full warps and one warp with 6 busy lanes: the kernel above
-// issues three warps of FP64 work per clip for 2.19 warps' worth of channels, and it is bound by the
-// FP64 pipe.  Here the left-over channels (C mod 32 per clip) of G = floor(32 / (C mod 32)) clips
-// share ONE warp (C = 70: 5 clips x 6 channels = 30 lanes), so a clip costs 2.2 warps.  A unit is a
-// warp: units [0, clips * fw) are (clip, 32 channels) as before (samples broadcast by shuffles),
-// the rest are left-over groups.  A left-over warp needs the samples of G clips: they are staged
-// per warp in shared memory (cp.async, 8 bytes per lane and clip, double-buffered: the next 32
-// samples of every clip land while these are consumed), rows 33 doubles apart so that the lanes of
-// different clips read different banks; one LDS.64 replaces the two SHFL of the broadcast.
+// ---- the same filter chain, one WARP per unit of work ("units" forms, CDB_ITERF0_CHAN) -------------
+// Two things the CTA-per-clip kernel above leaves on the table (r02R / r02S timings):
+//  * its stores: a lane writes 16 bytes of ITS row per 4 samples, so one store instruction is 32
+//    partial-sector requests to 32 rows 4 n_pad bytes apart -- the kernel's time follows the number
+//    of bytes stored (~1.3 TB/s of 16-byte requests), not the FP64 work (a warp alone runs 3x
+//    faster per sample; dropping a third of the warps changes nothing).  TR: the lanes park their
+//    outputs in a per-warp shared-memory ring [32 rows][32 samples] (rows 36 floats apart:
+//    conflict-free 128-bit accesses both ways) and every 32 samples the warp writes the block out
+//    transposed -- 8 lanes x 16 bytes = one full 128-byte line of one row, 4 rows per instruction
+//    (row pointers travel by shuffle); the zero fill of [n, n_pad) is written the same way.
+//  * with C = 70 channels a clip is two full warps and one warp with 6 busy lanes.  Here the
+//    left-over channels (C mod 32 per clip) of G = floor(32 / (C mod 32)) clips share ONE warp
+//    (C = 70: 5 clips x 6 channels = 30 lanes), so a clip costs 2.2 warps instead of 3.  A unit is
+//    a warp: the left-over groups first, then (clip, 32 channels) units as before (samples
+//    broadcast by shuffles).  A left-over warp needs the samples of G clips: they are staged per
+//    warp in shared memory (cp.async, 8 bytes per lane and clip, double-buffered: the next 32
+//    samples of every clip land while these are consumed), rows 33 doubles apart so that the
+//    lanes of different clips read different banks; one LDS.64 replaces the two SHFL.
 // Every (clip, channel) runs exactly the instruction sequence of iterf0_channel_kernel: identical
-// output.  Units of the two kinds take the same time and are dealt to the SMs by the same grid, so
-// there is no serial tail (the two-kernel form of this idea had one).
-constexpr int kChanMaxGroup = 8;
-// UPC = units (warps) per CTA: 1 -> 24 CTAs per SM, 3 -> 8 CTAs of 96 threads per SM
+// output (GPU test, bit for bit).
+constexpr int kChanMaxGroup = 5;
+constexpr int kRingStride = 36;  // floats per ring row (32 samples + 4: rows 144 bytes apart)
 
 template <bool STRUCTURED>
 struct ChanLane {
@@ -180,10 +187,47 @@ struct ChanLane {
   iff::SosState<NB2> r2a, r2b;
   iff::SosState<3> lp;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, v4 = 0.0;
-  float* dst;
+  float* dst;  // this lane's row; nullptr: idle lane (nothing is stored)
+
+  // TR: write the ring's block of samples [B0, B0 + 32) of all 32 rows, 4 rows per instruction
+  __device__ __forceinline__ void flush(const float* ring, int lane, int64_t B0, int64_t n) const {
+    const int c4 = (lane & 7) * 4;
+    const int64_t t = B0 + c4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = 4 * it + (lane >> 3);
+      const float4 v = *reinterpret_cast<const float4*>(ring + row * kRingStride + c4);
+      float* p = reinterpret_cast<float*>(
+          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), row));
+      if (p != nullptr && t < n) {
+        if (t + 4 <= n) {
+          *reinterpret_cast<float4*>(p + t) = v;
+        } else {
+          const float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (t + q < n) p[t + q] = o[q];
+        }
+      }
+    }
+  }
+  // TR: zero [n, n_pad) of all 32 rows, a row at a time (128-byte lines; n_pad is a multiple of the
+  // frame size, a power of two >= 64, and rows start 16-byte aligned)
+  __device__ __forceinline__ void zero_fill(int lane, int64_t n, int64_t n_pad) const {
+    const int64_t a0 = (n + 3) & ~(int64_t)3;  // <= n_pad
+    for (int row = 0; row < 32; ++row) {
+      float* p = reinterpret_cast<float*>(
+          __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), row));
+      if (p == nullptr) continue;  // (warp-uniform)
+      if (n + lane < a0) p[n + lane] = 0.0f;
+      for (int64_t t = a0 + 4 * lane; t < n_pad; t += 128)
+        *reinterpret_cast<float4*>(p + t) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
   // 32 samples T .. T + 31 (getx(i) = whitened sample T + i of this lane's clip)
-  template <class GetX>
-  __device__ __forceinline__ void chunk(int64_t T, int64_t n, bool active, GetX getx) {
+  template <bool TR, class GetX>
+  __device__ __forceinline__ void chunk(int64_t T, int64_t n, GetX getx, float* ring, int lane) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       float out[4];
@@ -199,7 +243,16 @@ struct ChanLane {
         s1 = r1a.step(k1, x);
       }
       const int64_t t0 = T + 4 * g - kChanLag;  // out[j] belongs to sample t0 + j (16-byte aligned group)
-      if (active && t0 >= 0 && t0 < n) {
+      if (TR) {
+        // ring column of sample t0: (4 g - 4) mod 32; the block [T - 32, T) is complete after g = 0
+        *reinterpret_cast<float4*>(ring + lane * kRingStride + ((4 * g + 28) & 31)) =
+            make_float4(out[0], out[1], out[2], out[3]);
+        if (g == 0) {
+          __syncwarp();
+          if (T >= 32) flush(ring, lane, T - 32, n);
+          __syncwarp();
+        }
+      } else if (dst != nullptr && t0 >= 0 && t0 < n) {
         if (t0 + 4 <= n) {
           *reinterpret_cast<float4*>(dst + t0) = make_float4(out[0], out[1], out[2], out[3]);
         } else {
@@ -210,28 +263,39 @@ struct ChanLane {
       }
     }
   }
+  // after the last chunk (the first T >= n + kChanLag is Tend): the pending block and the padding
+  template <bool TR>
+  __device__ __forceinline__ void finish(int64_t Tend, int64_t n, int64_t n_pad, const float* ring, int lane) {
+    if (TR) {
+      __syncwarp();
+      flush(ring, lane, Tend - 32, n);  // (columns 28..31 are samples >= n: masked)
+      zero_fill(lane, n, n_pad);
+    } else if (dst != nullptr) {
+      for (int64_t t = n; t < n_pad; ++t) dst[t] = 0.0f;
+    }
+  }
 };
 
-template <bool STRUCTURED, int UPC>
-__global__ void __launch_bounds__(32 * UPC, 24 / UPC)
+template <bool STRUCTURED, bool TR>
+__global__ void __launch_bounds__(32, 24)
     iterf0_channel_units_kernel(const IterArgs a, const int fw, const int lo, const int G, const int dbg) {
-  __shared__ __align__(16) double stage[UPC][2][kChanMaxGroup][33];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t u = (int64_t)blockIdx.x * UPC + warp;
+  __shared__ __align__(16) double stage[2][kChanMaxGroup][33];
+  __shared__ __align__(16) float ring[TR ? 32 * kRingStride : 4];
+  const int lane = threadIdx.x;
+  const int64_t u = blockIdx.x;
   const int64_t n_full = (int64_t)a.n_batch_clips * fw;
   const int64_t n_left = lo ? ((int64_t)a.n_batch_clips + G - 1) / G : 0;
-  if (u >= n_full + n_left) return;  // (warp-uniform; no block barrier in this kernel)
-  // the left-over groups come FIRST in the grid (dbg bit 0: last): they are the slower kind of unit
-  // and would otherwise form the tail of the launch
+  if (u >= n_full + n_left) return;
+  // the left-over groups come FIRST in the grid (dbg bit 0: last)
   const bool left_last = dbg & 1;
   const bool left = left_last ? u >= n_full : u < n_left;
-  const int64_t uf = left_last ? u : u - n_left;        // full unit index
-  const int64_t ul = left_last ? u - n_full : u;        // left-over group index
-  if ((dbg & 2) && left) return;   // timing aids: full units only / left-over units only
+  const int64_t uf = left_last ? u : u - n_left;  // full unit index
+  const int64_t ul = left_last ? u - n_full : u;  // left-over group index
+  if ((dbg & 2) && left) return;  // timing aids: full units only / left-over units only
   if ((dbg & 4) && !left) return;
   const int64_t n = a.clip_len;
-  int64_t lc;       // clip of this lane (within the batch)
-  int ch, ci = 0;   // channel; row of the lane's clip in the stage
+  int64_t lc;      // clip of this lane (within the batch)
+  int ch, ci = 0;  // channel; row of the lane's clip in the stage
   bool active = true;
   if (!left) {
     lc = uf / fw;
@@ -253,25 +317,25 @@ __global__ void __launch_bounds__(32 * UPC, 24 / UPC)
     L.k1.init(coef);
     L.k2.init(coef + 6);
     L.kl.init(coef + 12);
-    L.dst = a.yc + (lc * a.C + ch) * a.n_pad;
+    L.dst = active ? a.yc + (lc * a.C + ch) * a.n_pad : nullptr;
   }
+  int64_t T = 0;
   if (!left) {
     const double* w = a.w + lc * n;
     double cur = lane < n ? w[lane] : 0.0;
-    for (int64_t T = 0; T < n + kChanLag; T += 32) {
+    for (; T < n + kChanLag; T += 32) {
       const int64_t tn = T + 32 + lane;
       const double nxt = tn < n ? w[tn] : 0.0;
-      L.chunk(T, n, true, [&](int i) { return __shfl_sync(0xffffffffu, cur, i); });
+      L.template chunk<TR>(T, n, [&](int i) { return __shfl_sync(0xffffffffu, cur, i); }, ring, lane);
       cur = nxt;
     }
   } else {
-    double (*st)[kChanMaxGroup][33] = stage[warp];
     const int64_t g0 = ul * G;  // first clip of the group
     const double* wg = a.w + g0 * n;
-    auto fetch = [&](int buf, int64_t T0) {  // samples T0 .. T0 + 31 of the group's clips -> st[buf]
+    auto fetch = [&](int buf, int64_t T0) {  // samples T0 .. T0 + 31 of the group's clips -> stage[buf]
       const int64_t tn = T0 + lane;
       for (int r = 0; r < G; ++r) {
-        double* d = &st[buf][r][lane];
+        double* d = &stage[buf][r][lane];
         if (g0 + r < a.n_batch_clips && tn < n) {
           const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(wg + (int64_t)r * n + tn)
@@ -285,17 +349,16 @@ __global__ void __launch_bounds__(32 * UPC, 24 / UPC)
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     int b = 0;
-    for (int64_t T = 0; T < n + kChanLag; T += 32) {
+    for (; T < n + kChanLag; T += 32) {
       fetch(b ^ 1, T + 32);
-      const double* row = st[b][ci];
-      L.chunk(T, n, active, [&](int i) { return row[i]; });
+      const double* row = stage[b][ci];
+      L.template chunk<TR>(T, n, [&](int i) { return row[i]; }, ring, lane);
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();
       b ^= 1;
     }
   }
-  if (active)
-    for (int64_t t = n; t < a.n_pad; ++t) L.dst[t] = 0.0f;
+  L.template finish<TR>(T, n, a.n_pad, ring, lane);
 }
 
 constexpr int kSpecMaxPerThread = 8192 / kSpecThreads + 1;  // accumulators per thread (F <= 8192)
@@ -952,12 +1015,13 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   if (const char* fm = std::getenv("CDB_ITERF0_FILTER"))
     if (fm[0] == 'c') hoisted = false;
   // CDB_ITERF0_CHAN = clip (default: a CTA per clip, a thread per channel) | units (a warp per 32
-  // channels of a clip or per group of left-over channels of several clips)
-  bool chan_units = false;
-  if (const char* cm = std::getenv("CDB_ITERF0_CHAN"))
-    if (cm[0] == 'u') chan_units = true;
-  int chan_upc = 1;  // CDB_ITERF0_CHAN_UPC: units per CTA of the units kernel (1 or 3)
-  if (const char* um = std::getenv("CDB_ITERF0_CHAN_UPC")) chan_upc = std::atoi(um) == 3 ? 3 : 1;
+  // channels of a clip or per group of left-over channels of several clips) | tr (units + stores
+  // transposed through shared memory: full 128-byte lines)
+  int chan_mode = 0;
+  if (const char* cm = std::getenv("CDB_ITERF0_CHAN")) {
+    if (cm[0] == 'u') chan_mode = 1;
+    if (cm[0] == 't') chan_mode = 2;
+  }
   int chan_dbg = 0;  // CDB_ITERF0_CHAN_DBG: 1 = left-over groups last, 2 / 4 = timing aids (wrong results)
   if (const char* dm = std::getenv("CDB_ITERF0_CHAN_DBG")) chan_dbg = std::atoi(dm);
   a.structured = 1;
@@ -1013,24 +1077,15 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       cdb_mark(h, st, "iterf0_whiten_kernel");
       const int chan_threads = 32 * ((a.C + 31) / 32);
       const int fw = a.C / 32, lo = a.C % 32;
-      if (chan_units && lo > 0) {  // one warp per unit, left-over channels of G clips in one warp
-        const int G = std::min(32 / lo, kChanMaxGroup);
-        const int64_t units = (int64_t)nb * fw + ((int64_t)nb + G - 1) / G;
-        auto launch = [&](auto kern, int upc) -> cudaError_t {
-          if (chan_dbg & 8) {  // ask for the largest shared-memory carve-out (24 CTAs x 4 KB per SM)
-            const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                       cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-          }
-          kern<<<(unsigned)((units + upc - 1) / upc), 32 * upc, 0, st>>>(a, fw, lo, G, chan_dbg);
-          return cudaSuccess;
-        };
-        if (chan_upc == 3) {
-          if (a.structured) CDB_CUDA(h, launch(iterf0_channel_units_kernel<true, 3>, 3));
-          else CDB_CUDA(h, launch(iterf0_channel_units_kernel<false, 3>, 3));
+      if (chan_mode) {  // one warp per unit, left-over channels of G clips in one warp
+        const int G = lo ? std::min(32 / lo, kChanMaxGroup) : 1;
+        const int64_t units = (int64_t)nb * fw + (lo ? ((int64_t)nb + G - 1) / G : 0);
+        if (chan_mode == 2) {
+          if (a.structured) iterf0_channel_units_kernel<true, true><<<(unsigned)units, 32, 0, st>>>(a, fw, lo, G, chan_dbg);
+          else iterf0_channel_units_kernel<false, true><<<(unsigned)units, 32, 0, st>>>(a, fw, lo, G, chan_dbg);
         } else {
-          if (a.structured) CDB_CUDA(h, launch(iterf0_channel_units_kernel<true, 1>, 1));
-          else CDB_CUDA(h, launch(iterf0_channel_units_kernel<false, 1>, 1));
+          if (a.structured) iterf0_channel_units_kernel<true, false><<<(unsigned)units, 32, 0, st>>>(a, fw, lo, G, chan_dbg);
+          else iterf0_channel_units_kernel<false, false><<<(unsigned)units, 32, 0, st>>>(a, fw, lo, G, chan_dbg);
         }
       } else if (a.structured) iterf0_channel_kernel<true><<<nb, chan_threads, 0, st>>>(a);
       else iterf0_channel_kernel<false><<<nb, chan_threads, 0, st>>>(a);

@@ -169,21 +169,26 @@ def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
     _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-12)
 
 
-@pytest.mark.parametrize("n_clips,channels", [(1, 70), (5, 70), (7, 70), (11, 70), (6, 40), (10, 33), (3, 64)])
-def test_iterf0_channel_units_kernel_equals_clip_kernel(n_clips, channels, monkeypatch):
+@pytest.mark.parametrize("mode", ["units", "tr"])
+@pytest.mark.parametrize("n_clips,channels,n", [(1, 70, 2 * 8192 + 1237), (5, 70, 2 * 8192 + 1237),
+                                                (7, 70, 8192 + 30), (11, 70, 3 * 8192), (6, 40, 8192 + 1),
+                                                (10, 33, 2 * 8192 - 3), (3, 64, 8192 + 4099), (2, 70, 29)])
+def test_iterf0_channel_units_kernel_equals_clip_kernel(n_clips, channels, n, mode, monkeypatch):
     """CDB_ITERF0_CHAN=units (a warp per 32 channels of a clip, the left-over channels of G clips
-    packed into one warp and fed from a shared-memory stage) against the CTA-per-clip kernel: whole
-    and ragged groups, a clip length that ends inside a 32-sample chunk, channel counts with
-    G = 5 (70), 4 (40), the cap of 8 (33) and no left-over warp at all (64: falls back)."""
+    packed into one warp and fed from a shared-memory stage) and tr (the same with the stores
+    transposed through a shared-memory ring into full 128-byte lines, zero padding included) against
+    the CTA-per-clip kernel: whole and ragged groups, clip lengths that end anywhere in a 32-sample
+    chunk (also shorter than one), channel counts with G = 5 (70), 4 (40), the cap of 5 (33) and no
+    left-over warp at all (64)."""
     from chord_detection_b200 import ops
 
     freqs = None if channels == 70 else rn.iterf0_channels(channels)
-    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=300 + i, fs=22050, n=2 * 8192 + 1237))[0]
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=300 + i, fs=22050, n=n))[0]
                      for i in range(n_clips)])
     xd = torch.from_numpy(rows).to(_dev())
     monkeypatch.setenv("CDB_ITERF0_CHAN", "clip")
     a = ops.iterative_f0(xd, 22050, channel_freqs=freqs, per_clip=True, per_frame=True, voices=True)
-    monkeypatch.setenv("CDB_ITERF0_CHAN", "units")
+    monkeypatch.setenv("CDB_ITERF0_CHAN", mode)
     b = ops.iterative_f0(xd, 22050, channel_freqs=freqs, per_clip=True, per_frame=True, voices=True)
     torch.cuda.synchronize()
     # every (clip, channel) runs the same instruction sequence in both kernels: identical bits
