@@ -523,9 +523,17 @@ __device__ __forceinline__ double warp_max_f64(double v) {
   return dkey_inv(((unsigned long long)mh << 32) | ml);
 }
 
-__global__ void __launch_bounds__(1024) iterf0_periodicity_kernel(const IterArgs a) {
+// URG ("global", CDB_ITERF0_PER=global): the residual spectrum lives in GLOBAL memory (behind the
+// CTA's Ud slice; 128 KB per CTA, L1 / L2 resident) instead of 128 KB of shared memory, so that
+// TWO CTAs fit an SM (<= 640 threads at <= 48 registers): the search is a latency chain (two
+// barriers, a division and a serial sum per split), and a second CTA fills the gaps the first one
+// leaves.  A range maximum then costs an L1 / L2 load latency instead of a shared-memory one; the
+// block-maxima tables stay in shared memory.  Same arithmetic, same order: identical results.
+template <bool URG>
+__global__ void __launch_bounds__(URG ? 640 : 1024, URG ? 2 : 1) iterf0_periodicity_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  double* Ur = reinterpret_cast<double*>(smem);  // [nb]
+  double* Ur = URG ? a.Ud + ((int64_t)gridDim.x + blockIdx.x) * (2 * (int64_t)a.M)
+                   : reinterpret_cast<double*>(smem);  // [nb]
   __shared__ double part[2][32];  // [which][harmonic]: weighted range maximum
   __shared__ int s_go;
   __shared__ double s_lo_b, s_up_b, s_tau, s_best;
@@ -976,8 +984,15 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   const int F = p->frame_size;
   const int64_t fpc = cdb_num_frames(clip_len, F, F);
   const int64_t n_pad = fpc * F;
-  const int pgrid_max = h->num_sms;
-  const int64_t fixed = ud_bytes(p, pgrid_max) + 2048;  // + alignment slack
+  // CDB_ITERF0_PER = shared (default: residual spectrum in shared memory, one CTA per SM) | global
+  // (residual spectrum in global memory, two CTAs per SM; needs <= 640 threads = M <= 20 harmonics)
+  bool per_global = false;
+  if (const char* pm = std::getenv("CDB_ITERF0_PER"))
+    if (pm[0] == 'g' && 32 * p->M <= 640 && 4 * h->num_sms <= 1024) per_global = true;
+  // CTAs of the periodicity kernel; the workspace holds one Ud (and, per_global, one Ur) per CTA
+  const int pgrid_max = per_global ? 2 * h->num_sms : h->num_sms;
+  const int ud_slices = per_global ? 2 * pgrid_max : pgrid_max;  // <= 1024 (cdb_iterf0_workspace_bytes)
+  const int64_t fixed = ud_bytes(p, ud_slices) + 2048;  // + alignment slack
   const int64_t per = per_clip_bytes(p, clip_len);
   if (!d_workspace || workspace_bytes < fixed + per)
     return cdb_fail(h, CDB_E_INVALID, "workspace too small: need at least %lld bytes",
@@ -1014,13 +1029,13 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   bool hoisted = true;
   if (const char* fm = std::getenv("CDB_ITERF0_FILTER"))
     if (fm[0] == 'c') hoisted = false;
-  // CDB_ITERF0_CHAN = clip (default: a CTA per clip, a thread per channel) | units (a warp per 32
-  // channels of a clip or per group of left-over channels of several clips) | tr (units + stores
-  // transposed through shared memory: full 128-byte lines)
-  int chan_mode = 0;
+  // CDB_ITERF0_CHAN = tr (default: a warp per 32 channels of a clip or per group of left-over
+  // channels of several clips, stores transposed through shared memory into full 128-byte lines) |
+  // units (the same with per-lane 16-byte stores) | clip (a CTA per clip, a thread per channel)
+  int chan_mode = 2;
   if (const char* cm = std::getenv("CDB_ITERF0_CHAN")) {
     if (cm[0] == 'u') chan_mode = 1;
-    if (cm[0] == 't') chan_mode = 2;
+    if (cm[0] == 'c') chan_mode = 0;
   }
   int chan_dbg = 0;  // CDB_ITERF0_CHAN_DBG: 1 = left-over groups last, 2 / 4 = timing aids (wrong results)
   if (const char* dm = std::getenv("CDB_ITERF0_CHAN_DBG")) chan_dbg = std::atoi(dm);
@@ -1045,7 +1060,7 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   unsigned char* w = reinterpret_cast<unsigned char*>(d_workspace);
   w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 255) & ~(uintptr_t)255);
   a.Ud = reinterpret_cast<double*>(w);
-  unsigned char* wrest = w + ud_bytes(p, pgrid_max);
+  unsigned char* wrest = w + ud_bytes(p, ud_slices);
 
   const size_t spec_smem = (size_t)pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum_kernel,
@@ -1058,7 +1073,7 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   }
   const size_t per_smem = (size_t)2 * pl->M * 8;
-  CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel,
+  CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_smem));
   for (int64_t c0 = 0; c0 < n_clips; c0 += bmax) {
     const int nb = (int)std::min<int64_t>(bmax, n_clips - c0);
@@ -1104,7 +1119,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");
     const int pgrid = (int)std::min<int64_t>(nframes, pgrid_max);
-    iterf0_periodicity_kernel<<<pgrid, 32 * p->M, per_smem, st>>>(a);
+    // (per_global: every CTA finds its Ur slice at Ud + (gridDim.x + blockIdx.x) slices, and
+    // gridDim.x <= pgrid_max, so the slices stay inside the 2 * pgrid_max reserved above)
+    if (per_global) iterf0_periodicity_kernel<true><<<pgrid, 32 * p->M, 0, st>>>(a);
+    else iterf0_periodicity_kernel<false><<<pgrid, 32 * p->M, per_smem, st>>>(a);
     cdb_mark(h, st, "iterf0_periodicity_kernel");
     h->launches += 3;
     CDB_CUDA(h, cudaGetLastError());

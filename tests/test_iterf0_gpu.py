@@ -175,9 +175,9 @@ def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
                                                 (10, 33, 2 * 8192 - 3), (3, 64, 8192 + 4099), (2, 70, 29)])
 def test_iterf0_channel_units_kernel_equals_clip_kernel(n_clips, channels, n, mode, monkeypatch):
     """CDB_ITERF0_CHAN=units (a warp per 32 channels of a clip, the left-over channels of G clips
-    packed into one warp and fed from a shared-memory stage) and tr (the same with the stores
-    transposed through a shared-memory ring into full 128-byte lines, zero padding included) against
-    the CTA-per-clip kernel: whole and ragged groups, clip lengths that end anywhere in a 32-sample
+    packed into one warp and fed from a shared-memory stage) and tr (the default: the same with the
+    stores transposed through a shared-memory ring into full 128-byte lines, zero padding included)
+    against the CTA-per-clip kernel (CDB_ITERF0_CHAN=clip): whole and ragged groups, clip lengths that end anywhere in a 32-sample
     chunk (also shorter than one), channel counts with G = 5 (70), 4 (40), the cap of 5 (33) and no
     left-over warp at all (64)."""
     from chord_detection_b200 import ops
@@ -192,6 +192,25 @@ def test_iterf0_channel_units_kernel_equals_clip_kernel(n_clips, channels, n, mo
     b = ops.iterative_f0(xd, 22050, channel_freqs=freqs, per_clip=True, per_frame=True, voices=True)
     torch.cuda.synchronize()
     # every (clip, channel) runs the same instruction sequence in both kernels: identical bits
+    assert np.array_equal(a.extra.cpu().numpy(), b.extra.cpu().numpy())
+    assert torch.equal(a.frames, b.frames)
+    _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-12)
+
+
+def test_iterf0_periodicity_global_residual_equals_shared(monkeypatch):
+    """CDB_ITERF0_PER=global keeps the residual spectrum in global memory (two CTAs per SM) instead
+    of shared memory: same arithmetic in the same order, so every voice and every frame's chroma is
+    identical; more frames than CTAs, so that every CTA reuses its slices."""
+    from chord_detection_b200 import ops
+
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=340 + (i % 7), fs=22050, n=4 * 8192 - 100))[0]
+                     for i in range(100)])
+    xd = torch.from_numpy(rows).to(_dev())
+    monkeypatch.setenv("CDB_ITERF0_PER", "shared")
+    a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    monkeypatch.setenv("CDB_ITERF0_PER", "global")
+    b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    torch.cuda.synchronize()
     assert np.array_equal(a.extra.cpu().numpy(), b.extra.cpu().numpy())
     assert torch.equal(a.frames, b.frames)
     _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-12)
