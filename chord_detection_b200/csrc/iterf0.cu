@@ -523,7 +523,7 @@ __device__ __forceinline__ double warp_max_f64(double v) {
   return dkey_inv(((unsigned long long)mh << 32) | ml);
 }
 
-// URG ("global", CDB_ITERF0_PER=global): the residual spectrum lives in GLOBAL memory (behind the
+// URG (default; CDB_ITERF0_PER=shared selects the other form): the residual spectrum lives in GLOBAL memory (behind the
 // CTA's Ud slice; 128 KB per CTA, L1 / L2 resident) instead of 128 KB of shared memory, so that
 // TWO CTAs fit an SM (<= 640 threads at <= 48 registers): the search is a latency chain (two
 // barriers, a division and a serial sum per split), and a second CTA fills the gaps the first one
@@ -984,11 +984,12 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   const int F = p->frame_size;
   const int64_t fpc = cdb_num_frames(clip_len, F, F);
   const int64_t n_pad = fpc * F;
-  // CDB_ITERF0_PER = shared (default: residual spectrum in shared memory, one CTA per SM) | global
-  // (residual spectrum in global memory, two CTAs per SM; needs <= 640 threads = M <= 20 harmonics)
-  bool per_global = false;
+  // CDB_ITERF0_PER = global (default: residual spectrum in global memory, two CTAs per SM; needs
+  // <= 640 threads = M <= 20 harmonics, else shared) | shared (residual spectrum in shared memory,
+  // one CTA per SM)
+  bool per_global = 32 * p->M <= 640 && 4 * h->num_sms <= 1024;
   if (const char* pm = std::getenv("CDB_ITERF0_PER"))
-    if (pm[0] == 'g' && 32 * p->M <= 640 && 4 * h->num_sms <= 1024) per_global = true;
+    if (pm[0] == 's') per_global = false;
   // CTAs of the periodicity kernel; the workspace holds one Ud (and, per_global, one Ur) per CTA
   const int pgrid_max = per_global ? 2 * h->num_sms : h->num_sms;
   const int ud_slices = per_global ? 2 * pgrid_max : pgrid_max;  // <= 1024 (cdb_iterf0_workspace_bytes)
