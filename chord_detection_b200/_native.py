@@ -331,8 +331,9 @@ def host_iterf0_filter(x, coef, lam, taps, pipelined=True):
 
 def host_iterf0_spectrum8k(yc, variant=0):
     """Host execution of the frame-8192 summary-spectrum kernel (test hook, no GPU).
-    yc: [C, 8192] float32 filtered channels -> U[8193] float64.  variant 0: P3 + MAG phases,
-    1: the pair phase (CDB_ITERF0_SPEC=pair)."""
+    yc: [C, 8192] float32 filtered channels -> U[8193] float64.  variant bit 0: 0 = P3 + MAG phases,
+    1 = the pair phase (device default); bit 1: half inter-pass twiddle table, bit 2: half window
+    table (CDB_ITERF0_SPEC_OPT bits 1 and 2)."""
     import numpy as np
 
     yc = np.ascontiguousarray(np.atleast_2d(yc), dtype=np.float32)

@@ -28,6 +28,7 @@ struct IterF0Plan {
   cdb_iterf0_params p;
   int M, log2M;  // complex FFT size = frame_size
   float* d_win = nullptr;      // [frame_size] hamming
+  bool win_symmetric = false;  // win[F - 1 - n] == win[n] bit for bit (s8k::p1 OPT bit 2 relies on it)
   float2* d_tw = nullptr;      // [M/2] W_M^q
   float2* d_wsplit = nullptr;  // [M+1] (cos, sin)(2*pi*k/(2M))
   double* d_coef = nullptr;    // [channels][30]: res1 b,a | res2 b,a | lp b,a (each 3) ... see below
@@ -461,7 +462,8 @@ static s8k::Tables s8k_tables(const float* win, const float2* t) {
 // PAIR (default): P3 and MAG as one phase on Hermitian row pairs (s8k::p3mag: no P3 stores, no MAG
 // row loads, one complex product per two bins, three barriers per channel); !PAIR: the four phases
 // P1 | P2 | P3 | MAG (CDB_ITERF0_SPEC=s8k).  Same arithmetic per bin: identical results.
-template <bool PAIR>
+// OPT: s8k::p1's input / twiddle options (CDB_ITERF0_SPEC_OPT).
+template <bool PAIR, int OPT>
 __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(const IterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   c64* buf = reinterpret_cast<c64*>(smem);
@@ -474,8 +476,9 @@ __global__ void __launch_bounds__(s8k::kThreads, 2) iterf0_spectrum8k_kernel(con
 #pragma unroll
     for (int j = 0; j < 16; ++j) U[h][j] = 0.f;
   const float* src = a.yc + (int64_t)lc * a.C * a.n_pad + f * s8k::kM;
+  const c64 w16 = a.s8.tw1[16 * 256 + t];
   for (int ch = 0; ch < a.C; ++ch, src += a.n_pad) {
-    s8k::p1(t, src, a.s8, buf);
+    s8k::p1<OPT>(t, src, a.s8, buf, w16);
     __syncthreads();
     s8k::p2(t, a.s8, buf);
     __syncthreads();
@@ -850,6 +853,9 @@ static int iterf0_get_plan(cdb_handle* h, const cdb_iterf0_params* p, IterF0Plan
       return rc;
     }
   }
+  pl->win_symmetric = true;
+  for (int n = 0; n < F / 2; ++n)
+    if (win[n] != win[F - 1 - n]) pl->win_symmetric = false;
   if ((rc = cdb_upload(h, win, &pl->d_win)) || (rc = cdb_upload(h, tw, &pl->d_tw)) ||
       (rc = cdb_upload(h, ws, &pl->d_wsplit)) || (rc = cdb_upload(h, coef, &pl->d_coef))) {
     delete pl;
@@ -910,9 +916,13 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
 
 // Host execution (CPU tests, no GPU) of iterf0_spectrum8k_kernel for one frame: yc = the filtered
 // channels [C][8192] (fp32), U[8193] = sum over channels of |rfft(hamming * yc_c, 16384)|.
-// variant 0: P3 + MAG phases (iterf0_spectrum8k_kernel<false>), 1: the pair phase (<true>, default).
+// variant bit 0: 0 = P3 + MAG phases (iterf0_spectrum8k_kernel<false, 0>), 1 = the pair phase
+// (<true, .>, default); bits 1, 2: s8k::p1's OPT bits 1 (half inter-pass twiddle table) and 2 (half
+// window table).
 int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U) {
-  if (!yc || !U || C < 1 || variant < 0 || variant > 1) return -1;
+  if (!yc || !U || C < 1 || variant < 0 || variant > 7) return -1;
+  const bool pair = variant & 1;
+  const int opt = variant & 6;  // s8k::p1 OPT bits 1 (half twiddle table) and 2 (half window table)
   const int F = s8k::kM;
   const double pi = 3.14159265358979323846;
   std::vector<float> win(F);
@@ -929,9 +939,15 @@ int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U)
   std::memset(acc.data(), 0, acc.size() * sizeof(Acc));
   for (int ch = 0; ch < C; ++ch) {
     const float* src = yc + (size_t)ch * F;
-    for (int t = 0; t < s8k::kThreads; ++t) s8k::p1(t, src, T, buf.data());
+    for (int t = 0; t < s8k::kThreads; ++t) {
+      const c64 w16 = T.tw1[16 * 256 + t];
+      if (opt == 6) s8k::p1<6>(t, src, T, buf.data(), w16);
+      else if (opt == 4) s8k::p1<4>(t, src, T, buf.data(), w16);
+      else if (opt == 2) s8k::p1<2>(t, src, T, buf.data(), w16);
+      else s8k::p1<0>(t, src, T, buf.data(), w16);
+    }
     for (int t = 0; t < s8k::kThreads; ++t) s8k::p2(t, T, buf.data());
-    if (variant == 1) {
+    if (pair) {
       for (int t = 0; t < s8k::kThreads; ++t) s8k::p3mag(t, buf.data(), T, acc[t].U, acc[t].nyq);
     } else {
       for (int t = 0; t < s8k::kThreads; ++t) s8k::p3(t, buf.data());
@@ -941,7 +957,7 @@ int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U)
   for (int t = 0; t < s8k::kThreads; ++t)
     for (int h = 0; h < 2; ++h)
       for (int j = 0; j < 16; ++j)
-        U[variant == 1 ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)acc[t].U[h][j];
+        U[pair ? s8k::pair_bin_of(t, h, j) : s8k::bin_of(t, h, j)] = (double)acc[t].U[h][j];
   U[F] = (double)acc[0].nyq;
   return 0;
 }
@@ -1025,6 +1041,12 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
     if (sm[0] == 's') s8k_pair = false;
   }
+  // CDB_ITERF0_SPEC_OPT (pair kernel; 0, 1, 5 or 7): bit 0 = input frames loaded without L1
+  // allocation, bit 2 = half window table (symmetry, exact), bit 1 = half inter-pass twiddle table
+  // (rows >= 16 as a product with W_8192^(16 t))
+  int s8k_opt = 0;
+  if (const char* om = std::getenv("CDB_ITERF0_SPEC_OPT")) s8k_opt = std::atoi(om) & 7;
+  if (pl->d_s8k != nullptr && !pl->win_symmetric) s8k_opt &= 3;
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
   bool hoisted = true;
@@ -1068,10 +1090,10 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_smem));
   const size_t s8k_smem = (size_t)s8k::kBufLen * sizeof(c64);
   if (use_s8k) {
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
-    CDB_CUDA(h, cudaFuncSetAttribute(iterf0_spectrum8k_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
+    for (auto kern : {iterf0_spectrum8k_kernel<false, 0>, iterf0_spectrum8k_kernel<true, 0>,
+                      iterf0_spectrum8k_kernel<true, 1>, iterf0_spectrum8k_kernel<true, 5>,
+                      iterf0_spectrum8k_kernel<true, 7>})
+      CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   }
   const size_t per_smem = (size_t)2 * pl->M * 8;
   CDB_CUDA(h, cudaFuncSetAttribute(iterf0_periodicity_kernel<false>,
@@ -1112,10 +1134,14 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
       cdb_mark(h, st, "iterf0_filter_kernel");
     }
     const int64_t nframes = (int64_t)nb * fpc;
-    if (use_s8k && s8k_pair)
-      iterf0_spectrum8k_kernel<true><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
-    else if (use_s8k)
-      iterf0_spectrum8k_kernel<false><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    if (use_s8k && s8k_pair) {
+      auto kern = s8k_opt == 7   ? iterf0_spectrum8k_kernel<true, 7>
+                  : s8k_opt == 5 ? iterf0_spectrum8k_kernel<true, 5>
+                  : s8k_opt == 1 ? iterf0_spectrum8k_kernel<true, 1>
+                                 : iterf0_spectrum8k_kernel<true, 0>;
+      kern<<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
+    } else if (use_s8k)
+      iterf0_spectrum8k_kernel<false, 0><<<(unsigned)nframes, s8k::kThreads, s8k_smem, st>>>(a);
     else
       iterf0_spectrum_kernel<<<(unsigned)nframes, kSpecThreads, spec_smem, st>>>(a);
     cdb_mark(h, st, use_s8k ? "iterf0_spectrum8k_kernel" : "iterf0_spectrum_kernel");

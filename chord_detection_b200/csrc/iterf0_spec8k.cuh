@@ -70,22 +70,50 @@ F32X2_HD void dft16(const c64 (&in)[16], c64 (&v)[16]) {
   fft16p_dit_tail(v);
 }
 
-// src: the 8192 filtered samples of this (frame, channel)
-F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf) {
+// 64-bit load of streaming data that is read exactly once: no L1 allocation, so that the input
+// frames do not evict the twiddle / window tables (read-only path: nothing writes yc in this kernel)
+F32X2_HD c64 ld_stream(const c64* p) {
+#ifdef __CUDA_ARCH__
+  c64 v;
+  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+
+// src: the 8192 filtered samples of this (frame, channel).
+// OPT bit 0: the samples are loaded with ld_stream.  OPT bit 1: only rows k1 < 16 of the inter-pass
+// twiddle table are read; W_8192^(t k1) for k1 >= 16 is tw1[k1 - 16][t] * w16 with w16 =
+// W_8192^(16 t) = tw1[16][t] kept in a register (one more packed complex product per value, half
+// the table: the tables then fit the L1 that two 72 KB buffers leave; the products are within
+// 1.2e-7 of the tabulated values).  OPT bit 2: half window table (exact, see below).
+template <int OPT>
+F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf, c64 w16) {
   const c64* s2 = reinterpret_cast<const c64*>(src);  // (x[2m], x[2m+1]) pairs, 8-byte aligned
   c64 v[32];
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const int n1 = br5(2 * p);  // < 16; its butterfly partner n1 + 16 is zero padding
     const int m = 256 * n1 + t;
-    const c64 x = mul2(s2[m], T.win2[m]);
+    // OPT bit 2: the Hamming table is symmetric bit for bit (w[8191 - n] == w[n] in fp32, checked when
+    // the plan is built), so (w[2m], w[2m+1]) for m >= 2048 is the swapped pair 4095 - m: only the
+    // first half of the table is read
+    const c64 wv = ((OPT & 4) && n1 >= 8) ? swp(T.win2[4095 - m]) : T.win2[m];
+    const c64 x = mul2((OPT & 1) ? ld_stream(s2 + m) : s2[m], wv);
     v[2 * p] = x;
     v[2 * p + 1] = x;
   }
   fft32p_dit_tail<-1>(v);
   buf[pad(t)] = v[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 32; ++k1) buf[pad(k1 * 256 + t)] = cmul2(v[k1], T.tw1[k1 * 256 + t]);
+  for (int k1 = 1; k1 < 32; ++k1) {
+    c64 tw;
+    if ((OPT & 2) && k1 == 16) tw = w16;
+    else if ((OPT & 2) && k1 > 16) tw = cmul2(T.tw1[(k1 - 16) * 256 + t], w16);
+    else tw = T.tw1[k1 * 256 + t];
+    buf[pad(k1 * 256 + t)] = cmul2(v[k1], tw);
+  }
 }
 
 F32X2_HD void p2(int t, const Tables& T, c64* buf) {

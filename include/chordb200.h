@@ -182,8 +182,9 @@ int cdb_host_iterf0_filter(const float* x, int64_t n, const double* coef, double
  * kernel for one frame (iterative_f0.py:75-85): yc = filtered channels [C][8192] fp32,
  * U[8193] = sum_c |rfft(hamming(8192) * yc[c], 16384)|. */
 int cdb_host_iterf0_spectrum8k(const float* yc, int C, double* U);
-/* the same with the kernel variant: 0 = P3 + MAG phases (what cdb_host_iterf0_spectrum8k runs),
- * 1 = the pair phase (CDB_ITERF0_SPEC=pair: both rows of a Hermitian pair in one thread's registers) */
+/* the same with the kernel variant: bit 0: 0 = P3 + MAG phases (what cdb_host_iterf0_spectrum8k runs),
+ * 1 = the pair phase (the device default: both rows of a Hermitian pair in one thread's registers);
+ * bit 1 = half inter-pass twiddle table, bit 2 = half window table (CDB_ITERF0_SPEC_OPT bits 1, 2) */
 int cdb_host_iterf0_spectrum8k_v(const float* yc, int C, int variant, double* U);
 /* cdb_host_esacf_acf: host execution (CPU tests, no GPU) of the device FFT autocorrelation
  * (esacf.py:93-129: sum over the two channels of |DFT_N|^k, real inverse DFT, first (N-1)/2 lags,

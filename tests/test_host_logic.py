@@ -218,6 +218,12 @@ def test_host_iterf0_spectrum8k_matches_numpy_rfft():
         # the pair phase (CDB_ITERF0_SPEC=pair: both rows of a Hermitian pair in one thread's
         # registers, one complex product per two bins) must give the same bits
         assert np.array_equal(nat.host_iterf0_spectrum8k(yc32, variant=1), got)
+        # half window table (the fp32 Hamming table is symmetric bit for bit): exact as well
+        assert np.array_equal(nat.host_iterf0_spectrum8k(yc32, variant=1 | 4), got)
+        # half inter-pass twiddle table (rows >= 16 as products): the same transform to fp32 rounding
+        alt = nat.host_iterf0_spectrum8k(yc32, variant=1 | 2 | 4)
+        assert np.max(np.abs(alt - want)) <= 2e-6 * max(np.max(want), 1e-30)
+        assert np.max(np.abs(alt - got)) <= 1e-6 * max(np.max(want), 1e-30)
     with pytest.raises(ValueError):
         nat.host_iterf0_spectrum8k(np.zeros((1, 4096), dtype=np.float32))
 

@@ -214,3 +214,34 @@ def test_iterf0_periodicity_global_residual_equals_shared(monkeypatch):
     assert np.array_equal(a.extra.cpu().numpy(), b.extra.cpu().numpy())
     assert torch.equal(a.frames, b.frames)
     _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-12)
+
+
+@pytest.mark.parametrize("opt", [0, 1, 5, 7])
+def test_iterf0_spectrum_table_options(opt, monkeypatch):
+    """CDB_ITERF0_SPEC_OPT of the pair kernel: bit 0 (input frames loaded without L1 allocation) and
+    bit 2 (half window table, by the table's exact symmetry) change no arithmetic -- identical bits
+    to the four-phase kernel; bit 1 (half inter-pass twiddle table, rows >= 16 as products) moves
+    the spectrum by fp32 rounding: voices to 1e-9 / 1e-5, chroma to 1e-6, and the oracle still holds."""
+    from chord_detection_b200 import ops
+
+    rows = np.stack([cases.make_input(dict(fn="s_poly", seed=360 + i, fs=22050, n=3 * 8192 + 517))[0]
+                     for i in range(6)])
+    xd = torch.from_numpy(rows).to(_dev())
+    monkeypatch.setenv("CDB_ITERF0_SPEC", "s8k")
+    a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    monkeypatch.setenv("CDB_ITERF0_SPEC", "pair")
+    monkeypatch.setenv("CDB_ITERF0_SPEC_OPT", str(opt))
+    b = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
+    torch.cuda.synchronize()
+    va, vb = a.extra.cpu().numpy(), b.extra.cpu().numpy()
+    if opt & 2:
+        assert np.allclose(va[:, 4:], vb[:, 4:], rtol=1e-9, atol=0)
+        assert np.allclose(va[:, :4], vb[:, :4], rtol=1e-5, atol=0)
+        _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-6)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.stack([rn.iterf0(r, 22050) for r in rows[:2]])
+        _close(b.clips[:2].cpu().numpy(), want)
+    else:
+        assert np.array_equal(va, vb)
+        assert torch.equal(a.frames, b.frames)
