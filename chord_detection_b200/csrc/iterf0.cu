@@ -1041,11 +1041,11 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     if (sm[0] == 'g') use_s8k = false;  // generic radix-2 kernel
     if (sm[0] == 's') s8k_pair = false;
   }
-  // CDB_ITERF0_SPEC_OPT (pair kernel; 0, 1, 5 or 7): bit 0 = input frames loaded without L1
+  // CDB_ITERF0_SPEC_OPT (pair kernel; 0, 1, 5, 7, 13 or 15): bit 0 = input frames loaded without L1
   // allocation, bit 2 = half window table (symmetry, exact), bit 1 = half inter-pass twiddle table
-  // (rows >= 16 as a product with W_8192^(16 t))
+  // (rows >= 16 as a product with W_8192^(16 t)), bit 3 = window / twiddle loads marked evict-last
   int s8k_opt = 0;
-  if (const char* om = std::getenv("CDB_ITERF0_SPEC_OPT")) s8k_opt = std::atoi(om) & 7;
+  if (const char* om = std::getenv("CDB_ITERF0_SPEC_OPT")) s8k_opt = std::atoi(om) & 15;
   if (pl->d_s8k != nullptr && !pl->win_symmetric) s8k_opt &= 3;
   if (use_s8k) a.s8 = s8k_tables(pl->d_win, pl->d_s8k);
   // CDB_ITERF0_FILTER = hoisted (default: whitener once per clip) | chain (reference order per channel)
@@ -1092,7 +1092,8 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
   if (use_s8k) {
     for (auto kern : {iterf0_spectrum8k_kernel<false, 0>, iterf0_spectrum8k_kernel<true, 0>,
                       iterf0_spectrum8k_kernel<true, 1>, iterf0_spectrum8k_kernel<true, 5>,
-                      iterf0_spectrum8k_kernel<true, 7>})
+                      iterf0_spectrum8k_kernel<true, 7>, iterf0_spectrum8k_kernel<true, 13>,
+                      iterf0_spectrum8k_kernel<true, 15>})
       CDB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s8k_smem));
   }
   const size_t per_smem = (size_t)2 * pl->M * 8;
@@ -1135,7 +1136,9 @@ int cdb_iterf0_chroma(cdb_handle* h, const cdb_iterf0_params* p, const float* d_
     }
     const int64_t nframes = (int64_t)nb * fpc;
     if (use_s8k && s8k_pair) {
-      auto kern = s8k_opt == 7   ? iterf0_spectrum8k_kernel<true, 7>
+      auto kern = s8k_opt == 15  ? iterf0_spectrum8k_kernel<true, 15>
+                  : s8k_opt == 13 ? iterf0_spectrum8k_kernel<true, 13>
+                  : s8k_opt == 7 ? iterf0_spectrum8k_kernel<true, 7>
                   : s8k_opt == 5 ? iterf0_spectrum8k_kernel<true, 5>
                   : s8k_opt == 1 ? iterf0_spectrum8k_kernel<true, 1>
                                  : iterf0_spectrum8k_kernel<true, 0>;

@@ -82,8 +82,19 @@ F32X2_HD c64 ld_stream(const c64* p) {
 #endif
 }
 
+// 64-bit load of table data that should stay in L1 (evicted last)
+F32X2_HD c64 ld_keep(const c64* p) {
+#ifdef __CUDA_ARCH__
+  c64 v;
+  asm volatile("ld.global.nc.L1::evict_last.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+
 // src: the 8192 filtered samples of this (frame, channel).
-// OPT bit 0: the samples are loaded with ld_stream.  OPT bit 1: only rows k1 < 16 of the inter-pass
+// OPT bit 3: window and twiddle tables loaded with ld_keep.  OPT bit 0: the samples are loaded with ld_stream.  OPT bit 1: only rows k1 < 16 of the inter-pass
 // twiddle table are read; W_8192^(t k1) for k1 >= 16 is tw1[k1 - 16][t] * w16 with w16 =
 // W_8192^(16 t) = tw1[16][t] kept in a register (one more packed complex product per value, half
 // the table: the tables then fit the L1 that two 72 KB buffers leave; the products are within
@@ -99,7 +110,9 @@ F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf, c64 w16) {
     // OPT bit 2: the Hamming table is symmetric bit for bit (w[8191 - n] == w[n] in fp32, checked when
     // the plan is built), so (w[2m], w[2m+1]) for m >= 2048 is the swapped pair 4095 - m: only the
     // first half of the table is read
-    const c64 wv = ((OPT & 4) && n1 >= 8) ? swp(T.win2[4095 - m]) : T.win2[m];
+    const c64* wp = ((OPT & 4) && n1 >= 8) ? T.win2 + (4095 - m) : T.win2 + m;
+    const c64 wl = (OPT & 8) ? ld_keep(wp) : *wp;
+    const c64 wv = ((OPT & 4) && n1 >= 8) ? swp(wl) : wl;
     const c64 x = mul2((OPT & 1) ? ld_stream(s2 + m) : s2[m], wv);
     v[2 * p] = x;
     v[2 * p + 1] = x;
@@ -109,9 +122,13 @@ F32X2_HD void p1(int t, const float* src, const Tables& T, c64* buf, c64 w16) {
 #pragma unroll
   for (int k1 = 1; k1 < 32; ++k1) {
     c64 tw;
-    if ((OPT & 2) && k1 == 16) tw = w16;
-    else if ((OPT & 2) && k1 > 16) tw = cmul2(T.tw1[(k1 - 16) * 256 + t], w16);
-    else tw = T.tw1[k1 * 256 + t];
+    if ((OPT & 2) && k1 == 16) {
+      tw = w16;
+    } else {
+      const c64* tp = T.tw1 + (((OPT & 2) && k1 > 16) ? k1 - 16 : k1) * 256 + t;
+      tw = (OPT & 8) ? ld_keep(tp) : *tp;
+      if ((OPT & 2) && k1 > 16) tw = cmul2(tw, w16);
+    }
     buf[pad(k1 * 256 + t)] = cmul2(v[k1], tw);
   }
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Summary-spectrum kernel times (library event marks) under CDB_ITERF0_SPEC_OPT = 0 / 1 / 5 / 7
-(input frames without L1 allocation, half window table, half inter-pass twiddle table).
+"""Summary-spectrum kernel times (library event marks) under CDB_ITERF0_SPEC_OPT = 0 / 1 / 5 / 13 / 7 / 15
+(input frames without L1 allocation, half window table, half inter-pass twiddle table, evict-last tables).
 Last line: `BEST <opt>` (fastest on the C4 batch shape)."""
 import json
 import os
@@ -19,7 +19,7 @@ for n, length in ((2048, 65536), (2048, 44100)):
     base = torch.from_numpy(np.stack([synth.s_poly(3 + i, 22050, length) for i in range(8)])).to(dev)
     x = base.repeat((n + 7) // 8, 1)[:n].contiguous()
     ref = None
-    for opt in (0, 1, 5, 7):
+    for opt in (0, 1, 5, 13, 7, 15):
         os.environ["CDB_ITERF0_SPEC_OPT"] = str(opt)
         r = ops.iterative_f0(x, 22050, per_frame=True)
         torch.cuda.synchronize()
@@ -35,4 +35,4 @@ for n, length in ((2048, 65536), (2048, 44100)):
             spectrum_ms=round(best, 3), frames_equal=bool(torch.equal(ref, fr)),
             max_rel=float((ref - fr).abs().max() / ref.abs().max()))
 print(json.dumps(out, indent=1))
-print("BEST", min((0, 1, 5, 7), key=lambda o: out["2048x65536/opt%d" % o]["spectrum_ms"]))
+print("BEST", min((0, 1, 5, 13, 7, 15), key=lambda o: out["2048x65536/opt%d" % o]["spectrum_ms"]))

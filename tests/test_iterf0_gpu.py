@@ -216,10 +216,11 @@ def test_iterf0_periodicity_global_residual_equals_shared(monkeypatch):
     _close(a.clips.cpu().numpy(), b.clips.cpu().numpy(), tol=1e-12)
 
 
-@pytest.mark.parametrize("opt", [0, 1, 5, 7])
+@pytest.mark.parametrize("opt", [0, 1, 5, 13, 7, 15])
 def test_iterf0_spectrum_table_options(opt, monkeypatch):
     """CDB_ITERF0_SPEC_OPT of the pair kernel: bit 0 (input frames loaded without L1 allocation) and
-    bit 2 (half window table, by the table's exact symmetry) change no arithmetic -- identical bits
+    bit 2 (half window table, by the table's exact symmetry) and bit 3 (evict-last table loads)
+    change no arithmetic -- identical bits
     to the four-phase kernel; bit 1 (half inter-pass twiddle table, rows >= 16 as products) moves
     the spectrum by fp32 rounding: voices to 1e-9 / 1e-5, chroma to 1e-6, and the oracle still holds."""
     from chord_detection_b200 import ops
