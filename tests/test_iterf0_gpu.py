@@ -159,6 +159,7 @@ def test_iterf0_pair_spectrum_equals_four_phase(monkeypatch):
     rows = np.stack([cases.make_input(dict(fn="s_poly", seed=260 + i, fs=22050, n=3 * 8192 + 517))[0]
                      for i in range(6)])
     xd = torch.from_numpy(rows).to(_dev())
+    monkeypatch.delenv("CDB_ITERF0_SPEC_OPT", raising=False)  # the default table options are exact
     monkeypatch.setenv("CDB_ITERF0_SPEC", "s8k")
     a = ops.iterative_f0(xd, 22050, per_clip=True, per_frame=True, voices=True)
     monkeypatch.setenv("CDB_ITERF0_SPEC", "pair")
