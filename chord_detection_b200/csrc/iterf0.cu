@@ -1,20 +1,28 @@
 // Iterative F0 (method 3, Klapuri) — replaces /root/reference/chord_detection/iterative_f0.py:54-96
 // (+ :171-193 filterbank, dsp/wfir.py:25-43, dsp/lowpass.py:6-8) and the whole of periodicity.py.
 //
-// Three kernels per batch of clips (workspace supplied by the caller):
-//   iterf0_filter_kernel      one thread per (clip, channel): the auditory channel is an IIR chain
-//                             over the WHOLE clip (state spans frames, iterative_f0.py:57-65):
-//                             2+2 resonator biquads (:182-191), 12 all-passes + 13 taps (wfir),
-//                             |.| (:60), (y + lowpass_fc(y))/2 (:61-63).  FP64 recurrences; the
-//                             result is stored as fp32 [clip][channel][n], zero past the clip end.
-//   iterf0_spectrum_kernel    one CTA per (clip, frame): for each channel, Hamming window (:75),
-//                             zero-pad x2 (:76), 2*frame_size-point real FFT (as a frame_size-point
-//                             complex FFT in shared memory, fp32) and U[k] += |X_c[k]|^power in
-//                             fp64 (:80-85).  Only k <= frame_size is kept (|X[N-k]| = |X[k]|).
-//   iterf0_periodicity_kernel one CTA per frame (one warp per harmonic): the interval-splitting
-//                             tau search (periodicity.py:114-163), polyphony test (:72-75),
-//                             harmonic cancellation with the 9-tap spread (:78-99), up to
-//                             max_voices voices, fs/tau -> pitch class (:105-110).
+// Four kernels per batch of clips (workspace supplied by the caller); the defaults, with the
+// earlier forms kept behind environment switches:
+//   iterf0_whiten_kernel         the warped-FIR whitener (12 all-passes + 13 taps, dsp/wfir.py) ONCE
+//                                per clip, time-parallel in 2048-sample chunks with a 512-sample
+//                                warm-up (it commutes with the resonators: both are LTI, zero state)
+//   iterf0_channel_units_kernel  a warp per 32 channels of a clip (left-over channels of 5 clips
+//                                share a warp): 2+2 resonator biquads (:182-191), |.| (:60),
+//                                (y + lowpass_fc(y))/2 (:61-63) over the WHOLE clip (state spans
+//                                frames, :57-65), FP64 recurrences; fp32 [clip][channel][n_pad],
+//                                written as full 128-byte lines through a shared-memory transpose.
+//                                (iterf0_channel_kernel: a CTA per clip; iterf0_filter_kernel: the
+//                                reference's order, resonators then whitener, per (clip, channel))
+//   iterf0_spectrum8k_kernel     one CTA per (clip, frame), frame_size 8192 and power 1: for each
+//                                channel, Hamming window (:75), zero-pad x2 (:76), 16384-point real
+//                                FFT as one register-resident 8192-point complex FFT in packed
+//                                FP32x2 arithmetic, U[k] += |X_c[k]| (:80-85), k <= 8192
+//                                (iterf0_spec8k.cuh).  iterf0_spectrum_kernel: any frame size /
+//                                power, radix-2 in shared memory, fp64 accumulation.
+//   iterf0_periodicity_kernel    one CTA per frame (one warp per harmonic), two CTAs per SM: the
+//                                interval-splitting tau search (periodicity.py:114-163), polyphony
+//                                test (:72-75), harmonic cancellation with the 9-tap spread
+//                                (:78-99), up to max_voices voices, fs/tau -> pitch class (:105-110).
 #include <cmath>
 #include <cstring>
 
