@@ -429,3 +429,43 @@ def test_host_he8192_team_fft_matches_numpy():
             xw = sig.astype(np.float64) * w
             want = np.fft.fft(xw[0::2] + 1j * xw[1::2])
             assert np.max(np.abs(got - want)) <= 5e-7 * max(np.max(np.abs(want)), 1e-30), kind
+
+
+def test_iterf0_channel_units_cover_every_clip_channel_once():
+    """Index algebra of iterf0_channel_units_kernel (csrc/iterf0.cu), restated: a unit is a warp; the
+    left-over groups come first (G clips x (C mod 32) channels per warp), then (clip, 32 channels)
+    units.  Every (clip, channel) must be owned by exactly one active lane, whatever the batch size
+    and channel count, and the ring positions of the transposed stores must tile every 32-sample
+    block exactly once."""
+    for nb, C in ((1, 70), (5, 70), (7, 70), (2048, 70), (6, 40), (10, 33), (3, 64), (4, 6), (9, 31)):
+        fw, lo = C // 32, C % 32
+        G = min(32 // lo, 5) if lo else 1
+        n_left = (nb + G - 1) // G if lo else 0
+        owners = {}
+        for u in range(nb * fw + n_left):
+            for lane in range(32):
+                if u < n_left:
+                    ci = lane // lo
+                    lc, ch = u * G + ci, fw * 32 + (lane - ci * lo)
+                    if not (ci < G and lc < nb):
+                        continue
+                else:
+                    uf = u - n_left
+                    lc = uf // fw
+                    ch = (uf - lc * fw) * 32 + lane
+                assert ch < C
+                assert (lc, ch) not in owners
+                owners[(lc, ch)] = (u, lane)
+        assert len(owners) == nb * C
+    # ring column of the group g of iteration T (samples T + 4 g - 4 ...): (4 g + 28) & 31; the block
+    # [T - 32, T) is complete after g = 0 of iteration T
+    for T in (32, 64):
+        cols = {}
+        for Tw in (T - 32, T):
+            for g in range(8):
+                t0 = Tw + 4 * g - 4
+                for q in range(4):
+                    if T - 32 <= t0 + q < T:
+                        assert (Tw == T) == (g == 0)  # only g = 0 of iteration T still belongs to it
+                        cols[t0 + q - (T - 32)] = ((4 * g + 28) & 31) + q
+        assert cols == {c: c for c in range(32)}
